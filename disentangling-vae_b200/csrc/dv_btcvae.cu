@@ -1,0 +1,420 @@
+// beta-TCVAE log-density decomposition: the B x B (x D) pairwise Gaussian log-density "matrix"
+// of the reference and its three logsumexp reductions, evaluated without materialising anything
+// larger than O(B*D).
+//
+// Reference: disvae/models/losses.py:523-544 (_get_log_pz_qz_prodzi_qzCx), :369-373 (mi/tc/dw_kl),
+//            disvae/utils/math.py:8-51 (matrix_log_density_gaussian), :54-73 (importance weights).
+//
+//   m[i,j,d] = -0.5*(log 2pi + lv[j,d]) - 0.5*(z[i,d]-mu[j,d])^2 * exp(-lv[j,d])
+//   lw[i,j]  = log W[i,j]  (MSS; column-structured, trap T3)     or 0 (is_mss = False, trap T4)
+//   log_qz[i]       = LSE_j ( sum_d m[i,j,d] + D*lw[i,j] )        (trap T2: D-fold weight)
+//   log_prod_qzi[i] = sum_d LSE_j ( m[i,j,d] + lw[i,j] )
+//
+// Mapping: a warp is 4 rows (i) x 8 column-lanes (j); the 8 warps of a block split the j range,
+// so a block owns 4 rows and the grid is B/4 blocks.  Per-column parameters are precomputed once
+// by a prep kernel as float4 {c, hiv, mu, z} * in a [D][B] array that every block streams from
+// L1/L2: one 128-bit load fetches everything a (j,d) pair needs, 8 consecutive j per request,
+// broadcast over the warp's 4 rows.  All exponent arithmetic is done in the log2 domain
+// (c and hiv pre-multiplied by log2 e) so that each (i,j,d) costs one MUFU.EX2 and no extra
+// multiply.  Each logsumexp is an exact two-sweep (max, then sum of exp2) reduction; cross-lane
+// merges are warp shuffles, cross-warp merges go through a few hundred bytes of shared memory.
+#include "dv_common.cuh"
+
+namespace dv {
+
+constexpr float kLog2Pi = 1.8378770664093453f;
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+constexpr int kRows = 4;          // rows per warp (and per block)
+constexpr int kJL = 8;            // column lanes per warp
+constexpr int kBtWarps = 8;
+constexpr int kWsHeader = 16;     // floats before the float4 array (keeps it 64-byte aligned)
+
+struct LogW { float ln, ls, lm; int mss; int B; };   // log2 of 1/N, strat, 1/M
+__device__ __forceinline__ float logw2(const LogW& w, int i, int j) {
+  if (!w.mss) return 0.f;
+  if (j == 0) return (i == w.B - 2) ? w.ls : w.ln;
+  return (j == 1) ? w.ls : w.lm;
+}
+
+// rowstats is a structure of arrays [4 + D][B]: log_pz, log_qz, log_prod_qzi, log_q_zCx, P[d]
+// (natural-log units).  pj[d][b] = { c*log2e, hiv*log2e, mu, z } of batch row b.
+__global__ void btcvae_prep_kernel(const float* __restrict__ z, const float* __restrict__ mu, const float* __restrict__ logvar,
+                                   int ld, int row_stride, int B, int D, float4* __restrict__ pj, float* __restrict__ rowstats) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= B) return;
+  float lq = 0.f, lp = 0.f;
+  for (int d = lane; d < D; d += 32) {
+    const float m = mu[(long long)row * row_stride + (long long)d * ld];
+    const float lv = logvar[(long long)row * row_stride + (long long)d * ld];
+    const float zz = z[(long long)row * D + d];
+    const float cc = -0.5f * (kLog2Pi + lv);
+    const float iv = expf(-lv);
+    pj[(long long)d * B + row] = make_float4(cc * kLog2e, 0.5f * iv * kLog2e, m, zz);
+    const float t = zz - m;
+    lq += cc - 0.5f * (t * t * iv);                 // log N(z; mu, lv)      (math.py:48-51)
+    lp += -0.5f * kLog2Pi - 0.5f * (zz * zz);       // log N(z; 0, 0)        (losses.py:531-532)
+  }
+  lq = warp_sum(lq); lp = warp_sum(lp);
+  if (lane == 0) { rowstats[row] = lp; rowstats[3LL * B + row] = lq; }
+}
+
+// merge of (max, sum) logsumexp states, log2 domain
+__device__ __forceinline__ void lse_merge2(float& m, float& s, float m2, float s2) {
+  const float nm = fmaxf(m, m2);
+  if (nm == -INFINITY) { s = 0.f; return; }
+  s = s * exp2f(m - nm) + s2 * exp2f(m2 - nm);
+  m = nm;
+}
+
+// DC: latent dims held in registers per chunk.  FUSE: D <= DC, single chunk, the log_qz sweep is
+// fused into the max sweep.  EXACT: D == DC (no per-dim guards).
+template <int DC, bool FUSE, bool EXACT>
+__global__ void __launch_bounds__(kBtWarps * 32)
+btcvae_fwd_kernel(int B, int D, LogW lw, float* __restrict__ ws, float* __restrict__ rowstats, float* __restrict__ terms) {
+  __shared__ float sm_max[kBtWarps][kRows][DC];
+  __shared__ float sm_sum[kBtWarps][kRows][DC];
+  __shared__ float sm_am[kBtWarps][kRows], sm_as[kBtWarps][kRows];
+  __shared__ float sm_prod[kRows];
+  __shared__ bool is_last;
+  const float4* __restrict__ pj = reinterpret_cast<const float4*>(ws + kWsHeader);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r = lane >> 3, jl = lane & 7;
+  const int i = min((int)blockIdx.x * kRows + r, B - 1);       // tail rows recompute row B-1 (never stored)
+  const int slice = ((B + kBtWarps - 1) / kBtWarps + kJL - 1) / kJL * kJL;
+  const int j_begin = warp * slice, j_end = min(B, j_begin + slice);
+  const float Df = (float)D;
+
+  float am = -INFINITY, as = 0.f;                              // log_qz state (log2 domain)
+  if (!FUSE) {
+    for (int j = j_begin + jl; j < j_end; j += kJL) {
+      float sa = 0.f;
+      for (int d = 0; d < D; ++d) {
+        const float4 p = __ldg(pj + (long long)d * B + j);
+        const float t = __ldg(&pj[(long long)d * B + i].w) - p.z;
+        sa += p.x - p.y * (t * t);
+      }
+      const float a = sa + Df * logw2(lw, i, j);
+      const float nm = fmaxf(am, a);
+      as = as * exp2f(am - nm) + exp2f(a - nm);
+      am = nm;
+    }
+  }
+  if (threadIdx.x < kRows) sm_prod[threadIdx.x] = 0.f;
+
+  for (int d0 = 0; d0 < D; d0 += DC) {
+    const int nd = EXACT ? DC : min(DC, D - d0);
+    float zc[DC], mx[DC], sx[DC];
+#pragma unroll
+    for (int k = 0; k < DC; ++k) {
+      zc[k] = (EXACT || k < nd) ? __ldg(&pj[(long long)(d0 + k) * B + i].w) : 0.f;
+      mx[k] = -INFINITY; sx[k] = 0.f;
+    }
+    // ---- sweep 1: per-dimension max (and, fused, the log_qz online logsumexp) ----
+    for (int j = j_begin + jl; j < j_end; j += kJL) {
+      const float w = logw2(lw, i, j);
+      float sa = 0.f;
+#pragma unroll
+      for (int k = 0; k < DC; ++k) {
+        if (EXACT || k < nd) {
+          const float4 p = __ldg(pj + (long long)(d0 + k) * B + j);
+          const float t = zc[k] - p.z;
+          const float m = p.x - p.y * (t * t);
+          mx[k] = fmaxf(mx[k], m + w);
+          if (FUSE) sa += m;
+        }
+      }
+      if (FUSE) {
+        const float a = sa + Df * w;
+        const float nm = fmaxf(am, a);
+        as = as * exp2f(am - nm) + exp2f(a - nm);
+        am = nm;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < DC; ++k) {
+#pragma unroll
+      for (int o = 1; o < kJL; o <<= 1) mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
+      if (jl == 0) sm_max[warp][r][k] = mx[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < DC; ++k) {
+      float m = sm_max[0][r][k];
+#pragma unroll
+      for (int w2 = 1; w2 < kBtWarps; ++w2) m = fmaxf(m, sm_max[w2][r][k]);
+      mx[k] = m;                                               // block-wide max for (row, dim)
+    }
+    // ---- sweep 2: sum of exp2 ----
+    for (int j = j_begin + jl; j < j_end; j += kJL) {
+      const float w = logw2(lw, i, j);
+#pragma unroll
+      for (int k = 0; k < DC; ++k) {
+        if (EXACT || k < nd) {
+          const float4 p = __ldg(pj + (long long)(d0 + k) * B + j);
+          const float t = zc[k] - p.z;
+          sx[k] += exp2f((p.x - p.y * (t * t)) + (w - mx[k]));
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < DC; ++k) {
+#pragma unroll
+      for (int o = 1; o < kJL; o <<= 1) sx[k] += __shfl_xor_sync(0xffffffffu, sx[k], o);
+      if (jl == 0) sm_sum[warp][r][k] = sx[k];
+    }
+    __syncthreads();
+    if (warp == 0) {
+      for (int e = lane; e < kRows * DC; e += 32) {
+        const int rr = e / DC, k = e % DC;
+        if (k < nd) {
+          float s = 0.f;
+          for (int w2 = 0; w2 < kBtWarps; ++w2) s += sm_sum[w2][rr][k];
+          float m = sm_max[0][rr][k];
+          for (int w2 = 1; w2 < kBtWarps; ++w2) m = fmaxf(m, sm_max[w2][rr][k]);
+          const float P = (m + log2f(s)) * kLn2;
+          const int ii = blockIdx.x * kRows + rr;
+          if (ii < B) rowstats[(long long)(4 + d0 + k) * B + ii] = P;
+          sm_sum[0][rr][k] = P;                                // stash for the ordered row sum
+        }
+      }
+      __syncwarp();
+      if (lane < kRows) {
+        float p = sm_prod[lane];
+        for (int k = 0; k < nd; ++k) p += sm_sum[0][lane][k];
+        sm_prod[lane] = p;
+      }
+    }
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int o = 1; o < kJL; o <<= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, am, o), s2 = __shfl_xor_sync(0xffffffffu, as, o);
+    lse_merge2(am, as, m2, s2);
+  }
+  if (jl == 0) { sm_am[warp][r] = am; sm_as[warp][r] = as; }
+  __syncthreads();
+  if (threadIdx.x < kRows) {
+    const int rr = threadIdx.x, ii = blockIdx.x * kRows + rr;
+    float m = sm_am[0][rr], s = sm_as[0][rr];
+    for (int w2 = 1; w2 < kBtWarps; ++w2) lse_merge2(m, s, sm_am[w2][rr], sm_as[w2][rr]);
+    if (ii < B) {
+      rowstats[1LL * B + ii] = (m + log2f(s)) * kLn2;          // log_qz
+      rowstats[2LL * B + ii] = sm_prod[rr];                    // log_prod_qzi
+    }
+  }
+
+  // ---- last block: mi / tc / dw_kl means in a fixed order (losses.py:369-373) ----
+  unsigned* counter = reinterpret_cast<unsigned*>(ws);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  if (warp == 0) {
+    float mi = 0.f, tc = 0.f, dw = 0.f;
+    for (int ii = lane; ii < B; ii += 32) {
+      const float lpz = rowstats[ii], lqz = rowstats[1LL * B + ii], lprod = rowstats[2LL * B + ii], lqc = rowstats[3LL * B + ii];
+      mi += lqc - lqz; tc += lqz - lprod; dw += lprod - lpz;
+    }
+    mi = warp_sum(mi); tc = warp_sum(tc); dw = warp_sum(dw);
+    if (lane == 0) { terms[0] = mi / (float)B; terms[1] = tc / (float)B; terms[2] = dw / (float)B; *counter = 0u; }
+  }
+}
+
+// ---- backward ---------------------------------------------------------------------
+// G[i,j,d] = cq * S[i,j] + cp * T[i,j,d],  S = exp(A[i,j] - log_qz[i]),  T = exp(M[i,j,d] - P[i,d])
+// role 0 (rows):    g_z[i,d]  = sum_j G * (-(z_i - mu_j) * iv_j)            + direct terms
+// role 1 (columns): g_mu[j,d] = sum_i G * ( (z_i - mu_j) * iv_j)            + direct terms
+//                   g_lv[j,d] = sum_i G * (-0.5 + 0.5 (z_i - mu_j)^2 iv_j)  + direct terms
+// The thread owns a "line" (i for role 0, j for role 1) and sweeps the other index.
+template <int ROLE, int DC, bool FUSE, bool EXACT>
+__device__ __forceinline__ void btcvae_bwd_body(int B, int D, const LogW& lw, const float* __restrict__ ws,
+                                                const float* __restrict__ rowstats, float cq, float cp, float cqc, float cpz,
+                                                float* __restrict__ g_z, float* __restrict__ g_mu, float* __restrict__ g_lv,
+                                                int block) {
+  __shared__ float sm_a[kBtWarps][kRows][DC];
+  __shared__ float sm_b[kBtWarps][kRows][DC];
+  const float4* __restrict__ pj = reinterpret_cast<const float4*>(ws + kWsHeader);
+  const float* __restrict__ lqz = rowstats + 1LL * B;
+  const float* __restrict__ P = rowstats + 4LL * B;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r = lane >> 3, ol = lane & 7;
+  const int line = min(block * kRows + r, B - 1);
+  const int slice = ((B + kBtWarps - 1) / kBtWarps + kJL - 1) / kJL * kJL;
+  const int o_begin = warp * slice, o_end = min(B, o_begin + slice);
+  const float Df = (float)D;
+  const float own_lqz2 = lqz[line] * kLog2e;
+
+  for (int d0 = 0; d0 < D; d0 += DC) {
+    const int nd = EXACT ? DC : min(DC, D - d0);
+    float4 own[DC];                // role 0: {., ., ., z_i} + P_i*log2e in .x ; role 1: {c, hiv, mu, .} of column j
+    float acc_a[DC], acc_b[DC];
+#pragma unroll
+    for (int k = 0; k < DC; ++k) {
+      acc_a[k] = 0.f; acc_b[k] = 0.f;
+      if (EXACT || k < nd) {
+        own[k] = __ldg(pj + (long long)(d0 + k) * B + line);
+        if (ROLE == 0) own[k].x = P[(long long)(d0 + k) * B + line] * kLog2e;
+      } else own[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int o = o_begin + ol; o < o_end; o += kJL) {
+      const int i = (ROLE == 0) ? line : o;
+      const int j = (ROLE == 0) ? o : line;
+      const float w = logw2(lw, i, j);
+      float mk[DC], tk[DC], hk[DC], pk[DC];
+      float sa = 0.f;
+#pragma unroll
+      for (int k = 0; k < DC; ++k) {
+        if (EXACT || k < nd) {
+          const float4 q = __ldg(pj + (long long)(d0 + k) * B + o);
+          float t, h, cc;
+          if (ROLE == 0) { t = own[k].w - q.z; h = q.y; cc = q.x; pk[k] = own[k].x; }
+          else           { t = q.w - own[k].z; h = own[k].y; cc = own[k].x; pk[k] = P[(long long)(d0 + k) * B + o] * kLog2e; }
+          tk[k] = t; hk[k] = h;
+          mk[k] = cc - h * (t * t);
+          sa += mk[k];
+        } else { mk[k] = 0.f; tk[k] = 0.f; hk[k] = 0.f; pk[k] = 0.f; }
+      }
+      if (!FUSE) {                 // A[i,j] needs ALL dims, not only this chunk
+        sa = 0.f;
+        for (int d = 0; d < D; ++d) {
+          const float4 pi = __ldg(pj + (long long)d * B + i), pjv = __ldg(pj + (long long)d * B + j);
+          const float t = pi.w - pjv.z;
+          sa += pjv.x - pjv.y * (t * t);
+        }
+      }
+      const float lq2 = (ROLE == 0) ? own_lqz2 : lqz[i] * kLog2e;
+      const float gS = cq * exp2f(sa + Df * w - lq2);
+#pragma unroll
+      for (int k = 0; k < DC; ++k) {
+        if (EXACT || k < nd) {
+          const float T = exp2f(mk[k] + (w - pk[k]));
+          const float G = gS + cp * T;
+          // hk is 0.5*iv*log2e: (z-mu)*iv = 2*hk*t/log2e ; 0.5 (z-mu)^2 iv = hk t^2 / log2e
+          const float tiv = (2.f * kLn2) * hk[k] * tk[k];
+          if (ROLE == 0) acc_a[k] -= G * tiv;
+          else { acc_a[k] += G * tiv; acc_b[k] += G * (kLn2 * hk[k] * (tk[k] * tk[k]) - 0.5f); }
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < DC; ++k) {
+#pragma unroll
+      for (int o = 1; o < kJL; o <<= 1) {
+        acc_a[k] += __shfl_xor_sync(0xffffffffu, acc_a[k], o);
+        if (ROLE == 1) acc_b[k] += __shfl_xor_sync(0xffffffffu, acc_b[k], o);
+      }
+      if (ol == 0) { sm_a[warp][r][k] = acc_a[k]; if (ROLE == 1) sm_b[warp][r][k] = acc_b[k]; }
+    }
+    __syncthreads();
+    if (warp == 0) {
+      for (int e = lane; e < kRows * DC; e += 32) {
+        const int rr = e / DC, k = e % DC;
+        const int ln = block * kRows + rr;
+        if (k < nd && ln < B) {
+          float a = 0.f, b = 0.f;
+          for (int w2 = 0; w2 < kBtWarps; ++w2) { a += sm_a[w2][rr][k]; if (ROLE == 1) b += sm_b[w2][rr][k]; }
+          const float4 q = __ldg(pj + (long long)(d0 + k) * B + ln);
+          const float t = q.w - q.z;
+          const float tiv = (2.f * kLn2) * q.y * t;              // (z-mu) iv  of the diagonal pair
+          if (ROLE == 0) {
+            // d log_q_zCx / dz = -(z-mu) iv ; d log_pz / dz = -z
+            if (g_z) g_z[(long long)ln * D + d0 + k] = a - cqc * tiv - cpz * q.w;
+          } else {
+            if (g_mu) g_mu[(long long)ln * D + d0 + k] = a + cqc * tiv;
+            if (g_lv) g_lv[(long long)ln * D + d0 + k] = b + cqc * (kLn2 * q.y * (t * t) - 0.5f);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <int DC, bool FUSE, bool EXACT>
+__global__ void __launch_bounds__(kBtWarps * 32)
+btcvae_bwd_kernel(int B, int D, LogW lw, const float* __restrict__ ws, const float* __restrict__ rowstats,
+                  const float* __restrict__ g_terms, float* __restrict__ g_z, float* __restrict__ g_mu, float* __restrict__ g_lv) {
+  const float invB = 1.f / (float)B;
+  const float g_mi = g_terms[0], g_tc = g_terms[1], g_dw = g_terms[2];
+  const float cq = (g_tc - g_mi) * invB;       // d loss / d log_qz[i]
+  const float cp = (g_dw - g_tc) * invB;       // d loss / d log_prod_qzi[i]
+  const float cqc = g_mi * invB;               // d loss / d log_q_zCx[i]
+  const float cpz = -g_dw * invB;              // d loss / d log_pz[i]
+  const int nblk = (B + kRows - 1) / kRows;
+  if ((int)blockIdx.x < nblk)
+    btcvae_bwd_body<0, DC, FUSE, EXACT>(B, D, lw, ws, rowstats, cq, cp, cqc, cpz, g_z, g_mu, g_lv, blockIdx.x);
+  else
+    btcvae_bwd_body<1, DC, FUSE, EXACT>(B, D, lw, ws, rowstats, cq, cp, cqc, cpz, g_z, g_mu, g_lv, blockIdx.x - nblk);
+}
+
+static LogW make_logw(int B, long long n_data, int is_mss) {
+  LogW w; w.mss = is_mss; w.B = B;
+  const double N = (double)n_data, M = (double)(B - 1);
+  // math.py:66-73: the weights are stored in an fp32 tensor, then .log() in fp32
+  w.ln = logf((float)(1.0 / N)) * kLog2e;
+  w.ls = logf((float)((N - M) / (N * M))) * kLog2e;
+  w.lm = logf((float)(1.0 / M)) * kLog2e;
+  return w;
+}
+
+#define DV_BT_DISPATCH(D, CALL)                                   \
+  do {                                                            \
+    if ((D) == 10)      { CALL(10, true, true); }                 \
+    else if ((D) == 16) { CALL(16, true, true); }                 \
+    else if ((D) == 8)  { CALL(8, true, true); }                  \
+    else if ((D) <= 4)  { CALL(4, true, false); }                 \
+    else if ((D) < 8)   { CALL(8, true, false); }                 \
+    else if ((D) < 16)  { CALL(16, true, false); }                \
+    else if ((D) % 16 == 0) { CALL(16, false, true); }            \
+    else                { CALL(16, false, false); }               \
+  } while (0)
+
+}  // namespace dv
+
+using namespace dv;
+
+extern "C" {
+
+size_t dv_btcvae_workspace_bytes(int B, int D) { return (size_t)(kWsHeader + 4LL * B * D) * sizeof(float); }
+
+int dv_btcvae_fwd(const float* z, const float* mu, const float* logvar, int ld, int row_stride, int B, int D,
+                  long long n_data, int is_mss, float* rowstats, float* terms, void* workspace, void* stream) {
+  if (!z || !mu || !logvar || !rowstats || !terms || !workspace) return DV_ERR_BAD_ARG;
+  if (B < 2 || D < 1 || n_data < 1) return DV_ERR_BAD_SHAPE;
+  if ((uintptr_t)workspace & 15) return DV_ERR_BAD_ARG;
+  float* ws = reinterpret_cast<float*>(workspace);
+  cudaStream_t st = as_stream(stream);
+  btcvae_prep_kernel<<<(B + 3) / 4, 128, 0, st>>>(z, mu, logvar, ld, row_stride, B, D,
+                                                  reinterpret_cast<float4*>(ws + kWsHeader), rowstats);
+  int rc = check_launch();
+  if (rc != DV_OK) return rc;
+  const LogW lw = make_logw(B, n_data, is_mss);
+  const int grid = (B + kRows - 1) / kRows;
+#define DV_FWD_CALL(DC, FUSE, EXACT) \
+  btcvae_fwd_kernel<DC, FUSE, EXACT><<<grid, kBtWarps * 32, 0, st>>>(B, D, lw, ws, rowstats, terms)
+  DV_BT_DISPATCH(D, DV_FWD_CALL);
+#undef DV_FWD_CALL
+  return check_launch();
+}
+
+int dv_btcvae_bwd(int B, int D, long long n_data, int is_mss, const float* rowstats, const void* workspace,
+                  const float* g_terms, float* g_z, float* g_mu, float* g_logvar, void* stream) {
+  if (!rowstats || !g_terms || !workspace) return DV_ERR_BAD_ARG;
+  if (B < 2 || D < 1) return DV_ERR_BAD_SHAPE;
+  const float* ws = reinterpret_cast<const float*>(workspace);
+  cudaStream_t st = as_stream(stream);
+  const LogW lw = make_logw(B, n_data, is_mss);
+  const int grid = 2 * ((B + kRows - 1) / kRows);
+#define DV_BWD_CALL(DC, FUSE, EXACT) \
+  btcvae_bwd_kernel<DC, FUSE, EXACT><<<grid, kBtWarps * 32, 0, st>>>(B, D, lw, ws, rowstats, g_terms, g_z, g_mu, g_logvar)
+  DV_BT_DISPATCH(D, DV_BWD_CALL);
+#undef DV_BWD_CALL
+  return check_launch();
+}
+
+}  // extern "C"

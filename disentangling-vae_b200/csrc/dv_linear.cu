@@ -1,0 +1,159 @@
+// Fully-connected layers: one tiled FP32 GEMM with fused bias / activation / activation-gradient
+// epilogues.  Replaces nn.Linear + ReLU / LeakyReLU in disvae/models/encoders.py:81-86,
+// disvae/models/decoders.py:71-73, disvae/models/discriminator.py:63-68 and their backward.
+//
+//   C[m][n] = sum_r A(m, r) * Bm(r, n)         (r = reduction index)
+//   A(m, r)  = A[m * a_sm + r * a_sr]
+//   Bm(r, n) = Bp[r * b_sr + n * b_sn]
+// fwd  : A = x[M,K]  (a_sm=K, a_sr=1), Bm = w[N,K]^T (b_sr=1, b_sn=K), R = K
+// dgrad: A = g[M,N]  (a_sm=N, a_sr=1), Bm = w[N,K]   (b_sr=K, b_sn=1), R = N, output [M,K]
+// wgrad: A = g[M,N]^T(a_sm=1, a_sr=N), Bm = x[M,K]   (b_sr=K, b_sn=1), R = M, output [N,K]
+#include "dv_common.cuh"
+
+namespace dv {
+
+constexpr int BM = 64, BN = 64, BK = 16;
+
+struct GemmEpilogue {
+  const float* bias;       // per output column (may be null)
+  const float* mask_src;   // same shape as C: C *= act'(mask_src)   (may be null)
+  int act;                 // forward activation, or the activation whose gradient masks
+  float slope;
+};
+
+// A_R_CONTIG: A's reduction index is contiguous (a_sr == 1); else A's m index is contiguous.
+// B_R_CONTIG: B's reduction index is contiguous (b_sr == 1); else B's n index is contiguous.
+template <bool A_R_CONTIG, bool B_R_CONTIG>
+__global__ void __launch_bounds__(256)
+gemm_kernel(const float* __restrict__ A, const float* __restrict__ Bp, float* __restrict__ C,
+            int Mo, int No, int R, long long a_sm, long long a_sr, long long b_sr, long long b_sn,
+            GemmEpilogue ep) {
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Bs[BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;              // 16 x 16 threads, 4 x 4 outputs each
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int r0 = 0; r0 < R; r0 += BK) {
+    // ---- stage A tile (BM x BK) ----
+    if (A_R_CONTIG) {
+      const int m = tid >> 2, rq = (tid & 3) * 4;       // 64 rows x 4 quads of r
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int gm = m0 + m, gr = r0 + rq + e;
+        As[rq + e][m] = (gm < Mo && gr < R) ? __ldg(A + gm * a_sm + gr * a_sr) : 0.f;
+      }
+    } else {
+      const int r = tid >> 4, mq = (tid & 15) * 4;      // 16 r x 16 quads of m
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int gm = m0 + mq + e, gr = r0 + r;
+        As[r][mq + e] = (gm < Mo && gr < R) ? __ldg(A + gm * a_sm + gr * a_sr) : 0.f;
+      }
+    }
+    // ---- stage B tile (BK x BN) ----
+    if (B_R_CONTIG) {
+      const int n = tid >> 2, rq = (tid & 3) * 4;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int gn = n0 + n, gr = r0 + rq + e;
+        Bs[rq + e][n] = (gn < No && gr < R) ? __ldg(Bp + gr * b_sr + gn * b_sn) : 0.f;
+      }
+    } else {
+      const int r = tid >> 4, nq = (tid & 15) * 4;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int gn = n0 + nq + e, gr = r0 + r;
+        Bs[r][nq + e] = (gn < No && gr < R) ? __ldg(Bp + gr * b_sr + gn * b_sn) : 0.f;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gm = m0 + ty * 4 + i;
+    if (gm >= Mo) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gn = n0 + tx * 4 + j;
+      if (gn >= No) continue;
+      float v = acc[i][j];
+      const long long idx = (long long)gm * No + gn;
+      if (ep.mask_src) {
+        const float y = ep.mask_src[idx];
+        if (ep.act == DV_ACT_RELU) v = y > 0.f ? v : 0.f;
+        else if (ep.act == DV_ACT_LEAKY) v = y > 0.f ? v : v * ep.slope;
+      } else {
+        if (ep.bias) v += ep.bias[gn];
+        v = apply_act(v, ep.act, ep.slope);
+      }
+      C[idx] = v;
+    }
+  }
+}
+
+// out[n] = sum_m g[m][n]  (bias gradient), one thread per column, fixed order.
+__global__ void colsum_kernel(const float* __restrict__ g, float* __restrict__ out, int M, int N) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float s = 0.f;
+  for (int m = 0; m < M; ++m) s += g[(long long)m * N + n];
+  out[n] = s;
+}
+
+}  // namespace dv
+
+using namespace dv;
+
+extern "C" {
+
+int dv_linear_fwd(const float* x, const float* w, const float* bias, float* y, int M, int N, int K,
+                  int act, float slope, void* stream) {
+  if (!x || !w || !y) return DV_ERR_BAD_ARG;
+  if (M <= 0 || N <= 0 || K <= 0) return DV_ERR_BAD_SHAPE;
+  if (act < DV_ACT_NONE || act > DV_ACT_LEAKY) return DV_ERR_BAD_ARG;
+  GemmEpilogue ep{bias, nullptr, act, slope};
+  dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
+  gemm_kernel<true, true><<<grid, 256, 0, as_stream(stream)>>>(x, w, y, M, N, K, K, 1, 1, K, ep);
+  return check_launch();
+}
+
+int dv_linear_dgrad(const float* g, const float* w, const float* mask_src, float* dx, int M, int N, int K,
+                    int act, float slope, void* stream) {
+  if (!g || !w || !dx) return DV_ERR_BAD_ARG;
+  if (M <= 0 || N <= 0 || K <= 0) return DV_ERR_BAD_SHAPE;
+  GemmEpilogue ep{nullptr, mask_src, mask_src ? act : DV_ACT_NONE, slope};
+  dim3 grid((K + BN - 1) / BN, (M + BM - 1) / BM);
+  gemm_kernel<true, false><<<grid, 256, 0, as_stream(stream)>>>(g, w, dx, M, K, N, N, 1, K, 1, ep);
+  return check_launch();
+}
+
+int dv_linear_wgrad(const float* g, const float* x, float* dw, float* dbias, int M, int N, int K, void* stream) {
+  if (!g || !x || !dw) return DV_ERR_BAD_ARG;
+  if (M <= 0 || N <= 0 || K <= 0) return DV_ERR_BAD_SHAPE;
+  GemmEpilogue ep{nullptr, nullptr, DV_ACT_NONE, 0.f};
+  dim3 grid((K + BN - 1) / BN, (N + BM - 1) / BM);
+  gemm_kernel<false, false><<<grid, 256, 0, as_stream(stream)>>>(g, x, dw, N, K, M, 1, N, K, 1, ep);
+  int rc = check_launch();
+  if (rc != DV_OK || !dbias) return rc;
+  colsum_kernel<<<(N + 127) / 128, 128, 0, as_stream(stream)>>>(g, dbias, M, N);
+  return check_launch();
+}
+
+}  // extern "C"

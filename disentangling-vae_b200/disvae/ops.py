@@ -1,0 +1,486 @@
+"""torch.autograd.Function wrappers over the C ABI (include/disvae_b200.h).
+
+PyTorch is plumbing here: it owns device memory, streams and the autograd tape between the
+big nodes (encoder, decoder, discriminator, loss heads).  Every FLOP of the hot path runs in
+libdisvae_b200.so.  All functions require CUDA fp32 tensors and raise otherwise.
+"""
+import torch
+from torch.autograd import Function
+
+from . import _native as N
+from ._native import ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_SIGMOID, call, ptr, stream
+
+LO_CH = 32
+FLAT = 512          # 32 channels x 4 x 4  (encoders.py:63, decoders.py:55)
+DISC_SLOPE = 0.2    # discriminator.py:10
+
+# ---------------------------------------------------------------------------------------
+# persistent, zero-initialised scratch (kernels that use a "last block done" counter leave
+# it at zero, so one buffer per device can be reused across calls on the same stream)
+# ---------------------------------------------------------------------------------------
+_persist = {}
+
+
+def _zero_ws(key, nbytes, device):
+    k = (key, device.index)
+    buf = _persist.get(k)
+    if buf is None or buf.numel() * 4 < nbytes:
+        buf = torch.zeros((nbytes + 3) // 4, dtype=torch.float32, device=device)
+        _persist[k] = buf
+    return buf
+
+
+def _scratch(key, nbytes, device):
+    """Non-zeroed scratch, grown on demand (channel sums, wgrad partials)."""
+    k = (key, device.index)
+    buf = _persist.get(k)
+    if buf is None or buf.numel() * 4 < nbytes:
+        buf = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=device)
+        _persist[k] = buf
+    return buf
+
+
+def _new(shape, like):
+    return torch.empty(shape, dtype=torch.float32, device=like.device)
+
+
+# ---------------------------------------------------------------------------------------
+# thin functional layer (one C call each) -- also what the per-kernel parity tests use
+# ---------------------------------------------------------------------------------------
+def conv_pack(w, CH):
+    wp = _new((N.lib().dv_conv_packed_floats(CH),), w)
+    call("dv_conv_pack_weights", ptr(w), ptr(wp), CH, stream())
+    return wp
+
+
+def conv_down(hi, wp, bias, mask, B, H, W, CH, nchw, act):
+    lo = _new((B, H, W, LO_CH), hi)
+    call("dv_conv_down", ptr(hi), ptr(wp), ptr(bias), ptr(mask), ptr(lo), B, H, W, CH, nchw, act, stream())
+    return lo
+
+
+def conv_up(lo, wp, bias, mask, B, H, W, CH, nchw, act):
+    hi = _new((B, CH, 2 * H, 2 * W) if nchw else (B, 2 * H, 2 * W, CH), lo)
+    call("dv_conv_up", ptr(lo), ptr(wp), ptr(bias), ptr(mask), ptr(hi), B, H, W, CH, nchw, act, stream())
+    return hi
+
+
+def conv_wgrad(lo, hi, B, H, W, CH, nchw, want_dbias_lo):
+    L = N.lib()
+    nbytes = L.dv_conv_wgrad_workspace_bytes(B, H, W, CH)
+    ws = _scratch("wgrad", nbytes, lo.device)
+    dw = _new((LO_CH, CH, 4, 4), lo)
+    db = _new((LO_CH,), lo) if want_dbias_lo else None
+    call("dv_conv_wgrad", ptr(lo), ptr(hi), ptr(dw), ptr(db), ptr(ws), nbytes, B, H, W, CH, nchw, stream())
+    return dw, db
+
+
+def channel_sum(x, rows, C, nchw, hw):
+    ws = _scratch("chansum", N.lib().dv_channel_sum_workspace_bytes(), x.device)
+    out = _new((C,), x)
+    call("dv_channel_sum", ptr(x), ptr(out), rows, C, nchw, hw, ptr(ws), stream())
+    return out
+
+
+def flat_transpose(src, B, to_nhwc):
+    dst = torch.empty_like(src)
+    call("dv_flat_transpose", ptr(src), ptr(dst), B, LO_CH, 16, int(to_nhwc), stream())
+    return dst
+
+
+def act_bwd(dy, y, act, slope=0.0):
+    g = torch.empty_like(y)
+    call("dv_act_bwd", ptr(dy), ptr(y), ptr(g), y.numel(), act, slope, stream())
+    return g
+
+
+def linear_fwd(x, w, b, act, slope=0.0):
+    M, K = x.shape
+    Nn = w.shape[0]
+    y = _new((M, Nn), x)
+    call("dv_linear_fwd", ptr(x), ptr(w), ptr(b), ptr(y), M, Nn, K, act, slope, stream())
+    return y
+
+
+def linear_dgrad(g, w, mask_src, act, slope=0.0):
+    M, Nn = g.shape
+    K = w.shape[1]
+    dx = _new((M, K), g)
+    call("dv_linear_dgrad", ptr(g), ptr(w), ptr(mask_src), ptr(dx), M, Nn, K, act, slope, stream())
+    return dx
+
+
+def linear_wgrad(g, x, want_bias=True):
+    M, Nn = g.shape
+    K = x.shape[1]
+    dw = _new((Nn, K), g)
+    db = _new((Nn,), g) if want_bias else None
+    call("dv_linear_wgrad", ptr(g), ptr(x), ptr(dw), ptr(db), M, Nn, K, stream())
+    return dw, db
+
+
+def _c(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ---------------------------------------------------------------------------------------
+# Burgess encoder (disvae/models/encoders.py:69-89) as ONE autograd node
+# ---------------------------------------------------------------------------------------
+class EncoderFn(Function):
+    """x[B,C,S,S] -> mu_logvar[B,2z].  params = (conv w,b) * n_conv + (lin w,b) * 3."""
+
+    @staticmethod
+    def forward(ctx, x, n_conv, *params):
+        N.require_cuda_f32(x, *params)
+        x = _c(x)
+        params = [_c(p) for p in params]
+        B, C, S, _ = x.shape
+        convs = [(params[2 * i], params[2 * i + 1]) for i in range(n_conv)]
+        lins = [(params[2 * n_conv + 2 * i], params[2 * n_conv + 2 * i + 1]) for i in range(3)]
+        acts, packed = [], []
+        hi, CH, nchw, H = x, C, 1, S // 2
+        for w, b in convs:
+            wp = conv_pack(w, CH)
+            lo = conv_down(hi, wp, b, None, B, H, H, CH, nchw, ACT_RELU)
+            acts.append(lo)
+            packed.append(wp)
+            hi, CH, nchw, H = lo, LO_CH, 0, H // 2
+        flat = flat_transpose(acts[-1].view(B, FLAT), B, to_nhwc=False)          # -> [B, 32*4*4] in NCHW order
+        h1 = linear_fwd(flat, lins[0][0], lins[0][1], ACT_RELU)
+        h2 = linear_fwd(h1, lins[1][0], lins[1][1], ACT_RELU)
+        ml = linear_fwd(h2, lins[2][0], lins[2][1], ACT_NONE)
+        ctx.n_conv = n_conv
+        ctx.save_for_backward(x, flat, h1, h2, *acts, *packed, *params)
+        return ml
+
+    @staticmethod
+    def backward(ctx, g_ml):
+        n_conv = ctx.n_conv
+        saved = ctx.saved_tensors
+        x, flat, h1, h2 = saved[:4]
+        acts = saved[4:4 + n_conv]
+        packed = saved[4 + n_conv:4 + 2 * n_conv]
+        params = saved[4 + 2 * n_conv:]
+        lins = [(params[2 * n_conv + 2 * i], params[2 * n_conv + 2 * i + 1]) for i in range(3)]
+        B, C, S, _ = x.shape
+        g = _c(g_ml)
+        dlw3, dlb3 = linear_wgrad(g, h2)
+        g2 = linear_dgrad(g, lins[2][0], h2, ACT_RELU)
+        dlw2, dlb2 = linear_wgrad(g2, h1)
+        g1 = linear_dgrad(g2, lins[1][0], h1, ACT_RELU)
+        dlw1, dlb1 = linear_wgrad(g1, flat)
+        gflat = linear_dgrad(g1, lins[0][0], flat, ACT_RELU)                     # masked by the last conv's ReLU
+        g_lo = flat_transpose(gflat, B, to_nhwc=True)
+        conv_grads = [None] * (2 * n_conv)
+        dx = None
+        for l in range(n_conv - 1, -1, -1):
+            H = S >> (l + 1)
+            if l > 0:
+                dw, db = conv_wgrad(g_lo, acts[l - 1], B, H, H, LO_CH, 0, True)
+                g_lo = conv_up(g_lo, packed[l], None, acts[l - 1], B, H, H, LO_CH, 0, ACT_NONE)
+            else:
+                dw, db = conv_wgrad(g_lo, x, B, H, H, C, 1, True)
+                if ctx.needs_input_grad[0]:
+                    dx = conv_up(g_lo, packed[0], None, None, B, H, H, C, 1, ACT_NONE)
+            conv_grads[2 * l], conv_grads[2 * l + 1] = dw, db
+        return (dx, None, *conv_grads, dlw1, dlb1, dlw2, dlb2, dlw3, dlb3)
+
+
+# ---------------------------------------------------------------------------------------
+# Burgess decoder (disvae/models/decoders.py:67-84) as ONE autograd node
+# ---------------------------------------------------------------------------------------
+class DecoderFn(Function):
+    """z[B,D] -> recon[B,C,S,S].  params = (lin w,b) * 3 + (convT w,b) * n_convT."""
+
+    @staticmethod
+    def forward(ctx, z, n_convT, n_chan, *params):
+        N.require_cuda_f32(z, *params)
+        z = _c(z)
+        params = [_c(p) for p in params]
+        B = z.shape[0]
+        lins = [(params[2 * i], params[2 * i + 1]) for i in range(3)]
+        convTs = [(params[6 + 2 * i], params[6 + 2 * i + 1]) for i in range(n_convT)]
+        h1 = linear_fwd(z, lins[0][0], lins[0][1], ACT_RELU)
+        h2 = linear_fwd(h1, lins[1][0], lins[1][1], ACT_RELU)
+        h3 = linear_fwd(h2, lins[2][0], lins[2][1], ACT_RELU)                    # [B,512] == view(B,32,4,4)
+        lo = flat_transpose(h3, B, to_nhwc=True).view(B, 4, 4, LO_CH)
+        acts, packed = [lo], []
+        H = 4
+        for t, (w, b) in enumerate(convTs):
+            last = (t == n_convT - 1)
+            CH = n_chan if last else LO_CH
+            wp = conv_pack(w, CH)
+            packed.append(wp)
+            hi = conv_up(lo, wp, b, None, B, H, H, CH, 1 if last else 0, ACT_SIGMOID if last else ACT_RELU)
+            if not last:
+                acts.append(hi)
+            lo, H = hi, 2 * H
+        recon = lo
+        ctx.n_convT, ctx.n_chan = n_convT, n_chan
+        ctx.save_for_backward(z, h1, h2, recon, *acts, *packed, *params)
+        return recon
+
+    @staticmethod
+    def backward(ctx, d_recon):
+        n_convT, C = ctx.n_convT, ctx.n_chan
+        saved = ctx.saved_tensors
+        z, h1, h2, recon = saved[:4]
+        acts = saved[4:4 + n_convT]                 # acts[t] = input of convT t (NHWC)
+        packed = saved[4 + n_convT:4 + 2 * n_convT]
+        params = saved[4 + 2 * n_convT:]
+        lins = [(params[2 * i], params[2 * i + 1]) for i in range(3)]
+        B = z.shape[0]
+        S = recon.shape[-1]
+        g_hi = act_bwd(_c(d_recon), recon, ACT_SIGMOID)                            # NCHW, C channels
+        convT_grads = [None] * (2 * n_convT)
+        for t in range(n_convT - 1, -1, -1):
+            last = (t == n_convT - 1)
+            H = 4 << t                                   # input resolution of convT t
+            CH, nchw = (C, 1) if last else (LO_CH, 0)
+            if last:
+                db = channel_sum(g_hi, B, C, 1, S * S)
+            else:
+                db = channel_sum(g_hi, B * 4 * H * H, LO_CH, 0, 0)
+            dw, _ = conv_wgrad(acts[t], g_hi, B, H, H, CH, nchw, False)
+            g_hi = conv_down(g_hi, packed[t], None, acts[t], B, H, H, CH, nchw, ACT_NONE)   # masked by acts[t] > 0
+            convT_grads[2 * t], convT_grads[2 * t + 1] = dw, db
+        g3 = flat_transpose(g_hi.view(B, FLAT), B, to_nhwc=False)                  # grad of lin3 pre-activation
+        dlw3, dlb3 = linear_wgrad(g3, h2)
+        g2 = linear_dgrad(g3, lins[2][0], h2, ACT_RELU)
+        dlw2, dlb2 = linear_wgrad(g2, h1)
+        g1 = linear_dgrad(g2, lins[1][0], h1, ACT_RELU)
+        dlw1, dlb1 = linear_wgrad(g1, z)
+        dz = linear_dgrad(g1, lins[0][0], None, ACT_NONE) if ctx.needs_input_grad[0] else None
+        return (dz, None, None, dlw1, dlb1, dlw2, dlb2, dlw3, dlb3, *convT_grads)
+
+
+# ---------------------------------------------------------------------------------------
+# FactorVAE discriminator (disvae/models/discriminator.py:60-70) as ONE autograd node
+# ---------------------------------------------------------------------------------------
+class MlpFn(Function):
+    """x -> lin(act(...)): LeakyReLU(slope) after every layer but the last."""
+
+    @staticmethod
+    def forward(ctx, x, slope, *params):
+        N.require_cuda_f32(x, *params)
+        x = _c(x)
+        params = [_c(p) for p in params]
+        n = len(params) // 2
+        hs = [x]
+        h = x
+        for i in range(n):
+            h = linear_fwd(h, params[2 * i], params[2 * i + 1], ACT_LEAKY if i < n - 1 else ACT_NONE, slope)
+            hs.append(h)
+        ctx.slope, ctx.n = slope, n
+        ctx.save_for_backward(*hs[:-1], *params)
+        return h
+
+    @staticmethod
+    def backward(ctx, g_out):
+        n, slope = ctx.n, ctx.slope
+        saved = ctx.saved_tensors
+        hs, params = saved[:n], saved[n:]
+        g = _c(g_out)
+        grads = [None] * (2 * n)
+        dx = None
+        for i in range(n - 1, -1, -1):
+            grads[2 * i], grads[2 * i + 1] = linear_wgrad(g, hs[i])
+            if i > 0:
+                g = linear_dgrad(g, params[2 * i], hs[i], ACT_LEAKY, slope)
+            elif ctx.needs_input_grad[0]:
+                dx = linear_dgrad(g, params[0], None, ACT_NONE)
+        return (dx, None, *grads)
+
+
+# ---------------------------------------------------------------------------------------
+# reparameterisation (disvae/models/vae.py:65-68)
+# ---------------------------------------------------------------------------------------
+def _strides(mu, logvar):
+    """(ld, row_stride) if mu/logvar are [B,D] views with identical strides, else None."""
+    if mu.stride() == logvar.stride() and mu.dim() == 2:
+        return mu.stride(1), mu.stride(0)
+    return None
+
+
+class ReparamFn(Function):
+    @staticmethod
+    def forward(ctx, mu, logvar, eps, seed, offset_dev):
+        N.require_cuda_f32(mu, logvar, eps)
+        st = _strides(mu, logvar)
+        if st is None:
+            mu, logvar = mu.contiguous(), logvar.contiguous()
+            st = _strides(mu, logvar)
+        B, D = mu.shape
+        z = _new((B, D), mu)
+        if eps is not None:
+            eps = _c(eps)
+            call("dv_reparam_fwd", ptr(mu), ptr(logvar), st[0], st[1], ptr(eps), 0, None, ptr(z), None, B, D, stream())
+        else:
+            eps = _new((B, D), mu)
+            call("dv_reparam_fwd", ptr(mu), ptr(logvar), st[0], st[1], None, seed, ptr(offset_dev), ptr(z), ptr(eps),
+                 B, D, stream())
+        ctx.st = st
+        ctx.save_for_backward(logvar, eps)
+        return z
+
+    @staticmethod
+    def backward(ctx, g_z):
+        logvar, eps = ctx.saved_tensors
+        B, D = eps.shape
+        g_z = _c(g_z)
+        g_mu, g_lv = torch.empty_like(eps), torch.empty_like(eps)
+        call("dv_reparam_bwd", ptr(g_z), ptr(logvar), ctx.st[0], ctx.st[1], ptr(eps), ptr(g_mu), ptr(g_lv), B, D, stream())
+        return g_mu, g_lv, None, None, None
+
+
+# ---------------------------------------------------------------------------------------
+# fused reconstruction loss + KL (losses.py:394-449, 452-480)
+# ---------------------------------------------------------------------------------------
+class VaeLossFn(Function):
+    """-> out[2 + D] = (recon_loss, kl_total, kl_dim_0 .. kl_dim_{D-1}).
+    Only out[0] and out[1] carry gradient; out[2:] are logging values (kl_loss_<i>)."""
+
+    @staticmethod
+    def forward(ctx, recon, data, mu, logvar, dist):
+        N.require_cuda_f32(recon, data, mu, logvar)
+        recon, data = _c(recon), _c(data)
+        st = _strides(mu, logvar)
+        if st is None:
+            mu, logvar = mu.contiguous(), logvar.contiguous()
+            st = _strides(mu, logvar)
+        B, D = mu.shape
+        n_img = recon.numel() // B
+        ws = _zero_ws("vae_loss", N.lib().dv_vae_loss_workspace_bytes(B, n_img), recon.device)
+        out = _new((2 + D,), recon)
+        call("dv_vae_loss_fwd", ptr(recon), ptr(data), n_img, B, dist, ptr(mu), ptr(logvar), st[0], st[1], D,
+             ptr(out), ptr(ws), stream())
+        ctx.meta = (n_img, B, D, dist, st)
+        ctx.save_for_backward(recon, data, mu, logvar, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        recon, data, mu, logvar, out = ctx.saved_tensors
+        n_img, B, D, dist, st = ctx.meta
+        g_out = _c(g_out)
+        g_recon = torch.empty_like(recon) if ctx.needs_input_grad[0] else None
+        g_mu = _new((B, D), mu) if ctx.needs_input_grad[2] else None
+        g_lv = _new((B, D), mu) if ctx.needs_input_grad[3] else None
+        call("dv_vae_loss_bwd", ptr(recon), ptr(data), n_img, B, dist, ptr(mu), ptr(logvar), st[0], st[1], D,
+             ptr(out), ptr(g_out), ptr(g_recon), ptr(g_mu), ptr(g_lv), stream())
+        return g_recon, None, g_mu, g_lv, None
+
+
+# ---------------------------------------------------------------------------------------
+# beta-TCVAE decomposition (losses.py:523-544 + 369-373)
+# ---------------------------------------------------------------------------------------
+class BtcvaeFn(Function):
+    """-> terms[3] = (mi, tc, dw_kl).  ctx keeps the [4+D][B] row statistics."""
+
+    @staticmethod
+    def forward(ctx, z, mu, logvar, n_data, is_mss):
+        N.require_cuda_f32(z, mu, logvar)
+        z = _c(z)
+        st = _strides(mu, logvar)
+        if st is None:
+            mu, logvar = mu.contiguous(), logvar.contiguous()
+            st = _strides(mu, logvar)
+        B, D = z.shape
+        nbytes = N.lib().dv_btcvae_workspace_bytes(B, D)
+        ws = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=z.device)
+        ws[:16].zero_()
+        rowstats = _new((4 + D, B), z)
+        terms = _new((3,), z)
+        call("dv_btcvae_fwd", ptr(z), ptr(mu), ptr(logvar), st[0], st[1], B, D, int(n_data), int(bool(is_mss)),
+             ptr(rowstats), ptr(terms), ptr(ws), stream())
+        ctx.meta = (B, D, int(n_data), int(bool(is_mss)))
+        ctx.save_for_backward(rowstats, ws)
+        return terms
+
+    @staticmethod
+    def backward(ctx, g_terms):
+        rowstats, ws = ctx.saved_tensors
+        B, D, n_data, is_mss = ctx.meta
+        g_terms = _c(g_terms)
+        g_z = _new((B, D), rowstats) if ctx.needs_input_grad[0] else None
+        g_mu = _new((B, D), rowstats) if ctx.needs_input_grad[1] else None
+        g_lv = _new((B, D), rowstats) if ctx.needs_input_grad[2] else None
+        call("dv_btcvae_bwd", B, D, n_data, is_mss, ptr(rowstats), ptr(ws), ptr(g_terms), ptr(g_z), ptr(g_mu),
+             ptr(g_lv), stream())
+        return g_z, g_mu, g_lv, None, None
+
+
+def btcvae_rowstats(z, mu, logvar, n_data, is_mss=True):
+    """(log_pz, log_qz, log_prod_qzi, log_q_zCx) like losses.py:523-544 (no autograd)."""
+    with torch.no_grad():
+        z = _c(z)
+        st = _strides(mu, logvar)
+        if st is None:
+            mu, logvar = mu.contiguous(), logvar.contiguous()
+            st = _strides(mu, logvar)
+        B, D = z.shape
+        nbytes = N.lib().dv_btcvae_workspace_bytes(B, D)
+        ws = torch.zeros((nbytes + 3) // 4, dtype=torch.float32, device=z.device)
+        rowstats = _new((4 + D, B), z)
+        terms = _new((3,), z)
+        call("dv_btcvae_fwd", ptr(z), ptr(mu), ptr(logvar), st[0], st[1], B, D, int(n_data), int(bool(is_mss)),
+             ptr(rowstats), ptr(terms), ptr(ws), stream())
+    return rowstats[0], rowstats[1], rowstats[2], rowstats[3]
+
+
+# ---------------------------------------------------------------------------------------
+# FactorVAE heads (losses.py:265, 291-295, 483-508)
+# ---------------------------------------------------------------------------------------
+def permute_dims(z, perms=None, seed=0, offset_dev=None):
+    N.require_cuda_f32(z)
+    z = _c(z.detach())
+    B, D = z.shape
+    out = torch.empty_like(z)
+    if perms is not None:
+        perms = perms.to(device=z.device, dtype=torch.int64).contiguous()
+        call("dv_permute_dims", ptr(z), ptr(perms), 0, None, ptr(out), B, D, stream())
+    else:
+        call("dv_permute_dims", ptr(z), None, seed, ptr(offset_dev), ptr(out), B, D, stream())
+    return out
+
+
+class FactorTcFn(Function):
+    @staticmethod
+    def forward(ctx, d_z):
+        N.require_cuda_f32(d_z)
+        d_z = _c(d_z)
+        tc = _new((), d_z)
+        call("dv_factor_tc_fwd", ptr(d_z), d_z.shape[0], ptr(tc), stream())
+        ctx.h = d_z.shape[0]
+        return tc
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _c(g)
+        out = torch.empty((ctx.h, 2), dtype=torch.float32, device=g.device)
+        call("dv_factor_tc_bwd", ptr(g), ctx.h, ptr(out), stream())
+        return out
+
+
+class FactorCeFn(Function):
+    @staticmethod
+    def forward(ctx, d_z, d_perm):
+        N.require_cuda_f32(d_z, d_perm)
+        d_z, d_perm = _c(d_z), _c(d_perm)
+        out = _new((), d_z)
+        call("dv_factor_ce_fwd", ptr(d_z), ptr(d_perm), d_z.shape[0], ptr(out), stream())
+        ctx.save_for_backward(d_z, d_perm)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        d_z, d_perm = ctx.saved_tensors
+        g = _c(g)
+        g_z, g_p = torch.empty_like(d_z), torch.empty_like(d_perm)
+        call("dv_factor_ce_bwd", ptr(d_z), ptr(d_perm), ptr(g), d_z.shape[0], ptr(g_z), ptr(g_p), stream())
+        return g_z, g_p
+
+
+def adam_step(param_flat, grad_flat, exp_avg, exp_avg_sq, step_dev, lr, betas, eps, grad_scale=1.0):
+    call("dv_adam_step", ptr(param_flat), ptr(grad_flat), ptr(exp_avg), ptr(exp_avg_sq), ptr(step_dev),
+         param_flat.numel(), lr, betas[0], betas[1], eps, grad_scale, stream())

@@ -1,0 +1,63 @@
+"""Data-parallel plumbing: one process per GPU, one flat fp32 gradient buffer, ONE NCCL
+all-reduce per step over NVLink/NVSwitch.  The reference has no
+distributed code at all; semantics are defined as "rank r computes the reference loss on its
+shard, gradients are averaged over ranks, every rank applies the same optimizer step"."""
+import torch
+import torch.distributed as dist
+
+
+def is_distributed():
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+class FlatGradSync:
+    """Packs the gradients of `params` into one contiguous buffer, all-reduces it (sum) and
+    scatters the mean back.  The buffer is allocated once; `.grad` tensors are re-pointed to
+    views of it so the copy-in happens only the first time."""
+
+    def __init__(self, params, group=None):
+        self.params = [p for p in params if p.requires_grad]
+        self.group = group
+        self.numel = sum(p.numel() for p in self.params)
+        p0 = self.params[0]
+        self.flat = torch.zeros(self.numel, dtype=p0.dtype, device=p0.device)
+        self.views = []
+        off = 0
+        for p in self.params:
+            self.views.append(self.flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
+
+    def world_size(self):
+        return dist.get_world_size(self.group) if is_distributed() else 1
+
+    def sync(self):
+        """Average gradients over ranks in place.  No-op for world_size 1."""
+        ws = self.world_size()
+        if ws == 1:
+            return
+        for p, v in zip(self.params, self.views):
+            if p.grad is None:
+                v.zero_()
+            elif p.grad.data_ptr() != v.data_ptr():
+                v.copy_(p.grad)
+                p.grad = v
+        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+        self.flat.mul_(1.0 / ws)
+
+
+def shard_batch(data, rank=None, world_size=None):
+    """Contiguous, equal shard of a global batch for this rank."""
+    if rank is None:
+        rank = dist.get_rank() if is_distributed() else 0
+    if world_size is None:
+        world_size = dist.get_world_size() if is_distributed() else 1
+    per = data.size(0) // world_size
+    return data[rank * per:(rank + 1) * per]
+
+
+def broadcast_parameters(module, src=0):
+    """Make every rank start from rank `src`'s parameters."""
+    if not is_distributed():
+        return
+    for p in module.parameters():
+        dist.broadcast(p.data, src=src)

@@ -1,0 +1,148 @@
+"""Training loop with the reference's Trainer API (disvae/training.py:17-196).
+
+Differences from the reference are in HOW, not WHAT: the per-step `loss.item()` host sync
+(training.py:164) is replaced by an on-device running sum read once per epoch (and every
+`sync_every` steps for the progress bar), and under torch.distributed (one process per GPU)
+gradients are averaged with one flat all-reduce per step (disvae.parallel).
+"""
+import logging
+import os
+from collections import defaultdict
+from timeit import default_timer
+
+import torch
+from tqdm import trange
+
+from disvae.parallel import FlatGradSync, is_distributed
+from disvae.utils.modelIO import save_model
+
+TRAIN_LOSSES_LOGFILE = "train_losses.log"
+
+
+class Trainer():
+    """Trainer(model, optimizer, loss_f, device, logger, save_dir, gif_visualizer, is_progress_bar)
+    -- training.py:46-62."""
+
+    def __init__(self, model, optimizer, loss_f, device=torch.device("cpu"), logger=logging.getLogger(__name__),
+                 save_dir="results", gif_visualizer=None, is_progress_bar=True):
+        self.device = device
+        self.model = model.to(self.device)
+        self.loss_f = loss_f
+        self.optimizer = optimizer
+        self.save_dir = save_dir
+        self.is_progress_bar = is_progress_bar
+        self.logger = logger
+        self.losses_logger = LossesLogger(os.path.join(self.save_dir, TRAIN_LOSSES_LOGFILE))
+        self.gif_visualizer = gif_visualizer
+        self.sync_every = 50                      # progress-bar refresh (host sync) period
+        self._grad_sync = None
+        self._grad_sync_d = None
+        self.logger.info("Training Device: {}".format(self.device))
+
+    def __call__(self, data_loader, epochs=10, checkpoint_every=10):
+        """training.py:64-102"""
+        start = default_timer()
+        self.model.train()
+        for epoch in range(epochs):
+            storer = defaultdict(list)
+            mean_epoch_loss = self._train_epoch(data_loader, storer, epoch)
+            self.logger.info('Epoch: {} Average loss per image: {:.2f}'.format(epoch + 1, mean_epoch_loss))
+            self.losses_logger.log(epoch, storer)
+            if self.gif_visualizer is not None:
+                self.gif_visualizer()
+            if epoch % checkpoint_every == 0:
+                save_model(self.model, self.save_dir, filename="model-{}.pt".format(epoch))
+        if self.gif_visualizer is not None:
+            self.gif_visualizer.save_reset()
+        self.model.eval()
+        delta_time = (default_timer() - start) / 60
+        self.logger.info('Finished training after {:.1f} min.'.format(delta_time))
+
+    def _train_epoch(self, data_loader, storer, epoch):
+        """training.py:104-135; the epoch loss is accumulated on the device."""
+        epoch_loss = None
+        kwargs = dict(desc="Epoch {}".format(epoch + 1), leave=False, disable=not self.is_progress_bar)
+        with trange(len(data_loader), **kwargs) as t:
+            for i, (data, _) in enumerate(data_loader):
+                loss = self._step(data, storer)
+                epoch_loss = loss if epoch_loss is None else epoch_loss + loss
+                if self.is_progress_bar and i % self.sync_every == 0:
+                    t.set_postfix(loss=loss.item())
+                t.update()
+        return epoch_loss.item() / len(data_loader)
+
+    def _step(self, data, storer):
+        """One optimisation step; returns the loss as a detached 0-dim device tensor."""
+        data = data.to(self.device, non_blocking=True)
+        try:
+            recon_batch, latent_dist, latent_sample = self.model(data)
+            loss = self.loss_f(data, recon_batch, latent_dist, self.model.training, storer, latent_sample=latent_sample)
+            self.optimizer.zero_grad()
+            loss.backward()
+            self._sync_grads()
+            self.optimizer.step()
+        except ValueError:
+            # losses with several optimizers (FactorVAE): training.py:160-162
+            if is_distributed():
+                loss = self._factor_step_distributed(data, storer)
+            else:
+                loss = self.loss_f.call_optimize(data, self.model, self.optimizer, storer)
+        return loss.detach()
+
+    def _train_iteration(self, data, storer):
+        """training.py:137-164 (returns a Python float, i.e. synchronises)."""
+        return self._step(data, storer).item()
+
+    # -- data parallel ---------------------------------------------------------------------
+    def _sync_grads(self):
+        if not is_distributed():
+            return
+        if self._grad_sync is None:
+            self._grad_sync = FlatGradSync(list(self.model.parameters()))
+        self._grad_sync.sync()
+
+    def _factor_step_distributed(self, data, storer):
+        """FactorVAE step with the optimizer updates deferred until gradients are averaged."""
+        class _Deferred:
+            def __init__(self, opt):
+                self.opt = opt
+            def zero_grad(self, *a, **k):
+                return self.opt.zero_grad(*a, **k)
+            def step(self):
+                return None
+        lf = self.loss_f
+        real_d = lf.optimizer_d
+        lf.optimizer_d = _Deferred(real_d)
+        try:
+            loss = lf.call_optimize(data, self.model, _Deferred(self.optimizer), storer)
+        finally:
+            lf.optimizer_d = real_d
+        self._sync_grads()
+        if self._grad_sync_d is None:
+            self._grad_sync_d = FlatGradSync(list(lf.discriminator.parameters()))
+        self._grad_sync_d.sync()
+        self.optimizer.step()
+        real_d.step()
+        return loss
+
+
+class LossesLogger(object):
+    """CSV "Epoch,Loss,Value" writer (training.py:167-190)."""
+
+    def __init__(self, file_path_name):
+        if os.path.isfile(file_path_name):
+            os.remove(file_path_name)
+        self.logger = logging.getLogger("losses_logger")
+        self.logger.setLevel(1)
+        file_handler = logging.FileHandler(file_path_name)
+        file_handler.setLevel(1)
+        self.logger.addHandler(file_handler)
+        self.logger.debug(",".join(["Epoch", "Loss", "Value"]))
+
+    def log(self, epoch, losses_storer):
+        for k, v in losses_storer.items():
+            self.logger.debug(",".join(str(item) for item in [epoch, k, mean(v)]))
+
+
+def mean(l):
+    return sum(l) / len(l)

@@ -1,0 +1,209 @@
+"""CPU-side tests: package surface, seeded init, checkpoint compatibility, loss host logic,
+C-ABI symbol export, no-CPU-fallback guarantee, data-parallel plumbing on gloo."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "disentangling-vae_b200")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+SEED = 1234
+
+import disvae  # noqa: E402
+from disvae.models import losses as L  # noqa: E402
+from disvae.models.discriminator import Discriminator  # noqa: E402
+from disvae.models.vae import MODELS  # noqa: E402
+
+
+def digest_close(t, dg, rtol=0.0):
+    t = t.detach().double().flatten()
+    assert t.numel() == dg["n"]
+    assert torch.allclose(t[:8].float(), dg["head"], rtol=rtol, atol=0)
+    assert torch.allclose(t[-8:].float(), dg["tail"], rtol=rtol, atol=0)
+    assert abs(t.sum().item() - dg["sum"]) <= 1e-12 * max(1.0, dg["abssum"])
+
+
+@pytest.mark.parametrize("img_size,z", [((1, 32, 32), 10), ((1, 64, 64), 10), ((3, 64, 64), 10), ((3, 64, 64), 64)])
+def test_seeded_init_and_state_dict_match_reference(golden, img_size, z):
+    g = golden("init.pt")["vae_%dx%dx%d_z%d" % (img_size + (z,))]
+    torch.manual_seed(SEED)
+    m = disvae.init_specific_model("Burgess", img_size, z)
+    sd = m.state_dict()
+    assert list(sd.keys()) == g["keys"]
+    for k, v in sd.items():
+        assert tuple(v.shape) == g["shapes"][k]
+        digest_close(v, g["digest"][k])
+    assert m.model_type == "Burgess" and m.latent_dim == z and m.num_pixels == img_size[1] * img_size[2]
+
+
+@pytest.mark.parametrize("z", [10, 64])
+def test_seeded_discriminator_init_matches_reference(golden, z):
+    g = golden("init.pt")["disc_z%d" % z]
+    torch.manual_seed(SEED)
+    d = Discriminator(latent_dim=z)
+    assert list(d.state_dict().keys()) == g["keys"]
+    for k, v in d.state_dict().items():
+        digest_close(v, g["digest"][k])
+
+
+def test_model_factory_errors():
+    assert MODELS == ["Burgess"]
+    with pytest.raises(ValueError):
+        disvae.init_specific_model("resnet", (1, 32, 32), 10)
+    with pytest.raises(RuntimeError):
+        disvae.init_specific_model("Burgess", (1, 28, 28), 10)
+
+
+@pytest.mark.parametrize("name,img_size", [("btcvae_dsprites", (1, 64, 64)), ("VAE_mnist", (1, 32, 32))])
+def test_reference_checkpoints_load(name, img_size):
+    m = disvae.init_specific_model("Burgess", img_size, 10)
+    sd = torch.load(os.path.join(GOLDEN, "ckpt", name + ".pt"))
+    missing, unexpected = m.load_state_dict(sd, strict=True)
+    assert not missing and not unexpected
+
+
+def test_save_and_load_model_roundtrip(tmp_path):
+    from disvae.utils.modelIO import load_metadata, load_model, save_model
+    torch.manual_seed(0)
+    m = disvae.init_specific_model("Burgess", (1, 32, 32), 10)
+    save_model(m, str(tmp_path), metadata=dict(img_size=[1, 32, 32], latent_dim=10, model_type="Burgess", dataset="mnist"))
+    assert load_metadata(str(tmp_path))["dataset"] == "mnist"
+    m2 = load_model(str(tmp_path), is_gpu=False)
+    assert not m2.training
+    for (k, a), (_, b) in zip(m.state_dict().items(), m2.state_dict().items()):
+        assert torch.equal(a, b), k
+
+
+def test_no_cpu_fallback():
+    m = disvae.init_specific_model("Burgess", (1, 32, 32), 10)
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        m(torch.rand(2, 1, 32, 32))
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        m.decoder(torch.rand(2, 10))
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        Discriminator()(torch.rand(2, 10))
+    lf = L.get_loss_f("VAE", rec_dist="bernoulli", reg_anneal=0)
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        lf(torch.rand(2, 1, 32, 32), torch.rand(2, 1, 32, 32), (torch.rand(2, 10), torch.rand(2, 10)), True, None)
+
+
+def test_product_package_never_imports_oracle():
+    for dp, _, files in os.walk(PKG):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dp, f)).read()
+                assert "oracle" not in src.replace("# oracle", ""), os.path.join(dp, f)
+
+
+KW = dict(rec_dist="bernoulli", reg_anneal=0, betaH_B=4, betaB_initC=0, betaB_finC=25, betaB_G=100, factor_G=6,
+          latent_dim=10, lr_disc=5e-5, btcvae_A=1, btcvae_B=6, btcvae_G=1, device=torch.device("cpu"), n_data=1000,
+          some_unrelated_argparse_key=3)
+
+
+def test_get_loss_f_dispatch_and_attributes():
+    assert L.LOSSES == ["VAE", "betaH", "betaB", "factor", "btcvae"]
+    assert L.RECON_DIST == ["bernoulli", "laplace", "gaussian"]
+    assert isinstance(L.get_loss_f("VAE", **KW), L.BetaHLoss) and L.get_loss_f("VAE", **KW).beta == 1
+    assert L.get_loss_f("betaH", **KW).beta == 4
+    b = L.get_loss_f("betaB", **KW)
+    assert (b.C_init, b.C_fin, b.gamma) == (0, 25, 100)
+    t = L.get_loss_f("btcvae", **KW)
+    assert (t.n_data, t.alpha, t.beta, t.gamma, t.is_mss) == (1000, 1, 6, 1, True)
+    f = L.get_loss_f("factor", **KW)
+    assert f.gamma == 6 and isinstance(f.discriminator, Discriminator)
+    assert f.optimizer_d.defaults["lr"] == 5e-5 and f.optimizer_d.defaults["betas"] == (0.5, 0.9)
+    for lf in (b, t, f):
+        assert lf.n_train_steps == 0 and lf.record_loss_every == 50 and lf.rec_dist == "bernoulli" and lf.steps_anneal == 0
+    with pytest.raises(ValueError):
+        L.get_loss_f("nope", **KW)
+    with pytest.raises(ValueError):
+        f(None, None, None, True, None)           # training.py:160 relies on this
+
+
+def test_linear_annealing_and_record_policy():
+    assert L.linear_annealing(0, 1, 5, 0) == 1
+    assert L.linear_annealing(0, 1, 5, 10) == 0.5
+    assert L.linear_annealing(0, 25, 200, 100) == 25
+    with pytest.raises(AssertionError):
+        L.linear_annealing(1, 0, 1, 10)
+    lf = L.get_loss_f("VAE", **KW)
+    st = {}
+    assert lf._pre_call(True, st) is st and lf.n_train_steps == 1           # step 1 records
+    assert lf._pre_call(True, st) is None and lf.n_train_steps == 2
+    for _ in range(48):
+        lf._pre_call(True, st)
+    assert lf._pre_call(True, st) is st and lf.n_train_steps == 51          # 51 % 50 == 1
+    assert lf._pre_call(False, st) is st and lf.n_train_steps == 51         # eval: always, no increment
+
+
+def test_importance_weight_matrix_structure(golden):
+    from disvae.utils.math import log_importance_weight_matrix
+    G = golden("btcvae_density.pt")
+    for b, n in [(64, 737280), (256, 202599), (7, 1000), (2, 50)]:
+        assert torch.equal(log_importance_weight_matrix(b, n), G["logiw_b%d" % b])
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "disvae_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(dv_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from disvae import _native
+    if not os.path.exists(_native.LIB_PATH):
+        sys.path.insert(0, PKG)
+        import build as dv_build
+        dv_build.build()
+    lib = ctypes.CDLL(_native.LIB_PATH)
+    syms = _header_symbols()
+    assert len(syms) >= 30
+    for s in syms:
+        assert hasattr(lib, s), "missing export " + s
+    assert set(_native.SIGNATURES) == set(syms)
+    h = _native.lib()
+    assert h.dv_built_arch() == 100 and h.dv_version() >= 100
+    assert h.dv_status_string(-1).decode() == "unsupported shape"
+    assert h.dv_conv_packed_floats(32) == 2 * 32 * 32 * 16
+    out = subprocess.run(["cuobjdump", "-lelf", _native.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def _ddp_worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from disvae.parallel import FlatGradSync, broadcast_parameters, shard_batch
+    torch.manual_seed(rank)                                   # different init per rank on purpose
+    m = disvae.init_specific_model("Burgess", (1, 32, 32), 10)
+    broadcast_parameters(m)
+    ref = torch.cat([p.detach().flatten() for p in m.parameters()])
+    gathered = [torch.empty_like(ref) for _ in range(world)]
+    dist.all_gather(gathered, ref)
+    same = all(torch.equal(gathered[0], g) for g in gathered)
+    for i, p in enumerate(m.parameters()):
+        p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
+    sync = FlatGradSync(list(m.parameters()))
+    sync.sync()
+    expect = sum(range(1, world + 1)) / world
+    ok = all(torch.allclose(p.grad, torch.full_like(p, expect * (i + 1))) for i, p in enumerate(m.parameters()))
+    views = all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(sync.params, sync.views))
+    x = torch.arange(8).view(8, 1)
+    shard = shard_batch(x)
+    ok_shard = shard.flatten().tolist() == list(range(rank * 4, rank * 4 + 4))
+    if rank == 0:
+        torch.save(dict(same=same, ok=ok, views=views, ok_shard=ok_shard), out)
+    dist.destroy_process_group()
+
+
+def test_flat_grad_allreduce_world2_gloo(tmp_path):
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "r.pt")
+    mp.spawn(_ddp_worker, args=(2, 29561, out), nprocs=2, join=True)
+    r = torch.load(out)
+    assert r == dict(same=True, ok=True, views=True, ok_shard=True)
