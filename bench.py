@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""bench.py -- disvae training hot path on B200 (contract: see the task statement / DESIGN.md).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c5]
+
+One "step" = one full optimisation step (forward, loss, backward, gradient all-reduce for N>1,
+Adam) over one synthetic batch.  Workload at every N: BASELINE.json configs[1]
+(btcvae, 1x64x64, batch 1024 PER GPU, z=10, bernoulli, MSS, Adam lr 5e-4) -- weak scaling.
+
+  value  : images/s with the batches already resident in HBM (CUDA events, max over ranks)
+  e2e    : the same through disvae.Trainer._train_iteration with PINNED HOST batches: H2D copy of
+           the batch and D2H read of the loss inside the timed region, every step
+  roofline / roofline_logdensity / cpu_baseline / clocks / gpu_launches : see DESIGN.md section 6
+
+--impl reference times the CPU oracle port (oracle/disvae_oracle.py, validated against the
+reference; the Python reference itself cannot travel to the GPU box) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "disentangling-vae_b200"))
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (loss, img_size, per-GPU batch, latent, n_data, loss kwargs, lr)
+    "c2": ("btcvae", (1, 64, 64), 1024, 10, 737280, dict(btcvae_A=1, btcvae_B=6, btcvae_G=1), 5e-4),
+    "c3": ("betaH", (3, 64, 64), 512, 10, 202599, dict(betaH_B=10), 5e-4),
+    "c5": ("btcvae", (3, 64, 64), 256, 64, 202599, dict(btcvae_A=1, btcvae_B=6, btcvae_G=1), 5e-4),
+}
+# algorithmic work per image, forward + backward: conv FLOPs
+CONV_FLOP_PER_IMG = {(1, 64, 64): 71.30e6, (3, 64, 64): 81.79e6, (1, 32, 32): 17.04e6}
+N_ROTATE = 8            # distinct resident batches cycled through (8 x 16.8 MB > 126 MB L2)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], bf16=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="measured")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi sampling DURING the timed region (profiling guide, clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx = max(mx, float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return None
+        load = sorted(s for s in sm if s >= 0.5 * max(sm)) or sorted(sm)
+        return dict(sm_mhz=load[len(load) // 2], sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+
+
+def build_job(workload, device):
+    import disvae
+    from disvae.models.losses import get_loss_f
+    loss_name, img, B, z, n_data, lkw, lr = WORKLOADS[workload]
+    torch.manual_seed(1234)
+    model = disvae.init_specific_model("Burgess", img, z).to(device)
+    from disvae.parallel import broadcast_parameters
+    broadcast_parameters(model)
+    opt = torch.optim.Adam(model.parameters(), lr=lr)
+    kw = dict(rec_dist="bernoulli", reg_anneal=0, betaH_B=4, betaB_initC=0, betaB_finC=25, betaB_G=100, factor_G=6,
+              latent_dim=z, lr_disc=5e-5, btcvae_A=1, btcvae_B=6, btcvae_G=1, device=device, n_data=n_data)
+    kw.update(lkw)
+    loss_f = get_loss_f(loss_name, **kw)
+    import logging
+    import tempfile
+    trainer = disvae.Trainer(model, opt, loss_f, device=device, logger=logging.getLogger("bench"),
+                             save_dir=tempfile.mkdtemp(prefix="dvbench"), is_progress_bar=False)
+    model.train()
+    return trainer, (loss_name, img, B, z, n_data, lr)
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (ours) needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    from disvae import _native
+    L = _native.lib()
+    assert L.dv_device_check() == 0, "not an sm_100 device"
+
+    trainer, (loss_name, img, B, z, n_data, lr) = build_job(args.workload, device)
+    g = torch.Generator().manual_seed(1234 + rank)
+    host = [torch.rand(B, *img, generator=g).pin_memory() for _ in range(N_ROTATE)]
+    resident = [h.to(device) for h in host]
+    K, Wm = args.steps, max(args.warmup, 3)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    step_res = lambda i: trainer._step(resident[i % N_ROTATE], None)            # noqa: E731
+    step_e2e = lambda i: trainer._train_iteration(host[i % N_ROTATE], None)     # noqa: E731
+
+    for i in range(Wm):
+        step_res(i)
+    clk = ClockSampler(local)
+    if rank == 0:
+        clk.start()
+    l0 = L.dv_launch_count()
+    ms = timed(step_res, K)
+    launches = L.dv_launch_count() - l0
+    clocks = clk.stop() if rank == 0 else None
+    for i in range(2):
+        step_e2e(i)
+    ms_e2e = timed(step_e2e, K)
+
+    out = None
+    if rank == 0:
+        pk = peaks()
+        imgs = B * world * K
+        value = imgs / (ms / 1e3)
+        e2e_v = imgs / (ms_e2e / 1e3)
+        conv_flop = CONV_FLOP_PER_IMG[img]
+        out = {
+            "metric": "images/sec", "value": round(value, 1), "unit": "img/s", "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": round(ms / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic (torch.rand, seed 1234+rank); random-init weights (seed 1234)",
+            "config": {"workload": "BASELINE.json configs[1]: btcvae dsprites-shape" if args.workload == "c2" else args.workload,
+                       "loss": loss_name, "img_size": list(img), "batch_per_gpu": B, "global_batch": B * world,
+                       "latent_dim": z, "n_data": n_data, "rec_dist": "bernoulli", "optimizer": "Adam lr %g" % lr,
+                       "parallelism": "dp%d" % world if world > 1 else "single",
+                       "l2": "inputs larger than L2: %d distinct resident batches rotated (%.0f MB)" % (
+                           N_ROTATE, N_ROTATE * B * img[0] * img[1] * img[2] * 4 / 1e6)},
+            "e2e": {"value": round(e2e_v, 1), "unit": "img/s", "h2d_bytes_per_step": B * img[0] * img[1] * img[2] * 4,
+                    "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / K, 4),
+                    "api": "disvae.Trainer._train_iteration(pinned host batch) -> float"},
+            "gpu_launches": int(launches),
+            "conv_flop_fraction_of_bf16_peak": round(value / world * conv_flop / (pk["bf16_sustained"] * 1e12), 5),
+            "clocks": clocks,
+        }
+    # ---- roofline of the dominant kernel + the named log-density kernel (rank 0, N=1 semantics) ----
+    if rank == 0:
+        try:
+            out.update(kernel_rooflines(trainer, resident, K, B, img, z, n_data, device))
+        except Exception as e:                                     # never lose the headline line
+            out["roofline_error"] = repr(e)
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                out["cpu_baseline"] = cpu_baseline(args.workload, budget_s=20.0)
+            except Exception as e:
+                out["cpu_baseline_error"] = repr(e)
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def kernel_rooflines(trainer, resident, K, B, img, z, n_data, device):
+    """Per-entry-point device time inside K more steps (CUDA events around every C-ABI call on the
+    launching stream), then the roofline of the dominant one and of the beta-TCVAE kernel."""
+    from disvae import _native, ops
+    pk = peaks()
+    prof = _native.enable_profiling()
+    for i in range(K):
+        trainer._step(resident[i % len(resident)], None)
+    torch.cuda.synchronize()
+    table = _native.disable_profiling()          # name -> (total ms, calls)
+    total = sum(t for t, _ in table.values())
+    top = sorted(table.items(), key=lambda kv: -kv[1][0])
+    res = {"kernel_share": {k: round(v[0] / total, 4) for k, v in top[:8]}}
+    name, (tms, calls) = top[0]
+    C = img[0]
+    # algorithmic FLOPs of the conv entry points per step (2*MACs), all layers they serve
+    conv_layers = [(32, C), (16, 32), (8, 32), (4, 32)] if img[1] == 64 else [(16, C), (8, 32), (4, 32)]
+    macs = sum(B * h * h * 32 * 16 * ch for h, ch in conv_layers)     # one pass over every conv layer
+    flops_per_step = {"dv_conv_down": 2 * 2 * macs, "dv_conv_up": 2 * 2 * macs, "dv_conv_wgrad": 2 * 2 * macs}
+    if name in flops_per_step:
+        # down: enc fwd + dec dgrad; up: dec fwd + enc dgrad (conv1 dgrad skipped); wgrad: enc + dec
+        f = flops_per_step[name]
+        if name == "dv_conv_up":
+            f -= 2 * B * conv_layers[0][0] ** 2 * 32 * 16 * C
+        if name == "dv_conv_down" or name == "dv_conv_up" or name == "dv_conv_wgrad":
+            ach = f * K / (tms / 1e3) / 1e12
+            res["roofline"] = {"kernel": name, "bound": "tensor", "achieved": round(ach, 3), "peak": pk["bf16_sustained"],
+                               "unit": "TFLOP/s", "frac": round(ach / pk["bf16_sustained"], 5), "traffic": None,
+                               "peak_source": pk["src"] + " bf16 sustained (kernel timed inside a long step)",
+                               "note": "fp32 CUDA-core path; algorithmic conv FLOPs of all layers served by this entry point",
+                               "launches_per_step": calls // K, "ms_per_step": round(tms / K, 4)}
+    if "roofline" not in res:
+        res["roofline"] = {"kernel": name, "bound": "hbm", "achieved": None, "peak": pk["hbm"], "unit": "GB/s", "frac": None,
+                           "traffic": None, "ms_per_step": round(tms / K, 4)}
+    # the named kernel, timed alone (burst peak): virtual bytes 4*B^2*D + 12*B*D + 16*B
+    Bk, Dk = 1024, 10
+    torch.manual_seed(1)
+    mu = torch.randn(Bk, Dk, device=device)
+    lv = torch.randn(Bk, Dk, device=device) * 0.5 - 1
+    zz = mu + torch.exp(0.5 * lv) * torch.randn(Bk, Dk, device=device)
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=device)
+    for _ in range(5):
+        ops.btcvae_rowstats(zz, mu, lv, n_data, True)
+    ts = []
+    for _ in range(20):
+        flush.fill_(1.0)                                         # L2 flush between timed iterations
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        _native.PROFILE_ONLY = "dv_btcvae_fwd"
+        prof = _native.enable_profiling()
+        ops.btcvae_rowstats(zz, mu, lv, n_data, True)
+        torch.cuda.synchronize()
+        t = _native.disable_profiling()
+        ts.append(t["dv_btcvae_fwd"][0])
+    _native.PROFILE_ONLY = None
+    ts.sort()
+    t_med = ts[len(ts) // 2]
+    vbytes = 4 * Bk * Bk * Dk + 12 * Bk * Dk + 16 * Bk
+    ach = vbytes / (t_med / 1e3) / 1e9
+    res["roofline_logdensity"] = {"kernel": "dv_btcvae_fwd (prep + main)", "bound": "hbm", "B": Bk, "D": Dk,
+                                  "achieved": round(ach, 1), "peak": pk["hbm"], "unit": "GB/s (virtual bytes of the "
+                                  "reference's B*B*D matrix)", "frac": round(ach / pk["hbm"], 4), "us": round(t_med * 1e3, 2),
+                                  "virtual_bytes": vbytes, "compulsory_bytes": 12 * Bk * Dk + 16 * Bk, "traffic": None,
+                                  "l2": "256 MB flush before every timed launch"}
+    return res
+
+
+def oracle_job(workload, batch=None):
+    from oracle import disvae_oracle as O
+    loss_name, img, B, z, n_data, lkw, lr = WORKLOADS[workload]
+    B = batch or B
+    torch.manual_seed(1234)
+    p = O.make_leaf_params(O.init_vae_params(img, z))
+    opt = O.make_adam(p, lr)
+    cfg = dict(rec_dist="bernoulli", reg_anneal=0, n_data=n_data, betaH_B=4, btcvae_A=1, btcvae_B=6, btcvae_G=1)
+    cfg.update(lkw)
+    x = torch.rand(B, *img)
+    state = dict(step=0)
+
+    def step():
+        state["step"] += 1
+        O.train_step(p, opt, x, loss_name, cfg, state["step"])
+    return step, B
+
+
+def cpu_baseline(workload, budget_s=20.0):
+    """Oracle port (plain PyTorch CPU ops == what the reference executes) on the host cores."""
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step, B = oracle_job(workload)
+    step()                                                   # warm-up
+    t0 = time.perf_counter()
+    n = 0
+    while n < 3 or (time.perf_counter() - t0 < budget_s and n < 50):
+        step()
+        n += 1
+    dt = time.perf_counter() - t0
+    return {"value": round(B * n / dt, 1), "unit": "img/s", "cores": cores, "kind": "port",
+            "sample": "%d full steps of the same workload (batch %d) after 1 warm-up, %.1f s" % (n, B, dt),
+            "torch": torch.__version__}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    loss_name, img, B, z, n_data, lkw, lr = WORKLOADS[args.workload]
+    step, Bs = oracle_job(args.workload)
+    t0 = time.perf_counter()
+    step()
+    t_one = time.perf_counter() - t0
+    sample = "full batch %d per step" % Bs
+    if t_one * (args.steps + args.warmup) > 240.0:                     # keep the arm within a few minutes
+        Bs = max(64, B // 4)
+        step, Bs = oracle_job(args.workload, batch=Bs)
+        sample = "bounded sample: batch %d per step (of %d) -- the B^2 term of the loss is 1/16 per step" % (Bs, B)
+    for _ in range(max(args.warmup - 1, 1)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    v = round(Bs * args.steps / dt, 1)
+    out = {"impl": "reference", "metric": "images/sec", "value": v, "unit": "img/s", "n_gpus": world, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "BASELINE.json configs[1]: btcvae dsprites-shape" if args.workload == "c2" else args.workload,
+                      "loss": loss_name, "img_size": list(img), "batch_per_gpu": B, "latent_dim": z, "n_data": n_data},
+           "cpu_baseline": {"value": v, "unit": "img/s", "cores": cores, "kind": "port", "sample": sample,
+                            "torch": torch.__version__},
+           "e2e": {"value": v, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

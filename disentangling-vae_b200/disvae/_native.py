@@ -102,7 +102,38 @@ def check(status, what):
         raise RuntimeError("disvae_b200.%s failed: %s%s" % (what, msg, extra))
 
 
+# ---- optional per-entry-point device timing (bench.py roofline pass) ----------------------
+_prof_events = None      # list of (name, start_event, end_event) while profiling is enabled
+PROFILE_ONLY = None      # restrict to one entry point
+
+
+def enable_profiling():
+    """Bracket every C-ABI call with CUDA events on the launching (current) stream."""
+    global _prof_events
+    _prof_events = []
+    return _prof_events
+
+
+def disable_profiling():
+    """Stop profiling; returns {entry point: (total ms, calls)}."""
+    global _prof_events
+    ev, _prof_events = _prof_events, None
+    torch.cuda.synchronize()
+    table = {}
+    for name, e0, e1 in ev or []:
+        t, n = table.get(name, (0.0, 0))
+        table[name] = (t + e0.elapsed_time(e1), n + 1)
+    return table
+
+
 def call(name, *args):
+    if _prof_events is not None and (PROFILE_ONLY is None or PROFILE_ONLY == name):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(getattr(lib(), name)(*args), name)
+        e1.record()
+        _prof_events.append((name, e0, e1))
+        return
     check(getattr(lib(), name)(*args), name)
 
 
