@@ -10,6 +10,7 @@
 // Reference call sites replaced: disvae/models/encoders.py:73-77 (Conv2d+ReLU),
 // disvae/models/decoders.py:77-82 (ConvTranspose2d+ReLU/sigmoid) and their autograd
 // backward (disvae/training.py:157).
+#include <stdlib.h>
 #include "dv_common.cuh"
 
 namespace dv {
@@ -545,18 +546,45 @@ static int wgrad_nsplit(int B, int H, int W, long long* chunk) {
 
 }  // namespace dv
 
+namespace dv {
+namespace tc {
+int pack_tc(const float* w, float* wd, float* wu, cudaStream_t st);
+int conv_down32_tc(const float* hi, const float* wd_packed, const float* bias, const float* mask, float* lo,
+                   int B, int H, int W, int act, cudaStream_t st);
+}  // namespace tc
+
+// packed-weight sections for CH == 32 (floats): [0,16K) ffma down, [16K,32K) ffma up,
+// [32K,64K) tcgen05 down (hi|lo), [64K,96K) tcgen05 up (hi|lo)
+constexpr int kPackFfma = 2 * kLoCh * 32 * kTaps;
+constexpr int kPackTcSection = kTaps * 64 * 32;
+
+// DV_CONV_IMPL=ffma forces the CUDA-core kernels for the 32-channel layers (A/B testing)
+static bool use_tc() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DV_CONV_IMPL");
+    v = (e && e[0] == 'f') ? 0 : 1;
+  }
+  return v == 1;
+}
+}  // namespace dv
+
 using namespace dv;
 
 extern "C" {
 
-size_t dv_conv_packed_floats(int CH) { return (size_t)2 * kLoCh * CH * kTaps; }
+size_t dv_conv_packed_floats(int CH) {
+  return CH == 32 ? (size_t)kPackFfma + 2 * kPackTcSection : (size_t)2 * kLoCh * CH * kTaps;
+}
 
 int dv_conv_pack_weights(const float* w, float* w_packed, int CH, void* stream) {
   if (!w || !w_packed) return DV_ERR_BAD_ARG;
   if (CH != 1 && CH != 3 && CH != 32) return DV_ERR_BAD_SHAPE;
   const int n = kLoCh * CH * kTaps;
   conv_pack_kernel<<<(n + 255) / 256, 256, 0, as_stream(stream)>>>(w, w_packed, CH);
-  return check_launch();
+  int rc = check_launch();
+  if (rc != DV_OK || CH != 32) return rc;
+  return tc::pack_tc(w, w_packed + kPackFfma, w_packed + kPackFfma + kPackTcSection, as_stream(stream));
 }
 
 int dv_conv_down(const float* hi, const float* w_packed, const float* bias, const float* mask, float* lo,
@@ -566,6 +594,8 @@ int dv_conv_down(const float* hi, const float* w_packed, const float* bias, cons
   if (act != DV_ACT_NONE && act != DV_ACT_RELU) return DV_ERR_BAD_ARG;
   if ((CH == 32) == (hi_nchw != 0)) return DV_ERR_BAD_SHAPE;   // CH==32 <=> NHWC
   const long long groups = ((long long)B * H * W + kDownPxPerWarp - 1) / kDownPxPerWarp;
+  if (CH == 32 && use_tc())
+    return tc::conv_down32_tc(hi, w_packed + kPackFfma, bias, mask, lo, B, H, W, act, as_stream(stream));
   if (CH == 32) {
     const int smem = kTaps * 32 * kLoCh * sizeof(float);
     static bool attr_set = false;

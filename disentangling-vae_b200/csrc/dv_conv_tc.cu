@@ -1,0 +1,294 @@
+// tcgen05 implicit-GEMM convolutions for the 32-channel Burgess layers (sm_100a).
+//
+// down (Conv2d forward / ConvTranspose2d input-gradient), per 128-pixel tile of lo:
+//     D[128 px][32 cl] = sum over 16 taps, 32 hi-channels of  A_tap[128 px][32 c] * W_tap[32 cl][32 c]
+//   * A_tap is fetched by ONE TMA tiled load per tap straight from the NHWC activation tensor:
+//     box {32 c, W cols, TR rows, TB images} with element strides {1,2,2,1} and start coordinate
+//     (0, kw-1, 2*i0-1+kh, b0) -- the stride-2 gather and the zero padding (out-of-bounds fill) are
+//     done by the TMA unit, nothing is im2col'ed in memory.  128 pixel rows x 128 bytes land in
+//     shared memory in the SWIZZLE_128B K-major layout tcgen05.mma consumes.
+//   * fp32 parity on tf32 tensor cores: error-compensated 3xTF32.  a = a_hi + a_lo with a_hi = a
+//     with the low 13 mantissa bits cleared (exact in tf32), a_lo = a - a_hi (exact in fp32);
+//     D += a_hi*b_hi + a_hi*b_lo + a_lo*b_hi.  Weights are split once by the pack kernel and kept
+//     resident in shared memory as [tap][b_hi(32 rows) | b_lo(32 rows)], so the first two products are
+//     ONE N=64 MMA (accumulator columns 0-31 and 32-63, added in the epilogue) and the third an N=32
+//     MMA: 2 MMAs per K=8 slice instead of 3, and a_hi is read from shared memory once.
+//   * warp roles (384 threads, 1 CTA/SM, persistent over tiles): warp 0 TMA producer, warp 1 MMA
+//     issuer, warp 2 TMEM allocator, warps 4-7 epilogue (TMEM -> registers -> bias/ReLU/mask ->
+//     128-byte NHWC pixel lines), warps 8-11 split the raw fp32 tile into hi/lo planes.
+//     mbarrier pipelines: raw-full / split-ready / stage-empty (3 stages), accumulator full / empty
+//     (2 TMEM stages of 64 columns).
+#include "dv_common.cuh"
+#include "dv_ptx.cuh"
+
+namespace dv {
+namespace tc {
+
+using namespace ptx;
+
+constexpr int kStages = 3;
+constexpr int kATile = 128 * 128;            // bytes: 128 pixel rows x 32 fp32
+constexpr int kBTap = 64 * 128;              // bytes: (32 hi + 32 lo) rows x 32 fp32
+constexpr int kBBytes = kTaps * kBTap;       // 131072
+constexpr int kAccCols = 64;
+constexpr int kThreads = 384;
+constexpr uint32_t kHiMask = 0xFFFFE000u;    // keep sign, exponent and the 10 tf32 mantissa bits
+
+struct Barriers {
+  uint64_t raw_full[kStages];
+  uint64_t ready[kStages];
+  uint64_t empty[kStages];
+  uint64_t b_full;
+  uint64_t acc_full[2];
+  uint64_t acc_empty[2];
+  uint32_t tmem_base;
+  float bias[32];
+};
+constexpr int kSmemBytes = kBBytes + kStages * 2 * kATile + 1024 /*alignment slack*/ + 512 /*Barriers*/;
+static_assert(sizeof(Barriers) <= 512, "barrier block too large");
+static_assert(kSmemBytes <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
+
+struct DownGeom {
+  int B, H, W;          // lo geometry
+  int rows_per_tile;    // 128 / W image-rows of lo per tile
+  int num_tiles;
+  long long total_px;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_down32_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                      const float* __restrict__ bias, const float* __restrict__ mask, float* __restrict__ lo,
+                      DownGeom g, int act) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* Bs = smem;                                       // [tap][64 rows][128 B]
+  uint8_t* Ahi = smem + kBBytes;                            // [stage][128 rows][128 B]
+  uint8_t* Alo = Ahi + kStages * kATile;
+  Barriers* bars = reinterpret_cast<Barriers*>(Alo + kStages * kATile);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&bars->raw_full[s], 1); mbar_init(&bars->ready[s], 128); mbar_init(&bars->empty[s], 1); }
+    mbar_init(&bars->b_full, 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(&bars->acc_full[a], 1); mbar_init(&bars->acc_empty[a], 128); }
+    fence_mbar_init();
+  }
+  if (threadIdx.x < 32) bars->bias[threadIdx.x] = bias ? bias[threadIdx.x] : 0.f;
+  if (warp == 2) tmem_alloc(&bars->tmem_base, 128);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b);
+    mbar_arrive_expect_tx(&bars->b_full, kBBytes);
+    for (int tap = 0; tap < kTaps; ++tap) tma_load_2d(Bs + tap * kBTap, &tmap_b, &bars->b_full, 0, tap * 64);
+    int stage = 0; uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+      const int r0 = tile * g.rows_per_tile;
+      const int b0 = r0 / g.H, i0 = r0 % g.H;
+      for (int tap = 0; tap < kTaps; ++tap) {
+        const int kh = tap >> 2, kw = tap & 3;
+        mbar_wait(&bars->empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&bars->raw_full[stage], kATile);
+        tma_load_4d(Ahi + stage * kATile, &tmap_a, &bars->raw_full[stage], 0, kw - 1, 2 * i0 - 1 + kh, b0);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer (single thread) =====================
+    constexpr uint32_t idesc64 = umma_idesc_tf32(128, 64), idesc32 = umma_idesc_tf32(128, 32);
+    mbar_wait(&bars->b_full, 0);
+    int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+      mbar_wait(&bars->acc_empty[acc], acc_phase ^ 1);
+      tc_fence_after_sync();
+      const uint32_t d_tmem = tmem_base + acc * kAccCols;
+      for (int tap = 0; tap < kTaps; ++tap) {
+        mbar_wait(&bars->ready[stage], phase);
+        tc_fence_after_sync();
+        const uint64_t a_hi = umma_desc_sw128_kmajor(smem_u32(Ahi + stage * kATile));
+        const uint64_t a_lo = umma_desc_sw128_kmajor(smem_u32(Alo + stage * kATile));
+        const uint64_t b_d = umma_desc_sw128_kmajor(smem_u32(Bs + tap * kBTap));
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) {                   // K = 8 tf32 (32 bytes) per MMA: advance start address
+          umma_tf32_ss(d_tmem, a_hi + 2 * k4, b_d + 2 * k4, idesc64, (tap | k4) != 0);    // a_hi * [b_hi | b_lo]
+          umma_tf32_ss(d_tmem, a_lo + 2 * k4, b_d + 2 * k4, idesc32, 1);                  // a_lo * b_hi
+        }
+        umma_commit(&bars->empty[stage]);                  // stage free once these MMAs have read it
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(&bars->acc_full[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===================== epilogue: TMEM -> registers -> global =====================
+    const int q = warp & 3;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+      mbar_wait(&bars->acc_full[acc], acc_phase);
+      tc_fence_after_sync();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccCols;
+      uint32_t r0[32], r1[32];
+      tmem_ld_32x32b_x32(taddr, r0);
+      tmem_ld_32x32b_x32(taddr + 32, r1);
+      tmem_ld_wait();
+      tc_fence_before_sync();
+      mbar_arrive(&bars->acc_empty[acc]);
+      const long long p = (long long)tile * 128 + q * 32 + lane;
+      if (p < g.total_px) {
+        float* dst = lo + p * 32;
+        const float* mk = mask ? mask + p * 32 : nullptr;
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          float v[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int c = c4 * 4 + e;
+            float x = __uint_as_float(r0[c]) + __uint_as_float(r1[c]) + bars->bias[c];
+            if (act == DV_ACT_RELU) x = fmaxf(x, 0.f);
+            v[e] = x;
+          }
+          if (mk) {
+            const float4 m4 = ldg4(mk + c4 * 4);
+            v[0] = m4.x > 0.f ? v[0] : 0.f; v[1] = m4.y > 0.f ? v[1] : 0.f;
+            v[2] = m4.z > 0.f ? v[2] : 0.f; v[3] = m4.w > 0.f ? v[3] : 0.f;
+          }
+          *reinterpret_cast<float4*>(dst + c4 * 4) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= 8) {
+    // ===================== hi/lo split of the raw fp32 tile =====================
+    const int t = threadIdx.x - 256;
+    int stage = 0; uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+      for (int tap = 0; tap < kTaps; ++tap) {
+        mbar_wait(&bars->raw_full[stage], phase);
+        uint4* hi = reinterpret_cast<uint4*>(Ahi + stage * kATile);
+        uint4* lo4 = reinterpret_cast<uint4*>(Alo + stage * kATile);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int idx = t + 128 * k;
+          const uint4 v = hi[idx];
+          uint4 h, l;
+          h.x = v.x & kHiMask; h.y = v.y & kHiMask; h.z = v.z & kHiMask; h.w = v.w & kHiMask;
+          l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x));
+          l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y));
+          l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z));
+          l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w));
+          hi[idx] = h;
+          lo4[idx] = l;
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&bars->ready[stage]);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) { tc_fence_after_sync(); tmem_dealloc(tmem_base, 128); }
+}
+
+// ---- weight packing for the tensor-core kernels ------------------------------------------
+// w[cl][c][tap] ->  down: Wd[tap][row][c],  row <  32: tf32-exact hi of w[row][c][tap], row >= 32: lo
+//                   up  : Wu[tap][row][cl], row <  32: hi of w[cl][row][tap],          row >= 32: lo
+__global__ void conv_pack_tc_kernel(const float* __restrict__ w, float* __restrict__ wd, float* __restrict__ wu) {
+  const int n = kLoCh * 32 * kTaps;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
+    const int tap = idx % kTaps, c = (idx / kTaps) % 32, cl = idx / (kTaps * 32);
+    const float v = w[idx];
+    const float hi = __uint_as_float(__float_as_uint(v) & kHiMask);
+    const float lo = v - hi;
+    wd[(tap * 64 + cl) * 32 + c] = hi;
+    wd[(tap * 64 + 32 + cl) * 32 + c] = lo;
+    wu[(tap * 64 + c) * 32 + cl] = hi;
+    wu[(tap * 64 + 32 + c) * 32 + cl] = lo;
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// NHWC activation [B][HH][WW][32] fp32; box = {32, bw, bh, bb} traversed with element strides {1, sw, sh, 1}
+static bool make_act_tmap(CUtensorMap* m, const float* base, int B, int HH, int WW, int bw, int bh, int bb, int stride) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t gdim[4] = {32, (cuuint64_t)WW, (cuuint64_t)HH, (cuuint64_t)B};
+  cuuint64_t gstr[3] = {128, (cuuint64_t)WW * 128, (cuuint64_t)HH * WW * 128};
+  cuuint32_t box[4] = {32, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bb};
+  cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), gdim, gstr, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// packed weights [16*64 rows][32] fp32, box = one tap (64 rows)
+static bool make_w_tmap(CUtensorMap* m, const float* base) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t gdim[2] = {32, (cuuint64_t)kTaps * 64};
+  cuuint64_t gstr[1] = {128};
+  cuuint32_t box[2] = {32, 64};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+int pack_tc(const float* w, float* wd, float* wu, cudaStream_t st) {
+  conv_pack_tc_kernel<<<64, 256, 0, st>>>(w, wd, wu);
+  return check_launch();
+}
+
+// lo[B,H,W,32] = act(down(hi[B,2H,2W,32]) + bias) * [mask > 0]
+int conv_down32_tc(const float* hi, const float* wd_packed, const float* bias, const float* mask, float* lo,
+                   int B, int H, int W, int act, cudaStream_t st) {
+  if (W > 128 || 128 % W != 0) return DV_ERR_BAD_SHAPE;
+  DownGeom g;
+  g.B = B; g.H = H; g.W = W;
+  g.rows_per_tile = 128 / W;
+  const int TR = g.rows_per_tile < H ? g.rows_per_tile : H;
+  if (H % TR != 0 || g.rows_per_tile % TR != 0) return DV_ERR_BAD_SHAPE;
+  const int TB = g.rows_per_tile / TR;
+  g.total_px = (long long)B * H * W;
+  g.num_tiles = (int)((g.total_px + 127) / 128);
+  CUtensorMap ta, tb;
+  if (!make_act_tmap(&ta, hi, B, 2 * H, 2 * W, 2 * W, 2 * TR, TB, 2)) return DV_ERR_CUDA;
+  if (!make_w_tmap(&tb, wd_packed)) return DV_ERR_CUDA;
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(conv_down32_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess) {
+      g_last_cuda_error = (int)cudaGetLastError();
+      return DV_ERR_CUDA;
+    }
+    attr = true;
+  }
+  const int grid = g.num_tiles < kNumSMs ? g.num_tiles : kNumSMs;
+  conv_down32_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(ta, tb, bias, mask, lo, g, act);
+  return check_launch();
+}
+
+}  // namespace tc
+}  // namespace dv

@@ -241,6 +241,7 @@ def test_trainer_runs_epochs_logs_and_checkpoints(tmp_path):
     m = disvae.init_specific_model("Burgess", (1, 32, 32), 10)
     opt = torch.optim.Adam(m.parameters(), lr=1e-3)
     lf = get_loss_f("btcvae", rec_dist="bernoulli", reg_anneal=0, btcvae_A=1, btcvae_B=6, btcvae_G=1, n_data=640)
+    lf.record_loss_every = 5                      # record inside every epoch of this short run
     torch.manual_seed(3)
     base = (torch.rand(1, 1, 32, 32) > 0.5).float()
     batches = [((base.repeat(64, 1, 1, 1) * (torch.rand(64, 1, 32, 32) > 0.1).float()), torch.zeros(64)) for _ in range(10)]
