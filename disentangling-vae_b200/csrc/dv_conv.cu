@@ -11,6 +11,7 @@
 // disvae/models/decoders.py:77-82 (ConvTranspose2d+ReLU/sigmoid) and their autograd
 // backward (disvae/training.py:157).
 #include <stdlib.h>
+#include <string.h>
 #include "dv_common.cuh"
 
 namespace dv {
@@ -551,6 +552,9 @@ namespace tc {
 int pack_tc(const float* w, float* wd, float* wu, cudaStream_t st);
 int conv_down32_tc(const float* hi, const float* wd_packed, const float* bias, const float* mask, float* lo,
                    int B, int H, int W, int act, cudaStream_t st);
+int conv_wgrad32_tc(const float* lo, const float* hi, float* ws, int B, int H, int W, int* nsplit, cudaStream_t st);
+int conv_up32_tc(const float* lo, const float* wu_packed, const float* bias, const float* mask, float* hi,
+                 int B, int H, int W, int act, cudaStream_t st);
 }  // namespace tc
 
 // packed-weight sections for CH == 32 (floats): [0,16K) ffma down, [16K,32K) ffma up,
@@ -559,13 +563,17 @@ constexpr int kPackFfma = 2 * kLoCh * 32 * kTaps;
 constexpr int kPackTcSection = kTaps * 64 * 32;
 
 // DV_CONV_IMPL=ffma forces the CUDA-core kernels for the 32-channel layers (A/B testing)
-static bool use_tc() {
+// DV_TC_DISABLE=down,up,wgrad switches individual tensor-core kernels off.
+static bool use_tc(const char* which = nullptr) {
   static int v = -1;
+  static const char* dis = nullptr;
   if (v < 0) {
     const char* e = getenv("DV_CONV_IMPL");
     v = (e && e[0] == 'f') ? 0 : 1;
+    dis = getenv("DV_TC_DISABLE");
   }
-  return v == 1;
+  if (v != 1) return false;
+  return !(which && dis && strstr(dis, which));
 }
 }  // namespace dv
 
@@ -594,7 +602,7 @@ int dv_conv_down(const float* hi, const float* w_packed, const float* bias, cons
   if (act != DV_ACT_NONE && act != DV_ACT_RELU) return DV_ERR_BAD_ARG;
   if ((CH == 32) == (hi_nchw != 0)) return DV_ERR_BAD_SHAPE;   // CH==32 <=> NHWC
   const long long groups = ((long long)B * H * W + kDownPxPerWarp - 1) / kDownPxPerWarp;
-  if (CH == 32 && use_tc())
+  if (CH == 32 && use_tc("down"))
     return tc::conv_down32_tc(hi, w_packed + kPackFfma, bias, mask, lo, B, H, W, act, as_stream(stream));
   if (CH == 32) {
     const int smem = kTaps * 32 * kLoCh * sizeof(float);
@@ -621,6 +629,8 @@ int dv_conv_up(const float* lo, const float* w_packed, const float* bias, const 
   if (act != DV_ACT_NONE && act != DV_ACT_RELU && act != DV_ACT_SIGMOID) return DV_ERR_BAD_ARG;
   if ((CH == 32) == (hi_nchw != 0)) return DV_ERR_BAD_SHAPE;
   const float* wu = w_packed + kLoCh * CH * kTaps;
+  if (CH == 32 && use_tc("up") && act != DV_ACT_SIGMOID)
+    return tc::conv_up32_tc(lo, w_packed + kPackFfma + kPackTcSection, bias, mask, hi, B, H, W, act, as_stream(stream));
   if (CH == 32) {
     const int smem = kTaps * 32 * kLoCh * sizeof(float);
     static bool attr_set = false;
@@ -642,7 +652,8 @@ int dv_conv_up(const float* lo, const float* w_packed, const float* bias, const 
 
 size_t dv_conv_wgrad_workspace_bytes(int B, int H, int W, int CH) {
   long long chunk;
-  const int ns = wgrad_nsplit(B, H, W, &chunk);
+  int ns = wgrad_nsplit(B, H, W, &chunk);
+  if (ns < kNumSMs) ns = kNumSMs;                    // the tcgen05 path uses at most one CTA per SM
   return (size_t)ns * (kTaps * CH + 1) * kLoCh * sizeof(float);
 }
 
@@ -656,6 +667,14 @@ int dv_conv_wgrad(const float* lo, const float* hi, float* dw, float* dbias_lo, 
   const int ns = wgrad_nsplit(B, H, W, &chunk);
   float* ws = reinterpret_cast<float*>(workspace);
   cudaStream_t st = as_stream(stream);
+  if (CH == 32 && use_tc("wgrad")) {
+    int nsplit_tc = 0;
+    int rc = tc::conv_wgrad32_tc(lo, hi, ws, B, H, W, &nsplit_tc, st);
+    if (rc != DV_OK) return rc;
+    const int n = (kTaps * CH + 1) * kLoCh;
+    conv_wgrad_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(ws, dw, dbias_lo, CH, nsplit_tc);
+    return check_launch();
+  }
   if (CH == 32)      conv_wgrad32_kernel<<<ns, kWgWarps * 32, 0, st>>>(lo, hi, ws, B, H, W, chunk);
   else if (CH == 3)  conv_wgrad_small_kernel<3><<<ns, kWgWarps * 32, 0, st>>>(lo, hi, ws, B, H, W, chunk);
   else               conv_wgrad_small_kernel<1><<<ns, kWgWarps * 32, 0, st>>>(lo, hi, ws, B, H, W, chunk);

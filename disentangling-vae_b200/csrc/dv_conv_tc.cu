@@ -30,7 +30,7 @@ constexpr int kStages = 3;
 constexpr int kATile = 128 * 128;            // bytes: 128 pixel rows x 32 fp32
 constexpr int kBTap = 64 * 128;              // bytes: (32 hi + 32 lo) rows x 32 fp32
 constexpr int kBBytes = kTaps * kBTap;       // 131072
-constexpr int kAccCols = 64;
+constexpr int kAccCols = 128;           // 2 chains x [hi*hi+lo*hi (32) | hi*lo (32)]
 constexpr int kThreads = 384;
 constexpr uint32_t kHiMask = 0xFFFFE000u;    // keep sign, exponent and the 10 tf32 mantissa bits
 
@@ -47,6 +47,24 @@ struct Barriers {
 constexpr int kSmemBytes = kBBytes + kStages * 2 * kATile + 1024 /*alignment slack*/ + 512 /*Barriers*/;
 static_assert(sizeof(Barriers) <= 512, "barrier block too large");
 static_assert(kSmemBytes <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
+
+
+// raw fp32 tile -> tf32-exact hi plane (in place) + residual lo plane; 128 threads, layout-agnostic
+__device__ __forceinline__ void split_hi_lo(uint4* hi, uint4* lo4, int t) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int idx = t + 128 * k;
+    const uint4 v = hi[idx];
+    uint4 h, l;
+    h.x = v.x & kHiMask; h.y = v.y & kHiMask; h.z = v.z & kHiMask; h.w = v.w & kHiMask;
+    l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x));
+    l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y));
+    l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z));
+    l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w));
+    hi[idx] = h;
+    lo4[idx] = l;
+  }
+}
 
 struct DownGeom {
   int B, H, W;          // lo geometry
@@ -75,7 +93,7 @@ conv_down32_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     fence_mbar_init();
   }
   if (threadIdx.x < 32) bars->bias[threadIdx.x] = bias ? bias[threadIdx.x] : 0.f;
-  if (warp == 2) tmem_alloc(&bars->tmem_base, 128);
+  if (warp == 2) tmem_alloc(&bars->tmem_base, 256);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -115,8 +133,11 @@ conv_down32_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         const uint64_t b_d = umma_desc_sw128_kmajor(smem_u32(Bs + tap * kBTap));
 #pragma unroll
         for (int k4 = 0; k4 < 4; ++k4) {                   // K = 8 tf32 (32 bytes) per MMA: advance start address
-          umma_tf32_ss(d_tmem, a_hi + 2 * k4, b_d + 2 * k4, idesc64, (tap | k4) != 0);    // a_hi * [b_hi | b_lo]
-          umma_tf32_ss(d_tmem, a_lo + 2 * k4, b_d + 2 * k4, idesc32, 1);                  // a_lo * b_hi
+          // two independent accumulation chains (k4 parity): the tensor core truncates when it adds into
+          // the fp32 accumulator, so halving the chain length halves that bias; summed in the epilogue
+          const uint32_t d = d_tmem + (k4 & 1) * 64;
+          umma_tf32_ss(d, a_hi + 2 * k4, b_d + 2 * k4, idesc64, (tap | (k4 >> 1)) != 0);  // a_hi * [b_hi | b_lo]
+          umma_tf32_ss(d, a_lo + 2 * k4, b_d + 2 * k4, idesc32, 1);                        // a_lo * b_hi
         }
         umma_commit(&bars->empty[stage]);                  // stage free once these MMAs have read it
         if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -132,9 +153,11 @@ conv_down32_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       mbar_wait(&bars->acc_full[acc], acc_phase);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccCols;
-      uint32_t r0[32], r1[32];
+      uint32_t r0[32], r1[32], r2[32], r3[32];
       tmem_ld_32x32b_x32(taddr, r0);
       tmem_ld_32x32b_x32(taddr + 32, r1);
+      tmem_ld_32x32b_x32(taddr + 64, r2);
+      tmem_ld_32x32b_x32(taddr + 96, r3);
       tmem_ld_wait();
       tc_fence_before_sync();
       mbar_arrive(&bars->acc_empty[acc]);
@@ -148,7 +171,7 @@ conv_down32_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int c = c4 * 4 + e;
-            float x = __uint_as_float(r0[c]) + __uint_as_float(r1[c]) + bars->bias[c];
+            float x = ((__uint_as_float(r0[c]) + __uint_as_float(r2[c])) + (__uint_as_float(r1[c]) + __uint_as_float(r3[c]))) + bars->bias[c];
             if (act == DV_ACT_RELU) x = fmaxf(x, 0.f);
             v[e] = x;
           }
@@ -169,21 +192,7 @@ conv_down32_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
       for (int tap = 0; tap < kTaps; ++tap) {
         mbar_wait(&bars->raw_full[stage], phase);
-        uint4* hi = reinterpret_cast<uint4*>(Ahi + stage * kATile);
-        uint4* lo4 = reinterpret_cast<uint4*>(Alo + stage * kATile);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const int idx = t + 128 * k;
-          const uint4 v = hi[idx];
-          uint4 h, l;
-          h.x = v.x & kHiMask; h.y = v.y & kHiMask; h.z = v.z & kHiMask; h.w = v.w & kHiMask;
-          l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x));
-          l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y));
-          l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z));
-          l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w));
-          hi[idx] = h;
-          lo4[idx] = l;
-        }
+        split_hi_lo(reinterpret_cast<uint4*>(Ahi + stage * kATile), reinterpret_cast<uint4*>(Alo + stage * kATile), t);
         fence_proxy_async_smem();
         mbar_arrive(&bars->ready[stage]);
         if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -193,7 +202,342 @@ conv_down32_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
 
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 2) { tc_fence_after_sync(); tmem_dealloc(tmem_base, 128); }
+  if (warp == 2) { tc_fence_after_sync(); tmem_dealloc(tmem_base, 256); }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// up (ConvTranspose2d forward / Conv2d input-gradient), per tile of 128 lo positions:
+//   hi(2i+ph, 2j+pw)[c] = sum over the 2x2 taps with kh = ph+1-2*di, kw = pw+1-2*dj of
+//                          lo(i+di, j+dj)[cl] * w[cl][c][kh][kw]
+// Nine shifted lo tiles (di, dj in {-1,0,1}; unit-stride TMA boxes, zero fill at the borders)
+// feed the 16 (phase, tap) products; each of the 4 output phases owns a 64-column TMEM
+// accumulator ([a_hi*b_hi + a_lo*b_hi | a_hi*b_lo]), 16 accumulation steps per chain.
+// Same warp roles / pipelines as the down kernel; the pipeline unit is a shifted tile.
+// ------------------------------------------------------------------------------------------
+constexpr int kUpAccCols = 256;              // 4 phases x 64
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_up32_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const float* __restrict__ bias, const float* __restrict__ mask, float* __restrict__ hi_out,
+                    DownGeom g, int act) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* Bs = smem;
+  uint8_t* Ahi = smem + kBBytes;
+  uint8_t* Alo = Ahi + kStages * kATile;
+  Barriers* bars = reinterpret_cast<Barriers*>(Alo + kStages * kATile);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&bars->raw_full[s], 1); mbar_init(&bars->ready[s], 128); mbar_init(&bars->empty[s], 1); }
+    mbar_init(&bars->b_full, 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(&bars->acc_full[a], 1); mbar_init(&bars->acc_empty[a], 128); }
+    fence_mbar_init();
+  }
+  if (threadIdx.x < 32) bars->bias[threadIdx.x] = bias ? bias[threadIdx.x] : 0.f;
+  if (warp == 2) tmem_alloc(&bars->tmem_base, 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b);
+    mbar_arrive_expect_tx(&bars->b_full, kBBytes);
+    for (int tap = 0; tap < kTaps; ++tap) tma_load_2d(Bs + tap * kBTap, &tmap_b, &bars->b_full, 0, tap * 64);
+    int stage = 0; uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+      const int r0 = tile * g.rows_per_tile;
+      const int b0 = r0 / g.H, i0 = r0 % g.H;
+      for (int s = 0; s < 9; ++s) {
+        const int di = s / 3 - 1, dj = s % 3 - 1;
+        mbar_wait(&bars->empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&bars->raw_full[stage], kATile);
+        tma_load_4d(Ahi + stage * kATile, &tmap_a, &bars->raw_full[stage], 0, dj, i0 + di, b0);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    constexpr uint32_t idesc64 = umma_idesc_tf32(128, 64), idesc32 = umma_idesc_tf32(128, 32);
+    mbar_wait(&bars->b_full, 0);
+    int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+      mbar_wait(&bars->acc_empty[acc], acc_phase ^ 1);
+      tc_fence_after_sync();
+      uint32_t inited = 0;
+      for (int s = 0; s < 9; ++s) {
+        const int di = s / 3 - 1, dj = s % 3 - 1;
+        mbar_wait(&bars->ready[stage], phase);
+        tc_fence_after_sync();
+        const uint64_t a_hi = umma_desc_sw128_kmajor(smem_u32(Ahi + stage * kATile));
+        const uint64_t a_lo = umma_desc_sw128_kmajor(smem_u32(Alo + stage * kATile));
+        for (int ph = 0; ph < 2; ++ph) {
+          const int kh = ph + 1 - 2 * di;
+          if (kh < 0 || kh > 3) continue;
+          for (int pw = 0; pw < 2; ++pw) {
+            const int kw = pw + 1 - 2 * dj;
+            if (kw < 0 || kw > 3) continue;
+            const int pidx = ph * 2 + pw;
+            const uint32_t d = tmem_base + acc * kUpAccCols + pidx * 64;
+            const uint64_t b_d = umma_desc_sw128_kmajor(smem_u32(Bs + (kh * 4 + kw) * kBTap));
+            const uint32_t first = (inited >> pidx) & 1u;
+            inited |= 1u << pidx;
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+              umma_tf32_ss(d, a_hi + 2 * k4, b_d + 2 * k4, idesc64, (first | (uint32_t)k4) != 0);
+              umma_tf32_ss(d, a_lo + 2 * k4, b_d + 2 * k4, idesc32, 1);
+            }
+          }
+        }
+        umma_commit(&bars->empty[stage]);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(&bars->acc_full[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    const int q = warp & 3;
+    const int HH = 2 * g.H, WW = 2 * g.W;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+      mbar_wait(&bars->acc_full[acc], acc_phase);
+      tc_fence_after_sync();
+      const long long p = (long long)tile * 128 + q * 32 + lane;
+      const bool valid = p < g.total_px;
+      int b = 0, i = 0, j = 0;
+      if (valid) { j = (int)(p % g.W); i = (int)((p / g.W) % g.H); b = (int)(p / ((long long)g.W * g.H)); }
+#pragma unroll 1
+      for (int pidx = 0; pidx < 4; ++pidx) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kUpAccCols + pidx * 64;
+        uint32_t r0[32], r1[32];
+        tmem_ld_32x32b_x32(taddr, r0);
+        tmem_ld_32x32b_x32(taddr + 32, r1);
+        tmem_ld_wait();
+        if (pidx == 3) { tc_fence_before_sync(); mbar_arrive(&bars->acc_empty[acc]); }
+        if (valid) {
+          const int ph = pidx >> 1, pw = pidx & 1;
+          const long long o = ((long long)(b * HH + 2 * i + ph) * WW + 2 * j + pw) * 32;
+          float* dst = hi_out + o;
+          const float* mk = mask ? mask + o : nullptr;
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4) {
+            float v[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int c = c4 * 4 + e;
+              float x = (__uint_as_float(r0[c]) + __uint_as_float(r1[c])) + bars->bias[c];
+              if (act == DV_ACT_RELU) x = fmaxf(x, 0.f);
+              v[e] = x;
+            }
+            if (mk) {
+              const float4 m4 = ldg4(mk + c4 * 4);
+              v[0] = m4.x > 0.f ? v[0] : 0.f; v[1] = m4.y > 0.f ? v[1] : 0.f;
+              v[2] = m4.z > 0.f ? v[2] : 0.f; v[3] = m4.w > 0.f ? v[3] : 0.f;
+            }
+            *reinterpret_cast<float4*>(dst + c4 * 4) = make_float4(v[0], v[1], v[2], v[3]);
+          }
+        }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= 8) {
+    const int t = threadIdx.x - 256;
+    int stage = 0; uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+      for (int s = 0; s < 9; ++s) {
+        mbar_wait(&bars->raw_full[stage], phase);
+        split_hi_lo(reinterpret_cast<uint4*>(Ahi + stage * kATile), reinterpret_cast<uint4*>(Alo + stage * kATile), t);
+        fence_proxy_async_smem();
+        mbar_arrive(&bars->ready[stage]);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) { tc_fence_after_sync(); tmem_dealloc(tmem_base, 512); }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// wgrad: dw[cl][c][tap] = sum_p lo[p][cl] * hi(2i-1+kh, 2j-1+kw)[c]   (reduction over PIXELS)
+// Both operands arrive from TMA as [128 pixel rows][32 channels] tiles, i.e. with the reduction
+// index along the smem rows: they are fed to tcgen05.mma as MN-major operands (no transposition
+// anywhere).  One MMA (M=128, N=64, K=8 pixels):
+//      A rows = [T0_hi | T1_hi | T0_lo | T1_lo]   (two taps of the hi patch, hi/lo planes, 4 x 32 ch)
+//      B cols = [L_hi | L_lo]                      (the lo tile, hi/lo planes, 2 x 32 ch)
+// so D holds all four hi/lo cross products of two taps at once (full fp32-equivalent product);
+// 8 tap-pair accumulators x 64 columns = the whole 512-column TMEM, kept for the CTA's lifetime
+// (split-K over CTAs; partials reduced in a fixed order by conv_wgrad_reduce_kernel).
+// ------------------------------------------------------------------------------------------
+constexpr int kWgStages = 2;
+constexpr int kWgStageBytes = 4 * kATile;              // T0hi, T1hi, T0lo, T1lo
+constexpr int kWgLBytes = 2 * kATile;                  // Lhi, Llo
+struct WgBarriers {
+  uint64_t raw_full[kWgStages], ready[kWgStages], empty[kWgStages];
+  uint64_t l_raw_full[2], l_ready[2], l_empty[2];
+  uint64_t acc_full;
+  uint32_t tmem_base;
+  float lscr[128][4];
+};
+constexpr int kWgSmemBytes = kWgStages * kWgStageBytes + 2 * kWgLBytes + 1024 + 3072;
+static_assert(sizeof(WgBarriers) <= 3072, "barrier block too large");
+static_assert(kWgSmemBytes <= 232448, "smem");
+
+// MN-major SWIZZLE_128B operand: 128-byte channel groups LBO apart, 8-row K groups SBO (=1024 B) apart
+__device__ __forceinline__ uint64_t umma_desc_sw128_mnmajor(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         (1ull << 46) | (2ull << 61);
+}
+
+struct WgGeom {
+  int B, H, W, rows_per_tile, num_tiles, tiles_per_cta;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_wgrad32_tc_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ CUtensorMap tmap_lo,
+                       float* __restrict__ ws, WgGeom g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* St = smem;                                        // [stage][T0hi|T1hi|T0lo|T1lo]
+  uint8_t* Ls = smem + kWgStages * kWgStageBytes;            // [buf][Lhi|Llo]
+  WgBarriers* bars = reinterpret_cast<WgBarriers*>(Ls + 2 * kWgLBytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t_begin = blockIdx.x * g.tiles_per_cta;
+  const int t_end = min(g.num_tiles, t_begin + g.tiles_per_cta);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kWgStages; ++s) { mbar_init(&bars->raw_full[s], 1); mbar_init(&bars->ready[s], 128); mbar_init(&bars->empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&bars->l_raw_full[s], 1); mbar_init(&bars->l_ready[s], 128); mbar_init(&bars->l_empty[s], 1); }
+    mbar_init(&bars->acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(&bars->tmem_base, 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_hi); prefetch_tmap(&tmap_lo);
+    int stage = 0; uint32_t phase = 0; int lb = 0; uint32_t lphase = 0;
+    for (int tile = t_begin; tile < t_end; ++tile) {
+      const int r0 = tile * g.rows_per_tile;
+      const int b0 = r0 / g.H, i0 = r0 % g.H;
+      mbar_wait(&bars->l_empty[lb], lphase ^ 1);
+      mbar_arrive_expect_tx(&bars->l_raw_full[lb], kATile);
+      tma_load_4d(Ls + lb * kWgLBytes, &tmap_lo, &bars->l_raw_full[lb], 0, 0, i0, b0);
+      if (++lb == 2) { lb = 0; lphase ^= 1; }
+      for (int pr = 0; pr < 8; ++pr) {
+        mbar_wait(&bars->empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&bars->raw_full[stage], 2 * kATile);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int tap = 2 * pr + h, kh = tap >> 2, kw = tap & 3;
+          tma_load_4d(St + stage * kWgStageBytes + h * kATile, &tmap_hi, &bars->raw_full[stage], 0, kw - 1, 2 * i0 - 1 + kh, b0);
+        }
+        if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // M=128, N=64, tf32, both operands MN-major (bits 15 and 16)
+    constexpr uint32_t idesc = umma_idesc_tf32(128, 64) | (1u << 15) | (1u << 16);
+    int stage = 0; uint32_t phase = 0; int lb = 0; uint32_t lphase = 0;
+    for (int tile = t_begin; tile < t_end; ++tile) {
+      mbar_wait(&bars->l_ready[lb], lphase);
+      tc_fence_after_sync();
+      const uint32_t l_addr = smem_u32(Ls + lb * kWgLBytes);
+      for (int pr = 0; pr < 8; ++pr) {
+        mbar_wait(&bars->ready[stage], phase);
+        tc_fence_after_sync();
+        const uint32_t a_addr = smem_u32(St + stage * kWgStageBytes);
+        const uint32_t d = tmem_base + pr * 64;
+#pragma unroll 4
+        for (int kc = 0; kc < 16; ++kc) {                   // 8 pixels per MMA
+          umma_tf32_ss(d, umma_desc_sw128_mnmajor(a_addr + kc * 1024, kATile),
+                       umma_desc_sw128_mnmajor(l_addr + kc * 1024, kATile), idesc, (tile != t_begin) || (kc != 0));
+        }
+        umma_commit(&bars->empty[stage]);
+        if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(&bars->l_empty[lb]);
+      if (++lb == 2) { lb = 0; lphase ^= 1; }
+    }
+    umma_commit(&bars->acc_full);
+  } else if (warp >= 8) {
+    // split raw tiles into hi/lo planes; also accumulate the column sums of lo (bias gradient)
+    const int t = threadIdx.x - 256;
+    const int quad = (t & 7) ^ ((t >> 3) & 7);             // logical 16-byte chunk this thread always sees (swizzle)
+    float ls[4] = {0.f, 0.f, 0.f, 0.f};
+    int stage = 0; uint32_t phase = 0; int lb = 0; uint32_t lphase = 0;
+    for (int tile = t_begin; tile < t_end; ++tile) {
+      mbar_wait(&bars->l_raw_full[lb], lphase);
+      {
+        uint4* hi = reinterpret_cast<uint4*>(Ls + lb * kWgLBytes);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint4 v = hi[t + 128 * k];
+          ls[0] += __uint_as_float(v.x); ls[1] += __uint_as_float(v.y); ls[2] += __uint_as_float(v.z); ls[3] += __uint_as_float(v.w);
+        }
+        split_hi_lo(hi, reinterpret_cast<uint4*>(Ls + lb * kWgLBytes + kATile), t);
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&bars->l_ready[lb]);
+      if (++lb == 2) { lb = 0; lphase ^= 1; }
+      for (int pr = 0; pr < 8; ++pr) {
+        mbar_wait(&bars->raw_full[stage], phase);
+        uint8_t* base = St + stage * kWgStageBytes;
+        split_hi_lo(reinterpret_cast<uint4*>(base), reinterpret_cast<uint4*>(base + 2 * kATile), t);
+        split_hi_lo(reinterpret_cast<uint4*>(base + kATile), reinterpret_cast<uint4*>(base + 3 * kATile), t);
+        fence_proxy_async_smem();
+        mbar_arrive(&bars->ready[stage]);
+        if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+      }
+    }
+    // fixed-order reduction of the lo column sums (bias gradient): 16 of the 128 threads see each chunk
+#pragma unroll
+    for (int e = 0; e < 4; ++e) bars->lscr[t][e] = ls[e];
+    asm volatile("bar.sync 2, 128;" ::: "memory");
+    if (t < 32) {
+      const int want = t >> 2, e = t & 3;
+      float acc = 0.f;
+      for (int u = 0; u < 128; ++u)
+        if (((u & 7) ^ ((u >> 3) & 7)) == want) acc += bars->lscr[u][e];
+      ws[(long long)blockIdx.x * (kTaps * 32 + 1) * kLoCh + (kTaps * 32) * kLoCh + t] = acc;
+    }
+  }
+
+  // ---- epilogue (once per CTA): TMEM -> fold the 4 hi/lo quadrants -> workspace partial ----
+  if (warp >= 4 && warp < 8) {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    mbar_wait(&bars->acc_full, 0);
+    tc_fence_after_sync();
+    float* red = reinterpret_cast<float*>(St);              // all MMAs have completed: stage buffers are free
+    float* out = ws + (long long)blockIdx.x * (kTaps * 32 + 1) * kLoCh;
+    for (int pr = 0; pr < 8; ++pr) {
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + pr * 64;
+      uint32_t r0[32], r1[32];
+      tmem_ld_32x32b_x32(taddr, r0);
+      tmem_ld_32x32b_x32(taddr + 32, r1);
+      tmem_ld_wait();
+#pragma unroll
+      for (int cl = 0; cl < 32; ++cl) red[r * 33 + cl] = __uint_as_float(r0[cl]) + __uint_as_float(r1[cl]);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (r < 64) {
+        const int tap = pr * 2 + (r >> 5), c = r & 31;
+        float* dst = out + (tap * 32 + c) * kLoCh;
+#pragma unroll
+        for (int cl = 0; cl < 32; ++cl) dst[cl] = red[r * 33 + cl] + red[(r + 64) * 33 + cl];
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) { tc_fence_after_sync(); tmem_dealloc(tmem_base, 512); }
 }
 
 // ---- weight packing for the tensor-core kernels ------------------------------------------
@@ -289,6 +633,66 @@ int conv_down32_tc(const float* hi, const float* wd_packed, const float* bias, c
   conv_down32_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(ta, tb, bias, mask, lo, g, act);
   return check_launch();
 }
+
+
+// hi[B,2H,2W,32] = act(up(lo[B,H,W,32]) + bias) * [mask > 0]
+int conv_up32_tc(const float* lo, const float* wu_packed, const float* bias, const float* mask, float* hi,
+                 int B, int H, int W, int act, cudaStream_t st) {
+  if (W > 128 || 128 % W != 0) return DV_ERR_BAD_SHAPE;
+  DownGeom g;
+  g.B = B; g.H = H; g.W = W;
+  g.rows_per_tile = 128 / W;
+  const int TR = g.rows_per_tile < H ? g.rows_per_tile : H;
+  if (H % TR != 0 || g.rows_per_tile % TR != 0) return DV_ERR_BAD_SHAPE;
+  const int TB = g.rows_per_tile / TR;
+  g.total_px = (long long)B * H * W;
+  g.num_tiles = (int)((g.total_px + 127) / 128);
+  CUtensorMap ta, tb;
+  if (!make_act_tmap(&ta, lo, B, H, W, W, TR, TB, 1)) return DV_ERR_CUDA;
+  if (!make_w_tmap(&tb, wu_packed)) return DV_ERR_CUDA;
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(conv_up32_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess) {
+      g_last_cuda_error = (int)cudaGetLastError();
+      return DV_ERR_CUDA;
+    }
+    attr = true;
+  }
+  const int grid = g.num_tiles < kNumSMs ? g.num_tiles : kNumSMs;
+  conv_up32_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(ta, tb, bias, mask, hi, g, act);
+  return check_launch();
+}
+
+
+// partial sums of dw (and of lo, last row) per CTA into ws[grid][16*32+1][32]; returns the grid size in *nsplit
+int conv_wgrad32_tc(const float* lo, const float* hi, float* ws, int B, int H, int W, int* nsplit, cudaStream_t st) {
+  if (W > 128 || 128 % W != 0) return DV_ERR_BAD_SHAPE;
+  WgGeom g;
+  g.B = B; g.H = H; g.W = W;
+  g.rows_per_tile = 128 / W;
+  const int TR = g.rows_per_tile < H ? g.rows_per_tile : H;
+  if (H % TR != 0 || g.rows_per_tile % TR != 0) return DV_ERR_BAD_SHAPE;
+  const int TB = g.rows_per_tile / TR;
+  g.num_tiles = (int)(((long long)B * H * W + 127) / 128);
+  int grid = g.num_tiles < kNumSMs ? g.num_tiles : kNumSMs;
+  g.tiles_per_cta = (g.num_tiles + grid - 1) / grid;
+  grid = (g.num_tiles + g.tiles_per_cta - 1) / g.tiles_per_cta;
+  *nsplit = grid;
+  CUtensorMap thi, tlo;
+  if (!make_act_tmap(&thi, hi, B, 2 * H, 2 * W, 2 * W, 2 * TR, TB, 2)) return DV_ERR_CUDA;
+  if (!make_act_tmap(&tlo, lo, B, H, W, W, TR, TB, 1)) return DV_ERR_CUDA;
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(conv_wgrad32_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes) != cudaSuccess) {
+      g_last_cuda_error = (int)cudaGetLastError();
+      return DV_ERR_CUDA;
+    }
+    attr = true;
+  }
+  conv_wgrad32_tc_kernel<<<grid, kThreads, kWgSmemBytes, st>>>(thi, tlo, ws, g);
+  return check_launch();
+}
+int wgrad32_tc_max_splits() { return kNumSMs; }
 
 }  // namespace tc
 }  // namespace dv

@@ -46,6 +46,8 @@ def ops():
 
 CONV_CASES = [  # (B, H(lo), CH)
     (3, 16, 1), (2, 32, 3), (5, 16, 32), (4, 8, 32), (7, 4, 32), (3, 2 * 2, 32), (2, 32, 1), (1, 16, 3),
+    (170, 16, 32),      # 340 tiles of 128 pixels: several tiles per persistent CTA (pipeline phase wrap-around)
+    (301, 8, 32), (1201, 4, 32),
 ]
 
 
@@ -105,6 +107,28 @@ def test_conv_wgrad_matches_autograd(ops, B, H, CH):
     # determinism of the split-K reduction
     dw2, _ = ops.conv_wgrad(nhwc(g).to(dev()), hi, B, H, H, CH, int(CH < 32), True)
     assert torch.equal(dw, dw2)
+
+
+@pytest.mark.parametrize("B,H", [(16, 16), (9, 8), (40, 4), (200, 16)])
+def test_conv32_kernels_fp32_grade_accuracy(ops, B, H):
+    """The tensor-core (3xTF32) path must stay at fp32-grade accuracy, not tf32-grade: error against an
+    fp64 reference <= 4e-6 of the output scale (plain fp32 lands around 5e-7, single-pass tf32 at 5e-4)."""
+    torch.manual_seed(B + H)
+    x = torch.randn(B, 32, 2 * H, 2 * H)
+    lo = torch.randn(B, 32, H, H)
+    w = torch.randn(32, 32, 4, 4) * 0.1
+    wp = ops.conv_pack(w.to(dev()), 32)
+    ref_d = F.conv2d(x.double(), w.double(), None, stride=2, padding=1)
+    got_d = nchw(ops.conv_down(nhwc(x).to(dev()), wp, None, None, B, H, H, 32, 0, 0).cpu())
+    assert_close(got_d, ref_d, tol=4e-6, what="down vs fp64")
+    ref_u = F.conv_transpose2d(lo.double(), w.double(), None, stride=2, padding=1)
+    got_u = nchw(ops.conv_up(nhwc(lo).to(dev()), wp, None, None, B, H, H, 32, 0, 0).cpu())
+    assert_close(got_u, ref_u, tol=4e-6, what="up vs fp64")
+    wz = torch.zeros(32, 32, 4, 4, dtype=torch.float64, requires_grad=True)
+    (F.conv2d(x.double(), wz, None, stride=2, padding=1) * lo.double()).sum().backward()
+    dw, db = ops.conv_wgrad(nhwc(lo).to(dev()), nhwc(x).to(dev()), B, H, H, 32, 0, True)
+    assert_close(dw.cpu(), wz.grad, tol=4e-6, what="wgrad vs fp64")
+    assert_close(db.cpu(), lo.double().sum((0, 2, 3)), tol=4e-6, what="dbias vs fp64")
 
 
 def test_conv_transpose_weight_gradient_is_same_kernel(ops):

@@ -278,6 +278,7 @@ def test_evaluator_losses():
     class Loader(list):
         dataset = list(range(64))
     torch.manual_seed(0)
+    m.eval()                      # Evaluator.__call__ does this before compute_losses (evaluate.py:75)
     ev = disvae.Evaluator(m, lf, device=torch.device(DEV), logger=logging.getLogger("t"), is_progress_bar=False)
     losses = ev.compute_losses(Loader([(torch.rand(16, 1, 32, 32), None)] * 4))
     assert {"recon_loss", "kl_loss", "loss", "tc_loss", "kl_loss_0"} <= set(losses)
