@@ -386,10 +386,13 @@ constexpr int kWgSmemBytes = kWgStages * kWgStageBytes + 2 * kWgLBytes + 1024 + 
 static_assert(sizeof(WgBarriers) <= 3072, "barrier block too large");
 static_assert(kWgSmemBytes <= 232448, "smem");
 
-// MN-major SWIZZLE_128B operand: 128-byte channel groups LBO apart, 8-row K groups SBO (=1024 B) apart
+// MN-major tf32 operand.  32-bit MN-major data must use the "128B swizzle, 32-byte atom" layout
+// (cute::UMMA::LayoutType::SWIZZLE_128B_BASE32B = 1; TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): rows of
+// 128 B (32 channels), 32-byte chunks XOR-ed with (row & 3), i.e. a K atom is 4 rows (512 B).
+// LBO = distance between 32-channel groups, SBO = distance between 4-row K atoms.
 __device__ __forceinline__ uint64_t umma_desc_sw128_mnmajor(uint32_t smem_addr, uint32_t lbo_bytes) {
-  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
-         (1ull << 46) | (2ull << 61);
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) |
+         (1ull << 46) | (1ull << 61);
 }
 
 struct WgGeom {
@@ -469,7 +472,8 @@ conv_wgrad32_tc_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid
   } else if (warp >= 8) {
     // split raw tiles into hi/lo planes; also accumulate the column sums of lo (bias gradient)
     const int t = threadIdx.x - 256;
-    const int quad = (t & 7) ^ ((t >> 3) & 7);             // logical 16-byte chunk this thread always sees (swizzle)
+    // logical 16-byte chunk this thread always sees under the 32B-atom swizzle (row & 3 == (t >> 3) & 3)
+    const int quad = ((((t & 7) >> 1) ^ ((t >> 3) & 3)) << 1) | (t & 1);
     float ls[4] = {0.f, 0.f, 0.f, 0.f};
     int stage = 0; uint32_t phase = 0; int lb = 0; uint32_t lphase = 0;
     for (int tile = t_begin; tile < t_end; ++tile) {
@@ -504,7 +508,7 @@ conv_wgrad32_tc_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid
       const int want = t >> 2, e = t & 3;
       float acc = 0.f;
       for (int u = 0; u < 128; ++u)
-        if (((u & 7) ^ ((u >> 3) & 7)) == want) acc += bars->lscr[u][e];
+        if ((((((u & 7) >> 1) ^ ((u >> 3) & 3)) << 1) | (u & 1)) == want) acc += bars->lscr[u][e];
       ws[(long long)blockIdx.x * (kTaps * 32 + 1) * kLoCh + (kTaps * 32) * kLoCh + t] = acc;
     }
   }
@@ -577,7 +581,8 @@ static EncodeTiledFn get_encode() {
 }
 
 // NHWC activation [B][HH][WW][32] fp32; box = {32, bw, bh, bb} traversed with element strides {1, sw, sh, 1}
-static bool make_act_tmap(CUtensorMap* m, const float* base, int B, int HH, int WW, int bw, int bh, int bb, int stride) {
+static bool make_act_tmap(CUtensorMap* m, const float* base, int B, int HH, int WW, int bw, int bh, int bb, int stride,
+                          CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return false;
   cuuint64_t gdim[4] = {32, (cuuint64_t)WW, (cuuint64_t)HH, (cuuint64_t)B};
@@ -585,7 +590,7 @@ static bool make_act_tmap(CUtensorMap* m, const float* base, int B, int HH, int 
   cuuint32_t box[4] = {32, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bb};
   cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
   return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), gdim, gstr, box, estr,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 // packed weights [16*64 rows][32] fp32, box = one tap (64 rows)
@@ -679,8 +684,8 @@ int conv_wgrad32_tc(const float* lo, const float* hi, float* ws, int B, int H, i
   grid = (g.num_tiles + g.tiles_per_cta - 1) / g.tiles_per_cta;
   *nsplit = grid;
   CUtensorMap thi, tlo;
-  if (!make_act_tmap(&thi, hi, B, 2 * H, 2 * W, 2 * W, 2 * TR, TB, 2)) return DV_ERR_CUDA;
-  if (!make_act_tmap(&tlo, lo, B, H, W, W, TR, TB, 1)) return DV_ERR_CUDA;
+  if (!make_act_tmap(&thi, hi, B, 2 * H, 2 * W, 2 * W, 2 * TR, TB, 2, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return DV_ERR_CUDA;
+  if (!make_act_tmap(&tlo, lo, B, H, W, W, TR, TB, 1, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return DV_ERR_CUDA;
   static bool attr = false;
   if (!attr) {
     if (cudaFuncSetAttribute(conv_wgrad32_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes) != cudaSuccess) {
