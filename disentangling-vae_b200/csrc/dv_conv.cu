@@ -552,6 +552,10 @@ namespace tc {
 int pack_tc(const float* w, float* wd, float* wu, cudaStream_t st);
 int conv_down32_tc(const float* hi, const float* wd_packed, const float* bias, const float* mask, float* lo,
                    int B, int H, int W, int act, cudaStream_t st);
+int pack_small_tc(const float* w, float* wd, int CH, cudaStream_t st);
+int conv_down_small_tc(const float* x, const float* wd, const float* bias, const float* mask, float* lo,
+                       int B, int H, int W, int CH, int act, cudaStream_t st);
+int conv_wgrad_small_tc(const float* lo, const float* x, float* ws, int B, int H, int W, int CH, int* nsplit, cudaStream_t st);
 int conv_wgrad32_tc(const float* lo, const float* hi, float* ws, int B, int H, int W, int* nsplit, cudaStream_t st);
 int conv_up32_tc(const float* lo, const float* wu_packed, const float* bias, const float* mask, float* hi,
                  int B, int H, int W, int act, cudaStream_t st);
@@ -581,8 +585,11 @@ using namespace dv;
 
 extern "C" {
 
+// CH in {1,3}: [0, 512*CH) ffma down, [512*CH, 1024*CH) ffma up, then the tcgen05 down operand
+// [kb][64][32] (kb = ceil(16*CH/32) K blocks)
+static size_t small_tc_floats(int CH) { return (size_t)((16 * CH + 31) / 32) * 64 * 32; }
 size_t dv_conv_packed_floats(int CH) {
-  return CH == 32 ? (size_t)kPackFfma + 2 * kPackTcSection : (size_t)2 * kLoCh * CH * kTaps;
+  return CH == 32 ? (size_t)kPackFfma + 2 * kPackTcSection : (size_t)2 * kLoCh * CH * kTaps + small_tc_floats(CH);
 }
 
 int dv_conv_pack_weights(const float* w, float* w_packed, int CH, void* stream) {
@@ -591,7 +598,8 @@ int dv_conv_pack_weights(const float* w, float* w_packed, int CH, void* stream) 
   const int n = kLoCh * CH * kTaps;
   conv_pack_kernel<<<(n + 255) / 256, 256, 0, as_stream(stream)>>>(w, w_packed, CH);
   int rc = check_launch();
-  if (rc != DV_OK || CH != 32) return rc;
+  if (rc != DV_OK) return rc;
+  if (CH != 32) return tc::pack_small_tc(w, w_packed + 2 * kLoCh * CH * kTaps, CH, as_stream(stream));
   return tc::pack_tc(w, w_packed + kPackFfma, w_packed + kPackFfma + kPackTcSection, as_stream(stream));
 }
 
@@ -604,6 +612,8 @@ int dv_conv_down(const float* hi, const float* w_packed, const float* bias, cons
   const long long groups = ((long long)B * H * W + kDownPxPerWarp - 1) / kDownPxPerWarp;
   if (CH == 32 && use_tc("down"))
     return tc::conv_down32_tc(hi, w_packed + kPackFfma, bias, mask, lo, B, H, W, act, as_stream(stream));
+  if (CH != 32 && use_tc("dsmall") && W <= 128 && 128 % W == 0)
+    return tc::conv_down_small_tc(hi, w_packed + 2 * kLoCh * CH * kTaps, bias, mask, lo, B, H, W, CH, act, as_stream(stream));
   if (CH == 32) {
     const int smem = kTaps * 32 * kLoCh * sizeof(float);
     static bool attr_set = false;
@@ -667,9 +677,10 @@ int dv_conv_wgrad(const float* lo, const float* hi, float* dw, float* dbias_lo, 
   const int ns = wgrad_nsplit(B, H, W, &chunk);
   float* ws = reinterpret_cast<float*>(workspace);
   cudaStream_t st = as_stream(stream);
-  if (CH == 32 && use_tc("wgrad")) {
+  if ((CH == 32 && use_tc("wgrad")) || (CH != 32 && use_tc("wsmall"))) {
     int nsplit_tc = 0;
-    int rc = tc::conv_wgrad32_tc(lo, hi, ws, B, H, W, &nsplit_tc, st);
+    int rc = CH == 32 ? tc::conv_wgrad32_tc(lo, hi, ws, B, H, W, &nsplit_tc, st)
+                      : tc::conv_wgrad_small_tc(lo, hi, ws, B, H, W, CH, &nsplit_tc, st);
     if (rc != DV_OK) return rc;
     const int n = (kTaps * CH + 1) * kLoCh;
     conv_wgrad_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(ws, dw, dbias_lo, CH, nsplit_tc);

@@ -544,6 +544,339 @@ conv_wgrad32_tc_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid
   if (warp == 2) { tc_fence_after_sync(); tmem_dealloc(tmem_base, 512); }
 }
 
+
+// ==========================================================================================
+// Image-boundary layers (CH in {1,3}, NCHW hi) on the tensor cores.
+// The im2col patch of a lo pixel is only 16*CH floats, far too narrow for TMA tiles, so four
+// "builder" warps gather it with ordinary loads (one thread per pixel of the 128-pixel tile),
+// split it into hi/lo planes and store it straight into the swizzled operand layout the MMA
+// expects.  K is padded to a multiple of 32 with zeros (the MMAs over all-padding slices are skipped).
+// ==========================================================================================
+template <int CH>
+__device__ __forceinline__ void load_patch(const float* __restrict__ x, int HH, int WW, int b, int i, int j, bool valid,
+                                           float (&v)[16 * CH]) {
+  const long long plane = (long long)HH * WW;
+#pragma unroll
+  for (int kh = 0; kh < 4; ++kh) {
+    const int ih = 2 * i - 1 + kh;
+    const bool rv = valid && (unsigned)ih < (unsigned)HH;
+#pragma unroll
+    for (int kw = 0; kw < 4; ++kw) {
+      const int iw = 2 * j - 1 + kw;
+      const bool ok = rv && (unsigned)iw < (unsigned)WW;
+#pragma unroll
+      for (int c = 0; c < CH; ++c)
+        v[(kh * 4 + kw) * CH + c] = ok ? __ldg(x + ((long long)b * CH + c) * plane + (long long)ih * WW + iw) : 0.f;
+    }
+  }
+}
+
+// ---- down, CH small: D[128 px][32 cl] = patch[128][Kp] * W[32 cl][Kp]^T (K-major, SWIZZLE_128B) ----
+template <int CH> struct SmallCfg {
+  static constexpr int K = 16 * CH;
+  static constexpr int NKB = (K + 31) / 32;                 // 128-byte K blocks
+  static constexpr int kStage = 2 * NKB * kATile;           // hi blocks then lo blocks
+  static constexpr int kNStages = (CH == 1) ? 3 : 2;
+  static constexpr int kBBytesS = NKB * kBTap;
+  static constexpr int kSmem = kBBytesS + kNStages * kStage + 1024 + 512;
+};
+
+template <int CH>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_down_small_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const float* __restrict__ x,
+                          const float* __restrict__ bias, const float* __restrict__ mask, float* __restrict__ lo,
+                          DownGeom g, int act) {
+  using C = SmallCfg<CH>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* Bs = smem;                                        // [kb][64 rows][128 B]
+  uint8_t* As = smem + C::kBBytesS;                          // [stage][hi kb.. | lo kb..][128 rows][128 B]
+  Barriers* bars = reinterpret_cast<Barriers*>(As + C::kNStages * C::kStage);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&bars->raw_full[s], 1); mbar_init(&bars->ready[s], 128); mbar_init(&bars->empty[s], 1); }
+    mbar_init(&bars->b_full, 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(&bars->acc_full[a], 1); mbar_init(&bars->acc_empty[a], 128); }
+    fence_mbar_init();
+  }
+  if (threadIdx.x < 32) bars->bias[threadIdx.x] = bias ? bias[threadIdx.x] : 0.f;
+  if (warp == 2) tmem_alloc(&bars->tmem_base, 128);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_b);
+    mbar_arrive_expect_tx(&bars->b_full, C::kBBytesS);
+    for (int kb = 0; kb < C::NKB; ++kb) tma_load_2d(Bs + kb * kBTap, &tmap_b, &bars->b_full, 0, kb * 64);
+  } else if (warp == 1 && lane == 0) {
+    constexpr uint32_t idesc64 = umma_idesc_tf32(128, 64), idesc32 = umma_idesc_tf32(128, 32);
+    mbar_wait(&bars->b_full, 0);
+    int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+      mbar_wait(&bars->acc_empty[acc], acc_phase ^ 1);
+      mbar_wait(&bars->ready[stage], phase);
+      tc_fence_after_sync();
+      const uint32_t d = tmem_base + acc * 64;
+      uint32_t accum = 0;
+#pragma unroll
+      for (int kb = 0; kb < C::NKB; ++kb) {
+        const uint64_t a_hi = umma_desc_sw128_kmajor(smem_u32(As + stage * C::kStage + kb * kATile));
+        const uint64_t a_lo = umma_desc_sw128_kmajor(smem_u32(As + stage * C::kStage + (C::NKB + kb) * kATile));
+        const uint64_t b_d = umma_desc_sw128_kmajor(smem_u32(Bs + kb * kBTap));
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) {
+          if (kb * 32 + k4 * 8 >= C::K) continue;           // all-zero padding slice
+          umma_tf32_ss(d, a_hi + 2 * k4, b_d + 2 * k4, idesc64, accum);
+          umma_tf32_ss(d, a_lo + 2 * k4, b_d + 2 * k4, idesc32, 1);
+          accum = 1;
+        }
+      }
+      umma_commit(&bars->empty[stage]);
+      umma_commit(&bars->acc_full[acc]);
+      if (++stage == C::kNStages) { stage = 0; phase ^= 1; }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    const int q = warp & 3;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+      mbar_wait(&bars->acc_full[acc], acc_phase);
+      tc_fence_after_sync();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 64;
+      uint32_t r0[32], r1[32];
+      tmem_ld_32x32b_x32(taddr, r0);
+      tmem_ld_32x32b_x32(taddr + 32, r1);
+      tmem_ld_wait();
+      tc_fence_before_sync();
+      mbar_arrive(&bars->acc_empty[acc]);
+      const long long p = (long long)tile * 128 + q * 32 + lane;
+      if (p < g.total_px) {
+        float* dst = lo + p * 32;
+        const float* mk = mask ? mask + p * 32 : nullptr;
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          float v[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int c = c4 * 4 + e;
+            float xx = (__uint_as_float(r0[c]) + __uint_as_float(r1[c])) + bars->bias[c];
+            if (act == DV_ACT_RELU) xx = fmaxf(xx, 0.f);
+            v[e] = xx;
+          }
+          if (mk) {
+            const float4 m4 = ldg4(mk + c4 * 4);
+            v[0] = m4.x > 0.f ? v[0] : 0.f; v[1] = m4.y > 0.f ? v[1] : 0.f;
+            v[2] = m4.z > 0.f ? v[2] : 0.f; v[3] = m4.w > 0.f ? v[3] : 0.f;
+          }
+          *reinterpret_cast<float4*>(dst + c4 * 4) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= 8) {
+    // ---- patch builders: thread r owns pixel row r of the tile ----
+    const int r = threadIdx.x - 256;
+    const int HH = 2 * g.H, WW = 2 * g.W;
+    int stage = 0; uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+      const long long p = (long long)tile * 128 + r;
+      const bool valid = p < g.total_px;
+      int b = 0, i = 0, j = 0;
+      if (valid) { j = (int)(p % g.W); i = (int)((p / g.W) % g.H); b = (int)(p / ((long long)g.W * g.H)); }
+      float v[16 * CH];
+      load_patch<CH>(x, HH, WW, b, i, j, valid, v);
+      mbar_wait(&bars->empty[stage], phase ^ 1);
+      uint8_t* st = As + stage * C::kStage;
+#pragma unroll
+      for (int kb = 0; kb < C::NKB; ++kb) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {                      // 16-byte chunk c of K block kb: k = kb*32 + 4c .. +3
+          uint4 h, l;
+          uint32_t* hp = &h.x; uint32_t* lp = &l.x;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int k = kb * 32 + c * 4 + e;
+            const float val = (k < C::K) ? v[k < C::K ? k : 0] : 0.f;
+            const uint32_t hb = __float_as_uint(val) & kHiMask;
+            hp[e] = hb;
+            lp[e] = __float_as_uint(val - __uint_as_float(hb));
+          }
+          const int off = r * 128 + ((c ^ (r & 7)) << 4);
+          *reinterpret_cast<uint4*>(st + kb * kATile + off) = h;
+          *reinterpret_cast<uint4*>(st + (C::NKB + kb) * kATile + off) = l;
+        }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&bars->ready[stage]);
+      if (++stage == C::kNStages) { stage = 0; phase ^= 1; }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) { tc_fence_after_sync(); tmem_dealloc(tmem_base, 128); }
+}
+
+// ---- wgrad, CH small: D[(plane,k)][(plane,cl)] += patch^T * lo over pixels (MN-major operands) ----
+template <int CH> struct SmallWgCfg {
+  static constexpr int K = 16 * CH;
+  static constexpr int G = (K + 31) / 32;                   // 32-wide MN groups of the patch (1 or 2)
+  static constexpr int kPStage = 4 * kATile;                // 4 MN groups are always addressed (M = 128)
+  static constexpr int kSmem = 2 * kPStage + 2 * kWgLBytes + 1024 + 3072;
+};
+
+template <int CH>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_wgrad_small_tc_kernel(const __grid_constant__ CUtensorMap tmap_lo, const float* __restrict__ x,
+                           float* __restrict__ ws, WgGeom g) {
+  using C = SmallWgCfg<CH>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* Ps = smem;                                        // [stage][P_hi groups | P_lo groups (| unused)]
+  uint8_t* Ls = smem + 2 * C::kPStage;                       // [buf][Lhi|Llo]
+  WgBarriers* bars = reinterpret_cast<WgBarriers*>(Ls + 2 * kWgLBytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t_begin = blockIdx.x * g.tiles_per_cta;
+  const int t_end = min(g.num_tiles, t_begin + g.tiles_per_cta);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2; ++s) { mbar_init(&bars->ready[s], 128); mbar_init(&bars->empty[s], 1); mbar_init(&bars->raw_full[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&bars->l_raw_full[s], 1); mbar_init(&bars->l_ready[s], 128); mbar_init(&bars->l_empty[s], 1); }
+    mbar_init(&bars->acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(&bars->tmem_base, 64);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_lo);
+    int lb = 0; uint32_t lphase = 0;
+    for (int tile = t_begin; tile < t_end; ++tile) {
+      const int r0 = tile * g.rows_per_tile;
+      const int b0 = r0 / g.H, i0 = r0 % g.H;
+      mbar_wait(&bars->l_empty[lb], lphase ^ 1);
+      mbar_arrive_expect_tx(&bars->l_raw_full[lb], kATile);
+      tma_load_4d(Ls + lb * kWgLBytes, &tmap_lo, &bars->l_raw_full[lb], 0, 0, i0, b0);
+      if (++lb == 2) { lb = 0; lphase ^= 1; }
+    }
+  } else if (warp == 1 && lane == 0) {
+    constexpr uint32_t idesc = umma_idesc_tf32(128, 64) | (1u << 15) | (1u << 16);
+    int stage = 0; uint32_t phase = 0; int lb = 0; uint32_t lphase = 0;
+    for (int tile = t_begin; tile < t_end; ++tile) {
+      mbar_wait(&bars->l_ready[lb], lphase);
+      mbar_wait(&bars->ready[stage], phase);
+      tc_fence_after_sync();
+      const uint32_t l_addr = smem_u32(Ls + lb * kWgLBytes);
+      const uint32_t a_addr = smem_u32(Ps + stage * C::kPStage);
+#pragma unroll 4
+      for (int kc = 0; kc < 16; ++kc)
+        umma_tf32_ss(tmem_base, umma_desc_sw128_mnmajor(a_addr + kc * 1024, kATile),
+                     umma_desc_sw128_mnmajor(l_addr + kc * 1024, kATile), idesc, (tile != t_begin) || (kc != 0));
+      umma_commit(&bars->empty[stage]);
+      umma_commit(&bars->l_empty[lb]);
+      if (++stage == 2) { stage = 0; phase ^= 1; }
+      if (++lb == 2) { lb = 0; lphase ^= 1; }
+    }
+    umma_commit(&bars->acc_full);
+  } else if (warp >= 8) {
+    // split the lo tile, accumulate its column sums, and build the patch operand
+    const int t = threadIdx.x - 256;
+    const int quad = ((((t & 7) >> 1) ^ ((t >> 3) & 3)) << 1) | (t & 1);
+    const int HH = 2 * g.H, WW = 2 * g.W;
+    float ls[4] = {0.f, 0.f, 0.f, 0.f};
+    int stage = 0; uint32_t phase = 0; int lb = 0; uint32_t lphase = 0;
+    for (int tile = t_begin; tile < t_end; ++tile) {
+      // patch row of pixel t (gathered while the lo tile is in flight)
+      const long long p = (long long)tile * 128 + t;
+      const bool valid = p < (long long)g.B * g.H * g.W;
+      int b = 0, i = 0, j = 0;
+      if (valid) { j = (int)(p % g.W); i = (int)((p / g.W) % g.H); b = (int)(p / ((long long)g.W * g.H)); }
+      float v[16 * CH];
+      load_patch<CH>(x, HH, WW, b, i, j, valid, v);
+      mbar_wait(&bars->empty[stage], phase ^ 1);
+      uint8_t* st = Ps + stage * C::kPStage;
+#pragma unroll
+      for (int gi = 0; gi < C::G; ++gi) {
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {                   // 32-byte chunk cc of group gi: k = gi*32 + 8cc .. +7
+          if (gi * 32 + cc * 8 >= C::K) continue;           // never read back (rows of D that are ignored)
+          uint32_t h[8], l[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int k = gi * 32 + cc * 8 + e;
+            const float val = (k < C::K) ? v[k < C::K ? k : 0] : 0.f;
+            h[e] = __float_as_uint(val) & kHiMask;
+            l[e] = __float_as_uint(val - __uint_as_float(h[e]));
+          }
+          const int off = t * 128 + ((cc ^ (t & 3)) << 5);
+          uint4* hd = reinterpret_cast<uint4*>(st + gi * kATile + off);
+          uint4* ld = reinterpret_cast<uint4*>(st + (C::G + gi) * kATile + off);
+          hd[0] = make_uint4(h[0], h[1], h[2], h[3]); hd[1] = make_uint4(h[4], h[5], h[6], h[7]);
+          ld[0] = make_uint4(l[0], l[1], l[2], l[3]); ld[1] = make_uint4(l[4], l[5], l[6], l[7]);
+        }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&bars->ready[stage]);
+      if (++stage == 2) { stage = 0; phase ^= 1; }
+
+      mbar_wait(&bars->l_raw_full[lb], lphase);
+      {
+        uint4* hi = reinterpret_cast<uint4*>(Ls + lb * kWgLBytes);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint4 u = hi[t + 128 * k];
+          ls[0] += __uint_as_float(u.x); ls[1] += __uint_as_float(u.y); ls[2] += __uint_as_float(u.z); ls[3] += __uint_as_float(u.w);
+        }
+        split_hi_lo(hi, reinterpret_cast<uint4*>(Ls + lb * kWgLBytes + kATile), t);
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&bars->l_ready[lb]);
+      if (++lb == 2) { lb = 0; lphase ^= 1; }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) bars->lscr[t][e] = ls[e];
+    asm volatile("bar.sync 2, 128;" ::: "memory");
+    if (t < 32) {
+      const int want = t >> 2, e = t & 3;
+      float acc = 0.f;
+      for (int u = 0; u < 128; ++u)
+        if ((((((u & 7) >> 1) ^ ((u >> 3) & 3)) << 1) | (u & 1)) == want) acc += bars->lscr[u][e];
+      ws[(long long)blockIdx.x * (C::K + 1) * kLoCh + C::K * kLoCh + t] = acc;
+    }
+  }
+
+  if (warp >= 4 && warp < 8) {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    mbar_wait(&bars->acc_full, 0);
+    tc_fence_after_sync();
+    float* red = reinterpret_cast<float*>(Ps);
+    float* out = ws + (long long)blockIdx.x * (C::K + 1) * kLoCh;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint32_t r0[32], r1[32];
+    tmem_ld_32x32b_x32(taddr, r0);
+    tmem_ld_32x32b_x32(taddr + 32, r1);
+    tmem_ld_wait();
+#pragma unroll
+    for (int cl = 0; cl < 32; ++cl) red[r * 33 + cl] = __uint_as_float(r0[cl]) + __uint_as_float(r1[cl]);
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    // D rows: [0, 32G) = P_hi (k = row), [32G, 64G) = P_lo
+    if (r < C::K) {
+      float* dst = out + r * kLoCh;
+#pragma unroll
+      for (int cl = 0; cl < 32; ++cl) dst[cl] = red[r * 33 + cl] + red[(r + 32 * C::G) * 33 + cl];
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) { tc_fence_after_sync(); tmem_dealloc(tmem_base, 64); }
+}
+
 // ---- weight packing for the tensor-core kernels ------------------------------------------
 // w[cl][c][tap] ->  down: Wd[tap][row][c],  row <  32: tf32-exact hi of w[row][c][tap], row >= 32: lo
 //                   up  : Wu[tap][row][cl], row <  32: hi of w[cl][row][tap],          row >= 32: lo
@@ -698,6 +1031,93 @@ int conv_wgrad32_tc(const float* lo, const float* hi, float* ws, int B, int H, i
   return check_launch();
 }
 int wgrad32_tc_max_splits() { return kNumSMs; }
+
+// small-CH down weights: [kb][64 rows = hi(32 cl) | lo(32 cl)][32 k], k = kb*32 + col = tap*CH + c, zero padded
+__global__ void conv_pack_small_tc_kernel(const float* __restrict__ w, float* __restrict__ wd, int CH, int nkb) {
+  const int n = nkb * 64 * 32;
+  const int K = 16 * CH;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
+    const int col = idx % 32, row = (idx / 32) % 64, kb = idx / (64 * 32);
+    const int k = kb * 32 + col, cl = row & 31;
+    float v = 0.f;
+    if (k < K) { const int tap = k / CH, c = k % CH; v = w[(cl * CH + c) * kTaps + tap]; }
+    const float hi = __uint_as_float(__float_as_uint(v) & kHiMask);
+    wd[idx] = (row < 32) ? hi : (v - hi);
+  }
+}
+int pack_small_tc(const float* w, float* wd, int CH, cudaStream_t st) {
+  conv_pack_small_tc_kernel<<<8, 256, 0, st>>>(w, wd, CH, (16 * CH + 31) / 32);
+  return check_launch();
+}
+static bool make_w_tmap_rows(CUtensorMap* m, const float* base, int rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t gdim[2] = {32, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {128};
+  cuuint32_t box[2] = {32, 64};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int CH>
+static int launch_down_small(const float* x, const float* wd, const float* bias, const float* mask, float* lo,
+                             DownGeom g, int act, cudaStream_t st) {
+  CUtensorMap tb;
+  if (!make_w_tmap_rows(&tb, wd, SmallCfg<CH>::NKB * 64)) return DV_ERR_CUDA;
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(conv_down_small_tc_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmallCfg<CH>::kSmem) != cudaSuccess) {
+      g_last_cuda_error = (int)cudaGetLastError();
+      return DV_ERR_CUDA;
+    }
+    attr = true;
+  }
+  const int grid = g.num_tiles < kNumSMs ? g.num_tiles : kNumSMs;
+  conv_down_small_tc_kernel<CH><<<grid, kThreads, SmallCfg<CH>::kSmem, st>>>(tb, x, bias, mask, lo, g, act);
+  return check_launch();
+}
+int conv_down_small_tc(const float* x, const float* wd, const float* bias, const float* mask, float* lo,
+                       int B, int H, int W, int CH, int act, cudaStream_t st) {
+  DownGeom g;
+  g.B = B; g.H = H; g.W = W; g.rows_per_tile = 0;
+  g.total_px = (long long)B * H * W;
+  g.num_tiles = (int)((g.total_px + 127) / 128);
+  return CH == 1 ? launch_down_small<1>(x, wd, bias, mask, lo, g, act, st) : launch_down_small<3>(x, wd, bias, mask, lo, g, act, st);
+}
+
+template <int CH>
+static int launch_wgrad_small(const float* lo, const float* x, float* ws, WgGeom g, int grid, cudaStream_t st) {
+  CUtensorMap tlo;
+  const int TR = g.rows_per_tile < g.H ? g.rows_per_tile : g.H;
+  const int TB = g.rows_per_tile / TR;
+  if (!make_act_tmap(&tlo, lo, g.B, g.H, g.W, g.W, TR, TB, 1, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return DV_ERR_CUDA;
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(conv_wgrad_small_tc_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmallWgCfg<CH>::kSmem) != cudaSuccess) {
+      g_last_cuda_error = (int)cudaGetLastError();
+      return DV_ERR_CUDA;
+    }
+    attr = true;
+  }
+  conv_wgrad_small_tc_kernel<CH><<<grid, kThreads, SmallWgCfg<CH>::kSmem, st>>>(tlo, x, ws, g);
+  return check_launch();
+}
+int conv_wgrad_small_tc(const float* lo, const float* x, float* ws, int B, int H, int W, int CH, int* nsplit, cudaStream_t st) {
+  if (W > 128 || 128 % W != 0) return DV_ERR_BAD_SHAPE;
+  WgGeom g;
+  g.B = B; g.H = H; g.W = W;
+  g.rows_per_tile = 128 / W;
+  const int TR = g.rows_per_tile < H ? g.rows_per_tile : H;
+  if (H % TR != 0 || g.rows_per_tile % TR != 0) return DV_ERR_BAD_SHAPE;
+  g.num_tiles = (int)(((long long)B * H * W + 127) / 128);
+  int grid = g.num_tiles < kNumSMs ? g.num_tiles : kNumSMs;
+  g.tiles_per_cta = (g.num_tiles + grid - 1) / grid;
+  grid = (g.num_tiles + g.tiles_per_cta - 1) / g.tiles_per_cta;
+  *nsplit = grid;
+  return CH == 1 ? launch_wgrad_small<1>(lo, x, ws, g, grid, st) : launch_wgrad_small<3>(lo, x, ws, g, grid, st);
+}
 
 }  // namespace tc
 }  // namespace dv

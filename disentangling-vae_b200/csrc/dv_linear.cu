@@ -23,56 +23,83 @@ struct GemmEpilogue {
 
 // A_R_CONTIG: A's reduction index is contiguous (a_sr == 1); else A's m index is contiguous.
 // B_R_CONTIG: B's reduction index is contiguous (b_sr == 1); else B's n index is contiguous.
+// The next K tile is fetched into registers while the current one is consumed from shared memory
+// (these GEMMs are small: without the prefetch every k-step exposes a full L2/HBM round trip).
+// blockIdx.z selects a split of the reduction range (split-K); partial results go to C + z*Mo*No.
 template <bool A_R_CONTIG, bool B_R_CONTIG>
 __global__ void __launch_bounds__(256)
 gemm_kernel(const float* __restrict__ A, const float* __restrict__ Bp, float* __restrict__ C,
             int Mo, int No, int R, long long a_sm, long long a_sr, long long b_sr, long long b_sn,
-            GemmEpilogue ep) {
+            GemmEpilogue ep, int r_per_split) {
   __shared__ __align__(16) float As[BK][BM + 4];
   __shared__ __align__(16) float Bs[BK][BN + 4];
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;              // 16 x 16 threads, 4 x 4 outputs each
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int r_begin = blockIdx.z * r_per_split;
+  const int r_end = min(R, r_begin + r_per_split);
+  C += (long long)blockIdx.z * Mo * No;
   float acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-  for (int r0 = 0; r0 < R; r0 += BK) {
-    // ---- stage A tile (BM x BK) ----
+  float ra[4], rb[4];
+  auto fetch = [&](int r0) {
     if (A_R_CONTIG) {
-      const int m = tid >> 2, rq = (tid & 3) * 4;       // 64 rows x 4 quads of r
+      const int m = tid >> 2, rq = (tid & 3) * 4;
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int gm = m0 + m, gr = r0 + rq + e;
-        As[rq + e][m] = (gm < Mo && gr < R) ? __ldg(A + gm * a_sm + gr * a_sr) : 0.f;
+        ra[e] = (gm < Mo && gr < r_end) ? __ldg(A + gm * a_sm + gr * a_sr) : 0.f;
       }
     } else {
-      const int r = tid >> 4, mq = (tid & 15) * 4;      // 16 r x 16 quads of m
+      const int r = tid >> 4, mq = (tid & 15) * 4;
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int gm = m0 + mq + e, gr = r0 + r;
-        As[r][mq + e] = (gm < Mo && gr < R) ? __ldg(A + gm * a_sm + gr * a_sr) : 0.f;
+        ra[e] = (gm < Mo && gr < r_end) ? __ldg(A + gm * a_sm + gr * a_sr) : 0.f;
       }
     }
-    // ---- stage B tile (BK x BN) ----
     if (B_R_CONTIG) {
       const int n = tid >> 2, rq = (tid & 3) * 4;
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int gn = n0 + n, gr = r0 + rq + e;
-        Bs[rq + e][n] = (gn < No && gr < R) ? __ldg(Bp + gr * b_sr + gn * b_sn) : 0.f;
+        rb[e] = (gn < No && gr < r_end) ? __ldg(Bp + gr * b_sr + gn * b_sn) : 0.f;
       }
     } else {
       const int r = tid >> 4, nq = (tid & 15) * 4;
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int gn = n0 + nq + e, gr = r0 + r;
-        Bs[r][nq + e] = (gn < No && gr < R) ? __ldg(Bp + gr * b_sr + gn * b_sn) : 0.f;
+        rb[e] = (gn < No && gr < r_end) ? __ldg(Bp + gr * b_sr + gn * b_sn) : 0.f;
       }
     }
+  };
+  auto stash = [&]() {
+    if (A_R_CONTIG) { const int m = tid >> 2, rq = (tid & 3) * 4;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) As[rq + e][m] = ra[e];
+    } else { const int r = tid >> 4, mq = (tid & 15) * 4;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) As[r][mq + e] = ra[e];
+    }
+    if (B_R_CONTIG) { const int n = tid >> 2, rq = (tid & 3) * 4;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) Bs[rq + e][n] = rb[e];
+    } else { const int r = tid >> 4, nq = (tid & 15) * 4;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) Bs[r][nq + e] = rb[e];
+    }
+  };
+
+  fetch(r_begin);
+  for (int r0 = r_begin; r0 < r_end; r0 += BK) {
+    stash();
     __syncthreads();
+    if (r0 + BK < r_end) fetch(r0 + BK);               // in flight while this tile is consumed
 #pragma unroll
     for (int k = 0; k < BK; ++k) {
       const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
@@ -108,13 +135,41 @@ gemm_kernel(const float* __restrict__ A, const float* __restrict__ Bp, float* __
   }
 }
 
-// out[n] = sum_m g[m][n]  (bias gradient), one thread per column, fixed order.
-__global__ void colsum_kernel(const float* __restrict__ g, float* __restrict__ out, int M, int N) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
+// fixed-order sum of split-K partials
+__global__ void splitk_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, long long n, int S) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int z = 0; z < S; ++z) s += part[(long long)z * n + i];
+    out[i] = s;
+  }
+}
+
+// out[n] = sum_m g[m][n]  (bias gradient): block = 32 columns x 8 row-slices, fixed order.
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ g, float* __restrict__ out, int M, int N) {
+  __shared__ float red[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + lane;
   float s = 0.f;
-  for (int m = 0; m < M; ++m) s += g[(long long)m * N + n];
-  out[n] = s;
+  if (n < N)
+    for (int m = warp; m < M; m += 8) s += g[(long long)m * N + n];
+  red[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0 && n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][lane];
+    out[n] = t;
+  }
+}
+
+static int wgrad_splits(int M, int N, int K) {
+  const int tiles = ((K + BN - 1) / BN) * ((N + BM - 1) / BM);
+  if (tiles >= 120) return 1;
+  int S = (2 * kNumSMs + tiles - 1) / tiles;
+  const int maxS = (M + 4 * BK - 1) / (4 * BK);         // at least 4 k-steps per split
+  if (S > maxS) S = maxS;
+  if (S > 32) S = 32;
+  return S < 1 ? 1 : S;
 }
 
 }  // namespace dv
@@ -130,7 +185,7 @@ int dv_linear_fwd(const float* x, const float* w, const float* bias, float* y, i
   if (act < DV_ACT_NONE || act > DV_ACT_LEAKY) return DV_ERR_BAD_ARG;
   GemmEpilogue ep{bias, nullptr, act, slope};
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
-  gemm_kernel<true, true><<<grid, 256, 0, as_stream(stream)>>>(x, w, y, M, N, K, K, 1, 1, K, ep);
+  gemm_kernel<true, true><<<grid, 256, 0, as_stream(stream)>>>(x, w, y, M, N, K, K, 1, 1, K, ep, K);
   return check_launch();
 }
 
@@ -140,19 +195,38 @@ int dv_linear_dgrad(const float* g, const float* w, const float* mask_src, float
   if (M <= 0 || N <= 0 || K <= 0) return DV_ERR_BAD_SHAPE;
   GemmEpilogue ep{nullptr, mask_src, mask_src ? act : DV_ACT_NONE, slope};
   dim3 grid((K + BN - 1) / BN, (M + BM - 1) / BM);
-  gemm_kernel<true, false><<<grid, 256, 0, as_stream(stream)>>>(g, w, dx, M, K, N, N, 1, K, 1, ep);
+  gemm_kernel<true, false><<<grid, 256, 0, as_stream(stream)>>>(g, w, dx, M, K, N, N, 1, K, 1, ep, N);
   return check_launch();
 }
 
-int dv_linear_wgrad(const float* g, const float* x, float* dw, float* dbias, int M, int N, int K, void* stream) {
+size_t dv_linear_wgrad_workspace_bytes(int M, int N, int K) {
+  const int S = wgrad_splits(M, N, K);
+  return S > 1 ? (size_t)S * N * K * sizeof(float) : 0;
+}
+
+int dv_linear_wgrad(const float* g, const float* x, float* dw, float* dbias, int M, int N, int K, void* workspace,
+                    void* stream) {
   if (!g || !x || !dw) return DV_ERR_BAD_ARG;
   if (M <= 0 || N <= 0 || K <= 0) return DV_ERR_BAD_SHAPE;
+  const int S = wgrad_splits(M, N, K);
+  if (S > 1 && !workspace) return DV_ERR_WORKSPACE;
   GemmEpilogue ep{nullptr, nullptr, DV_ACT_NONE, 0.f};
-  dim3 grid((K + BN - 1) / BN, (N + BM - 1) / BM);
-  gemm_kernel<false, false><<<grid, 256, 0, as_stream(stream)>>>(g, x, dw, N, K, M, 1, N, K, 1, ep);
+  cudaStream_t st = as_stream(stream);
+  const int per = ((M + S - 1) / S + BK - 1) / BK * BK;
+  dim3 grid((K + BN - 1) / BN, (N + BM - 1) / BM, S);
+  float* target = S > 1 ? reinterpret_cast<float*>(workspace) : dw;
+  gemm_kernel<false, false><<<grid, 256, 0, st>>>(g, x, target, N, K, M, 1, N, K, 1, ep, per);
   int rc = check_launch();
-  if (rc != DV_OK || !dbias) return rc;
-  colsum_kernel<<<(N + 127) / 128, 128, 0, as_stream(stream)>>>(g, dbias, M, N);
+  if (rc != DV_OK) return rc;
+  if (S > 1) {
+    const long long n = (long long)N * K;
+    int gr = (int)((n + 255) / 256); if (gr > 4 * kNumSMs) gr = 4 * kNumSMs;
+    splitk_reduce_kernel<<<gr, 256, 0, st>>>(target, dw, n, S);
+    rc = check_launch();
+    if (rc != DV_OK) return rc;
+  }
+  if (!dbias) return rc;
+  colsum_kernel<<<(N + 31) / 32, 256, 0, st>>>(g, dbias, M, N);
   return check_launch();
 }
 

@@ -37,7 +37,8 @@ SIGNATURES = {
     "dv_act_bwd": (I, [P, P, P, LL, I, F, P]),
     "dv_linear_fwd": (I, [P, P, P, P, I, I, I, I, F, P]),
     "dv_linear_dgrad": (I, [P, P, P, P, I, I, I, I, F, P]),
-    "dv_linear_wgrad": (I, [P, P, P, P, I, I, I, P]),
+    "dv_linear_wgrad_workspace_bytes": (SZ, [I, I, I]),
+    "dv_linear_wgrad": (I, [P, P, P, P, I, I, I, P, P]),
     "dv_reparam_fwd": (I, [P, P, I, I, P, ULL, P, P, P, I, I, P]),
     "dv_reparam_bwd": (I, [P, P, I, I, P, P, P, I, I, P]),
     "dv_vae_loss_workspace_bytes": (SZ, [I, LL]),

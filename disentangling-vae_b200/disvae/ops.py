@@ -115,7 +115,9 @@ def linear_wgrad(g, x, want_bias=True):
     K = x.shape[1]
     dw = _new((Nn, K), g)
     db = _new((Nn,), g) if want_bias else None
-    call("dv_linear_wgrad", ptr(g), ptr(x), ptr(dw), ptr(db), M, Nn, K, stream())
+    nbytes = N.lib().dv_linear_wgrad_workspace_bytes(M, Nn, K)
+    ws = _scratch("lin_wgrad", nbytes, g.device) if nbytes else None
+    call("dv_linear_wgrad", ptr(g), ptr(x), ptr(dw), ptr(db), M, Nn, K, ptr(ws), stream())
     return dw, db
 
 

@@ -103,9 +103,11 @@ int dv_linear_fwd(const float* x, const float* w, const float* bias, float* y, i
  * of the previous layer (NULL: no mask); act in {NONE, RELU, LEAKY}. */
 int dv_linear_dgrad(const float* g, const float* w, const float* mask_src, float* dx, int M, int N,
                     int K, int act, float slope, void* stream);
-/* dw[N,K] = g^T . x ; dbias[N] = column sums of g (may be NULL) */
+/* dw[N,K] = g^T . x ; dbias[N] = column sums of g (may be NULL).  Small N*K problems are split over
+ * the batch (deterministic split-K); workspace may be NULL when the query returns 0. */
+size_t dv_linear_wgrad_workspace_bytes(int M, int N, int K);
 int dv_linear_wgrad(const float* g, const float* x, float* dw, float* dbias, int M, int N, int K,
-                    void* stream);
+                    void* workspace, void* stream);
 
 /* ---- reparameterised sampling ------------------------------------------------------
  * Replaces VAE.reparameterize (disvae/models/vae.py:65-68): z = mu + exp(0.5*logvar)*eps.

@@ -48,6 +48,7 @@ CONV_CASES = [  # (B, H(lo), CH)
     (3, 16, 1), (2, 32, 3), (5, 16, 32), (4, 8, 32), (7, 4, 32), (3, 2 * 2, 32), (2, 32, 1), (1, 16, 3),
     (170, 16, 32),      # 340 tiles of 128 pixels: several tiles per persistent CTA (pipeline phase wrap-around)
     (301, 8, 32), (1201, 4, 32),
+    (40, 32, 1), (40, 32, 3),      # image-boundary layers, 320 tiles
 ]
 
 
@@ -161,7 +162,8 @@ def test_channel_sum_and_transpose_and_act_bwd(ops):
     assert_close(ops.act_bwd(dy.to(dev()), yy.to(dev()), 2).cpu(), dy * (1 - yy) * yy, tol=1e-6)
 
 
-LIN_CASES = [(64, 256, 512), (7, 20, 256), (130, 256, 10), (33, 1000, 1000), (256, 2, 1000), (5, 128, 64), (1, 512, 256)]
+LIN_CASES = [(64, 256, 512), (7, 20, 256), (130, 256, 10), (33, 1000, 1000), (256, 2, 1000), (5, 128, 64), (1, 512, 256),
+             (1024, 256, 512), (1000, 20, 256), (513, 256, 10)]
 
 
 @pytest.mark.parametrize("M,N,K", LIN_CASES)
