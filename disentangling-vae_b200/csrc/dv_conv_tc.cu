@@ -18,6 +18,7 @@
 //     128-byte NHWC pixel lines), warps 8-11 split the raw fp32 tile into hi/lo planes.
 //     mbarrier pipelines: raw-full / split-ready / stage-empty (3 stages), accumulator full / empty
 //     (2 TMEM stages of 64 columns).
+#include <stdlib.h>
 #include "dv_common.cuh"
 #include "dv_ptx.cuh"
 
@@ -545,6 +546,317 @@ conv_wgrad32_tc_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid
 }
 
 
+
+// ==========================================================================================
+// "TS" variants of down/up for CH == 32: the A operand of the MMA lives in TENSOR MEMORY.
+// The split warps read their pixel row from the TMA-swizzled raw tile (thread = row, conflict-free),
+// compute the hi/lo planes in registers and tcgen05.st them into TMEM (lane = pixel row, column = k),
+// so the shared-memory copy of the lo plane, its 32 KB/tap of write traffic and the 48 KB/tap of
+// operand reads disappear, and the freed shared memory deepens the TMA pipeline from 3 to 6 stages
+// (these kernels are latency-bound on TMA -> split -> MMA -> commit round trips otherwise).
+//   smem : weights 128 KB resident + 6 raw stages x 16 KB
+//   TMEM : columns [0,256) accumulators (2 stages), [256,512) A operand (4 stages x {hi 32 | lo 32})
+// ==========================================================================================
+constexpr int kTsRawStages = 6;
+constexpr int kTsAStages = 4;
+constexpr int kTsACol0 = 256;
+struct TsBarriers {
+  uint64_t raw_full[kTsRawStages], raw_empty[kTsRawStages];
+  uint64_t a_ready[kTsAStages], a_empty[kTsAStages];
+  uint64_t b_full;
+  uint64_t acc_full[2], acc_empty[2];
+  uint32_t tmem_base;
+  float bias[32];
+};
+constexpr int kTsSmemBytes = kBBytes + kTsRawStages * kATile + 1024 + 512;
+static_assert(sizeof(TsBarriers) <= 512, "barrier block too large");
+static_assert(kTsSmemBytes <= 232448, "smem");
+
+__device__ __forceinline__ void ts_init(TsBarriers* bars, const float* bias, int warp) {
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kTsRawStages; ++s) { mbar_init(&bars->raw_full[s], 1); mbar_init(&bars->raw_empty[s], 128); }
+    for (int s = 0; s < kTsAStages; ++s) { mbar_init(&bars->a_ready[s], 128); mbar_init(&bars->a_empty[s], 1); }
+    mbar_init(&bars->b_full, 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(&bars->acc_full[a], 1); mbar_init(&bars->acc_empty[a], 128); }
+    fence_mbar_init();
+  }
+  if (threadIdx.x < 32) bars->bias[threadIdx.x] = bias ? bias[threadIdx.x] : 0.f;
+  if (warp == 2) tmem_alloc(&bars->tmem_base, 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+}
+
+// split warps (warps 8-11): one raw tile -> hi/lo planes in TMEM stage `as`
+__device__ __forceinline__ void ts_split_tile(const uint8_t* raw, uint32_t tmem_base, int as, int q, int lane) {
+  const int row = q * 32 + lane;
+  uint32_t h[32], l[32];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const uint4 v = *reinterpret_cast<const uint4*>(raw + row * 128 + ((c ^ (row & 7)) << 4));
+    const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const uint32_t hb = vv[e] & kHiMask;
+      h[c * 4 + e] = hb;
+      l[c * 4 + e] = __float_as_uint(__uint_as_float(vv[e]) - __uint_as_float(hb));
+    }
+  }
+  const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + kTsACol0 + as * 64;
+  tmem_st_32x32b_x32(taddr, h);
+  tmem_st_32x32b_x32(taddr + 32, l);
+  tmem_st_wait();
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_down32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                      const float* __restrict__ bias, const float* __restrict__ mask, float* __restrict__ lo,
+                      DownGeom g, int act) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* Bs = smem;
+  uint8_t* Raw = smem + kBBytes;
+  TsBarriers* bars = reinterpret_cast<TsBarriers*>(Raw + kTsRawStages * kATile);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  ts_init(bars, bias, warp);
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b);
+    mbar_arrive_expect_tx(&bars->b_full, kBBytes);
+    for (int tap = 0; tap < kTaps; ++tap) tma_load_2d(Bs + tap * kBTap, &tmap_b, &bars->b_full, 0, tap * 64);
+    int stage = 0; uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+      const int r0 = tile * g.rows_per_tile;
+      const int b0 = r0 / g.H, i0 = r0 % g.H;
+      for (int tap = 0; tap < kTaps; ++tap) {
+        const int kh = tap >> 2, kw = tap & 3;
+        mbar_wait(&bars->raw_empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&bars->raw_full[stage], kATile);
+        tma_load_4d(Raw + stage * kATile, &tmap_a, &bars->raw_full[stage], 0, kw - 1, 2 * i0 - 1 + kh, b0);
+        if (++stage == kTsRawStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    constexpr uint32_t idesc64 = umma_idesc_tf32(128, 64), idesc32 = umma_idesc_tf32(128, 32);
+    mbar_wait(&bars->b_full, 0);
+    int as = 0; uint32_t aphase = 0; int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+      mbar_wait(&bars->acc_empty[acc], acc_phase ^ 1);
+      tc_fence_after_sync();
+      const uint32_t d_tmem = tmem_base + acc * 128;
+      for (int tap = 0; tap < kTaps; ++tap) {
+        mbar_wait(&bars->a_ready[as], aphase);
+        tc_fence_after_sync();
+        const uint32_t a_hi = tmem_base + kTsACol0 + as * 64, a_lo = a_hi + 32;
+        const uint64_t b_d = umma_desc_sw128_kmajor(smem_u32(Bs + tap * kBTap));
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) {
+          const uint32_t d = d_tmem + (k4 & 1) * 64;          // two accumulation chains, see the SS kernel
+          umma_tf32_ts(d, a_hi + 8 * k4, b_d + 2 * k4, idesc64, (tap | (k4 >> 1)) != 0);
+          umma_tf32_ts(d, a_lo + 8 * k4, b_d + 2 * k4, idesc32, 1);
+        }
+        umma_commit(&bars->a_empty[as]);
+        if (++as == kTsAStages) { as = 0; aphase ^= 1; }
+      }
+      umma_commit(&bars->acc_full[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    const int q = warp & 3;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+      mbar_wait(&bars->acc_full[acc], acc_phase);
+      tc_fence_after_sync();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 128;
+      uint32_t r0[32], r1[32], r2[32], r3[32];
+      tmem_ld_32x32b_x32(taddr, r0);
+      tmem_ld_32x32b_x32(taddr + 32, r1);
+      tmem_ld_32x32b_x32(taddr + 64, r2);
+      tmem_ld_32x32b_x32(taddr + 96, r3);
+      tmem_ld_wait();
+      tc_fence_before_sync();
+      mbar_arrive(&bars->acc_empty[acc]);
+      const long long p = (long long)tile * 128 + q * 32 + lane;
+      if (p < g.total_px) {
+        float* dst = lo + p * 32;
+        const float* mk = mask ? mask + p * 32 : nullptr;
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          float v[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int c = c4 * 4 + e;
+            float x = ((__uint_as_float(r0[c]) + __uint_as_float(r2[c])) + (__uint_as_float(r1[c]) + __uint_as_float(r3[c]))) + bars->bias[c];
+            if (act == DV_ACT_RELU) x = fmaxf(x, 0.f);
+            v[e] = x;
+          }
+          if (mk) {
+            const float4 m4 = ldg4(mk + c4 * 4);
+            v[0] = m4.x > 0.f ? v[0] : 0.f; v[1] = m4.y > 0.f ? v[1] : 0.f;
+            v[2] = m4.z > 0.f ? v[2] : 0.f; v[3] = m4.w > 0.f ? v[3] : 0.f;
+          }
+          *reinterpret_cast<float4*>(dst + c4 * 4) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= 8) {
+    const int q = warp & 3;
+    int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+      for (int tap = 0; tap < kTaps; ++tap) {
+        mbar_wait(&bars->raw_full[stage], phase);
+        mbar_wait(&bars->a_empty[as], aphase ^ 1);
+        tc_fence_after_sync();
+        ts_split_tile(Raw + stage * kATile, tmem_base, as, q, lane);
+        mbar_arrive(&bars->raw_empty[stage]);
+        tc_fence_before_sync();
+        mbar_arrive(&bars->a_ready[as]);
+        if (++stage == kTsRawStages) { stage = 0; phase ^= 1; }
+        if (++as == kTsAStages) { as = 0; aphase ^= 1; }
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) { tc_fence_after_sync(); tmem_dealloc(tmem_base, 512); }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_up32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const float* __restrict__ bias, const float* __restrict__ mask, float* __restrict__ hi_out,
+                    DownGeom g, int act) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* Bs = smem;
+  uint8_t* Raw = smem + kBBytes;
+  TsBarriers* bars = reinterpret_cast<TsBarriers*>(Raw + kTsRawStages * kATile);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  ts_init(bars, bias, warp);
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b);
+    mbar_arrive_expect_tx(&bars->b_full, kBBytes);
+    for (int tap = 0; tap < kTaps; ++tap) tma_load_2d(Bs + tap * kBTap, &tmap_b, &bars->b_full, 0, tap * 64);
+    int stage = 0; uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+      const int r0 = tile * g.rows_per_tile;
+      const int b0 = r0 / g.H, i0 = r0 % g.H;
+      for (int s = 0; s < 9; ++s) {
+        const int di = s / 3 - 1, dj = s % 3 - 1;
+        mbar_wait(&bars->raw_empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&bars->raw_full[stage], kATile);
+        tma_load_4d(Raw + stage * kATile, &tmap_a, &bars->raw_full[stage], 0, dj, i0 + di, b0);
+        if (++stage == kTsRawStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    constexpr uint32_t idesc32 = umma_idesc_tf32(128, 32);
+    mbar_wait(&bars->b_full, 0);
+    int as = 0; uint32_t aphase = 0; int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+      mbar_wait(&bars->acc_empty[acc], acc_phase ^ 1);
+      tc_fence_after_sync();
+      uint32_t inited = 0;
+      for (int s = 0; s < 9; ++s) {
+        const int di = s / 3 - 1, dj = s % 3 - 1;
+        mbar_wait(&bars->a_ready[as], aphase);
+        tc_fence_after_sync();
+        const uint32_t a_hi = tmem_base + kTsACol0 + as * 64, a_lo = a_hi + 32;
+        for (int ph = 0; ph < 2; ++ph) {
+          const int kh = ph + 1 - 2 * di;
+          if (kh < 0 || kh > 3) continue;
+          for (int pw = 0; pw < 2; ++pw) {
+            const int kw = pw + 1 - 2 * dj;
+            if (kw < 0 || kw > 3) continue;
+            const int pidx = ph * 2 + pw;
+            const uint32_t d = tmem_base + acc * 128 + pidx * 32;
+            const uint64_t b_hi = umma_desc_sw128_kmajor(smem_u32(Bs + (kh * 4 + kw) * kBTap));
+            const uint64_t b_lo = b_hi + (4096 >> 4);           // rows 32..63 of the tap tile
+            const uint32_t first = (inited >> pidx) & 1u;
+            inited |= 1u << pidx;
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+              umma_tf32_ts(d, a_hi + 8 * k4, b_hi + 2 * k4, idesc32, (first | (uint32_t)k4) != 0);
+              umma_tf32_ts(d, a_hi + 8 * k4, b_lo + 2 * k4, idesc32, 1);
+              umma_tf32_ts(d, a_lo + 8 * k4, b_hi + 2 * k4, idesc32, 1);
+            }
+          }
+        }
+        umma_commit(&bars->a_empty[as]);
+        if (++as == kTsAStages) { as = 0; aphase ^= 1; }
+      }
+      umma_commit(&bars->acc_full[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    const int q = warp & 3;
+    const int HH = 2 * g.H, WW = 2 * g.W;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+      mbar_wait(&bars->acc_full[acc], acc_phase);
+      tc_fence_after_sync();
+      const long long p = (long long)tile * 128 + q * 32 + lane;
+      const bool valid = p < g.total_px;
+      int b = 0, i = 0, j = 0;
+      if (valid) { j = (int)(p % g.W); i = (int)((p / g.W) % g.H); b = (int)(p / ((long long)g.W * g.H)); }
+#pragma unroll 1
+      for (int pidx = 0; pidx < 4; ++pidx) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 128 + pidx * 32;
+        uint32_t r0[32];
+        tmem_ld_32x32b_x32(taddr, r0);
+        tmem_ld_wait();
+        if (pidx == 3) { tc_fence_before_sync(); mbar_arrive(&bars->acc_empty[acc]); }
+        if (valid) {
+          const int ph = pidx >> 1, pw = pidx & 1;
+          const long long o = ((long long)(b * HH + 2 * i + ph) * WW + 2 * j + pw) * 32;
+          float* dst = hi_out + o;
+          const float* mk = mask ? mask + o : nullptr;
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4) {
+            float v[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int c = c4 * 4 + e;
+              float x = __uint_as_float(r0[c]) + bars->bias[c];
+              if (act == DV_ACT_RELU) x = fmaxf(x, 0.f);
+              v[e] = x;
+            }
+            if (mk) {
+              const float4 m4 = ldg4(mk + c4 * 4);
+              v[0] = m4.x > 0.f ? v[0] : 0.f; v[1] = m4.y > 0.f ? v[1] : 0.f;
+              v[2] = m4.z > 0.f ? v[2] : 0.f; v[3] = m4.w > 0.f ? v[3] : 0.f;
+            }
+            *reinterpret_cast<float4*>(dst + c4 * 4) = make_float4(v[0], v[1], v[2], v[3]);
+          }
+        }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= 8) {
+    const int q = warp & 3;
+    int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+      for (int s = 0; s < 9; ++s) {
+        mbar_wait(&bars->raw_full[stage], phase);
+        mbar_wait(&bars->a_empty[as], aphase ^ 1);
+        tc_fence_after_sync();
+        ts_split_tile(Raw + stage * kATile, tmem_base, as, q, lane);
+        mbar_arrive(&bars->raw_empty[stage]);
+        tc_fence_before_sync();
+        mbar_arrive(&bars->a_ready[as]);
+        if (++stage == kTsRawStages) { stage = 0; phase ^= 1; }
+        if (++as == kTsAStages) { as = 0; aphase ^= 1; }
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) { tc_fence_after_sync(); tmem_dealloc(tmem_base, 512); }
+}
+
 // ==========================================================================================
 // Image-boundary layers (CH in {1,3}, NCHW hi) on the tensor cores.
 // The im2col patch of a lo pixel is only 16*CH floats, far too narrow for TMA tiles, so four
@@ -895,6 +1207,12 @@ __global__ void conv_pack_tc_kernel(const float* __restrict__ w, float* __restri
 }
 
 // ---- host side ---------------------------------------------------------------------------
+// DV_TC_A=smem selects the variants that keep the A operand in shared memory (A/B testing).
+static bool use_ts() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DV_TC_A"); v = (e && e[0] == 's') ? 0 : 1; }
+  return v == 1;
+}
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -968,6 +1286,18 @@ int conv_down32_tc(const float* hi, const float* wd_packed, const float* bias, c
     attr = true;
   }
   const int grid = g.num_tiles < kNumSMs ? g.num_tiles : kNumSMs;
+  if (use_ts()) {
+    static bool attr2 = false;
+    if (!attr2) {
+      if (cudaFuncSetAttribute(conv_down32_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTsSmemBytes) != cudaSuccess) {
+        g_last_cuda_error = (int)cudaGetLastError();
+        return DV_ERR_CUDA;
+      }
+      attr2 = true;
+    }
+    conv_down32_ts_kernel<<<grid, kThreads, kTsSmemBytes, st>>>(ta, tb, bias, mask, lo, g, act);
+    return check_launch();
+  }
   conv_down32_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(ta, tb, bias, mask, lo, g, act);
   return check_launch();
 }
@@ -997,6 +1327,18 @@ int conv_up32_tc(const float* lo, const float* wu_packed, const float* bias, con
     attr = true;
   }
   const int grid = g.num_tiles < kNumSMs ? g.num_tiles : kNumSMs;
+  if (use_ts()) {
+    static bool attr2 = false;
+    if (!attr2) {
+      if (cudaFuncSetAttribute(conv_up32_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTsSmemBytes) != cudaSuccess) {
+        g_last_cuda_error = (int)cudaGetLastError();
+        return DV_ERR_CUDA;
+      }
+      attr2 = true;
+    }
+    conv_up32_ts_kernel<<<grid, kThreads, kTsSmemBytes, st>>>(ta, tb, bias, mask, hi, g, act);
+    return check_launch();
+  }
   conv_up32_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(ta, tb, bias, mask, hi, g, act);
   return check_launch();
 }
