@@ -557,6 +557,7 @@ conv_wgrad32_tc_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid
 //   smem : weights 128 KB resident + 6 raw stages x 16 KB
 //   TMEM : columns [0,256) accumulators (2 stages), [256,512) A operand (4 stages x {hi 32 | lo 32})
 // ==========================================================================================
+constexpr int kTsThreads = 512;          // warps 8-11 and 12-15: two split groups working on alternate tiles
 constexpr int kTsRawStages = 6;
 constexpr int kTsAStages = 4;
 constexpr int kTsACol0 = 256;
@@ -608,7 +609,7 @@ __device__ __forceinline__ void ts_split_tile(const uint8_t* raw, uint32_t tmem_
   tmem_st_wait();
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kTsThreads, 1)
 conv_down32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                       const float* __restrict__ bias, const float* __restrict__ mask, float* __restrict__ lo,
                       DownGeom g, int act) {
@@ -669,11 +670,15 @@ conv_down32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       mbar_wait(&bars->acc_full[acc], acc_phase);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 128;
-      uint32_t r0[32], r1[32], r2[32], r3[32];
+      uint32_t r0[32], r1[32];
+      float sum[32];
       tmem_ld_32x32b_x32(taddr, r0);
-      tmem_ld_32x32b_x32(taddr + 32, r1);
-      tmem_ld_32x32b_x32(taddr + 64, r2);
-      tmem_ld_32x32b_x32(taddr + 96, r3);
+      tmem_ld_32x32b_x32(taddr + 64, r1);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 32; ++c) sum[c] = __uint_as_float(r0[c]) + __uint_as_float(r1[c]);
+      tmem_ld_32x32b_x32(taddr + 32, r0);
+      tmem_ld_32x32b_x32(taddr + 96, r1);
       tmem_ld_wait();
       tc_fence_before_sync();
       mbar_arrive(&bars->acc_empty[acc]);
@@ -687,7 +692,7 @@ conv_down32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int c = c4 * 4 + e;
-            float x = ((__uint_as_float(r0[c]) + __uint_as_float(r2[c])) + (__uint_as_float(r1[c]) + __uint_as_float(r3[c]))) + bars->bias[c];
+            float x = (sum[c] + (__uint_as_float(r0[c]) + __uint_as_float(r1[c]))) + bars->bias[c];
             if (act == DV_ACT_RELU) x = fmaxf(x, 0.f);
             v[e] = x;
           }
@@ -702,19 +707,19 @@ conv_down32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 8) {
-    const int q = warp & 3;
-    int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0;
+    const int q = warp & 3, grp = (warp - 8) >> 2;
+    uint32_t n = 0;                                           // sequence number of the raw tile within this CTA
     for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
-      for (int tap = 0; tap < kTaps; ++tap) {
-        mbar_wait(&bars->raw_full[stage], phase);
-        mbar_wait(&bars->a_empty[as], aphase ^ 1);
+      for (int tap = 0; tap < kTaps; ++tap, ++n) {
+        if ((int)(n & 1u) != grp) continue;
+        const int stage = n % kTsRawStages, as = n % kTsAStages;
+        mbar_wait(&bars->raw_full[stage], (n / kTsRawStages) & 1u);
+        mbar_wait(&bars->a_empty[as], ((n / kTsAStages) & 1u) ^ 1u);
         tc_fence_after_sync();
         ts_split_tile(Raw + stage * kATile, tmem_base, as, q, lane);
         mbar_arrive(&bars->raw_empty[stage]);
         tc_fence_before_sync();
         mbar_arrive(&bars->a_ready[as]);
-        if (++stage == kTsRawStages) { stage = 0; phase ^= 1; }
-        if (++as == kTsAStages) { as = 0; aphase ^= 1; }
       }
     }
   }
@@ -723,7 +728,7 @@ conv_down32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   if (warp == 2) { tc_fence_after_sync(); tmem_dealloc(tmem_base, 512); }
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kTsThreads, 1)
 conv_up32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const float* __restrict__ bias, const float* __restrict__ mask, float* __restrict__ hi_out,
                     DownGeom g, int act) {
@@ -836,19 +841,19 @@ conv_up32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 8) {
-    const int q = warp & 3;
-    int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0;
+    const int q = warp & 3, grp = (warp - 8) >> 2;
+    uint32_t n = 0;                                           // sequence number of the raw tile within this CTA
     for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
-      for (int s = 0; s < 9; ++s) {
-        mbar_wait(&bars->raw_full[stage], phase);
-        mbar_wait(&bars->a_empty[as], aphase ^ 1);
+      for (int s = 0; s < 9; ++s, ++n) {
+        if ((int)(n & 1u) != grp) continue;
+        const int stage = n % kTsRawStages, as = n % kTsAStages;
+        mbar_wait(&bars->raw_full[stage], (n / kTsRawStages) & 1u);
+        mbar_wait(&bars->a_empty[as], ((n / kTsAStages) & 1u) ^ 1u);
         tc_fence_after_sync();
         ts_split_tile(Raw + stage * kATile, tmem_base, as, q, lane);
         mbar_arrive(&bars->raw_empty[stage]);
         tc_fence_before_sync();
         mbar_arrive(&bars->a_ready[as]);
-        if (++stage == kTsRawStages) { stage = 0; phase ^= 1; }
-        if (++as == kTsAStages) { as = 0; aphase ^= 1; }
       }
     }
   }
@@ -1295,7 +1300,7 @@ int conv_down32_tc(const float* hi, const float* wd_packed, const float* bias, c
       }
       attr2 = true;
     }
-    conv_down32_ts_kernel<<<grid, kThreads, kTsSmemBytes, st>>>(ta, tb, bias, mask, lo, g, act);
+    conv_down32_ts_kernel<<<grid, kTsThreads, kTsSmemBytes, st>>>(ta, tb, bias, mask, lo, g, act);
     return check_launch();
   }
   conv_down32_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(ta, tb, bias, mask, lo, g, act);
@@ -1336,7 +1341,7 @@ int conv_up32_tc(const float* lo, const float* wu_packed, const float* bias, con
       }
       attr2 = true;
     }
-    conv_up32_ts_kernel<<<grid, kThreads, kTsSmemBytes, st>>>(ta, tb, bias, mask, hi, g, act);
+    conv_up32_ts_kernel<<<grid, kTsThreads, kTsSmemBytes, st>>>(ta, tb, bias, mask, hi, g, act);
     return check_launch();
   }
   conv_up32_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(ta, tb, bias, mask, hi, g, act);
