@@ -553,6 +553,9 @@ int pack_tc(const float* w, float* wd, float* wu, cudaStream_t st);
 int conv_down32_tc(const float* hi, const float* wd_packed, const float* bias, const float* mask, float* lo,
                    int B, int H, int W, int act, cudaStream_t st);
 int pack_small_tc(const float* w, float* wd, int CH, cudaStream_t st);
+int pack_up_small_tc(const float* w, float* wu, int CH, cudaStream_t st);
+int conv_up_halo(const float* lo, const float* wu, const float* bias, const float* mask, float* hi,
+                 int B, int H, int W, int CH, int act, cudaStream_t st);
 int conv_down_small_tc(const float* x, const float* wd, const float* bias, const float* mask, float* lo,
                        int B, int H, int W, int CH, int act, cudaStream_t st);
 int conv_wgrad_small_tc(const float* lo, const float* x, float* ws, int B, int H, int W, int CH, int* nsplit, cudaStream_t st);
@@ -588,8 +591,10 @@ extern "C" {
 // CH in {1,3}: [0, 512*CH) ffma down, [512*CH, 1024*CH) ffma up, then the tcgen05 down operand
 // [kb][64][32] (kb = ceil(16*CH/32) K blocks)
 static size_t small_tc_floats(int CH) { return (size_t)((16 * CH + 31) / 32) * 64 * 32; }
+constexpr int kPackUpSmall = kTaps * 16 * 32;     // tcgen05 up operand of the CH small layers: [tap][hi 8 | lo 8][32 cl]
 size_t dv_conv_packed_floats(int CH) {
-  return CH == 32 ? (size_t)kPackFfma + 2 * kPackTcSection : (size_t)2 * kLoCh * CH * kTaps + small_tc_floats(CH);
+  return CH == 32 ? (size_t)kPackFfma + 2 * kPackTcSection
+                  : (size_t)2 * kLoCh * CH * kTaps + small_tc_floats(CH) + kPackUpSmall;
 }
 
 int dv_conv_pack_weights(const float* w, float* w_packed, int CH, void* stream) {
@@ -599,7 +604,11 @@ int dv_conv_pack_weights(const float* w, float* w_packed, int CH, void* stream) 
   conv_pack_kernel<<<(n + 255) / 256, 256, 0, as_stream(stream)>>>(w, w_packed, CH);
   int rc = check_launch();
   if (rc != DV_OK) return rc;
-  if (CH != 32) return tc::pack_small_tc(w, w_packed + 2 * kLoCh * CH * kTaps, CH, as_stream(stream));
+  if (CH != 32) {
+    rc = tc::pack_small_tc(w, w_packed + 2 * kLoCh * CH * kTaps, CH, as_stream(stream));
+    if (rc != DV_OK) return rc;
+    return tc::pack_up_small_tc(w, w_packed + 2 * kLoCh * CH * kTaps + small_tc_floats(CH), CH, as_stream(stream));
+  }
   return tc::pack_tc(w, w_packed + kPackFfma, w_packed + kPackFfma + kPackTcSection, as_stream(stream));
 }
 
@@ -639,6 +648,10 @@ int dv_conv_up(const float* lo, const float* w_packed, const float* bias, const 
   if (act != DV_ACT_NONE && act != DV_ACT_RELU && act != DV_ACT_SIGMOID) return DV_ERR_BAD_ARG;
   if ((CH == 32) == (hi_nchw != 0)) return DV_ERR_BAD_SHAPE;
   const float* wu = w_packed + kLoCh * CH * kTaps;
+  if (use_tc("halo") && (CH != 32 || act != DV_ACT_SIGMOID) && W + 2 <= 40)
+    return tc::conv_up_halo(lo, CH == 32 ? w_packed + kPackFfma + kPackTcSection
+                                          : w_packed + 2 * kLoCh * CH * kTaps + small_tc_floats(CH),
+                            bias, mask, hi, B, H, W, CH, act, as_stream(stream));
   if (CH == 32 && use_tc("up") && act != DV_ACT_SIGMOID)
     return tc::conv_up32_tc(lo, w_packed + kPackFfma + kPackTcSection, bias, mask, hi, B, H, W, act, as_stream(stream));
   if (CH == 32) {

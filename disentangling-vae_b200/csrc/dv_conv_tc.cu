@@ -862,6 +862,257 @@ conv_up32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (warp == 2) { tc_fence_after_sync(); tmem_dealloc(tmem_base, 512); }
 }
 
+
+// ==========================================================================================
+// up, halo-resident ("one load per input pixel"), all CH:
+// The nine shifted operand tiles of the up convolution overlap almost completely, so instead of
+// nine TMA loads per 128 positions ONE zero-padded halo tile [(TR+2) rows][W+2 cols][32 ch] is
+// loaded per tile (box start (-1, i0-1): the padding is TMA out-of-bounds fill).  MMA rows enumerate
+// consecutive pixels q of that padded grid, so the operand of shift (di,dj) is simply the rows
+// q + di*(W+2) + dj of the resident tile: the split warps read them (un-swizzling by the absolute
+// row index), split hi/lo and tcgen05.st them to TMEM.  Rows that fall on padding columns / halo
+// rows produce garbage that the epilogue skips (each output row depends only on its own A rows).
+// L2->smem traffic drops 9x, and the kernel becomes MMA-bound (CH = 32) or split-bound (CH small).
+//   CH == 32 : per phase N = 32, three MMAs per K slice (hi*hi, hi*lo, lo*hi), weights 128 KB resident
+//   CH in {1,3}: per phase N = 16 = [b_hi (8 rows) | b_lo (8 rows)], two MMAs (a_hi, a_lo) -> all four
+//              cross products; NCHW sigmoid epilogue (convT3 of the decoder)
+// ==========================================================================================
+constexpr int kHaloStageBytes = 26 * 1024;      // 208 pixel rows: the largest box (<= 176 px) + over-read slack
+constexpr int kHaloStages = 3;
+struct HaloGeom {
+  int B, H, W, Wp, TR, TB, tiles_per_img, num_tiles, img_px, q_start, box_bytes;
+};
+struct HaloBarriers {
+  uint64_t raw_full[kHaloStages], raw_empty[kHaloStages];
+  uint64_t a_ready[kTsAStages], a_empty[kTsAStages];
+  uint64_t b_full;
+  uint64_t acc_full[2], acc_empty[2];
+  uint32_t tmem_base;
+  float bias[32];
+};
+template <int CH> struct HaloCfg {
+  static constexpr int kBTapBytes = (CH == 32) ? kBTap : 16 * 128;
+  static constexpr int kBAll = kTaps * kBTapBytes;
+  static constexpr int kSmem = kBAll + kHaloStages * kHaloStageBytes + 1024 + 512;
+  static constexpr int kAccPerPhase = (CH == 32) ? 32 : 16;
+};
+
+template <int CH>
+__global__ void __launch_bounds__(kTsThreads, 1)
+conv_up_halo_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                       const float* __restrict__ bias, const float* __restrict__ mask, float* __restrict__ hi_out,
+                       HaloGeom g, int act) {
+  using C = HaloCfg<CH>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* Bs = smem;
+  uint8_t* Raw = smem + C::kBAll;
+  HaloBarriers* bars = reinterpret_cast<HaloBarriers*>(Raw + kHaloStages * kHaloStageBytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kHaloStages; ++s) { mbar_init(&bars->raw_full[s], 1); mbar_init(&bars->raw_empty[s], 9 * 128); }
+    for (int s = 0; s < kTsAStages; ++s) { mbar_init(&bars->a_ready[s], 128); mbar_init(&bars->a_empty[s], 1); }
+    mbar_init(&bars->b_full, 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(&bars->acc_full[a], 1); mbar_init(&bars->acc_empty[a], 128); }
+    fence_mbar_init();
+  }
+  if (threadIdx.x < 32) bars->bias[threadIdx.x] = (bias && (int)threadIdx.x < CH) ? bias[threadIdx.x] : 0.f;
+  if (warp == 2) tmem_alloc(&bars->tmem_base, 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b);
+    mbar_arrive_expect_tx(&bars->b_full, C::kBAll);
+    if (CH == 32) { for (int tap = 0; tap < kTaps; ++tap) tma_load_2d(Bs + tap * kBTap, &tmap_b, &bars->b_full, 0, tap * 64); }
+    else          { for (int h = 0; h < 4; ++h) tma_load_2d(Bs + h * 8192, &tmap_b, &bars->b_full, 0, h * 64); }
+    uint32_t t_seq = 0;
+    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++t_seq) {
+      const int stage = t_seq % kHaloStages;
+      int b0, i0;
+      if (g.TB > 1) { b0 = tile * g.TB; i0 = 0; } else { b0 = tile / g.tiles_per_img; i0 = (tile % g.tiles_per_img) * g.TR; }
+      mbar_wait(&bars->raw_empty[stage], ((t_seq / kHaloStages) & 1u) ^ 1u);
+      mbar_arrive_expect_tx(&bars->raw_full[stage], g.box_bytes);
+      tma_load_4d(Raw + stage * kHaloStageBytes, &tmap_a, &bars->raw_full[stage], 0, -1, i0 - 1, b0);
+    }
+  } else if (warp == 1 && lane == 0) {
+    constexpr uint32_t idescN = umma_idesc_tf32(128, C::kAccPerPhase);
+    mbar_wait(&bars->b_full, 0);
+    uint32_t n = 0; int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+      mbar_wait(&bars->acc_empty[acc], acc_phase ^ 1);
+      tc_fence_after_sync();
+      uint32_t inited = 0;
+      for (int s = 0; s < 9; ++s, ++n) {
+        const int di = s / 3 - 1, dj = s % 3 - 1;
+        const int as = n % kTsAStages;
+        mbar_wait(&bars->a_ready[as], (n / kTsAStages) & 1u);
+        tc_fence_after_sync();
+        const uint32_t a_hi = tmem_base + kTsACol0 + as * 64, a_lo = a_hi + 32;
+        for (int ph = 0; ph < 2; ++ph) {
+          const int kh = ph + 1 - 2 * di;
+          if (kh < 0 || kh > 3) continue;
+          for (int pw = 0; pw < 2; ++pw) {
+            const int kw = pw + 1 - 2 * dj;
+            if (kw < 0 || kw > 3) continue;
+            const int pidx = ph * 2 + pw;
+            const uint32_t d = tmem_base + acc * 128 + pidx * C::kAccPerPhase;
+            const uint64_t b_hi = umma_desc_sw128_kmajor(smem_u32(Bs + (kh * 4 + kw) * C::kBTapBytes));
+            const uint32_t first = (inited >> pidx) & 1u;
+            inited |= 1u << pidx;
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+              umma_tf32_ts(d, a_hi + 8 * k4, b_hi + 2 * k4, idescN, (first | (uint32_t)k4) != 0);
+              if (CH == 32) {
+                umma_tf32_ts(d, a_hi + 8 * k4, b_hi + (4096 >> 4) + 2 * k4, idescN, 1);      // a_hi * b_lo
+                umma_tf32_ts(d, a_lo + 8 * k4, b_hi + 2 * k4, idescN, 1);                    // a_lo * b_hi
+              } else {
+                umma_tf32_ts(d, a_lo + 8 * k4, b_hi + 2 * k4, idescN, 1);                    // a_lo * [b_hi | b_lo]
+              }
+            }
+          }
+        }
+        umma_commit(&bars->a_empty[as]);
+      }
+      umma_commit(&bars->acc_full[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    const int q = warp & 3;
+    const int HH = 2 * g.H, WW = 2 * g.W;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+      int b0, i0;
+      if (g.TB > 1) { b0 = tile * g.TB; i0 = 0; } else { b0 = tile / g.tiles_per_img; i0 = (tile % g.tiles_per_img) * g.TR; }
+      const int qq = g.q_start + q * 32 + lane;
+      const int tb = qq / g.img_px, rem = qq - tb * g.img_px;
+      const int rr = rem / g.Wp - 1, ww = rem % g.Wp - 1;
+      const int b = b0 + tb, i = i0 + rr, j = ww;
+      const bool valid = tb < g.TB && rr >= 0 && rr < g.TR && ww >= 0 && ww < g.W && b < g.B && i < g.H;
+      mbar_wait(&bars->acc_full[acc], acc_phase);
+      tc_fence_after_sync();
+      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 128;
+      if (CH == 32) {
+#pragma unroll 1
+        for (int pidx = 0; pidx < 4; ++pidx) {
+          uint32_t r0[32];
+          tmem_ld_32x32b_x32(tbase + pidx * 32, r0);
+          tmem_ld_wait();
+          if (pidx == 3) { tc_fence_before_sync(); mbar_arrive(&bars->acc_empty[acc]); }
+          if (valid) {
+            const int ph = pidx >> 1, pw = pidx & 1;
+            const long long o = ((long long)(b * HH + 2 * i + ph) * WW + 2 * j + pw) * 32;
+            float* dst = hi_out + o;
+            const float* mk = mask ? mask + o : nullptr;
+#pragma unroll
+            for (int c4 = 0; c4 < 8; ++c4) {
+              float v[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float x = __uint_as_float(r0[c4 * 4 + e]) + bars->bias[c4 * 4 + e];
+                if (act == DV_ACT_RELU) x = fmaxf(x, 0.f);
+                v[e] = x;
+              }
+              if (mk) {
+                const float4 m4 = ldg4(mk + c4 * 4);
+                v[0] = m4.x > 0.f ? v[0] : 0.f; v[1] = m4.y > 0.f ? v[1] : 0.f;
+                v[2] = m4.z > 0.f ? v[2] : 0.f; v[3] = m4.w > 0.f ? v[3] : 0.f;
+              }
+              *reinterpret_cast<float4*>(dst + c4 * 4) = make_float4(v[0], v[1], v[2], v[3]);
+            }
+          }
+        }
+      } else {
+        // 4 phases x [a*b_hi (8) | a*b_lo (8)] = 64 columns; NCHW output, float2 per (channel, row parity)
+        uint32_t r0[32], r1[32];
+        tmem_ld_32x32b_x32(tbase, r0);
+        tmem_ld_32x32b_x32(tbase + 32, r1);
+        tmem_ld_wait();
+        tc_fence_before_sync();
+        mbar_arrive(&bars->acc_empty[acc]);
+        if (valid) {
+#pragma unroll
+          for (int c = 0; c < CH; ++c) {
+#pragma unroll
+            for (int ph = 0; ph < 2; ++ph) {
+              float v[2];
+#pragma unroll
+              for (int pw = 0; pw < 2; ++pw) {
+                const int pidx = ph * 2 + pw;
+                const uint32_t* rr2 = (pidx < 2) ? r0 : r1;
+                const int o16 = (pidx & 1) * 16;
+                float x = (__uint_as_float(rr2[o16 + c]) + __uint_as_float(rr2[o16 + 8 + c])) + bars->bias[c];
+                if (act == DV_ACT_RELU) x = fmaxf(x, 0.f);
+                else if (act == DV_ACT_SIGMOID) x = 1.f / (1.f + expf(-x));
+                v[pw] = x;
+              }
+              const long long o = (((long long)b * CH + c) * HH + 2 * i + ph) * WW + 2 * j;
+              if (mask) { v[0] = mask[o] > 0.f ? v[0] : 0.f; v[1] = mask[o + 1] > 0.f ? v[1] : 0.f; }
+              *reinterpret_cast<float2*>(hi_out + o) = make_float2(v[0], v[1]);
+            }
+          }
+        }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= 8) {
+    const int q = warp & 3, grp = (warp - 8) >> 2;
+    const int row = q * 32 + lane;
+    uint32_t n = 0, t_seq = 0;
+    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++t_seq) {
+      const int stage = t_seq % kHaloStages;
+      const uint8_t* raw = Raw + stage * kHaloStageBytes;
+      bool waited = false;
+      for (int s = 0; s < 9; ++s, ++n) {
+        if ((int)(n & 1u) != grp) continue;
+        const int di = s / 3 - 1, dj = s % 3 - 1;
+        const int as = n % kTsAStages;
+        if (!waited) { mbar_wait(&bars->raw_full[stage], (t_seq / kHaloStages) & 1u); waited = true; }
+        const int p = g.q_start + row + di * g.Wp + dj;            // source pixel of the resident halo tile
+        uint32_t h[32], l[32];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint4 v = *reinterpret_cast<const uint4*>(raw + p * 128 + ((c ^ (p & 7)) << 4));
+          const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const uint32_t hb = vv[e] & kHiMask;
+            h[c * 4 + e] = hb;
+            l[c * 4 + e] = __float_as_uint(__uint_as_float(vv[e]) - __uint_as_float(hb));
+          }
+        }
+        mbar_arrive(&bars->raw_empty[stage]);                      // 9 x 128 arrivals release the halo tile
+        mbar_wait(&bars->a_empty[as], ((n / kTsAStages) & 1u) ^ 1u);
+        tc_fence_after_sync();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + kTsACol0 + as * 64;
+        tmem_st_32x32b_x32(taddr, h);
+        tmem_st_32x32b_x32(taddr + 32, l);
+        tmem_st_wait();
+        tc_fence_before_sync();
+        mbar_arrive(&bars->a_ready[as]);
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) { tc_fence_after_sync(); tmem_dealloc(tmem_base, 512); }
+}
+
+// up weights for CH small: [tap][16 rows][32 cl]; row r < 8: tf32 hi of w[cl][c = r][tap] (0 if r >= CH), r >= 8: lo
+__global__ void conv_pack_up_small_kernel(const float* __restrict__ w, float* __restrict__ wu, int CH) {
+  const int n = kTaps * 16 * 32;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
+    const int cl = idx % 32, r = (idx / 32) % 16, tap = idx / (16 * 32);
+    const int c = r & 7;
+    float v = (c < CH) ? w[(cl * CH + c) * kTaps + tap] : 0.f;
+    const float hi = __uint_as_float(__float_as_uint(v) & kHiMask);
+    wu[idx] = (r < 8) ? hi : (v - hi);
+  }
+}
+
 // ==========================================================================================
 // Image-boundary layers (CH in {1,3}, NCHW hi) on the tensor cores.
 // The im2col patch of a lo pixel is only 16*CH floats, far too narrow for TMA tiles, so four
@@ -1464,6 +1715,57 @@ int conv_wgrad_small_tc(const float* lo, const float* x, float* ws, int B, int H
   grid = (g.num_tiles + g.tiles_per_cta - 1) / g.tiles_per_cta;
   *nsplit = grid;
   return CH == 1 ? launch_wgrad_small<1>(lo, x, ws, g, grid, st) : launch_wgrad_small<3>(lo, x, ws, g, grid, st);
+}
+
+int pack_up_small_tc(const float* w, float* wu, int CH, cudaStream_t st) {
+  conv_pack_up_small_kernel<<<8, 256, 0, st>>>(w, wu, CH);
+  return check_launch();
+}
+
+template <int CH>
+static int launch_up_halo(const float* lo, const float* wu, const float* bias, const float* mask, float* hi,
+                          HaloGeom g, int act, cudaStream_t st) {
+  CUtensorMap ta, tb;
+  if (!make_act_tmap(&ta, lo, g.B, g.H, g.W, g.Wp, g.TR + 2, g.TB, 1)) return DV_ERR_CUDA;
+  if (!make_w_tmap_rows(&tb, wu, CH == 32 ? kTaps * 64 : kTaps * 16)) return DV_ERR_CUDA;
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(conv_up_halo_ts_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<CH>::kSmem) != cudaSuccess) {
+      g_last_cuda_error = (int)cudaGetLastError();
+      return DV_ERR_CUDA;
+    }
+    attr = true;
+  }
+  const int grid = g.num_tiles < kNumSMs ? g.num_tiles : kNumSMs;
+  conv_up_halo_ts_kernel<CH><<<grid, kTsThreads, HaloCfg<CH>::kSmem, st>>>(ta, tb, bias, mask, hi, g, act);
+  return check_launch();
+}
+
+// hi = act(up(lo) + bias) * [mask > 0]; hi is NHWC for CH == 32, NCHW for CH in {1,3}
+int conv_up_halo(const float* lo, const float* wu, const float* bias, const float* mask, float* hi,
+                 int B, int H, int W, int CH, int act, cudaStream_t st) {
+  HaloGeom g;
+  g.B = B; g.H = H; g.W = W; g.Wp = W + 2;
+  int tr = (128 + 2) / g.Wp;                       // largest TR with TR*Wp - 2 <= 128
+  if (tr < 1) return DV_ERR_BAD_SHAPE;
+  if (tr >= H) {
+    g.TR = H;
+    int tb = (128 + 2 + 2 * g.Wp) / ((H + 2) * g.Wp);   // largest TB with (TB*(H+2) - 2)*Wp - 2 <= 128
+    g.TB = tb < 1 ? 1 : tb;
+    if (g.TB > 1) { g.tiles_per_img = 1; g.num_tiles = (B + g.TB - 1) / g.TB; }
+    else { g.tiles_per_img = 1; g.num_tiles = B; }
+  } else {
+    g.TR = tr; g.TB = 1;
+    g.tiles_per_img = (H + tr - 1) / tr;
+    g.num_tiles = B * g.tiles_per_img;
+  }
+  g.img_px = (g.TR + 2) * g.Wp;
+  g.q_start = g.Wp + 1;
+  g.box_bytes = g.TB * g.img_px * 128;
+  if (g.box_bytes > kHaloStageBytes || g.q_start + 127 + g.Wp + 1 >= kHaloStageBytes / 128) return DV_ERR_BAD_SHAPE;
+  if (CH == 32) return launch_up_halo<32>(lo, wu, bias, mask, hi, g, act, st);
+  if (CH == 3) return launch_up_halo<3>(lo, wu, bias, mask, hi, g, act, st);
+  return launch_up_halo<1>(lo, wu, bias, mask, hi, g, act, st);
 }
 
 }  // namespace tc
