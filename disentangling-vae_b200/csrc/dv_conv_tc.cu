@@ -117,7 +117,7 @@ conv_down32_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {          // whole warp, warp-uniform control flow; one elected lane issues
     // ===================== MMA issuer (single thread) =====================
     constexpr uint32_t idesc64 = umma_idesc_tf32(128, 64), idesc32 = umma_idesc_tf32(128, 32);
     mbar_wait(&bars->b_full, 0);
@@ -259,7 +259,7 @@ conv_up32_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {          // whole warp, warp-uniform control flow; one elected lane issues
     constexpr uint32_t idesc64 = umma_idesc_tf32(128, 64), idesc32 = umma_idesc_tf32(128, 32);
     mbar_wait(&bars->b_full, 0);
     int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
@@ -445,7 +445,7 @@ conv_wgrad32_tc_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid
         if (++stage == kWgStages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {          // whole warp, warp-uniform control flow; one elected lane issues
     // M=128, N=64, tf32, both operands MN-major (bits 15 and 16)
     constexpr uint32_t idesc = umma_idesc_tf32(128, 64) | (1u << 15) | (1u << 16);
     int stage = 0; uint32_t phase = 0; int lb = 0; uint32_t lphase = 0;
@@ -638,7 +638,7 @@ conv_down32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         if (++stage == kTsRawStages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {          // whole warp, warp-uniform control flow; one elected lane issues
     constexpr uint32_t idesc64 = umma_idesc_tf32(128, 64), idesc32 = umma_idesc_tf32(128, 32);
     mbar_wait(&bars->b_full, 0);
     int as = 0; uint32_t aphase = 0; int acc = 0; uint32_t acc_phase = 0;
@@ -757,7 +757,7 @@ conv_up32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (++stage == kTsRawStages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {          // whole warp, warp-uniform control flow; one elected lane issues
     constexpr uint32_t idesc32 = umma_idesc_tf32(128, 32);
     mbar_wait(&bars->b_full, 0);
     int as = 0; uint32_t aphase = 0; int acc = 0; uint32_t acc_phase = 0;
@@ -938,7 +938,7 @@ conv_up_halo_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
       mbar_arrive_expect_tx(&bars->raw_full[stage], g.box_bytes);
       tma_load_4d(Raw + stage * kHaloStageBytes, &tmap_a, &bars->raw_full[stage], 0, -1, i0 - 1, b0);
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {          // whole warp, warp-uniform control flow; one elected lane issues
     constexpr uint32_t idescN = umma_idesc_tf32(128, C::kAccPerPhase);
     mbar_wait(&bars->b_full, 0);
     uint32_t n = 0; int acc = 0; uint32_t acc_phase = 0;
@@ -1179,7 +1179,7 @@ conv_down_small_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const floa
     prefetch_tmap(&tmap_b);
     mbar_arrive_expect_tx(&bars->b_full, C::kBBytesS);
     for (int kb = 0; kb < C::NKB; ++kb) tma_load_2d(Bs + kb * kBTap, &tmap_b, &bars->b_full, 0, kb * 64);
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {          // whole warp, warp-uniform control flow; one elected lane issues
     constexpr uint32_t idesc64 = umma_idesc_tf32(128, 64), idesc32 = umma_idesc_tf32(128, 32);
     mbar_wait(&bars->b_full, 0);
     int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
@@ -1332,7 +1332,7 @@ conv_wgrad_small_tc_kernel(const __grid_constant__ CUtensorMap tmap_lo, const fl
       tma_load_4d(Ls + lb * kWgLBytes, &tmap_lo, &bars->l_raw_full[lb], 0, 0, i0, b0);
       if (++lb == 2) { lb = 0; lphase ^= 1; }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {          // whole warp, warp-uniform control flow; one elected lane issues
     constexpr uint32_t idesc = umma_idesc_tf32(128, 64) | (1u << 15) | (1u << 16);
     int stage = 0; uint32_t phase = 0; int lb = 0; uint32_t lphase = 0;
     for (int tile = t_begin; tile < t_end; ++tile) {
