@@ -189,6 +189,44 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 }
 __global__ void bump_step_kernel(float* step_dev) { *step_dev += 1.f; }
 
+// ---- multi-tensor Adam: every parameter tensor of a model in ONE launch -------------------------
+// The tensor table travels by value in kernel-parameter space (no device-side table to upload, so the
+// per-step gradient tensors handed out by autograd can be consumed where they are).
+constexpr int kAdamMaxTensors = 48;
+constexpr int kAdamChunk = 4096;                 // elements per block-iteration
+struct AdamTable {
+  float* p[kAdamMaxTensors];
+  const float* g[kAdamMaxTensors];
+  float* m[kAdamMaxTensors];
+  float* v[kAdamMaxTensors];
+  int chunk_begin[kAdamMaxTensors + 1];          // prefix sum of ceil(n / kAdamChunk)
+  int n[kAdamMaxTensors];
+  int count;
+};
+__global__ void __launch_bounds__(256)
+adam_multi_kernel(const __grid_constant__ AdamTable t, const float* __restrict__ step_dev, float lr, float b1, float b2,
+                  float eps, float gscale) {
+  const float step = *step_dev + 1.f;
+  const float bc1 = 1.f - powf(b1, step), bc2 = 1.f - powf(b2, step);
+  const float step_size = lr / bc1;
+  const float bc2_sqrt = sqrtf(bc2);
+  const int total_chunks = t.chunk_begin[t.count];
+  for (int chunk = blockIdx.x; chunk < total_chunks; chunk += gridDim.x) {
+    int ti = 0;
+    while (chunk >= t.chunk_begin[ti + 1]) ++ti;               // <= 48 entries, block-uniform
+    const int base = (chunk - t.chunk_begin[ti]) * kAdamChunk;
+    const int end = min(t.n[ti], base + kAdamChunk);
+    float* p = t.p[ti]; const float* g = t.g[ti]; float* m = t.m[ti]; float* v = t.v[ti];
+    for (int i = base + threadIdx.x; i < end; i += blockDim.x) {
+      const float gi = g[i] * gscale;
+      const float mi = m[i] + (gi - m[i]) * (1.f - b1);
+      const float vi = v[i] * b2 + (1.f - b2) * gi * gi;
+      m[i] = mi; v[i] = vi;
+      p[i] = p[i] - step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+    }
+  }
+}
+
 static int grid_for(long long n, int per_block, int max_blocks) {
   long long g = (n + per_block - 1) / per_block;
   if (g < 1) g = 1;
@@ -260,6 +298,31 @@ int dv_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg
   if (n <= 0) return DV_ERR_BAD_SHAPE;
   adam_kernel<<<grid_for(n, 1024, 4 * kNumSMs), 256, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, step_dev, n, lr,
                                                                            beta1, beta2, eps, grad_scale);
+  int rc = check_launch();
+  if (rc != DV_OK) return rc;
+  bump_step_kernel<<<1, 1, 0, as_stream(stream)>>>(step_dev);
+  return check_launch();
+}
+
+int dv_adam_multi_max_tensors(void) { return kAdamMaxTensors; }
+
+int dv_adam_multi(int count, float* const* params, const float* const* grads, float* const* exp_avg,
+                  float* const* exp_avg_sq, const long long* numel, float* step_dev, float lr, float beta1,
+                  float beta2, float eps, float grad_scale, void* stream) {
+  if (!params || !grads || !exp_avg || !exp_avg_sq || !numel || !step_dev) return DV_ERR_BAD_ARG;
+  if (count <= 0 || count > kAdamMaxTensors) return DV_ERR_BAD_SHAPE;
+  AdamTable t;
+  t.count = count;
+  t.chunk_begin[0] = 0;
+  for (int i = 0; i < count; ++i) {
+    if (!params[i] || !grads[i] || !exp_avg[i] || !exp_avg_sq[i] || numel[i] <= 0 || numel[i] >= (1LL << 31)) return DV_ERR_BAD_ARG;
+    t.p[i] = params[i]; t.g[i] = grads[i]; t.m[i] = exp_avg[i]; t.v[i] = exp_avg_sq[i];
+    t.n[i] = (int)numel[i];
+    t.chunk_begin[i + 1] = t.chunk_begin[i] + (int)((numel[i] + kAdamChunk - 1) / kAdamChunk);
+  }
+  int grid = t.chunk_begin[count];
+  if (grid > 4 * kNumSMs) grid = 4 * kNumSMs;
+  adam_multi_kernel<<<grid, 256, 0, as_stream(stream)>>>(t, step_dev, lr, beta1, beta2, eps, grad_scale);
   int rc = check_launch();
   if (rc != DV_OK) return rc;
   bump_step_kernel<<<1, 1, 0, as_stream(stream)>>>(step_dev);

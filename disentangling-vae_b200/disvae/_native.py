@@ -53,6 +53,8 @@ SIGNATURES = {
     "dv_factor_ce_fwd": (I, [P, P, I, P, P]),
     "dv_factor_ce_bwd": (I, [P, P, P, I, P, P, P]),
     "dv_adam_step": (I, [P, P, P, P, P, LL, F, F, F, F, F, P]),
+    "dv_adam_multi_max_tensors": (I, []),
+    "dv_adam_multi": (I, [I, P, P, P, P, P, P, F, F, F, F, F, P]),
 }
 
 _lib = None

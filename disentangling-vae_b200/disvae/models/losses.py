@@ -147,6 +147,17 @@ class FactorKLoss(BaseLoss):
         self.optimizer_d = optim.Adam(self.discriminator.parameters(), **optim_kwargs)
         self._perm_offset = None
         self._perm_queue = []          # injected permutations (parity tests), consumed FIFO
+        self._fused_d = None           # FusedAdam over optimizer_d (built lazily once the discriminator is on CUDA)
+
+    def _step_d(self):
+        """Discriminator Adam step: dv_adam_multi when optimizer_d is a plain CUDA Adam."""
+        from disvae.fused import FusedAdam
+        if self._fused_d is None:
+            self._fused_d = FusedAdam(self.optimizer_d) if FusedAdam.supports(self.optimizer_d) else False
+        if self._fused_d:
+            self._fused_d.step()
+        else:
+            self.optimizer_d.step()
 
     def __call__(self, *args, **kwargs):
         raise ValueError("Use `call_optimize` to also train the discriminator")
@@ -194,7 +205,10 @@ class FactorKLoss(BaseLoss):
         self.optimizer_d.zero_grad()
         d_tc_loss.backward()                                     # also reaches the encoder through d_z (trap T5)
         optimizer.step()
-        self.optimizer_d.step()
+        if type(self.optimizer_d).__name__ == "_Deferred":
+            self.optimizer_d.step()                               # data-parallel: the Trainer steps after the all-reduce
+        else:
+            self._step_d()
 
         _record(storer, ['recon_loss', 'kl_loss', _kl_names(kl_dims.numel()), 'loss', 'tc_loss', 'discrim_loss'],
                 [rec_loss, kl_loss, kl_dims, vae_loss, tc_loss, d_tc_loss])

@@ -13,6 +13,7 @@ from timeit import default_timer
 import torch
 from tqdm import trange
 
+from disvae.fused import FusedAdam
 from disvae.parallel import FlatGradSync, is_distributed
 from disvae.utils.modelIO import save_model
 
@@ -37,6 +38,10 @@ class Trainer():
         self.sync_every = 50                      # progress-bar refresh (host sync) period
         self._grad_sync = None
         self._grad_sync_d = None
+        self._fused = None                        # FusedAdam over `optimizer` (built lazily on the device)
+        self.use_cuda_graph = os.environ.get("DISVAE_CUDA_GRAPH", "1") != "0"
+        self._graphs = {}                         # input shape -> (CUDAGraph, static input, static loss)
+        self._eligible_steps = 0
         self.logger.info("Training Device: {}".format(self.device))
 
     def __call__(self, data_loader, epochs=10, checkpoint_every=10):
@@ -71,8 +76,66 @@ class Trainer():
                 t.update()
         return epoch_loss.item() / len(data_loader)
 
+    # -- optimizer ---------------------------------------------------------------------------
+    def _optimizer_step(self, grad_scale=1.0):
+        """Adam through dv_adam_multi when `optimizer` is a plain torch.optim.Adam on CUDA parameters,
+        else the optimizer's own step()."""
+        if self._fused is None:
+            self._fused = FusedAdam(self.optimizer) if FusedAdam.supports(self.optimizer) else False
+        if self._fused:
+            self._fused.step(grad_scale)
+        else:
+            self.optimizer.step()
+
+    # -- whole-step CUDA graph ------------------------------------------------------------------
+    def _graph_eligible(self, data, storer):
+        lf = self.loss_f
+        if not (self.use_cuda_graph and self.device.type == "cuda" and self.model.training):
+            return False
+        if is_distributed() or hasattr(lf, "call_optimize") or getattr(self.model, "_eps_queue", None):
+            return False
+        if lf.steps_anneal != 0 and lf.n_train_steps < lf.steps_anneal:
+            return False                                      # host-side annealing coefficient still moving
+        if storer is not None and (lf.n_train_steps + 1) % lf.record_loss_every == 1:
+            return False                                      # this step logs scalars (host sync): run eagerly
+        if self._fused is None:
+            self._fused = FusedAdam(self.optimizer) if FusedAdam.supports(self.optimizer) else False
+        return bool(self._fused)
+
+    def _graph_step(self, data):
+        """fwd + loss + bwd + Adam of one batch as ONE CUDA graph launch (static shapes)."""
+        key = (tuple(data.shape), str(data.dtype))
+        entry = self._graphs.get(key)
+        if entry is None:
+            static_x = torch.empty(data.shape, dtype=torch.float32, device=self.device)
+            static_x.copy_(data, non_blocking=True)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            steps_before = self.loss_f.n_train_steps
+            with torch.cuda.graph(g):
+                recon, dist, z = self.model(static_x)
+                loss = self.loss_f(static_x, recon, dist, True, None, latent_sample=z)
+                self.optimizer.zero_grad(set_to_none=True)
+                loss.backward()
+                self._fused.step()
+                static_loss = loss.detach()
+            self.loss_f.n_train_steps = steps_before          # capture executed nothing
+            self._fused.host_steps -= 1
+            entry = (g, static_x, static_loss)
+            self._graphs[key] = entry
+        g, static_x, static_loss = entry
+        static_x.copy_(data, non_blocking=True)
+        g.replay()
+        self.loss_f.n_train_steps += 1
+        self._fused.host_steps += 1
+        return static_loss
+
     def _step(self, data, storer):
         """One optimisation step; returns the loss as a detached 0-dim device tensor."""
+        if self._graph_eligible(data, storer):
+            self._eligible_steps += 1
+            if self._eligible_steps > 3 or (tuple(data.shape), str(data.dtype)) in self._graphs:   # 3 eager warm-up steps first
+                return self._graph_step(data)
         data = data.to(self.device, non_blocking=True)
         try:
             recon_batch, latent_dist, latent_sample = self.model(data)
@@ -80,13 +143,13 @@ class Trainer():
             self.optimizer.zero_grad()
             loss.backward()
             self._sync_grads()
-            self.optimizer.step()
+            self._optimizer_step()
         except ValueError:
             # losses with several optimizers (FactorVAE): training.py:160-162
             if is_distributed():
                 loss = self._factor_step_distributed(data, storer)
             else:
-                loss = self.loss_f.call_optimize(data, self.model, self.optimizer, storer)
+                loss = self.loss_f.call_optimize(data, self.model, _StepProxy(self.optimizer, self._optimizer_step), storer)
         return loss.detach()
 
     def _train_iteration(self, data, storer):
@@ -121,9 +184,23 @@ class Trainer():
         if self._grad_sync_d is None:
             self._grad_sync_d = FlatGradSync(list(lf.discriminator.parameters()))
         self._grad_sync_d.sync()
-        self.optimizer.step()
-        real_d.step()
+        self._optimizer_step()
+        lf._step_d()
         return loss
+
+
+class _StepProxy:
+    """What FactorKLoss.call_optimize sees as `optimizer`: zero_grad() of the real one, step() through
+    the Trainer's fused Adam."""
+
+    def __init__(self, optimizer, step_fn):
+        self._opt, self._step = optimizer, step_fn
+
+    def zero_grad(self, *a, **k):
+        return self._opt.zero_grad(*a, **k)
+
+    def step(self):
+        return self._step()
 
 
 class LossesLogger(object):

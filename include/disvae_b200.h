@@ -187,6 +187,14 @@ int dv_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg
                  float* step_dev, long long n, float lr, float beta1, float beta2, float eps,
                  float grad_scale, void* stream);
 
+/* Multi-tensor form: `count` (<= dv_adam_multi_max_tensors()) parameter tensors updated by ONE launch.
+ * The arrays are HOST arrays of device pointers / element counts; they are copied into kernel-parameter
+ * space, nothing is retained.  Same arithmetic and step counter semantics as dv_adam_step. */
+int dv_adam_multi_max_tensors(void);
+int dv_adam_multi(int count, float* const* params, const float* const* grads, float* const* exp_avg,
+                  float* const* exp_avg_sq, const long long* numel, float* step_dev, float lr, float beta1,
+                  float beta2, float eps, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -393,3 +393,26 @@ def test_adam_step_matches_torch(ops):
         ops.adam_step(pd, g.to(dev()), m, v, step, 5e-4, (0.9, 0.999), 1e-8)
     assert step.item() == 3
     assert_close(pd.cpu(), po.detach(), tol=1e-6)
+
+
+def test_fused_adam_multi_matches_torch_adam():
+    """disvae.fused.FusedAdam (dv_adam_multi, one launch for all tensors) == torch.optim.Adam, incl. shared state."""
+    from disvae.fused import FusedAdam
+    torch.manual_seed(6)
+    shapes = [(32, 1, 4, 4), (32,), (256, 512), (20, 256), (1000, 1000), (3,)]
+    ps_ref = [torch.randn(s, requires_grad=True) for s in shapes]
+    ps = [p.detach().clone().to(dev()).requires_grad_(True) for p in ps_ref]
+    opt_ref = torch.optim.Adam(ps_ref, lr=5e-4)
+    opt = torch.optim.Adam(ps, lr=5e-4)
+    assert FusedAdam.supports(opt) and not FusedAdam.supports(torch.optim.Adam(ps, lr=1e-3, weight_decay=0.1))
+    fused = FusedAdam(opt)
+    for _ in range(4):
+        for a, b in zip(ps_ref, ps):
+            g = torch.randn(a.shape)
+            a.grad = g.clone(); b.grad = g.to(dev())
+        opt_ref.step(); fused.step()
+    for a, b in zip(ps_ref, ps):
+        assert_close(b.detach().cpu(), a.detach(), tol=1e-6)
+        assert_close(opt.state[b]["exp_avg_sq"].cpu(), opt_ref.state[a]["exp_avg_sq"], tol=1e-6)
+    fused.flush_state()
+    assert float(opt.state[ps[0]]["step"]) == 4.0
