@@ -18,6 +18,7 @@
 // (c and hiv pre-multiplied by log2 e) so that each (i,j,d) costs one MUFU.EX2 and no extra
 // multiply.  Each logsumexp is an exact two-sweep (max, then sum of exp2) reduction; cross-lane
 // merges are warp shuffles, cross-warp merges go through a few hundred bytes of shared memory.
+#include <stdlib.h>
 #include "dv_common.cuh"
 
 namespace dv {
@@ -225,6 +226,148 @@ btcvae_fwd_kernel(int B, int D, LogW lw, float* __restrict__ ws, float* __restri
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Forward, second generation: (row-group x column-range) tiling.
+// The first kernel above streams every column's parameters through L1 for each group of 4 rows
+// (B/4 blocks x B*D*16 bytes x 2 sweeps = 82 MB of L2->SM traffic at (1024,10)) and is latency bound.
+// Here a block owns 32 rows (8 warps x 4 rows; the 8 lanes of a row split the columns) and ONE
+// column range of kJT columns whose parameters are staged once in shared memory (10 KB at D=10),
+// so both sweeps run out of shared memory with conflict-free 128-bit loads.  A block emits partial
+// logsumexp states (max, sum) per (row, dim) for its column range; btcvae_finalize_kernel merges
+// the ranges in a fixed order, forms the row statistics and the three means.  Grid: (B/32) x (B/kJT).
+// ------------------------------------------------------------------------------------------
+constexpr int kJT = 64;            // columns per block
+constexpr int kJPL = kJT / kJL;    // columns per lane (8)
+constexpr int kRG = 32;            // rows per block
+
+template <int DC, bool EXACT>
+__global__ void __launch_bounds__(kBtWarps * 32)
+btcvae_fwd2_kernel(int B, int D, LogW lw, const float4* __restrict__ pj, float2* __restrict__ part) {
+  __shared__ float4 sp[DC][kJT];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r = lane >> 3, jl = lane & 7;
+  const int i_raw = blockIdx.x * kRG + warp * kRows + r;
+  const int i = min(i_raw, B - 1);
+  const int js = blockIdx.y;
+  const int j0 = js * kJT;
+  const float Df = (float)D;
+  float sa[kJPL];
+#pragma unroll
+  for (int t = 0; t < kJPL; ++t) sa[t] = 0.f;
+  float wj[kJPL];
+#pragma unroll
+  for (int t = 0; t < kJPL; ++t) wj[t] = logw2(lw, i, j0 + jl + kJL * t);
+
+  for (int d0 = 0; d0 < D; d0 += DC) {
+    const int nd = EXACT ? DC : min(DC, D - d0);
+    if (d0 > 0) __syncthreads();                              // previous chunk fully consumed
+    for (int e = threadIdx.x; e < nd * kJT; e += blockDim.x) {
+      const int k = e / kJT, jj = e % kJT;
+      const int j = min(j0 + jj, B - 1);
+      sp[k][jj] = __ldg(pj + (long long)(d0 + k) * B + j);
+    }
+    __syncthreads();
+    float zc[DC], mx[DC], sx[DC];
+#pragma unroll
+    for (int k = 0; k < DC; ++k) {
+      zc[k] = (EXACT || k < nd) ? __ldg(&pj[(long long)(d0 + k) * B + i].w) : 0.f;
+      mx[k] = -INFINITY; sx[k] = 0.f;
+    }
+#pragma unroll
+    for (int t = 0; t < kJPL; ++t) {
+      if (j0 + jl + kJL * t < B) {
+#pragma unroll
+        for (int k = 0; k < DC; ++k) {
+          if (EXACT || k < nd) {
+            const float4 p = sp[k][jl + kJL * t];
+            const float tt = zc[k] - p.z;
+            const float m = p.x - p.y * (tt * tt);
+            mx[k] = fmaxf(mx[k], m + wj[t]);
+            sa[t] += m;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < DC; ++k)
+#pragma unroll
+      for (int o = 1; o < kJL; o <<= 1) mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
+#pragma unroll
+    for (int t = 0; t < kJPL; ++t) {
+      if (j0 + jl + kJL * t < B) {
+#pragma unroll
+        for (int k = 0; k < DC; ++k) {
+          if (EXACT || k < nd) {
+            const float4 p = sp[k][jl + kJL * t];
+            const float tt = zc[k] - p.z;
+            sx[k] += exp2f((p.x - p.y * (tt * tt)) + (wj[t] - mx[k]));
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < DC; ++k) {
+#pragma unroll
+      for (int o = 1; o < kJL; o <<= 1) sx[k] += __shfl_xor_sync(0xffffffffu, sx[k], o);
+      if (jl == 0 && i_raw < B && (EXACT || k < nd))
+        part[((long long)js * (D + 1) + d0 + k) * B + i] = make_float2(mx[k], sx[k]);
+    }
+  }
+  // log_qz partial: logsumexp over this block's columns of (sum_d m + D*lw)
+  float am = -INFINITY, as = 0.f;
+#pragma unroll
+  for (int t = 0; t < kJPL; ++t) {
+    if (j0 + jl + kJL * t < B) {
+      const float a = sa[t] + Df * wj[t];
+      const float nm = fmaxf(am, a);
+      as = as * exp2f(am - nm) + exp2f(a - nm);
+      am = nm;
+    }
+  }
+#pragma unroll
+  for (int o = 1; o < kJL; o <<= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, am, o), s2 = __shfl_xor_sync(0xffffffffu, as, o);
+    lse_merge2(am, as, m2, s2);
+  }
+  if (jl == 0 && i_raw < B) part[((long long)js * (D + 1) + D) * B + i] = make_float2(am, as);
+}
+
+// one block: merge the column ranges (fixed order), write rowstats rows 1, 2, 4.., then the three means
+__global__ void __launch_bounds__(1024)
+btcvae_finalize_kernel(int B, int D, int JS, const float2* __restrict__ part, float* __restrict__ rowstats,
+                       float* __restrict__ terms) {
+  __shared__ float red[3][32];
+  float mi = 0.f, tc = 0.f, dw = 0.f;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) {
+    float lprod = 0.f;
+    for (int d = 0; d <= D; ++d) {
+      float2 st = part[(long long)d * B + i];
+      float m = st.x, s = st.y;
+      for (int js = 1; js < JS; ++js) {
+        st = part[((long long)js * (D + 1) + d) * B + i];
+        lse_merge2(m, s, st.x, st.y);
+      }
+      const float v = (m + log2f(s)) * kLn2;
+      if (d < D) { rowstats[(long long)(4 + d) * B + i] = v; lprod += v; }
+      else rowstats[1LL * B + i] = v;                         // log_qz
+    }
+    rowstats[2LL * B + i] = lprod;
+    const float lpz = rowstats[i], lqz = rowstats[1LL * B + i], lqc = rowstats[3LL * B + i];
+    mi += lqc - lqz; tc += lqz - lprod; dw += lprod - lpz;
+  }
+  mi = warp_sum(mi); tc = warp_sum(tc); dw = warp_sum(dw);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { red[0][warp] = mi; red[1][warp] = tc; red[2][warp] = dw; }
+  __syncthreads();
+  if (warp == 0) {
+    const int nw = blockDim.x >> 5;
+    float a = lane < nw ? red[0][lane] : 0.f, b = lane < nw ? red[1][lane] : 0.f, c = lane < nw ? red[2][lane] : 0.f;
+    a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
+    if (lane == 0) { terms[0] = a / (float)B; terms[1] = b / (float)B; terms[2] = c / (float)B; }
+  }
+}
+
 // ---- backward ---------------------------------------------------------------------
 // G[i,j,d] = cq * S[i,j] + cp * T[i,j,d],  S = exp(A[i,j] - log_qz[i]),  T = exp(M[i,j,d] - P[i,d])
 // role 0 (rows):    g_z[i,d]  = sum_j G * (-(z_i - mu_j) * iv_j)            + direct terms
@@ -380,7 +523,12 @@ using namespace dv;
 
 extern "C" {
 
-size_t dv_btcvae_workspace_bytes(int B, int D) { return (size_t)(kWsHeader + 4LL * B * D) * sizeof(float); }
+// header | float4 pj[D][B] | float2 part[ceil(B/kJT)][D+1][B]
+static long long btcvae_part_offset_floats(int B, int D) { return kWsHeader + 4LL * B * D; }
+size_t dv_btcvae_workspace_bytes(int B, int D) {
+  const long long JS = (B + kJT - 1) / kJT;
+  return (size_t)(btcvae_part_offset_floats(B, D) + 2LL * JS * (D + 1) * B) * sizeof(float);
+}
 
 int dv_btcvae_fwd(const float* z, const float* mu, const float* logvar, int ld, int row_stride, int B, int D,
                   long long n_data, int is_mss, float* rowstats, float* terms, void* workspace, void* stream) {
@@ -394,11 +542,27 @@ int dv_btcvae_fwd(const float* z, const float* mu, const float* logvar, int ld, 
   int rc = check_launch();
   if (rc != DV_OK) return rc;
   const LogW lw = make_logw(B, n_data, is_mss);
-  const int grid = (B + kRows - 1) / kRows;
+  static int v1 = -1;
+  if (v1 < 0) { const char* e = getenv("DV_BTCVAE_V1"); v1 = (e && e[0] == '1') ? 1 : 0; }
+  if (v1) {
+    const int grid = (B + kRows - 1) / kRows;
 #define DV_FWD_CALL(DC, FUSE, EXACT) \
   btcvae_fwd_kernel<DC, FUSE, EXACT><<<grid, kBtWarps * 32, 0, st>>>(B, D, lw, ws, rowstats, terms)
-  DV_BT_DISPATCH(D, DV_FWD_CALL);
+    DV_BT_DISPATCH(D, DV_FWD_CALL);
 #undef DV_FWD_CALL
+    return check_launch();
+  }
+  const int JS = (B + kJT - 1) / kJT;
+  float2* part = reinterpret_cast<float2*>(ws + btcvae_part_offset_floats(B, D));
+  const float4* pjc = reinterpret_cast<const float4*>(ws + kWsHeader);
+  dim3 grid((B + kRG - 1) / kRG, JS);
+  if (D == 10)          btcvae_fwd2_kernel<10, true><<<grid, kBtWarps * 32, 0, st>>>(B, D, lw, pjc, part);
+  else if (D % 16 == 0) btcvae_fwd2_kernel<16, true><<<grid, kBtWarps * 32, 0, st>>>(B, D, lw, pjc, part);
+  else if (D <= 8)      btcvae_fwd2_kernel<8, false><<<grid, kBtWarps * 32, 0, st>>>(B, D, lw, pjc, part);
+  else                  btcvae_fwd2_kernel<16, false><<<grid, kBtWarps * 32, 0, st>>>(B, D, lw, pjc, part);
+  rc = check_launch();
+  if (rc != DV_OK) return rc;
+  btcvae_finalize_kernel<<<1, B >= 1024 ? 1024 : ((B + 31) / 32) * 32, 0, st>>>(B, D, JS, part, rowstats, terms);
   return check_launch();
 }
 

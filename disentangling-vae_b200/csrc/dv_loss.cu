@@ -172,16 +172,25 @@ __global__ void reparam_bwd_kernel(const float* __restrict__ g_z, const float* _
 }
 
 // ---- Adam (torch.optim.Adam, amsgrad=False, weight_decay=0, maximize=False) ---------
+// torch evaluates 1-beta and the bias corrections in Python doubles; 1-0.999 in fp32 would be off by 1.3e-5
+struct AdamCoef { float omb1, omb2, b2, step_size, bc2_sqrt; };
+__device__ __forceinline__ AdamCoef adam_coef(const float* step_dev, float lr, double b1, double b2) {
+  const double step = (double)(*step_dev) + 1.0;
+  const double bc1 = 1.0 - pow(b1, step), bc2 = 1.0 - pow(b2, step);
+  AdamCoef c;
+  c.omb1 = (float)(1.0 - b1); c.omb2 = (float)(1.0 - b2); c.b2 = (float)b2;
+  c.step_size = (float)((double)lr / bc1);
+  c.bc2_sqrt = (float)sqrt(bc2);
+  return c;
+}
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                            const float* __restrict__ step_dev, long long n, float lr, float b1, float b2, float eps, float gscale) {
-  const float step = *step_dev + 1.f;
-  const float bc1 = 1.f - powf(b1, step), bc2 = 1.f - powf(b2, step);
-  const float step_size = lr / bc1;
-  const float bc2_sqrt = sqrtf(bc2);
+                            const float* __restrict__ step_dev, long long n, float lr, double b1d, double b2d, float eps, float gscale) {
+  const AdamCoef c = adam_coef(step_dev, lr, b1d, b2d);
+  const float b2 = c.b2, step_size = c.step_size, bc2_sqrt = c.bc2_sqrt;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float gi = g[i] * gscale;
-    const float mi = m[i] + (gi - m[i]) * (1.f - b1);          // exp_avg.lerp_(grad, 1 - beta1)
-    const float vi = v[i] * b2 + (1.f - b2) * gi * gi;         // exp_avg_sq.mul_(b2).addcmul_(g, g, 1 - b2)
+    const float mi = m[i] + (gi - m[i]) * c.omb1;              // exp_avg.lerp_(grad, 1 - beta1)
+    const float vi = v[i] * b2 + c.omb2 * (gi * gi);           // exp_avg_sq.mul_(b2).addcmul_(g, g, 1 - b2)
     m[i] = mi; v[i] = vi;
     const float denom = sqrtf(vi) / bc2_sqrt + eps;
     p[i] = p[i] - step_size * (mi / denom);
@@ -204,12 +213,10 @@ struct AdamTable {
   int count;
 };
 __global__ void __launch_bounds__(256)
-adam_multi_kernel(const __grid_constant__ AdamTable t, const float* __restrict__ step_dev, float lr, float b1, float b2,
+adam_multi_kernel(const __grid_constant__ AdamTable t, const float* __restrict__ step_dev, float lr, double b1d, double b2d,
                   float eps, float gscale) {
-  const float step = *step_dev + 1.f;
-  const float bc1 = 1.f - powf(b1, step), bc2 = 1.f - powf(b2, step);
-  const float step_size = lr / bc1;
-  const float bc2_sqrt = sqrtf(bc2);
+  const AdamCoef c = adam_coef(step_dev, lr, b1d, b2d);
+  const float b2 = c.b2, step_size = c.step_size, bc2_sqrt = c.bc2_sqrt;
   const int total_chunks = t.chunk_begin[t.count];
   for (int chunk = blockIdx.x; chunk < total_chunks; chunk += gridDim.x) {
     int ti = 0;
@@ -219,8 +226,8 @@ adam_multi_kernel(const __grid_constant__ AdamTable t, const float* __restrict__
     float* p = t.p[ti]; const float* g = t.g[ti]; float* m = t.m[ti]; float* v = t.v[ti];
     for (int i = base + threadIdx.x; i < end; i += blockDim.x) {
       const float gi = g[i] * gscale;
-      const float mi = m[i] + (gi - m[i]) * (1.f - b1);
-      const float vi = v[i] * b2 + (1.f - b2) * gi * gi;
+      const float mi = m[i] + (gi - m[i]) * c.omb1;
+      const float vi = v[i] * b2 + c.omb2 * (gi * gi);
       m[i] = mi; v[i] = vi;
       p[i] = p[i] - step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
     }
@@ -293,7 +300,7 @@ int dv_reparam_bwd(const float* g_z, const float* logvar, int ld, int row_stride
 }
 
 int dv_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* step_dev, long long n,
-                 float lr, float beta1, float beta2, float eps, float grad_scale, void* stream) {
+                 float lr, double beta1, double beta2, float eps, float grad_scale, void* stream) {
   if (!param || !grad || !exp_avg || !exp_avg_sq || !step_dev) return DV_ERR_BAD_ARG;
   if (n <= 0) return DV_ERR_BAD_SHAPE;
   adam_kernel<<<grid_for(n, 1024, 4 * kNumSMs), 256, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, step_dev, n, lr,
@@ -307,8 +314,8 @@ int dv_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg
 int dv_adam_multi_max_tensors(void) { return kAdamMaxTensors; }
 
 int dv_adam_multi(int count, float* const* params, const float* const* grads, float* const* exp_avg,
-                  float* const* exp_avg_sq, const long long* numel, float* step_dev, float lr, float beta1,
-                  float beta2, float eps, float grad_scale, void* stream) {
+                  float* const* exp_avg_sq, const long long* numel, float* step_dev, float lr, double beta1,
+                  double beta2, float eps, float grad_scale, void* stream) {
   if (!params || !grads || !exp_avg || !exp_avg_sq || !numel || !step_dev) return DV_ERR_BAD_ARG;
   if (count <= 0 || count > kAdamMaxTensors) return DV_ERR_BAD_SHAPE;
   AdamTable t;

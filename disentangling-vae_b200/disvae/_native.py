@@ -5,7 +5,7 @@ If the shared object is missing, or a tensor is not a CUDA fp32 tensor, the call
 """
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_longlong, c_size_t, c_ulonglong, c_void_p
+from ctypes import c_char_p, c_double, c_float, c_int, c_longlong, c_size_t, c_ulonglong, c_void_p
 
 import torch
 
@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_PKG_DIR, "libdisvae_b200.so")
 ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_LEAKY = 0, 1, 2, 3
 DIST = {"bernoulli": 0, "gaussian": 1, "laplace": 2}
 
-P, I, LL, F, SZ, ULL = c_void_p, c_int, c_longlong, c_float, c_size_t, c_ulonglong
+P, I, LL, F, SZ, ULL, DBL = c_void_p, c_int, c_longlong, c_float, c_size_t, c_ulonglong, c_double
 
 # name -> (restype, argtypes); mirrors include/disvae_b200.h one to one
 SIGNATURES = {
@@ -52,12 +52,13 @@ SIGNATURES = {
     "dv_factor_tc_bwd": (I, [P, I, P, P]),
     "dv_factor_ce_fwd": (I, [P, P, I, P, P]),
     "dv_factor_ce_bwd": (I, [P, P, P, I, P, P, P]),
-    "dv_adam_step": (I, [P, P, P, P, P, LL, F, F, F, F, F, P]),
+    "dv_adam_step": (I, [P, P, P, P, P, LL, F, DBL, DBL, F, F, P]),
     "dv_adam_multi_max_tensors": (I, []),
-    "dv_adam_multi": (I, [I, P, P, P, P, P, P, F, F, F, F, F, P]),
+    "dv_adam_multi": (I, [I, P, P, P, P, P, P, F, DBL, DBL, F, F, P]),
 }
 
 _lib = None
+GRAPH_LAUNCHES = 0       # kernels launched through CUDA-graph replays (dv_launch_count() only sees direct launches)
 
 
 class NativeLibraryMissing(RuntimeError):
@@ -138,6 +139,11 @@ def call(name, *args):
         _prof_events.append((name, e0, e1))
         return
     check(getattr(lib(), name)(*args), name)
+
+
+def launch_count():
+    """Kernels of this library launched so far, including those replayed inside CUDA graphs."""
+    return lib().dv_launch_count() + GRAPH_LAUNCHES
 
 
 def require_cuda_f32(*tensors):

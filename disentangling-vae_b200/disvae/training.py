@@ -13,6 +13,7 @@ from timeit import default_timer
 import torch
 from tqdm import trange
 
+from disvae import _native
 from disvae.fused import FusedAdam
 from disvae.parallel import FlatGradSync, is_distributed
 from disvae.utils.modelIO import save_model
@@ -112,6 +113,7 @@ class Trainer():
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             steps_before = self.loss_f.n_train_steps
+            launches_before = _native.lib().dv_launch_count()
             with torch.cuda.graph(g):
                 recon, dist, z = self.model(static_x)
                 loss = self.loss_f(static_x, recon, dist, True, None, latent_sample=z)
@@ -121,11 +123,12 @@ class Trainer():
                 static_loss = loss.detach()
             self.loss_f.n_train_steps = steps_before          # capture executed nothing
             self._fused.host_steps -= 1
-            entry = (g, static_x, static_loss)
+            entry = (g, static_x, static_loss, _native.lib().dv_launch_count() - launches_before)
             self._graphs[key] = entry
-        g, static_x, static_loss = entry
+        g, static_x, static_loss, n_kernels = entry
         static_x.copy_(data, non_blocking=True)
         g.replay()
+        _native.GRAPH_LAUNCHES += n_kernels
         self.loss_f.n_train_steps += 1
         self._fused.host_steps += 1
         return static_loss

@@ -181,10 +181,11 @@ int dv_factor_ce_bwd(const float* d_z, const float* d_perm, const float* upstrea
 /* ---- optimiser -------------------------------------------------------
  * torch.optim.Adam semantics (main.py:208, losses.py:238): eps outside the sqrt, no weight
  * decay, bias correction from *step_dev (float, incremented by the kernel).  Operates on one
- * flat fp32 buffer so a whole model is one launch.  grad_scale multiplies the gradient
+ * flat fp32 buffer so a whole model is one launch.  betas are doubles: 1-beta and the bias corrections are
+ * evaluated in fp64 like torch's Python-side arithmetic.  grad_scale multiplies the gradient
  * (1/world_size after a sum-allreduce). */
 int dv_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
-                 float* step_dev, long long n, float lr, float beta1, float beta2, float eps,
+                 float* step_dev, long long n, float lr, double beta1, double beta2, float eps,
                  float grad_scale, void* stream);
 
 /* Multi-tensor form: `count` (<= dv_adam_multi_max_tensors()) parameter tensors updated by ONE launch.
@@ -192,8 +193,8 @@ int dv_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg
  * space, nothing is retained.  Same arithmetic and step counter semantics as dv_adam_step. */
 int dv_adam_multi_max_tensors(void);
 int dv_adam_multi(int count, float* const* params, const float* const* grads, float* const* exp_avg,
-                  float* const* exp_avg_sq, const long long* numel, float* step_dev, float lr, float beta1,
-                  float beta2, float eps, float grad_scale, void* stream);
+                  float* const* exp_avg_sq, const long long* numel, float* step_dev, float lr, double beta1,
+                  double beta2, float eps, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }
