@@ -333,15 +333,17 @@ btcvae_fwd2_kernel(int B, int D, LogW lw, const float4* __restrict__ pj, float2*
   if (jl == 0 && i_raw < B) part[((long long)js * (D + 1) + D) * B + i] = make_float2(am, as);
 }
 
-// one block: merge the column ranges (fixed order), write rowstats rows 1, 2, 4.., then the three means
-__global__ void __launch_bounds__(1024)
+// merge the column ranges in a fixed order: 16 lanes per row (lane l owns dims l, l+16, ... and lane
+// D%16.. the log_qz slot), rowstats rows 1, 2, 4.. written per row; the last block forms the three means.
+__global__ void __launch_bounds__(256)
 btcvae_finalize_kernel(int B, int D, int JS, const float2* __restrict__ part, float* __restrict__ rowstats,
-                       float* __restrict__ terms) {
-  __shared__ float red[3][32];
-  float mi = 0.f, tc = 0.f, dw = 0.f;
-  for (int i = threadIdx.x; i < B; i += blockDim.x) {
-    float lprod = 0.f;
-    for (int d = 0; d <= D; ++d) {
+                       float* __restrict__ terms, unsigned* __restrict__ counter) {
+  __shared__ bool is_last;
+  const int gl = threadIdx.x & 15;
+  const int i = blockIdx.x * 16 + (threadIdx.x >> 4);
+  float lprod = 0.f;
+  if (i < B) {
+    for (int d = gl; d <= D; d += 16) {
       float2 st = part[(long long)d * B + i];
       float m = st.x, s = st.y;
       for (int js = 1; js < JS; ++js) {
@@ -352,19 +354,31 @@ btcvae_finalize_kernel(int B, int D, int JS, const float2* __restrict__ part, fl
       if (d < D) { rowstats[(long long)(4 + d) * B + i] = v; lprod += v; }
       else rowstats[1LL * B + i] = v;                         // log_qz
     }
-    rowstats[2LL * B + i] = lprod;
-    const float lpz = rowstats[i], lqz = rowstats[1LL * B + i], lqc = rowstats[3LL * B + i];
-    mi += lqc - lqz; tc += lqz - lprod; dw += lprod - lpz;
+  }
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) lprod += __shfl_xor_sync(0xffffffffu, lprod, o);
+  if (i < B && gl == 0) rowstats[2LL * B + i] = lprod;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  __shared__ float red[3][8];
+  float mi = 0.f, tc = 0.f, dw = 0.f;
+  for (int r = threadIdx.x; r < B; r += blockDim.x) {
+    const float lpz = rowstats[r], lqz = rowstats[1LL * B + r], lp = rowstats[2LL * B + r], lqc = rowstats[3LL * B + r];
+    mi += lqc - lqz; tc += lqz - lp; dw += lp - lpz;
   }
   mi = warp_sum(mi); tc = warp_sum(tc); dw = warp_sum(dw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (lane == 0) { red[0][warp] = mi; red[1][warp] = tc; red[2][warp] = dw; }
   __syncthreads();
-  if (warp == 0) {
-    const int nw = blockDim.x >> 5;
-    float a = lane < nw ? red[0][lane] : 0.f, b = lane < nw ? red[1][lane] : 0.f, c = lane < nw ? red[2][lane] : 0.f;
-    a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
-    if (lane == 0) { terms[0] = a / (float)B; terms[1] = b / (float)B; terms[2] = c / (float)B; }
+  if (threadIdx.x == 0) {
+    float a = 0.f, b2 = 0.f, c = 0.f;
+    for (int w = 0; w < 8; ++w) { a += red[0][w]; b2 += red[1][w]; c += red[2][w]; }
+    terms[0] = a / (float)B; terms[1] = b2 / (float)B; terms[2] = c / (float)B;
+    *counter = 0u;
   }
 }
 
@@ -562,7 +576,7 @@ int dv_btcvae_fwd(const float* z, const float* mu, const float* logvar, int ld, 
   else                  btcvae_fwd2_kernel<16, false><<<grid, kBtWarps * 32, 0, st>>>(B, D, lw, pjc, part);
   rc = check_launch();
   if (rc != DV_OK) return rc;
-  btcvae_finalize_kernel<<<1, B >= 1024 ? 1024 : ((B + 31) / 32) * 32, 0, st>>>(B, D, JS, part, rowstats, terms);
+  btcvae_finalize_kernel<<<(B + 15) / 16, 256, 0, st>>>(B, D, JS, part, rowstats, terms, reinterpret_cast<unsigned*>(ws));
   return check_launch();
 }
 
