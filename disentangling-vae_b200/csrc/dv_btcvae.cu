@@ -63,6 +63,8 @@ __global__ void btcvae_prep_kernel(const float* __restrict__ z, const float* __r
 
 // merge of (max, sum) logsumexp states, log2 domain
 __device__ __forceinline__ void lse_merge2(float& m, float& s, float m2, float s2) {
+  if (s2 == 0.f) return;                                        // empty / fully underflowed state: identity
+  if (s == 0.f) { m = m2; s = s2; return; }
   const float nm = fmaxf(m, m2);
   if (nm == -INFINITY) { s = 0.f; return; }
   s = s * exp2f(m - nm) + s2 * exp2f(m2 - nm);
@@ -241,10 +243,17 @@ constexpr int kJT = 64;            // columns per block
 constexpr int kJPL = kJT / kJL;    // columns per lane (8)
 constexpr int kRG = 32;            // rows per block
 
+// Single sweep: instead of a max pass, every (row, dim) of a block uses the reference exponent
+//   ref = max( upper bound of the block's columns - 60,  the diagonal term if column i is in the block )
+// (log2 units).  The bound max_j (c_j + w_j) >= every term, so exp2(term - ref) <= 2^60 never overflows;
+// the diagonal term (always part of the sum) keeps the row's total from underflowing; a block whose terms
+// all underflow against its own bound contributes (ref, 0), which the merge treats as the identity -- such
+// terms are < 2^-66 of the block bound and far below the diagonal term.  One MUFU.EX2, ~8 FP32 ops per (i,j,d).
 template <int DC, bool EXACT>
 __global__ void __launch_bounds__(kBtWarps * 32)
 btcvae_fwd2_kernel(int B, int D, LogW lw, const float4* __restrict__ pj, float2* __restrict__ part) {
   __shared__ float4 sp[DC][kJT];
+  __shared__ float sbound[DC];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int r = lane >> 3, jl = lane & 7;
   const int i_raw = blockIdx.x * kRG + warp * kRows + r;
@@ -252,12 +261,10 @@ btcvae_fwd2_kernel(int B, int D, LogW lw, const float4* __restrict__ pj, float2*
   const int js = blockIdx.y;
   const int j0 = js * kJT;
   const float Df = (float)D;
-  float sa[kJPL];
+  const float w_col0_max = lw.mss ? fmaxf(lw.ln, lw.ls) : 0.f;
+  float sa[kJPL], wj[kJPL];
 #pragma unroll
-  for (int t = 0; t < kJPL; ++t) sa[t] = 0.f;
-  float wj[kJPL];
-#pragma unroll
-  for (int t = 0; t < kJPL; ++t) wj[t] = logw2(lw, i, j0 + jl + kJL * t);
+  for (int t = 0; t < kJPL; ++t) { sa[t] = 0.f; wj[t] = logw2(lw, i, j0 + jl + kJL * t); }
 
   for (int d0 = 0; d0 < D; d0 += DC) {
     const int nd = EXACT ? DC : min(DC, D - d0);
@@ -268,11 +275,39 @@ btcvae_fwd2_kernel(int B, int D, LogW lw, const float4* __restrict__ pj, float2*
       sp[k][jj] = __ldg(pj + (long long)(d0 + k) * B + j);
     }
     __syncthreads();
-    float zc[DC], mx[DC], sx[DC];
+    // per-dimension upper bound over this block's columns: 8 lanes scan 8 columns each
+    {                                                          // all threads take part (full-mask shuffles)
+      const int kk = threadIdx.x >> 3, l = threadIdx.x & 7;
+      const int k = min(kk, nd - 1);
+      float bmax = -INFINITY;
+#pragma unroll
+      for (int t = 0; t < kJPL; ++t) {
+        const int j = j0 + l + kJL * t;
+        if (j < B) {
+          const float w = !lw.mss ? 0.f : (j == 0 ? w_col0_max : (j == 1 ? lw.ls : lw.lm));
+          bmax = fmaxf(bmax, sp[k][l + kJL * t].x + w);
+        }
+      }
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) bmax = fmaxf(bmax, __shfl_xor_sync(0xffffffffu, bmax, o));
+      if (l == 0 && kk < nd) sbound[kk] = bmax;
+    }
+    __syncthreads();
+    float zc[DC], ref[DC], sx[DC];
+    const bool diag_here = (i >= j0 && i < j0 + kJT);
 #pragma unroll
     for (int k = 0; k < DC; ++k) {
-      zc[k] = (EXACT || k < nd) ? __ldg(&pj[(long long)(d0 + k) * B + i].w) : 0.f;
-      mx[k] = -INFINITY; sx[k] = 0.f;
+      sx[k] = 0.f;
+      if (EXACT || k < nd) {
+        zc[k] = __ldg(&pj[(long long)(d0 + k) * B + i].w);
+        float rf = sbound[k] - 60.f;
+        if (diag_here) {
+          const float4 p = sp[k][i - j0];
+          const float tt = zc[k] - p.z;
+          rf = fmaxf(rf, p.x - p.y * (tt * tt) + logw2(lw, i, i));
+        }
+        ref[k] = rf;
+      } else { zc[k] = 0.f; ref[k] = 0.f; }
     }
 #pragma unroll
     for (int t = 0; t < kJPL; ++t) {
@@ -283,25 +318,8 @@ btcvae_fwd2_kernel(int B, int D, LogW lw, const float4* __restrict__ pj, float2*
             const float4 p = sp[k][jl + kJL * t];
             const float tt = zc[k] - p.z;
             const float m = p.x - p.y * (tt * tt);
-            mx[k] = fmaxf(mx[k], m + wj[t]);
             sa[t] += m;
-          }
-        }
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < DC; ++k)
-#pragma unroll
-      for (int o = 1; o < kJL; o <<= 1) mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
-#pragma unroll
-    for (int t = 0; t < kJPL; ++t) {
-      if (j0 + jl + kJL * t < B) {
-#pragma unroll
-        for (int k = 0; k < DC; ++k) {
-          if (EXACT || k < nd) {
-            const float4 p = sp[k][jl + kJL * t];
-            const float tt = zc[k] - p.z;
-            sx[k] += exp2f((p.x - p.y * (tt * tt)) + (wj[t] - mx[k]));
+            sx[k] += exp2f(m + (wj[t] - ref[k]));
           }
         }
       }
@@ -311,7 +329,7 @@ btcvae_fwd2_kernel(int B, int D, LogW lw, const float4* __restrict__ pj, float2*
 #pragma unroll
       for (int o = 1; o < kJL; o <<= 1) sx[k] += __shfl_xor_sync(0xffffffffu, sx[k], o);
       if (jl == 0 && i_raw < B && (EXACT || k < nd))
-        part[((long long)js * (D + 1) + d0 + k) * B + i] = make_float2(mx[k], sx[k]);
+        part[((long long)js * (D + 1) + d0 + k) * B + i] = make_float2(ref[k], sx[k]);
     }
   }
   // log_qz partial: logsumexp over this block's columns of (sum_d m + D*lw)

@@ -336,6 +336,23 @@ def test_btcvae_extreme_variances_stay_finite(ops):
         assert_close(got.cpu(), r, tol=2e-5)
 
 
+def test_btcvae_outlier_rows_and_tiny_variances(ops):
+    """Rows far (100s of sigma) from every other column, tiny and huge variances mixed: the single-sweep
+    logsumexp (bounded reference exponent) must agree with the exact-max oracle and stay finite."""
+    torch.manual_seed(1)
+    B, D = 192, 10
+    mu = torch.randn(B, D)
+    lv = torch.randn(B, D) * 0.3 - 2.0
+    lv[5] = -20.0; lv[77] = 6.0; lv[130, :3] = -16.0
+    z = mu + torch.exp(0.5 * lv) * torch.randn(B, D)
+    z[9] += 40.0; z[100, 2] -= 25.0
+    ref = O.btcvae_log_densities(z, mu, lv, 50000)
+    stats = ops.btcvae_rowstats(z.to(dev()), mu.to(dev()), lv.to(dev()), 50000, True)
+    for got, r, name in zip(stats, ref, ["log_pz", "log_qz", "log_prod_qzi", "log_q_zCx"]):
+        assert torch.isfinite(got).all(), name
+        assert_close(got.cpu(), r, tol=2e-5, what=name)
+
+
 def test_permute_dims(ops, golden):
     g = golden("permute.pt")
     torch.manual_seed(1234 + 7)
