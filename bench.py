@@ -196,12 +196,14 @@ def run_ours(args):
             "conv_flop_fraction_of_bf16_peak": round(value / world * conv_flop / (pk["bf16_sustained"] * 1e12), 5),
             "clocks": clocks,
         }
-    # ---- roofline of the dominant kernel + the named log-density kernel (rank 0, N=1 semantics) ----
+    # ---- roofline of the dominant kernel + the named log-density kernel ----
+    # Every rank runs the profiled steps (they contain the gradient all-reduce); only rank 0 reports.
+    try:
+        roof = kernel_rooflines(trainer, resident, K, B, img, z, n_data, device)
+    except Exception as e:                                     # never lose the headline line
+        roof = {"roofline_error": repr(e)}
     if rank == 0:
-        try:
-            out.update(kernel_rooflines(trainer, resident, K, B, img, z, n_data, device))
-        except Exception as e:                                     # never lose the headline line
-            out["roofline_error"] = repr(e)
+        out.update(roof)
         if world == 1 and not args.no_cpu_baseline:
             try:
                 out["cpu_baseline"] = cpu_baseline(args.workload, budget_s=20.0)

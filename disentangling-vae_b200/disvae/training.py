@@ -93,7 +93,7 @@ class Trainer():
         lf = self.loss_f
         if not (self.use_cuda_graph and self.device.type == "cuda" and self.model.training):
             return False
-        if is_distributed() or hasattr(lf, "call_optimize") or getattr(self.model, "_eps_queue", None):
+        if hasattr(lf, "call_optimize") or getattr(self.model, "_eps_queue", None):
             return False
         if lf.steps_anneal != 0 and lf.n_train_steps < lf.steps_anneal:
             return False                                      # host-side annealing coefficient still moving
@@ -104,9 +104,13 @@ class Trainer():
         return bool(self._fused)
 
     def _graph_step(self, data):
-        """fwd + loss + bwd + Adam of one batch as ONE CUDA graph launch (static shapes)."""
+        """fwd + loss + bwd (+ Adam when not data-parallel) of one batch as ONE CUDA graph launch (static
+        shapes).  Data-parallel: the graph ends after the backward pass; its static gradient tensors are
+        gathered into the flat buffer (one kernel), all-reduced (one NCCL call) and consumed by the fused
+        Adam launch with grad_scale = 1/world."""
         key = (tuple(data.shape), str(data.dtype))
         entry = self._graphs.get(key)
+        ddp = is_distributed()
         if entry is None:
             static_x = torch.empty(data.shape, dtype=torch.float32, device=self.device)
             static_x.copy_(data, non_blocking=True)
@@ -119,16 +123,35 @@ class Trainer():
                 loss = self.loss_f(static_x, recon, dist, True, None, latent_sample=z)
                 self.optimizer.zero_grad(set_to_none=True)
                 loss.backward()
-                self._fused.step()
+                if not ddp:
+                    self._fused.step()
+                    self._fused.host_steps -= 1                   # capture executed nothing
                 static_loss = loss.detach()
-            self.loss_f.n_train_steps = steps_before          # capture executed nothing
-            self._fused.host_steps -= 1
-            entry = (g, static_x, static_loss, _native.lib().dv_launch_count() - launches_before)
+            self.loss_f.n_train_steps = steps_before
+            flat = None
+            if ddp:
+                params = [p for p in self.model.parameters() if p.grad is not None]
+                static_grads = [p.grad for p in params]           # written by every replay
+                flat_buf = torch.zeros(sum(t.numel() for t in static_grads), dtype=torch.float32, device=self.device)
+                off, views = 0, []
+                for p in params:                                  # Adam reads the all-reduced flat views
+                    views.append(flat_buf[off:off + p.numel()].view_as(p))
+                    off += p.numel()
+                flat = (flat_buf, [t.view(-1) for t in static_grads], params, views)
+            entry = (g, static_x, static_loss, _native.lib().dv_launch_count() - launches_before, flat)
             self._graphs[key] = entry
-        g, static_x, static_loss, n_kernels = entry
+        g, static_x, static_loss, n_kernels, flat = entry
         static_x.copy_(data, non_blocking=True)
         g.replay()
         _native.GRAPH_LAUNCHES += n_kernels
+        if flat is not None:
+            import torch.distributed as dist
+            torch.cat(flat[1], out=flat[0])
+            dist.all_reduce(flat[0], op=dist.ReduceOp.SUM)
+            for p, v in zip(flat[2], flat[3]):                    # (an eager step in between re-binds .grad)
+                p.grad = v
+            self._fused.step(grad_scale=1.0 / dist.get_world_size())
+            self._fused.host_steps -= 1
         self.loss_f.n_train_steps += 1
         self._fused.host_steps += 1
         return static_loss
