@@ -230,26 +230,35 @@ def kernel_rooflines(trainer, resident, K, B, img, z, n_data, device):
     trainer.use_cuda_graph = graph_was
     total = sum(t for t, _ in table.values())
     top = sorted(table.items(), key=lambda kv: -kv[1][0])
-    res = {"kernel_share": {k: round(v[0] / total, 4) for k, v in top[:8]}}
-    name, (tms, calls) = top[0]
-    C = img[0]
-    # algorithmic FLOPs of the conv entry points per step (2*MACs), all layers they serve
-    conv_layers = [(32, C), (16, 32), (8, 32), (4, 32)] if img[1] == 64 else [(16, C), (8, 32), (4, 32)]
-    macs = sum(B * h * h * 32 * 16 * ch for h, ch in conv_layers)     # one pass over every conv layer
-    flops_per_step = {"dv_conv_down": 2 * 2 * macs, "dv_conv_up": 2 * 2 * macs, "dv_conv_wgrad": 2 * 2 * macs}
-    if name in flops_per_step:
-        # down: enc fwd + dec dgrad; up: dec fwd + enc dgrad (conv1 dgrad skipped); wgrad: enc + dec
-        f = flops_per_step[name]
-        if name == "dv_conv_up":
-            f -= 2 * B * conv_layers[0][0] ** 2 * 32 * 16 * C
-        if name == "dv_conv_down" or name == "dv_conv_up" or name == "dv_conv_wgrad":
-            ach = f * K / (tms / 1e3) / 1e12
-            res["roofline"] = {"kernel": name, "bound": "tensor", "achieved": round(ach, 3), "peak": pk["bf16_sustained"],
-                               "unit": "TFLOP/s", "frac": round(ach / pk["bf16_sustained"], 5), "traffic": None,
-                               "peak_source": pk["src"] + " bf16 sustained (kernel timed inside a long step)",
-                               "note": "fp32 CUDA-core path; algorithmic conv FLOPs of all layers served by this entry point",
-                               "launches_per_step": calls // K, "ms_per_step": round(tms / K, 4)}
-    if "roofline" not in res:
+    # share per entry point (all layers) and the single heaviest (entry point, layer geometry)
+    by_entry = {}
+    for k, (t, n) in table.items():
+        e = k.split("[")[0]
+        by_entry[e] = by_entry.get(e, 0.0) + t
+    res = {"kernel_share": {k: round(v / total, 4) for k, v in sorted(by_entry.items(), key=lambda kv: -kv[1])[:8]}}
+    conv = [(k, v) for k, v in top if k.startswith("dv_conv_") and "[" in k]
+    name, (tms, calls) = conv[0] if conv else top[0]
+    if conv:
+        import re
+        H, CH = map(int, re.search(r"H=(\d+),CH=(\d+)", name).groups())
+        per_call_ms = tms / calls
+        flops = 2.0 * B * H * H * 32 * 16 * CH                      # algorithmic MACs*2 of one launch (counted once,
+        ach = flops / (per_call_ms / 1e3) / 1e12                    # the kernels issue 3 tf32 passes per product)
+        # algorithmic HBM bytes of one launch: read the hi and lo side once, write the output once
+        hi_b, lo_b = 4.0 * B * 4 * H * H * CH, 4.0 * B * H * H * 32
+        alg_bytes = hi_b + lo_b + (0 if "wgrad" in name else 0)
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get(name)
+        res["roofline"] = {"kernel": name, "bound": "tensor", "achieved": round(ach, 3), "peak": pk["bf16_sustained"],
+                           "unit": "TFLOP/s", "frac": round(ach / pk["bf16_sustained"], 5), "traffic": traffic,
+                           "algorithmic_flops_per_launch": flops, "algorithmic_hbm_bytes_per_launch": alg_bytes,
+                           "us_per_launch": round(per_call_ms * 1e3, 2), "launches_per_step": calls // K,
+                           "peak_source": pk["src"] + " bf16 sustained (kernel timed inside a long step)",
+                           "note": "tcgen05 kind::tf32, error-compensated 3xTF32 (three tensor passes per algorithmic "
+                                   "product; FLOPs counted once); time = CUDA events around the C-ABI call on its stream"}
+    else:
         res["roofline"] = {"kernel": name, "bound": "hbm", "achieved": None, "peak": pk["hbm"], "unit": "GB/s", "frac": None,
                            "traffic": None, "ms_per_step": round(tms / K, 4)}
     # the named kernel, timed alone (burst peak): virtual bytes 4*B^2*D + 12*B*D + 16*B

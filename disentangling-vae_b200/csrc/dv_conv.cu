@@ -591,7 +591,7 @@ extern "C" {
 // CH in {1,3}: [0, 512*CH) ffma down, [512*CH, 1024*CH) ffma up, then the tcgen05 down operand
 // [kb][64][32] (kb = ceil(16*CH/32) K blocks)
 static size_t small_tc_floats(int CH) { return (size_t)((16 * CH + 31) / 32) * 64 * 32; }
-constexpr int kPackUpSmall = kTaps * 16 * 32;     // tcgen05 up operand of the CH small layers: [tap][hi 8 | lo 8][32 cl]
+constexpr int kPackUpSmall = 320 * 32;            // tcgen05 up operand of the CH small layers: [shift][phase-merged hi|lo rows][32 cl]
 size_t dv_conv_packed_floats(int CH) {
   return CH == 32 ? (size_t)kPackFfma + 2 * kPackTcSection
                   : (size_t)2 * kLoCh * CH * kTaps + small_tc_floats(CH) + kPackUpSmall;

@@ -891,10 +891,17 @@ struct HaloBarriers {
   float bias[32];
 };
 template <int CH> struct HaloCfg {
-  static constexpr int kBTapBytes = (CH == 32) ? kBTap : 16 * 128;
-  static constexpr int kBAll = kTaps * kBTapBytes;
+  // CH == 32: one 64-row (hi|lo) weight tile per tap, one 32-column accumulator per output phase.
+  // CH small: the four output phases are MERGED along N: one weight tile per SHIFT with rows
+  //           n = phase*CH + c (hi half) and kNH + phase*CH + c (lo half), zero where the tap is invalid,
+  //           so a shift costs 2 MMAs per K slice (a_hi, a_lo) instead of up to 8.
+  static constexpr int kN = (CH == 32) ? 32 : (CH == 1 ? 16 : 32);       // MMA N
+  static constexpr int kNH = kN / 2;                                       // small CH: offset of the lo half
+  static constexpr int kBTapBytes = (CH == 32) ? kBTap : kN * 128;         // per tap (CH 32) / per shift (small)
+  static constexpr int kBTiles = (CH == 32) ? kTaps : 9;
+  static constexpr int kBAll = (CH == 32) ? kTaps * kBTap : 40 * 1024;     // small: 9 tiles padded to 5 whole 64-row TMA boxes
   static constexpr int kSmem = kBAll + kHaloStages * kHaloStageBytes + 1024 + 512;
-  static constexpr int kAccPerPhase = (CH == 32) ? 32 : 16;
+  static constexpr int kAccPerPhase = 32;
 };
 
 template <int CH>
@@ -928,7 +935,7 @@ conv_up_halo_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b);
     mbar_arrive_expect_tx(&bars->b_full, C::kBAll);
     if (CH == 32) { for (int tap = 0; tap < kTaps; ++tap) tma_load_2d(Bs + tap * kBTap, &tmap_b, &bars->b_full, 0, tap * 64); }
-    else          { for (int h = 0; h < 4; ++h) tma_load_2d(Bs + h * 8192, &tmap_b, &bars->b_full, 0, h * 64); }
+    else          { for (int h = 0; h < C::kBAll / 8192; ++h) tma_load_2d(Bs + h * 8192, &tmap_b, &bars->b_full, 0, h * 64); }
     uint32_t t_seq = 0;
     for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++t_seq) {
       const int stage = t_seq % kHaloStages;
@@ -939,7 +946,7 @@ conv_up_halo_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
       tma_load_4d(Raw + stage * kHaloStageBytes, &tmap_a, &bars->raw_full[stage], 0, -1, i0 - 1, b0);
     }
   } else if (warp == 1) {          // whole warp, warp-uniform control flow; one elected lane issues
-    constexpr uint32_t idescN = umma_idesc_tf32(128, C::kAccPerPhase);
+    constexpr uint32_t idescN = umma_idesc_tf32(128, C::kN);
     mbar_wait(&bars->b_full, 0);
     uint32_t n = 0; int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
@@ -952,27 +959,33 @@ conv_up_halo_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         mbar_wait(&bars->a_ready[as], (n / kTsAStages) & 1u);
         tc_fence_after_sync();
         const uint32_t a_hi = tmem_base + kTsACol0 + as * 64, a_lo = a_hi + 32;
-        for (int ph = 0; ph < 2; ++ph) {
-          const int kh = ph + 1 - 2 * di;
-          if (kh < 0 || kh > 3) continue;
-          for (int pw = 0; pw < 2; ++pw) {
-            const int kw = pw + 1 - 2 * dj;
-            if (kw < 0 || kw > 3) continue;
-            const int pidx = ph * 2 + pw;
-            const uint32_t d = tmem_base + acc * 128 + pidx * C::kAccPerPhase;
-            const uint64_t b_hi = umma_desc_sw128_kmajor(smem_u32(Bs + (kh * 4 + kw) * C::kBTapBytes));
-            const uint32_t first = (inited >> pidx) & 1u;
-            inited |= 1u << pidx;
+        if (CH == 32) {
+          for (int ph = 0; ph < 2; ++ph) {
+            const int kh = ph + 1 - 2 * di;
+            if (kh < 0 || kh > 3) continue;
+            for (int pw = 0; pw < 2; ++pw) {
+              const int kw = pw + 1 - 2 * dj;
+              if (kw < 0 || kw > 3) continue;
+              const int pidx = ph * 2 + pw;
+              const uint32_t d = tmem_base + acc * 128 + pidx * C::kAccPerPhase;
+              const uint64_t b_hi = umma_desc_sw128_kmajor(smem_u32(Bs + (kh * 4 + kw) * C::kBTapBytes));
+              const uint32_t first = (inited >> pidx) & 1u;
+              inited |= 1u << pidx;
 #pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4) {
-              umma_tf32_ts(d, a_hi + 8 * k4, b_hi + 2 * k4, idescN, (first | (uint32_t)k4) != 0);
-              if (CH == 32) {
+              for (int k4 = 0; k4 < 4; ++k4) {
+                umma_tf32_ts(d, a_hi + 8 * k4, b_hi + 2 * k4, idescN, (first | (uint32_t)k4) != 0);
                 umma_tf32_ts(d, a_hi + 8 * k4, b_hi + (4096 >> 4) + 2 * k4, idescN, 1);      // a_hi * b_lo
                 umma_tf32_ts(d, a_lo + 8 * k4, b_hi + 2 * k4, idescN, 1);                    // a_lo * b_hi
-              } else {
-                umma_tf32_ts(d, a_lo + 8 * k4, b_hi + 2 * k4, idescN, 1);                    // a_lo * [b_hi | b_lo]
               }
             }
+          }
+        } else {
+          const uint32_t d = tmem_base + acc * 128;
+          const uint64_t b_s = umma_desc_sw128_kmajor(smem_u32(Bs + s * C::kBTapBytes));
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            umma_tf32_ts(d, a_hi + 8 * k4, b_s + 2 * k4, idescN, (s | k4) != 0);            // a_hi * [b_hi | b_lo], all phases
+            umma_tf32_ts(d, a_lo + 8 * k4, b_s + 2 * k4, idescN, 1);                        // a_lo * [b_hi | b_lo]
           }
         }
         umma_commit(&bars->a_empty[as]);
@@ -1026,10 +1039,9 @@ conv_up_halo_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
           }
         }
       } else {
-        // 4 phases x [a*b_hi (8) | a*b_lo (8)] = 64 columns; NCHW output, float2 per (channel, row parity)
-        uint32_t r0[32], r1[32];
+        // columns: phase*CH + c (a*b_hi) and kNH + phase*CH + c (a*b_lo); NCHW output, float2 per (channel, row parity)
+        uint32_t r0[32];
         tmem_ld_32x32b_x32(tbase, r0);
-        tmem_ld_32x32b_x32(tbase + 32, r1);
         tmem_ld_wait();
         tc_fence_before_sync();
         mbar_arrive(&bars->acc_empty[acc]);
@@ -1041,10 +1053,8 @@ conv_up_halo_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
               float v[2];
 #pragma unroll
               for (int pw = 0; pw < 2; ++pw) {
-                const int pidx = ph * 2 + pw;
-                const uint32_t* rr2 = (pidx < 2) ? r0 : r1;
-                const int o16 = (pidx & 1) * 16;
-                float x = (__uint_as_float(rr2[o16 + c]) + __uint_as_float(rr2[o16 + 8 + c])) + bars->bias[c];
+                const int col = (ph * 2 + pw) * CH + c;
+                float x = (__uint_as_float(r0[col]) + __uint_as_float(r0[C::kNH + col])) + bars->bias[c];
                 if (act == DV_ACT_RELU) x = fmaxf(x, 0.f);
                 else if (act == DV_ACT_SIGMOID) x = 1.f / (1.f + expf(-x));
                 v[pw] = x;
@@ -1101,15 +1111,30 @@ conv_up_halo_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
   if (warp == 2) { tc_fence_after_sync(); tmem_dealloc(tmem_base, 512); }
 }
 
-// up weights for CH small: [tap][16 rows][32 cl]; row r < 8: tf32 hi of w[cl][c = r][tap] (0 if r >= CH), r >= 8: lo
-__global__ void conv_pack_up_small_kernel(const float* __restrict__ w, float* __restrict__ wu, int CH) {
-  const int n = kTaps * 16 * 32;
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
-    const int cl = idx % 32, r = (idx / 32) % 16, tap = idx / (16 * 32);
-    const int c = r & 7;
-    float v = (c < CH) ? w[(cl * CH + c) * kTaps + tap] : 0.f;
-    const float hi = __uint_as_float(__float_as_uint(v) & kHiMask);
-    wu[idx] = (r < 8) ? hi : (v - hi);
+// up weights for CH small, one tile per SHIFT s = (di+1)*3 + (dj+1): [s][N rows][32 cl] with row
+// n = phase*CH + c -> tf32 hi of w[cl][c][kh][kw], row NH + n -> lo, where kh = ph+1-2di, kw = pw+1-2dj
+// (zero when the tap does not exist for that phase).  Padded with zero rows to 320 rows (5 whole TMA boxes).
+__global__ void conv_pack_up_small_kernel(const float* __restrict__ w, float* __restrict__ wu, int CH, int N) {
+  const int NH = N / 2;
+  const int total = 320 * 32;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int cl = idx % 32, row = idx / 32;
+    const int s = row / N, n = row % N;
+    float out = 0.f;
+    if (s < 9) {
+      const int half = n / NH, nn = n % NH;
+      const int pidx = nn / CH, c = nn % CH;
+      if (pidx < 4) {
+        const int di = s / 3 - 1, dj = s % 3 - 1;
+        const int kh = (pidx >> 1) + 1 - 2 * di, kw = (pidx & 1) + 1 - 2 * dj;
+        if (kh >= 0 && kh <= 3 && kw >= 0 && kw <= 3) {
+          const float v = w[(cl * CH + c) * kTaps + kh * 4 + kw];
+          const float hi = __uint_as_float(__float_as_uint(v) & kHiMask);
+          out = half == 0 ? hi : (v - hi);
+        }
+      }
+    }
+    wu[idx] = out;
   }
 }
 
@@ -1718,7 +1743,7 @@ int conv_wgrad_small_tc(const float* lo, const float* x, float* ws, int B, int H
 }
 
 int pack_up_small_tc(const float* w, float* wu, int CH, cudaStream_t st) {
-  conv_pack_up_small_kernel<<<8, 256, 0, st>>>(w, wu, CH);
+  conv_pack_up_small_kernel<<<12, 256, 0, st>>>(w, wu, CH, CH == 1 ? 16 : 32);
   return check_launch();
 }
 
@@ -1727,7 +1752,7 @@ static int launch_up_halo(const float* lo, const float* wu, const float* bias, c
                           HaloGeom g, int act, cudaStream_t st) {
   CUtensorMap ta, tb;
   if (!make_act_tmap(&ta, lo, g.B, g.H, g.W, g.Wp, g.TR + 2, g.TB, 1)) return DV_ERR_CUDA;
-  if (!make_w_tmap_rows(&tb, wu, CH == 32 ? kTaps * 64 : kTaps * 16)) return DV_ERR_CUDA;
+  if (!make_w_tmap_rows(&tb, wu, CH == 32 ? kTaps * 64 : 320)) return DV_ERR_CUDA;
   static bool attr = false;
   if (!attr) {
     if (cudaFuncSetAttribute(conv_up_halo_ts_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<CH>::kSmem) != cudaSuccess) {

@@ -130,13 +130,14 @@ def disable_profiling():
     return table
 
 
-def call(name, *args):
+def call(name, *args, tag=None):
+    """Invoke a C-ABI entry point.  `tag` (e.g. the layer geometry) only labels profiling records."""
     if _prof_events is not None and (PROFILE_ONLY is None or PROFILE_ONLY == name):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         check(getattr(lib(), name)(*args), name)
         e1.record()
-        _prof_events.append((name, e0, e1))
+        _prof_events.append((name if tag is None else "%s%s" % (name, tag), e0, e1))
         return
     check(getattr(lib(), name)(*args), name)
 

@@ -55,13 +55,15 @@ def conv_pack(w, CH):
 
 def conv_down(hi, wp, bias, mask, B, H, W, CH, nchw, act):
     lo = _new((B, H, W, LO_CH), hi)
-    call("dv_conv_down", ptr(hi), ptr(wp), ptr(bias), ptr(mask), ptr(lo), B, H, W, CH, nchw, act, stream())
+    call("dv_conv_down", ptr(hi), ptr(wp), ptr(bias), ptr(mask), ptr(lo), B, H, W, CH, nchw, act, stream(),
+         tag="[H=%d,CH=%d]" % (H, CH))
     return lo
 
 
 def conv_up(lo, wp, bias, mask, B, H, W, CH, nchw, act):
     hi = _new((B, CH, 2 * H, 2 * W) if nchw else (B, 2 * H, 2 * W, CH), lo)
-    call("dv_conv_up", ptr(lo), ptr(wp), ptr(bias), ptr(mask), ptr(hi), B, H, W, CH, nchw, act, stream())
+    call("dv_conv_up", ptr(lo), ptr(wp), ptr(bias), ptr(mask), ptr(hi), B, H, W, CH, nchw, act, stream(),
+         tag="[H=%d,CH=%d]" % (H, CH))
     return hi
 
 
@@ -71,7 +73,8 @@ def conv_wgrad(lo, hi, B, H, W, CH, nchw, want_dbias_lo):
     ws = _scratch("wgrad", nbytes, lo.device)
     dw = _new((LO_CH, CH, 4, 4), lo)
     db = _new((LO_CH,), lo) if want_dbias_lo else None
-    call("dv_conv_wgrad", ptr(lo), ptr(hi), ptr(dw), ptr(db), ptr(ws), nbytes, B, H, W, CH, nchw, stream())
+    call("dv_conv_wgrad", ptr(lo), ptr(hi), ptr(dw), ptr(db), ptr(ws), nbytes, B, H, W, CH, nchw, stream(),
+         tag="[H=%d,CH=%d]" % (H, CH))
     return dw, db
 
 
