@@ -1094,13 +1094,16 @@ conv_up_halo_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             l[c * 4 + e] = __float_as_uint(__uint_as_float(vv[e]) - __uint_as_float(hb));
           }
         }
-        mbar_arrive(&bars->raw_empty[stage]);                      // 9 x 128 arrivals release the halo tile
         mbar_wait(&bars->a_empty[as], ((n / kTsAStages) & 1u) ^ 1u);
         tc_fence_after_sync();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + kTsACol0 + as * 64;
         tmem_st_32x32b_x32(taddr, h);
         tmem_st_32x32b_x32(taddr + 32, l);
         tmem_st_wait();
+        // Release the halo tile only now: the tcgen05.st above consumed every loaded value, so the shared-memory
+        // reads have certainly completed (an arrive issued right after the loads can overtake them and let the
+        // next TMA overwrite the tile under the reader).  9 x 128 arrivals free the stage.
+        mbar_arrive(&bars->raw_empty[stage]);
         tc_fence_before_sync();
         mbar_arrive(&bars->a_ready[as]);
       }

@@ -49,6 +49,7 @@ CONV_CASES = [  # (B, H(lo), CH)
     (170, 16, 32),      # 340 tiles of 128 pixels: several tiles per persistent CTA (pipeline phase wrap-around)
     (301, 8, 32), (1201, 4, 32),
     (40, 32, 1), (40, 32, 3),      # image-boundary layers, 320 tiles
+    (100, 32, 1),                  # halo up kernel: 1100 tiles, > 5 per CTA (every shared-memory stage is reused)
 ]
 
 
@@ -110,7 +111,7 @@ def test_conv_wgrad_matches_autograd(ops, B, H, CH):
     assert torch.equal(dw, dw2)
 
 
-@pytest.mark.parametrize("B,H", [(16, 16), (9, 8), (40, 4), (200, 16)])
+@pytest.mark.parametrize("B,H", [(16, 16), (9, 8), (40, 4), (200, 16), (330, 16), (700, 8)])
 def test_conv32_kernels_fp32_grade_accuracy(ops, B, H):
     """The tensor-core (3xTF32) path must stay at fp32-grade accuracy, not tf32-grade: error against an
     fp64 reference <= 4e-6 of the output scale (plain fp32 lands around 5e-7, single-pass tf32 at 5e-4)."""
