@@ -422,7 +422,8 @@ conv_wgrad32_tc_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  const uint32_t tmem_base = bars->tmem_base;
+  if (bars->tmem_base != 0u) __trap();                       // whole TMEM is ours: base column 0
+  constexpr uint32_t tmem_base = 0u;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_hi); prefetch_tmap(&tmap_lo);
@@ -620,7 +621,10 @@ conv_down32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   TsBarriers* bars = reinterpret_cast<TsBarriers*>(Raw + kTsRawStages * kATile);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   ts_init(bars, bias, warp);
-  const uint32_t tmem_base = bars->tmem_base;
+  // All 512 columns are ours (1 CTA/SM), so the allocation starts at column 0.  Using the literal keeps every
+  // tensor-memory address a compile-time/warp-uniform value (no per-MMA register -> uniform-register moves).
+  if (bars->tmem_base != 0u) __trap();
+  constexpr uint32_t tmem_base = 0u;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b);
@@ -739,7 +743,10 @@ conv_up32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   TsBarriers* bars = reinterpret_cast<TsBarriers*>(Raw + kTsRawStages * kATile);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   ts_init(bars, bias, warp);
-  const uint32_t tmem_base = bars->tmem_base;
+  // All 512 columns are ours (1 CTA/SM), so the allocation starts at column 0.  Using the literal keeps every
+  // tensor-memory address a compile-time/warp-uniform value (no per-MMA register -> uniform-register moves).
+  if (bars->tmem_base != 0u) __trap();
+  constexpr uint32_t tmem_base = 0u;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b);
@@ -929,7 +936,8 @@ conv_up_halo_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  const uint32_t tmem_base = bars->tmem_base;
+  if (bars->tmem_base != 0u) __trap();                       // whole TMEM is ours: base column 0 (see the TS kernels)
+  constexpr uint32_t tmem_base = 0u;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b);
