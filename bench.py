@@ -206,6 +206,10 @@ def run_ours(args):
         out.update(roof)
         if world == 1 and not args.no_cpu_baseline:
             try:
+                out["parity"] = parity_check(trainer, args.workload, device)
+            except Exception as e:
+                out["parity_error"] = repr(e)
+            try:
                 out["cpu_baseline"] = cpu_baseline(args.workload, budget_s=20.0)
             except Exception as e:
                 out["cpu_baseline_error"] = repr(e)
@@ -291,6 +295,40 @@ def kernel_rooflines(trainer, resident, K, B, img, z, n_data, device):
                                   "virtual_bytes": vbytes, "compulsory_bytes": 12 * Bk * Dk + 16 * Bk, "traffic": None,
                                   "l2": "256 MB flush before every timed launch"}
     return res
+
+
+def parity_check(trainer, workload, device):
+    """Full-size forward + loss of the trained-so-far model on one seeded batch: CUDA path vs the CPU oracle
+    (same weights, same input, same injected noise).  Guards the timed numbers against silently wrong kernels."""
+    from collections import OrderedDict
+    from disvae.models.losses import get_loss_f
+    from oracle import disvae_oracle as O
+    loss_name, img, B, z, n_data, lkw, lr = WORKLOADS[workload]
+    g = torch.Generator().manual_seed(4321)
+    x = torch.rand(B, *img, generator=g)
+    eps = torch.randn(B, z, generator=g)
+    model = trainer.model
+    was_training = model.training
+    model.train()
+    kw = dict(rec_dist="bernoulli", reg_anneal=0, betaH_B=4, betaB_initC=0, betaB_finC=25, betaB_G=100, factor_G=6,
+              latent_dim=z, lr_disc=5e-5, btcvae_A=1, btcvae_B=6, btcvae_G=1, device=device, n_data=n_data)
+    kw.update(lkw)
+    lf = get_loss_f(loss_name, **kw)
+    with torch.no_grad():
+        xd = x.to(device)
+        recon, (mu, lv), zz = model(xd, eps=eps.to(device))
+        loss = lf(xd, recon, (mu, lv), True, None, latent_sample=zz).item()
+        p = OrderedDict((k, v.detach().cpu()) for k, v in model.state_dict().items())
+        ro, (mo, lo), zo = O.vae_forward(p, x, eps)
+        if loss_name == "btcvae":
+            lo_, _ = O.loss_btcvae(x, ro, mo, lo, zo, n_data, kw["btcvae_A"], kw["btcvae_B"], kw["btcvae_G"], "bernoulli", 1, 0)
+        else:
+            lo_, _ = O.loss_betaH(x, ro, mo, lo, kw["betaH_B"] if loss_name == "betaH" else 1, "bernoulli", 1, 0)
+    model.train(was_training)
+    rel = abs(loss - lo_.item()) / abs(lo_.item())
+    rerr = (recon.cpu() - ro).abs().max().item()
+    return {"loss_cuda": loss, "loss_oracle": lo_.item(), "loss_rel_err": rel, "recon_max_abs_err": rerr,
+            "batch": B, "ok": bool(rel < 1e-4 and rerr < 1e-4)}
 
 
 def oracle_job(workload, batch=None):
