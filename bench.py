@@ -34,7 +34,13 @@ WORKLOADS = {
     "c2": ("btcvae", (1, 64, 64), 1024, 10, 737280, dict(btcvae_A=1, btcvae_B=6, btcvae_G=1), 5e-4),
     "c3": ("betaH", (3, 64, 64), 512, 10, 202599, dict(betaH_B=10), 5e-4),
     "c5": ("btcvae", (3, 64, 64), 256, 64, 202599, dict(btcvae_A=1, btcvae_B=6, btcvae_G=1), 5e-4),
+    "c1": ("VAE", (1, 32, 32), 64, 10, 60000, dict(), 5e-4),
+    # FactorVAE: `-b 256` doubled by main.py:191-194 -> loader batch 512 (two halves of 256); factor_celeba gamma 6.4
+    "c4": ("factor", (3, 64, 64), 512, 10, 202599, dict(factor_G=6.4, lr_disc=1e-5), 1e-4),
 }
+WORKLOAD_NAMES = {"c1": "BASELINE.json configs[0]: VAE mnist-shape", "c2": "BASELINE.json configs[1]: btcvae dsprites-shape",
+                  "c3": "BASELINE.json configs[2]: betaH celeba-shape", "c4": "BASELINE.json configs[3]: factor celeba-shape",
+                  "c5": "BASELINE.json configs[4]: btcvae celeba-shape z=64 (one GPU's shard of 256)"}
 # algorithmic work per image, forward + backward: conv FLOPs
 CONV_FLOP_PER_IMG = {(1, 64, 64): 71.30e6, (3, 64, 64): 81.79e6, (1, 32, 32): 17.04e6}
 N_ROTATE = 8            # distinct resident batches cycled through (8 x 16.8 MB > 126 MB L2)
@@ -182,7 +188,7 @@ def run_ours(args):
             "metric": "images/sec", "value": round(value, 1), "unit": "img/s", "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": round(ms / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic (torch.rand, seed 1234+rank); random-init weights (seed 1234)",
-            "config": {"workload": "BASELINE.json configs[1]: btcvae dsprites-shape" if args.workload == "c2" else args.workload,
+            "config": {"workload": WORKLOAD_NAMES[args.workload],
                        "loss": loss_name, "img_size": list(img), "batch_per_gpu": B, "global_batch": B * world,
                        "latent_dim": z, "n_data": n_data, "rec_dist": "bernoulli", "optimizer": "Adam lr %g" % lr,
                        "parallelism": "dp%d" % world if world > 1 else "single",
@@ -313,17 +319,18 @@ def parity_check(trainer, workload, device):
     kw = dict(rec_dist="bernoulli", reg_anneal=0, betaH_B=4, betaB_initC=0, betaB_finC=25, betaB_G=100, factor_G=6,
               latent_dim=z, lr_disc=5e-5, btcvae_A=1, btcvae_B=6, btcvae_G=1, device=device, n_data=n_data)
     kw.update(lkw)
-    lf = get_loss_f(loss_name, **kw)
+    cmp_loss = "VAE" if loss_name == "factor" else loss_name      # factor: compare the VAE part (rec + KL) of the step
+    lf = get_loss_f(cmp_loss, **kw)
     with torch.no_grad():
         xd = x.to(device)
         recon, (mu, lv), zz = model(xd, eps=eps.to(device))
         loss = lf(xd, recon, (mu, lv), True, None, latent_sample=zz).item()
         p = OrderedDict((k, v.detach().cpu()) for k, v in model.state_dict().items())
         ro, (mo, lo), zo = O.vae_forward(p, x, eps)
-        if loss_name == "btcvae":
+        if cmp_loss == "btcvae":
             lo_, _ = O.loss_btcvae(x, ro, mo, lo, zo, n_data, kw["btcvae_A"], kw["btcvae_B"], kw["btcvae_G"], "bernoulli", 1, 0)
         else:
-            lo_, _ = O.loss_betaH(x, ro, mo, lo, kw["betaH_B"] if loss_name == "betaH" else 1, "bernoulli", 1, 0)
+            lo_, _ = O.loss_betaH(x, ro, mo, lo, kw["betaH_B"] if cmp_loss == "betaH" else 1, "bernoulli", 1, 0)
     model.train(was_training)
     rel = abs(loss - lo_.item()) / abs(lo_.item())
     rerr = (recon.cpu() - ro).abs().max().item()
@@ -342,10 +349,16 @@ def oracle_job(workload, batch=None):
     cfg.update(lkw)
     x = torch.rand(B, *img)
     state = dict(step=0)
+    if loss_name == "factor":
+        dp = O.make_leaf_params(O.init_disc_params(z))
+        opt_d = O.make_adam(dp, cfg["lr_disc"], betas=(0.5, 0.9))
 
     def step():
         state["step"] += 1
-        O.train_step(p, opt, x, loss_name, cfg, state["step"])
+        if loss_name == "factor":
+            O.factor_step(p, dp, opt, opt_d, x, cfg, state["step"])
+        else:
+            O.train_step(p, opt, x, loss_name, cfg, state["step"])
     return step, B
 
 
@@ -393,7 +406,7 @@ def run_reference(args):
     out = {"impl": "reference", "metric": "images/sec", "value": v, "unit": "img/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "BASELINE.json configs[1]: btcvae dsprites-shape" if args.workload == "c2" else args.workload,
+           "config": {"workload": WORKLOAD_NAMES[args.workload],
                       "loss": loss_name, "img_size": list(img), "batch_per_gpu": B, "latent_dim": z, "n_data": n_data},
            "cpu_baseline": {"value": v, "unit": "img/s", "cores": cores, "kind": "port", "sample": sample,
                             "torch": torch.__version__},
