@@ -174,15 +174,40 @@ static int wgrad_splits(int M, int N, int K) {
 
 }  // namespace dv
 
+namespace dv { namespace ltc {
+size_t fwd_workspace_bytes(int M, int N, int K);
+size_t dgrad_workspace_bytes(int M, int N, int K);
+int fwd(const float* x, const float* w, const float* bias, float* y, int M, int N, int K, int act, float slope, float* ws,
+        cudaStream_t st);
+int dgrad(const float* g, const float* w, const float* mask_src, float* dx, int M, int N, int K, int act, float slope, float* ws,
+          cudaStream_t st);
+bool wgrad_ok(int M, int N, int K);
+size_t wgrad_workspace_bytes(int M, int N, int K);
+int wgrad(const float* g, const float* x, float* dw, float* ws, int M, int N, int K, int* nsplit, cudaStream_t st);
+} }
+
 using namespace dv;
 
 extern "C" {
 
+size_t dv_linear_fwd_workspace_bytes(int M, int N, int K) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  return ltc::fwd_workspace_bytes(M, N, K);
+}
+size_t dv_linear_dgrad_workspace_bytes(int M, int N, int K) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  return ltc::dgrad_workspace_bytes(M, N, K);
+}
+
 int dv_linear_fwd(const float* x, const float* w, const float* bias, float* y, int M, int N, int K,
-                  int act, float slope, void* stream) {
+                  int act, float slope, void* workspace, void* stream) {
   if (!x || !w || !y) return DV_ERR_BAD_ARG;
   if (M <= 0 || N <= 0 || K <= 0) return DV_ERR_BAD_SHAPE;
   if (act < DV_ACT_NONE || act > DV_ACT_LEAKY) return DV_ERR_BAD_ARG;
+  if (ltc::fwd_workspace_bytes(M, N, K) > 0) {
+    if (!workspace) return DV_ERR_WORKSPACE;
+    return ltc::fwd(x, w, bias, y, M, N, K, act, slope, reinterpret_cast<float*>(workspace), as_stream(stream));
+  }
   GemmEpilogue ep{bias, nullptr, act, slope};
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
   gemm_kernel<true, true><<<grid, 256, 0, as_stream(stream)>>>(x, w, y, M, N, K, K, 1, 1, K, ep, K);
@@ -190,9 +215,13 @@ int dv_linear_fwd(const float* x, const float* w, const float* bias, float* y, i
 }
 
 int dv_linear_dgrad(const float* g, const float* w, const float* mask_src, float* dx, int M, int N, int K,
-                    int act, float slope, void* stream) {
+                    int act, float slope, void* workspace, void* stream) {
   if (!g || !w || !dx) return DV_ERR_BAD_ARG;
   if (M <= 0 || N <= 0 || K <= 0) return DV_ERR_BAD_SHAPE;
+  if (ltc::dgrad_workspace_bytes(M, N, K) > 0) {
+    if (!workspace) return DV_ERR_WORKSPACE;
+    return ltc::dgrad(g, w, mask_src, dx, M, N, K, act, slope, reinterpret_cast<float*>(workspace), as_stream(stream));
+  }
   GemmEpilogue ep{nullptr, mask_src, mask_src ? act : DV_ACT_NONE, slope};
   dim3 grid((K + BN - 1) / BN, (M + BM - 1) / BM);
   gemm_kernel<true, false><<<grid, 256, 0, as_stream(stream)>>>(g, w, dx, M, K, N, N, 1, K, 1, ep, N);
@@ -200,6 +229,8 @@ int dv_linear_dgrad(const float* g, const float* w, const float* mask_src, float
 }
 
 size_t dv_linear_wgrad_workspace_bytes(int M, int N, int K) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if (ltc::wgrad_ok(M, N, K)) return ltc::wgrad_workspace_bytes(M, N, K);
   const int S = wgrad_splits(M, N, K);
   return S > 1 ? (size_t)S * N * K * sizeof(float) : 0;
 }
@@ -208,10 +239,26 @@ int dv_linear_wgrad(const float* g, const float* x, float* dw, float* dbias, int
                     void* stream) {
   if (!g || !x || !dw) return DV_ERR_BAD_ARG;
   if (M <= 0 || N <= 0 || K <= 0) return DV_ERR_BAD_SHAPE;
+  cudaStream_t st = as_stream(stream);
+  if (ltc::wgrad_ok(M, N, K)) {
+    if (ltc::wgrad_workspace_bytes(M, N, K) > 0 && !workspace) return DV_ERR_WORKSPACE;
+    int S = 1;
+    int rc = ltc::wgrad(g, x, dw, reinterpret_cast<float*>(workspace), M, N, K, &S, st);
+    if (rc != DV_OK) return rc;
+    if (S > 1) {
+      const long long n = (long long)N * K;
+      int gr = (int)((n + 255) / 256); if (gr > 4 * kNumSMs) gr = 4 * kNumSMs;
+      splitk_reduce_kernel<<<gr, 256, 0, st>>>(reinterpret_cast<const float*>(workspace), dw, n, S);
+      rc = check_launch();
+      if (rc != DV_OK) return rc;
+    }
+    if (!dbias) return rc;
+    colsum_kernel<<<(N + 31) / 32, 256, 0, st>>>(g, dbias, M, N);
+    return check_launch();
+  }
   const int S = wgrad_splits(M, N, K);
   if (S > 1 && !workspace) return DV_ERR_WORKSPACE;
   GemmEpilogue ep{nullptr, nullptr, DV_ACT_NONE, 0.f};
-  cudaStream_t st = as_stream(stream);
   const int per = ((M + S - 1) / S + BK - 1) / BK * BK;
   dim3 grid((K + BN - 1) / BN, (N + BM - 1) / BM, S);
   float* target = S > 1 ? reinterpret_cast<float*>(workspace) : dw;

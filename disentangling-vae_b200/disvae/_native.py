@@ -35,8 +35,10 @@ SIGNATURES = {
     "dv_channel_sum": (I, [P, P, LL, I, I, I, P, P]),
     "dv_flat_transpose": (I, [P, P, I, I, I, I, P]),
     "dv_act_bwd": (I, [P, P, P, LL, I, F, P]),
-    "dv_linear_fwd": (I, [P, P, P, P, I, I, I, I, F, P]),
-    "dv_linear_dgrad": (I, [P, P, P, P, I, I, I, I, F, P]),
+    "dv_linear_fwd_workspace_bytes": (SZ, [I, I, I]),
+    "dv_linear_dgrad_workspace_bytes": (SZ, [I, I, I]),
+    "dv_linear_fwd": (I, [P, P, P, P, I, I, I, I, F, P, P]),
+    "dv_linear_dgrad": (I, [P, P, P, P, I, I, I, I, F, P, P]),
     "dv_linear_wgrad_workspace_bytes": (SZ, [I, I, I]),
     "dv_linear_wgrad": (I, [P, P, P, P, I, I, I, P, P]),
     "dv_reparam_fwd": (I, [P, P, I, I, P, ULL, P, P, P, I, I, P]),

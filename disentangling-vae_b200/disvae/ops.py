@@ -101,7 +101,9 @@ def linear_fwd(x, w, b, act, slope=0.0):
     M, K = x.shape
     Nn = w.shape[0]
     y = _new((M, Nn), x)
-    call("dv_linear_fwd", ptr(x), ptr(w), ptr(b), ptr(y), M, Nn, K, act, slope, stream())
+    nbytes = N.lib().dv_linear_fwd_workspace_bytes(M, Nn, K)
+    ws = _scratch("lin_pack", nbytes, x.device) if nbytes else None
+    call("dv_linear_fwd", ptr(x), ptr(w), ptr(b), ptr(y), M, Nn, K, act, slope, ptr(ws), stream())
     return y
 
 
@@ -109,7 +111,9 @@ def linear_dgrad(g, w, mask_src, act, slope=0.0):
     M, Nn = g.shape
     K = w.shape[1]
     dx = _new((M, K), g)
-    call("dv_linear_dgrad", ptr(g), ptr(w), ptr(mask_src), ptr(dx), M, Nn, K, act, slope, stream())
+    nbytes = N.lib().dv_linear_dgrad_workspace_bytes(M, Nn, K)
+    ws = _scratch("lin_pack", nbytes, g.device) if nbytes else None
+    call("dv_linear_dgrad", ptr(g), ptr(w), ptr(mask_src), ptr(dx), M, Nn, K, act, slope, ptr(ws), stream())
     return dx
 
 

@@ -97,12 +97,17 @@ int dv_act_bwd(const float* dy, const float* y, float* g, long long n, int act, 
  * Replaces nn.Linear + activation: encoders.py:81-86, decoders.py:71-73, discriminator.py:63-68.
  * x[M,K], w[N,K] (torch layout), y[M,N].  slope is the LeakyReLU negative slope.
  */
+/* Shapes whose activation rows are 16-byte pitched run on the tensor cores (tcgen05, 3xTF32) and need
+ * a scratch buffer for the hi/lo split weight planes; the query returns 0 when the FFMA path is used
+ * (workspace may then be NULL). */
+size_t dv_linear_fwd_workspace_bytes(int M, int N, int K);
+size_t dv_linear_dgrad_workspace_bytes(int M, int N, int K);
 int dv_linear_fwd(const float* x, const float* w, const float* bias, float* y, int M, int N, int K,
-                  int act, float slope, void* stream);
+                  int act, float slope, void* workspace, void* stream);
 /* dx[M,K] = (g[M,N] . w[N,K]) * act'(mask_src[M,K]); mask_src is the POST-activation output
  * of the previous layer (NULL: no mask); act in {NONE, RELU, LEAKY}. */
 int dv_linear_dgrad(const float* g, const float* w, const float* mask_src, float* dx, int M, int N,
-                    int K, int act, float slope, void* stream);
+                    int K, int act, float slope, void* workspace, void* stream);
 /* dw[N,K] = g^T . x ; dbias[N] = column sums of g (may be NULL).  Small N*K problems are split over
  * the batch (deterministic split-K); workspace may be NULL when the query returns 0. */
 size_t dv_linear_wgrad_workspace_bytes(int M, int N, int K);

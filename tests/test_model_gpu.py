@@ -31,11 +31,14 @@ def assert_close(a, b, tol=RTOL, what=""):
 
 
 def digest_close(t, dg, rtol, atol=0.0):
-    """`atol`: extra absolute slack per element (and 4x that on the sums) -- see the Adam note below."""
+    """`atol`: extra absolute slack per element (and 4x that on the sums) -- see the Adam note below.
+    Head/tail elements are held to rtol of the TENSOR's scale (its mean magnitude, or the sample's own max if
+    larger): rounding differences are absolute at the tensor's scale, a sample of 8 elements can be 100x smaller."""
     t = t.detach().double().flatten().cpu()
     assert t.numel() == dg["n"]
+    scale = dg["abssum"] / max(1, dg["n"])
     for ours, ref in ((t[:8].float(), dg["head"]), (t[-8:].float(), dg["tail"])):
-        assert torch.allclose(ours, ref, rtol=rtol, atol=1e-7 + atol + rtol * ref.abs().max().item())
+        assert torch.allclose(ours, ref, rtol=rtol, atol=1e-7 + atol + rtol * max(scale, ref.abs().max().item()))
     tol = rtol * max(1.0, dg["abssum"]) + 4 * atol
     assert abs(t.sum().item() - dg["sum"]) <= tol
     assert abs(t.abs().sum().item() - dg["abssum"]) <= tol
