@@ -8,8 +8,8 @@ Adam) over one synthetic batch.  Workload at every N: BASELINE.json configs[1]
 (btcvae, 1x64x64, batch 1024 PER GPU, z=10, bernoulli, MSS, Adam lr 5e-4) -- weak scaling.
 
   value  : images/s with the batches already resident in HBM (CUDA events, max over ranks)
-  e2e    : the same through disvae.Trainer._train_iteration with PINNED HOST batches: H2D copy of
-           the batch and D2H read of the loss inside the timed region, every step
+  e2e    : the same through disvae.Trainer._train_epoch over a loader of PINNED HOST batches: H2D copy of
+           every batch and D2H copy of every step's loss inside the timed region (copies overlap compute)
   roofline / roofline_logdensity / cpu_baseline / clocks / gpu_launches : see DESIGN.md section 6
 
 --impl reference times the CPU oracle port (oracle/disvae_oracle.py, validated against the
@@ -162,7 +162,10 @@ def run_ours(args):
         return ms.item()
 
     step_res = lambda i: trainer._step(resident[i % N_ROTATE], None)            # noqa: E731
-    step_e2e = lambda i: trainer._train_iteration(host[i % N_ROTATE], None)     # noqa: E731
+    # end to end: the Trainer's epoch loop over a loader of PINNED HOST batches (H2D of every batch on the Trainer's
+    # copy stream one step ahead, async D2H of every step's loss, one blocking read of the epoch mean at the end)
+    loader = [(host[i % N_ROTATE], None) for i in range(K)]
+    epoch_e2e = lambda: trainer._train_epoch(loader, None, 0)                    # noqa: E731
 
     for i in range(Wm):
         step_res(i)
@@ -173,9 +176,8 @@ def run_ours(args):
     ms = timed(step_res, K)
     launches = _native.launch_count() - l0
     clocks = clk.stop() if rank == 0 else None
-    for i in range(2):
-        step_e2e(i)
-    ms_e2e = timed(step_e2e, K)
+    trainer._train_epoch(loader[:3], None, 0)
+    ms_e2e = timed(lambda i: epoch_e2e(), 1)
 
     out = None
     if rank == 0:
@@ -196,7 +198,7 @@ def run_ours(args):
                            N_ROTATE, N_ROTATE * B * img[0] * img[1] * img[2] * 4 / 1e6)},
             "e2e": {"value": round(e2e_v, 1), "unit": "img/s", "h2d_bytes_per_step": B * img[0] * img[1] * img[2] * 4,
                     "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / K, 4),
-                    "api": "disvae.Trainer._train_iteration(pinned host batch) -> float"},
+                    "api": "disvae.Trainer._train_epoch(loader of pinned host batches) -> mean loss (float)"},
             "cuda_graph": bool(trainer._graphs),
             "gpu_launches": int(launches),
             "conv_flop_fraction_of_bf16_peak": round(value / world * conv_flop / (pk["bf16_sustained"] * 1e12), 5),

@@ -432,14 +432,23 @@ conv_wgrad_small_kernel(const float* __restrict__ lo, const float* __restrict__ 
 }
 
 // dw[cl][c][tap] = sum_s ws[s][tap*CH + c][cl] ; dbias[cl] = sum_s ws[s][16*CH][cl]
-__global__ void conv_wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw,
-                                         float* __restrict__ dbias, int CH, int nsplit) {
+// block = 32 outputs x 8 split groups: group j sums splits j, j+8, ... (coalesced over the outputs), the eight group
+// sums are combined in a fixed order -> deterministic for a given nsplit.
+__global__ void __launch_bounds__(256)
+conv_wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, float* __restrict__ dbias, int CH, int nsplit) {
+  __shared__ float part[8][33];
   const int K = kTaps * CH;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (K + 1) * kLoCh) return;
-  const int cl = idx % kLoCh, k = idx / kLoCh;
+  const int n = (K + 1) * kLoCh;
+  const int o = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int idx = blockIdx.x * 32 + o;
   float s = 0.f;
-  for (int sp = 0; sp < nsplit; ++sp) s += ws[(long long)sp * (K + 1) * kLoCh + idx];
+  if (idx < n)
+    for (int sp = grp; sp < nsplit; sp += 8) s += ws[(long long)sp * n + idx];
+  part[grp][o] = s;
+  __syncthreads();
+  if (grp != 0 || idx >= n) return;
+  s = ((part[0][o] + part[1][o]) + (part[2][o] + part[3][o])) + ((part[4][o] + part[5][o]) + (part[6][o] + part[7][o]));
+  const int cl = idx % kLoCh, k = idx / kLoCh;
   if (k == K) { if (dbias) dbias[cl] = s; }
   else {
     const int tap = k / CH, c = k % CH;
@@ -563,6 +572,12 @@ int conv_wgrad32_tc(const float* lo, const float* hi, float* ws, int B, int H, i
 int conv_up32_tc(const float* lo, const float* wu_packed, const float* bias, const float* mask, float* hi,
                  int B, int H, int W, int act, cudaStream_t st);
 }  // namespace tc
+namespace c2i {
+size_t packed_floats(int CH);
+int pack(const float* w, float* wp, int CH, cudaStream_t st);
+bool shape_ok(int B, int H, int W, int CH);
+int conv_up(const float* lo, const float* wp, const float* bias, float* hi, int B, int H, int W, int CH, int act, cudaStream_t st);
+}  // namespace c2i
 
 // packed-weight sections for CH == 32 (floats): [0,16K) ffma down, [16K,32K) ffma up,
 // [32K,64K) tcgen05 down (hi|lo), [64K,96K) tcgen05 up (hi|lo)
@@ -594,7 +609,7 @@ static size_t small_tc_floats(int CH) { return (size_t)((16 * CH + 31) / 32) * 6
 constexpr int kPackUpSmall = 320 * 32;            // tcgen05 up operand of the CH small layers: [shift][phase-merged hi|lo rows][32 cl]
 size_t dv_conv_packed_floats(int CH) {
   return CH == 32 ? (size_t)kPackFfma + 2 * kPackTcSection
-                  : (size_t)2 * kLoCh * CH * kTaps + small_tc_floats(CH) + kPackUpSmall;
+                  : (size_t)2 * kLoCh * CH * kTaps + small_tc_floats(CH) + kPackUpSmall + c2i::packed_floats(CH);
 }
 
 int dv_conv_pack_weights(const float* w, float* w_packed, int CH, void* stream) {
@@ -607,7 +622,9 @@ int dv_conv_pack_weights(const float* w, float* w_packed, int CH, void* stream) 
   if (CH != 32) {
     rc = tc::pack_small_tc(w, w_packed + 2 * kLoCh * CH * kTaps, CH, as_stream(stream));
     if (rc != DV_OK) return rc;
-    return tc::pack_up_small_tc(w, w_packed + 2 * kLoCh * CH * kTaps + small_tc_floats(CH), CH, as_stream(stream));
+    rc = tc::pack_up_small_tc(w, w_packed + 2 * kLoCh * CH * kTaps + small_tc_floats(CH), CH, as_stream(stream));
+    if (rc != DV_OK) return rc;
+    return c2i::pack(w, w_packed + 2 * kLoCh * CH * kTaps + small_tc_floats(CH) + kPackUpSmall, CH, as_stream(stream));
   }
   return tc::pack_tc(w, w_packed + kPackFfma, w_packed + kPackFfma + kPackTcSection, as_stream(stream));
 }
@@ -648,6 +665,9 @@ int dv_conv_up(const float* lo, const float* w_packed, const float* bias, const 
   if (act != DV_ACT_NONE && act != DV_ACT_RELU && act != DV_ACT_SIGMOID) return DV_ERR_BAD_ARG;
   if ((CH == 32) == (hi_nchw != 0)) return DV_ERR_BAD_SHAPE;
   const float* wu = w_packed + kLoCh * CH * kTaps;
+  if (CH != 32 && !mask && use_tc("c2i") && c2i::shape_ok(B, H, W, CH))
+    return c2i::conv_up(lo, w_packed + 2 * kLoCh * CH * kTaps + small_tc_floats(CH) + kPackUpSmall, bias, hi, B, H, W, CH, act,
+                        as_stream(stream));
   if (use_tc("halo") && (CH != 32 || act != DV_ACT_SIGMOID) && W + 2 <= 40)
     return tc::conv_up_halo(lo, CH == 32 ? w_packed + kPackFfma + kPackTcSection
                                           : w_packed + 2 * kLoCh * CH * kTaps + small_tc_floats(CH),
@@ -696,7 +716,7 @@ int dv_conv_wgrad(const float* lo, const float* hi, float* dw, float* dbias_lo, 
                       : tc::conv_wgrad_small_tc(lo, hi, ws, B, H, W, CH, &nsplit_tc, st);
     if (rc != DV_OK) return rc;
     const int n = (kTaps * CH + 1) * kLoCh;
-    conv_wgrad_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(ws, dw, dbias_lo, CH, nsplit_tc);
+    conv_wgrad_reduce_kernel<<<(n + 31) / 32, 256, 0, st>>>(ws, dw, dbias_lo, CH, nsplit_tc);
     return check_launch();
   }
   if (CH == 32)      conv_wgrad32_kernel<<<ns, kWgWarps * 32, 0, st>>>(lo, hi, ws, B, H, W, chunk);
@@ -705,7 +725,7 @@ int dv_conv_wgrad(const float* lo, const float* hi, float* dw, float* dbias_lo, 
   int rc = check_launch();
   if (rc != DV_OK) return rc;
   const int n = (kTaps * CH + 1) * kLoCh;
-  conv_wgrad_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(ws, dw, dbias_lo, CH, ns);
+  conv_wgrad_reduce_kernel<<<(n + 31) / 32, 256, 0, st>>>(ws, dw, dbias_lo, CH, ns);
   return check_launch();
 }
 

@@ -1,9 +1,11 @@
 """Training loop with the reference's Trainer API (disvae/training.py:17-196).
 
 Differences from the reference are in HOW, not WHAT: the per-step `loss.item()` host sync
-(training.py:164) is replaced by an on-device running sum read once per epoch (and every
-`sync_every` steps for the progress bar), and under torch.distributed (one process per GPU)
-gradients are averaged with one flat all-reduce per step (disvae.parallel).
+(training.py:164) is replaced by an on-device running sum read once per epoch plus an asynchronous
+per-step copy of the loss into pinned host memory (the progress bar shows the latest value that has
+already landed), host batches are uploaded one step ahead on a copy stream (`_Prefetcher`), and under
+torch.distributed (one process per GPU) gradients are averaged with one flat all-reduce per step
+(disvae.parallel).
 """
 import logging
 import os
@@ -68,14 +70,24 @@ class Trainer():
         """training.py:104-135; the epoch loss is accumulated on the device."""
         epoch_loss = None
         kwargs = dict(desc="Epoch {}".format(epoch + 1), leave=False, disable=not self.is_progress_bar)
+        on_gpu = self.device.type == "cuda"
+        batches = _Prefetcher(data_loader, self.device) if on_gpu else data_loader
+        ring = self._loss_ring() if on_gpu else None
         with trange(len(data_loader), **kwargs) as t:
-            for i, (data, _) in enumerate(data_loader):
+            for i, (data, _) in enumerate(batches):
                 loss = self._step(data, storer)
                 epoch_loss = loss if epoch_loss is None else epoch_loss + loss
+                if ring is not None:
+                    ring.push(loss)                           # async D2H of this step's loss (4 bytes)
                 if self.is_progress_bar and i % self.sync_every == 0:
-                    t.set_postfix(loss=loss.item())
+                    t.set_postfix(loss=ring.latest() if ring is not None else loss.item())
                 t.update()
         return epoch_loss.item() / len(data_loader)
+
+    def _loss_ring(self):
+        if getattr(self, "_ring", None) is None:
+            self._ring = _HostLossRing(self.device)
+        return self._ring
 
     # -- optimizer ---------------------------------------------------------------------------
     def _optimizer_step(self, grad_scale=1.0):
@@ -213,6 +225,86 @@ class Trainer():
         self._optimizer_step()
         lf._step_d()
         return loss
+
+
+class _Prefetcher:
+    """Iterates a loader of (data, label) batches one step ahead: the host->device copy of batch i+1 is issued
+    on a copy stream while step i runs (two device buffers, reused).  Pageable host tensors still work (the copy
+    is then synchronous); batches already on the device pass through."""
+
+    def __init__(self, loader, device):
+        self.loader, self.device = loader, device
+        self.stream = torch.cuda.Stream(device)
+        self.bufs = [None, None]
+        self.consumed = [None, None]              # main-stream events: buffer may be overwritten after this
+
+    def _upload(self, item, slot):
+        data, label = item
+        if not torch.is_tensor(data) or data.device.type == "cuda":
+            return data, label, None
+        buf = self.bufs[slot]
+        if buf is None or buf.shape != data.shape or buf.dtype != data.dtype:
+            buf = self.bufs[slot] = torch.empty(data.shape, dtype=data.dtype, device=self.device)
+        with torch.cuda.stream(self.stream):
+            if self.consumed[slot] is not None:
+                self.stream.wait_event(self.consumed[slot])
+            buf.copy_(data, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(self.stream)
+        return buf, label, ready
+
+    def __iter__(self):
+        it = iter(self.loader)
+        slot = 0
+        try:
+            nxt = self._upload(next(it), slot)
+        except StopIteration:
+            return
+        while nxt is not None:
+            data, label, ready = nxt
+            cur_slot = slot
+            slot ^= 1
+            try:
+                nxt = self._upload(next(it), slot)            # overlaps with the step on `data`
+            except StopIteration:
+                nxt = None
+            main = torch.cuda.current_stream(self.device)
+            if ready is not None:
+                main.wait_event(ready)
+            yield data, label
+            if ready is not None:                             # the step that read `data` has been enqueued
+                ev = torch.cuda.Event()
+                ev.record(main)
+                self.consumed[cur_slot] = ev
+
+    def __len__(self):
+        return len(self.loader)
+
+
+class _HostLossRing:
+    """Per-step losses copied asynchronously into pinned host memory; `latest()` returns the newest value that
+    has already arrived (never blocks)."""
+
+    def __init__(self, device, size=64):
+        self.host = torch.zeros(size, dtype=torch.float32).pin_memory()
+        self.events = [None] * size
+        self.n = 0
+        self.size = size
+
+    def push(self, loss):
+        k = self.n % self.size
+        self.host[k:k + 1].copy_(loss.detach().reshape(1), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.events[k] = ev
+        self.n += 1
+
+    def latest(self):
+        for back in range(1, min(self.n, self.size) + 1):
+            k = (self.n - back) % self.size
+            if self.events[k] is not None and self.events[k].query():
+                return float(self.host[k])
+        return float("nan")
 
 
 class _StepProxy:

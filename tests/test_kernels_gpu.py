@@ -50,6 +50,7 @@ CONV_CASES = [  # (B, H(lo), CH)
     (301, 8, 32), (1201, 4, 32),
     (40, 32, 1), (40, 32, 3),      # image-boundary layers, 320 tiles
     (100, 32, 1),                  # halo up kernel: 1100 tiles, > 5 per CTA (every shared-memory stage is reused)
+    (330, 32, 1), (300, 16, 3),    # col2im up kernel: several images per persistent CTA (carry row reset between images)
 ]
 
 
@@ -109,6 +110,22 @@ def test_conv_wgrad_matches_autograd(ops, B, H, CH):
     # determinism of the split-K reduction
     dw2, _ = ops.conv_wgrad(nhwc(g).to(dev()), hi, B, H, H, CH, int(CH < 32), True)
     assert torch.equal(dw, dw2)
+
+
+@pytest.mark.parametrize("B,H,CH", [(5, 32, 1), (333, 32, 1), (150, 32, 3), (77, 16, 1), (200, 16, 3)])
+def test_conv_up_small_fp32_grade_accuracy(ops, B, H, CH):
+    """Decoder output layer (col2im tensor-core kernel): <= 4e-6 of the output scale against fp64, pre-activation
+    and through the sigmoid."""
+    torch.manual_seed(B + H + CH)
+    lo = torch.randn(B, 32, H, H)
+    w = torch.randn(32, CH, 4, 4) * 0.1
+    b = torch.randn(CH)
+    wp = ops.conv_pack(w.to(dev()), CH)
+    ref = F.conv_transpose2d(lo.double(), w.double(), b.double(), stride=2, padding=1)
+    got = ops.conv_up(nhwc(lo).to(dev()), wp, b.to(dev()), None, B, H, H, CH, 1, 0).cpu()
+    assert_close(got, ref, tol=4e-6, what="up small vs fp64")
+    got_s = ops.conv_up(nhwc(lo).to(dev()), wp, b.to(dev()), None, B, H, H, CH, 1, 2).cpu()
+    assert_close(got_s, torch.sigmoid(ref), tol=4e-6, what="up small sigmoid vs fp64")
 
 
 @pytest.mark.parametrize("B,H", [(16, 16), (9, 8), (40, 4), (200, 16), (330, 16), (700, 8)])
