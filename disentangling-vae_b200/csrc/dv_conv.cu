@@ -499,12 +499,22 @@ channel_sum_nchw_kernel(const float* __restrict__ x, float* __restrict__ partial
     __syncthreads();
   }
 }
-__global__ void channel_sum_final_kernel(const float* __restrict__ partial, float* __restrict__ out, int nblocks, int C) {
-  const int c = threadIdx.x;
-  if (c >= C) return;
+// 32 channels x 32 slices of the per-block partials, combined in a fixed order
+__global__ void __launch_bounds__(1024)
+channel_sum_final_kernel(const float* __restrict__ partial, float* __restrict__ out, int nblocks, int C) {
+  __shared__ float red[32][33];
+  const int c = threadIdx.x & 31, w = threadIdx.x >> 5;
   float s = 0.f;
-  for (int b = 0; b < nblocks; ++b) s += partial[b * 32 + c];
-  out[c] = s;
+  if (c < C)
+    for (int b = w; b < nblocks; b += 32) s += partial[b * 32 + c];
+  red[w][c] = s;
+  __syncthreads();
+  if (w == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) t += red[k][c];
+    out[c] = t;
+  }
 }
 
 __global__ void flat_transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, long long n, int C, int S, int to_nhwc) {
@@ -747,7 +757,7 @@ int dv_channel_sum(const float* x, float* out, long long rows, int C, int nchw, 
   }
   int rc = check_launch();
   if (rc != DV_OK) return rc;
-  channel_sum_final_kernel<<<1, 32, 0, st>>>(partial, out, nb, C);
+  channel_sum_final_kernel<<<1, 1024, 0, st>>>(partial, out, nb, C);
   return check_launch();
 }
 

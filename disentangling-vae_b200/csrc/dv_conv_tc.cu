@@ -72,6 +72,7 @@ struct DownGeom {
   int rows_per_tile;    // 128 / W image-rows of lo per tile
   int num_tiles;
   long long total_px;
+  int prefetch;         // L2-prefetch the next tile's hi rows (DV_TC_PREFETCH=0 switches it off)
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -398,6 +399,7 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_mnmajor(uint32_t smem_addr, 
 
 struct WgGeom {
   int B, H, W, rows_per_tile, num_tiles, tiles_per_cta;
+  int prefetch;
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -431,6 +433,12 @@ conv_wgrad32_tc_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid
     for (int tile = t_begin; tile < t_end; ++tile) {
       const int r0 = tile * g.rows_per_tile;
       const int b0 = r0 / g.H, i0 = r0 % g.H;
+      if (g.prefetch && tile + 1 < t_end) {                  // pull the next tile's hi rows (and lo tile) into L2
+        const int rn = (tile + 1) * g.rows_per_tile;
+        const int bn = rn / g.H, in_ = rn % g.H;
+        for (int t4 = 0; t4 < 4; ++t4) tma_prefetch_4d(&tmap_hi, 0, (t4 & 1), 2 * in_ + (t4 >> 1), bn);
+        tma_prefetch_4d(&tmap_lo, 0, 0, in_, bn);
+      }
       mbar_wait(&bars->l_empty[lb], lphase ^ 1);
       mbar_arrive_expect_tx(&bars->l_raw_full[lb], kATile);
       tma_load_4d(Ls + lb * kWgLBytes, &tmap_lo, &bars->l_raw_full[lb], 0, 0, i0, b0);
@@ -634,6 +642,12 @@ conv_down32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
       const int r0 = tile * g.rows_per_tile;
       const int b0 = r0 / g.H, i0 = r0 % g.H;
+      if (g.prefetch && tile + (int)gridDim.x < g.num_tiles) {
+        // the four taps (kh,kw) in {1,2}^2 touch every hi pixel of a tile exactly once: pull the NEXT tile into L2
+        const int rn = (tile + gridDim.x) * g.rows_per_tile;
+        const int bn = rn / g.H, in_ = rn % g.H;
+        for (int t4 = 0; t4 < 4; ++t4) tma_prefetch_4d(&tmap_a, 0, (t4 & 1), 2 * in_ + (t4 >> 1), bn);
+      }
       for (int tap = 0; tap < kTaps; ++tap) {
         const int kh = tap >> 2, kw = tap & 3;
         mbar_wait(&bars->raw_empty[stage], phase ^ 1);
@@ -1285,13 +1299,18 @@ conv_down_small_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const floa
     const int r = threadIdx.x - 256;
     const int HH = 2 * g.H, WW = 2 * g.W;
     int stage = 0; uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+    auto gather = [&](int tile, float (&dst)[16 * CH]) {
       const long long p = (long long)tile * 128 + r;
-      const bool valid = p < g.total_px;
+      const bool valid = tile < g.num_tiles && p < g.total_px;
       int b = 0, i = 0, j = 0;
       if (valid) { j = (int)(p % g.W); i = (int)((p / g.W) % g.H); b = (int)(p / ((long long)g.W * g.H)); }
-      float v[16 * CH];
-      load_patch<CH>(x, HH, WW, b, i, j, valid, v);
+      load_patch<CH>(x, HH, WW, b, i, j, valid, dst);
+    };
+    float v[16 * CH];
+    gather(blockIdx.x, v);
+    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+      float vn[16 * CH];
+      gather(tile + gridDim.x, vn);                       // next tile's patch is in flight while this one is written
       mbar_wait(&bars->empty[stage], phase ^ 1);
       uint8_t* st = As + stage * C::kStage;
 #pragma unroll
@@ -1316,6 +1335,8 @@ conv_down_small_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const floa
       fence_proxy_async_smem();
       mbar_arrive(&bars->ready[stage]);
       if (++stage == C::kNStages) { stage = 0; phase ^= 1; }
+#pragma unroll
+      for (int k = 0; k < 16 * CH; ++k) v[k] = vn[k];
     }
   }
   tc_fence_before_sync();
@@ -1394,14 +1415,18 @@ conv_wgrad_small_tc_kernel(const __grid_constant__ CUtensorMap tmap_lo, const fl
     const int HH = 2 * g.H, WW = 2 * g.W;
     float ls[4] = {0.f, 0.f, 0.f, 0.f};
     int stage = 0; uint32_t phase = 0; int lb = 0; uint32_t lphase = 0;
-    for (int tile = t_begin; tile < t_end; ++tile) {
-      // patch row of pixel t (gathered while the lo tile is in flight)
+    auto gather = [&](int tile, float (&dst)[16 * CH]) {     // patch row of pixel t of `tile`
       const long long p = (long long)tile * 128 + t;
-      const bool valid = p < (long long)g.B * g.H * g.W;
+      const bool valid = tile < t_end && p < (long long)g.B * g.H * g.W;
       int b = 0, i = 0, j = 0;
       if (valid) { j = (int)(p % g.W); i = (int)((p / g.W) % g.H); b = (int)(p / ((long long)g.W * g.H)); }
-      float v[16 * CH];
-      load_patch<CH>(x, HH, WW, b, i, j, valid, v);
+      load_patch<CH>(x, HH, WW, b, i, j, valid, dst);
+    };
+    float v[16 * CH];
+    gather(t_begin, v);
+    for (int tile = t_begin; tile < t_end; ++tile) {
+      float vn[16 * CH];
+      gather(tile + 1, vn);                                // in flight while this tile is written and split
       mbar_wait(&bars->empty[stage], phase ^ 1);
       uint8_t* st = Ps + stage * C::kPStage;
 #pragma unroll
@@ -1441,6 +1466,8 @@ conv_wgrad_small_tc_kernel(const __grid_constant__ CUtensorMap tmap_lo, const fl
       fence_proxy_async_smem();
       mbar_arrive(&bars->l_ready[lb]);
       if (++lb == 2) { lb = 0; lphase ^= 1; }
+#pragma unroll
+      for (int k = 0; k < 16 * CH; ++k) v[k] = vn[k];
     }
 #pragma unroll
     for (int e = 0; e < 4; ++e) bars->lscr[t][e] = ls[e];
@@ -1500,6 +1527,11 @@ __global__ void conv_pack_tc_kernel(const float* __restrict__ w, float* __restri
 
 // ---- host side ---------------------------------------------------------------------------
 // DV_TC_A=smem selects the variants that keep the A operand in shared memory (A/B testing).
+static int use_prefetch() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DV_TC_PREFETCH"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v;
+}
 static bool use_ts() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("DV_TC_A"); v = (e && e[0] == 's') ? 0 : 1; }
@@ -1559,7 +1591,7 @@ int conv_down32_tc(const float* hi, const float* wd_packed, const float* bias, c
                    int B, int H, int W, int act, cudaStream_t st) {
   if (W > 128 || 128 % W != 0) return DV_ERR_BAD_SHAPE;
   DownGeom g;
-  g.B = B; g.H = H; g.W = W;
+  g.B = B; g.H = H; g.W = W; g.prefetch = use_prefetch();
   g.rows_per_tile = 128 / W;
   const int TR = g.rows_per_tile < H ? g.rows_per_tile : H;
   if (H % TR != 0 || g.rows_per_tile % TR != 0) return DV_ERR_BAD_SHAPE;
@@ -1600,7 +1632,7 @@ int conv_up32_tc(const float* lo, const float* wu_packed, const float* bias, con
                  int B, int H, int W, int act, cudaStream_t st) {
   if (W > 128 || 128 % W != 0) return DV_ERR_BAD_SHAPE;
   DownGeom g;
-  g.B = B; g.H = H; g.W = W;
+  g.B = B; g.H = H; g.W = W; g.prefetch = use_prefetch();
   g.rows_per_tile = 128 / W;
   const int TR = g.rows_per_tile < H ? g.rows_per_tile : H;
   if (H % TR != 0 || g.rows_per_tile % TR != 0) return DV_ERR_BAD_SHAPE;
@@ -1640,7 +1672,7 @@ int conv_up32_tc(const float* lo, const float* wu_packed, const float* bias, con
 int conv_wgrad32_tc(const float* lo, const float* hi, float* ws, int B, int H, int W, int* nsplit, cudaStream_t st) {
   if (W > 128 || 128 % W != 0) return DV_ERR_BAD_SHAPE;
   WgGeom g;
-  g.B = B; g.H = H; g.W = W;
+  g.B = B; g.H = H; g.W = W; g.prefetch = use_prefetch();
   g.rows_per_tile = 128 / W;
   const int TR = g.rows_per_tile < H ? g.rows_per_tile : H;
   if (H % TR != 0 || g.rows_per_tile % TR != 0) return DV_ERR_BAD_SHAPE;
@@ -1715,7 +1747,7 @@ static int launch_down_small(const float* x, const float* wd, const float* bias,
 int conv_down_small_tc(const float* x, const float* wd, const float* bias, const float* mask, float* lo,
                        int B, int H, int W, int CH, int act, cudaStream_t st) {
   DownGeom g;
-  g.B = B; g.H = H; g.W = W; g.rows_per_tile = 0;
+  g.B = B; g.H = H; g.W = W; g.prefetch = use_prefetch(); g.rows_per_tile = 0;
   g.total_px = (long long)B * H * W;
   g.num_tiles = (int)((g.total_px + 127) / 128);
   return CH == 1 ? launch_down_small<1>(x, wd, bias, mask, lo, g, act, st) : launch_down_small<3>(x, wd, bias, mask, lo, g, act, st);
@@ -1741,7 +1773,7 @@ static int launch_wgrad_small(const float* lo, const float* x, float* ws, WgGeom
 int conv_wgrad_small_tc(const float* lo, const float* x, float* ws, int B, int H, int W, int CH, int* nsplit, cudaStream_t st) {
   if (W > 128 || 128 % W != 0) return DV_ERR_BAD_SHAPE;
   WgGeom g;
-  g.B = B; g.H = H; g.W = W;
+  g.B = B; g.H = H; g.W = W; g.prefetch = use_prefetch();
   g.rows_per_tile = 128 / W;
   const int TR = g.rows_per_tile < H ? g.rows_per_tile : H;
   if (H % TR != 0 || g.rows_per_tile % TR != 0) return DV_ERR_BAD_SHAPE;

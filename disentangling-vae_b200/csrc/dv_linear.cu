@@ -144,20 +144,29 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ part, float* __re
   }
 }
 
-// out[n] = sum_m g[m][n]  (bias gradient): block = 32 columns x 8 row-slices, fixed order.
-__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ g, float* __restrict__ out, int M, int N) {
-  __shared__ float red[8][32];
+// out[n] = sum_m g[m][n]  (bias gradient): block = 32 columns x 32 row-slices (4 independent partial sums each),
+// combined in a fixed order.
+__global__ void __launch_bounds__(1024) colsum_kernel(const float* __restrict__ g, float* __restrict__ out, int M, int N) {
+  __shared__ float red[32][33];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n = blockIdx.x * 32 + lane;
-  float s = 0.f;
-  if (n < N)
-    for (int m = warp; m < M; m += 8) s += g[(long long)m * N + n];
-  red[warp][lane] = s;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (n < N) {
+    int m = warp;
+    for (; m + 96 < M; m += 128) {
+      s0 += g[(long long)m * N + n];
+      s1 += g[(long long)(m + 32) * N + n];
+      s2 += g[(long long)(m + 64) * N + n];
+      s3 += g[(long long)(m + 96) * N + n];
+    }
+    for (; m < M; m += 32) s0 += g[(long long)m * N + n];
+  }
+  red[warp][lane] = (s0 + s1) + (s2 + s3);
   __syncthreads();
   if (warp == 0 && n < N) {
     float t = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) t += red[w][lane];
+    for (int w = 0; w < 32; ++w) t += red[w][lane];
     out[n] = t;
   }
 }
@@ -253,7 +262,7 @@ int dv_linear_wgrad(const float* g, const float* x, float* dw, float* dbias, int
       if (rc != DV_OK) return rc;
     }
     if (!dbias) return rc;
-    colsum_kernel<<<(N + 31) / 32, 256, 0, st>>>(g, dbias, M, N);
+    colsum_kernel<<<(N + 31) / 32, 1024, 0, st>>>(g, dbias, M, N);
     return check_launch();
   }
   const int S = wgrad_splits(M, N, K);
@@ -273,7 +282,7 @@ int dv_linear_wgrad(const float* g, const float* x, float* dw, float* dbias, int
     if (rc != DV_OK) return rc;
   }
   if (!dbias) return rc;
-  colsum_kernel<<<(N + 31) / 32, 256, 0, st>>>(g, dbias, M, N);
+  colsum_kernel<<<(N + 31) / 32, 1024, 0, st>>>(g, dbias, M, N);
   return check_launch();
 }
 
