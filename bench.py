@@ -297,7 +297,7 @@ def kernel_rooflines(trainer, resident, K, B, img, z, n_data, device):
     t_med = ts[len(ts) // 2]
     vbytes = 4 * Bk * Bk * Dk + 12 * Bk * Dk + 16 * Bk
     ach = vbytes / (t_med / 1e3) / 1e9
-    res["roofline_logdensity"] = {"kernel": "dv_btcvae_fwd (prep + main)", "bound": "hbm", "B": Bk, "D": Dk,
+    res["roofline_logdensity"] = {"kernel": "dv_btcvae_fwd (one launch: parameters + B x B x D sweep + means)", "bound": "hbm", "B": Bk, "D": Dk,
                                   "achieved": round(ach, 1), "peak": pk["hbm"], "unit": "GB/s (virtual bytes of the "
                                   "reference's B*B*D matrix)", "frac": round(ach / pk["hbm"], 4), "us": round(t_med * 1e3, 2),
                                   "virtual_bytes": vbytes, "compulsory_bytes": 12 * Bk * Dk + 16 * Bk, "traffic": None,

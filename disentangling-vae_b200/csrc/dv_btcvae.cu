@@ -400,6 +400,177 @@ btcvae_finalize_kernel(int B, int D, int JS, const float2* __restrict__ part, fl
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Forward, version 3 (small latent sizes, B <= ~1000): ONE launch, nothing but the O(B*D) outputs touches HBM.
+// Every block stages the parameters {c, hiv, mu, z}*[B][D] of ALL columns in shared memory (computing them from
+// z/mu/logvar itself: 3*B*D loads per block instead of a prep launch), so a block owning RPB rows sees whole rows
+// and finishes their logsumexps without any cross-block merge.  16 warps: warp 2r+h sweeps half h of the columns
+// of row r (single sweep, bounded reference exponent as in btcvae_fwd2_kernel; online logsumexp for log q(z)).
+// Row statistics go straight to `rowstats`; the block's contribution to the three means goes to `blockpart`, and
+// the last block to finish (device counter) adds the contributions in block order -> deterministic.
+// Shared memory: B * (DC+1) float4 (pitch DC+1 keeps the 128-bit row loads conflict free): 176 KB at B=1024, D=10.
+// ------------------------------------------------------------------------------------------
+constexpr int kF3Threads = 512;
+constexpr int kF3MaxRows = 8;
+
+template <int DC, bool EXACT>
+__global__ void __launch_bounds__(kF3Threads, 1)
+btcvae_fwd3_kernel(const float* __restrict__ z, const float* __restrict__ mu, const float* __restrict__ logvar, int ld,
+                   int row_stride, int B, int D, LogW lw, int rpb, float4* __restrict__ pj_out, float* __restrict__ rowstats,
+                   float* __restrict__ terms, float* __restrict__ blockpart, unsigned* __restrict__ counter) {
+  extern __shared__ float4 sp[];                               // [B][DP]
+  constexpr int DP = DC + 1;
+  __shared__ float s_red[kF3Threads / 32][DC];
+  __shared__ float sbound[DC];
+  __shared__ float s_sx[kF3MaxRows][DC];
+  __shared__ float2 s_q[kF3MaxRows];
+  __shared__ float s_means[kF3MaxRows][3];
+  __shared__ bool is_last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float Df = (float)D;
+
+  // ---- phase 1: parameters of every column -> shared memory ----
+  for (int e = tid; e < B * D; e += kF3Threads) {
+    const int j = e / D, k = e - j * D;
+    const float m = mu[(long long)j * row_stride + (long long)k * ld];
+    const float lv = logvar[(long long)j * row_stride + (long long)k * ld];
+    const float zz = z[e];
+    const float cc = -0.5f * (kLog2Pi + lv);
+    const float iv = expf(-lv);
+    sp[j * DP + k] = make_float4(cc * kLog2e, 0.5f * iv * kLog2e, m, zz);
+  }
+  __syncthreads();
+
+  // ---- phase 2: per-dimension upper bound of (c_j + w_j) over all columns ----
+  {
+    float bm[DC];
+#pragma unroll
+    for (int k = 0; k < DC; ++k) bm[k] = -INFINITY;
+    const float w_col0_max = lw.mss ? fmaxf(lw.ln, lw.ls) : 0.f;
+    for (int j = tid; j < B; j += kF3Threads) {
+      const float w = !lw.mss ? 0.f : (j == 0 ? w_col0_max : (j == 1 ? lw.ls : lw.lm));
+#pragma unroll
+      for (int k = 0; k < DC; ++k)
+        if (EXACT || k < D) bm[k] = fmaxf(bm[k], sp[j * DP + k].x + w);
+    }
+#pragma unroll
+    for (int k = 0; k < DC; ++k) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) bm[k] = fmaxf(bm[k], __shfl_xor_sync(0xffffffffu, bm[k], o));
+      if (lane == 0) s_red[warp][k] = bm[k];
+    }
+    __syncthreads();
+    if (tid < DC) {
+      float b = -INFINITY;
+#pragma unroll
+      for (int w = 0; w < kF3Threads / 32; ++w) b = fmaxf(b, s_red[w][tid]);
+      sbound[tid] = b;
+    }
+    __syncthreads();
+  }
+
+  // ---- phase 3: warp 2r+h sweeps half h of the columns of row r ----
+  const int row_local = warp >> 1, half = warp & 1;
+  const int i_raw = blockIdx.x * rpb + row_local;
+  const bool active = row_local < rpb && i_raw < B;
+  const int i = min(i_raw, B - 1);
+  float sx[DC], ref[DC], zc[DC];
+  float am = -INFINITY, as = 0.f;
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < DC; ++k) {
+      sx[k] = 0.f;
+      if (EXACT || k < D) {
+        const float4 p = sp[i * DP + k];
+        zc[k] = p.w;
+        const float tt = p.w - p.z;
+        ref[k] = fmaxf(sbound[k] - 60.f, p.x - p.y * (tt * tt) + logw2(lw, i, i));
+      } else { zc[k] = 0.f; ref[k] = 0.f; }
+    }
+    for (int j = lane + 32 * half; j < B; j += 64) {
+      const float wj = logw2(lw, i, j);
+      const float4* pr = sp + j * DP;
+      float a = 0.f;
+#pragma unroll
+      for (int k = 0; k < DC; ++k) {
+        if (EXACT || k < D) {
+          const float4 p = pr[k];
+          const float tt = zc[k] - p.z;
+          const float m = p.x - p.y * (tt * tt);
+          a += m;
+          sx[k] += exp2f(m + (wj - ref[k]));
+        }
+      }
+      a += Df * wj;
+      const float nm = fmaxf(am, a);
+      as = as * exp2f(am - nm) + exp2f(a - nm);
+      am = nm;
+    }
+#pragma unroll
+    for (int k = 0; k < DC; ++k) sx[k] = warp_sum(sx[k]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float m2 = __shfl_xor_sync(0xffffffffu, am, o), s2 = __shfl_xor_sync(0xffffffffu, as, o);
+      lse_merge2(am, as, m2, s2);
+    }
+    if (half == 1 && lane == 0) {
+#pragma unroll
+      for (int k = 0; k < DC; ++k) s_sx[row_local][k] = sx[k];
+      s_q[row_local] = make_float2(am, as);
+    }
+  }
+  __syncthreads();
+  if (active && half == 0) {
+    // this row's own Gaussian terms (what the prep kernel produced): lanes over latent dims
+    float lq = 0.f, lp = 0.f;
+    for (int d = lane; d < D; d += 32) {
+      const float4 p = sp[i * DP + d];
+      const float tt = p.w - p.z;
+      lq += (p.x - p.y * (tt * tt)) * kLn2;                    // log N(z; mu, lv)   (math.py:48-51)
+      lp += -0.5f * kLog2Pi - 0.5f * (p.w * p.w);              // log N(z; 0, 1)     (losses.py:531-532)
+      pj_out[(long long)d * B + i] = p;                        // the backward pass reads [D][B]
+    }
+    lq = warp_sum(lq); lp = warp_sum(lp);
+    if (lane == 0) {
+      float lprod = 0.f;
+#pragma unroll
+      for (int k = 0; k < DC; ++k) {
+        if (EXACT || k < D) {
+          const float v = (ref[k] + log2f(sx[k] + s_sx[row_local][k])) * kLn2;
+          rowstats[(long long)(4 + k) * B + i] = v;
+          lprod += v;
+        }
+      }
+      const float2 q = s_q[row_local];
+      lse_merge2(am, as, q.x, q.y);
+      const float lqz = (am + log2f(as)) * kLn2;
+      rowstats[i] = lp; rowstats[1LL * B + i] = lqz; rowstats[2LL * B + i] = lprod; rowstats[3LL * B + i] = lq;
+      s_means[row_local][0] = lq - lqz; s_means[row_local][1] = lqz - lprod; s_means[row_local][2] = lprod - lp;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float a = 0.f, b = 0.f, c = 0.f;
+    for (int r = 0; r < rpb; ++r)
+      if (blockIdx.x * rpb + r < B) { a += s_means[r][0]; b += s_means[r][1]; c += s_means[r][2]; }
+    blockpart[4 * blockIdx.x + 0] = a; blockpart[4 * blockIdx.x + 1] = b; blockpart[4 * blockIdx.x + 2] = c;
+    __threadfence();
+    is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last || warp != 0) return;
+  __threadfence();
+  float a = 0.f, b = 0.f, c = 0.f;
+  for (int g = lane; g < (int)gridDim.x; g += 32) {             // lane-strided, then a fixed shuffle tree
+    a += __ldcg(blockpart + 4 * g); b += __ldcg(blockpart + 4 * g + 1); c += __ldcg(blockpart + 4 * g + 2);
+  }
+  a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
+  if (lane == 0) {
+    terms[0] = a / (float)B; terms[1] = b / (float)B; terms[2] = c / (float)B;
+    *counter = 0u;
+  }
+}
+
 // ---- backward ---------------------------------------------------------------------
 // G[i,j,d] = cq * S[i,j] + cp * T[i,j,d],  S = exp(A[i,j] - log_qz[i]),  T = exp(M[i,j,d] - P[i,d])
 // role 0 (rows):    g_z[i,d]  = sum_j G * (-(z_i - mu_j) * iv_j)            + direct terms
@@ -569,11 +740,42 @@ int dv_btcvae_fwd(const float* z, const float* mu, const float* logvar, int ld, 
   if ((uintptr_t)workspace & 15) return DV_ERR_BAD_ARG;
   float* ws = reinterpret_cast<float*>(workspace);
   cudaStream_t st = as_stream(stream);
+  const LogW lw = make_logw(B, n_data, is_mss);
+  int rc;
+  {
+    // single-launch path: all columns' parameters fit in one block's shared memory
+    static int v3 = -1;
+    if (v3 < 0) { const char* e = getenv("DV_BTCVAE_V3"); v3 = (e && e[0] == '0') ? 0 : 1; }
+    const int dc = D == 10 ? 10 : 16;
+    const size_t smem = (size_t)B * (dc + 1) * sizeof(float4);
+    const int rpb = (B + kNumSMs - 1) / kNumSMs;
+    if (v3 && D <= 16 && smem <= 200 * 1024 && rpb <= kF3MaxRows) {
+      const int grid = (B + rpb - 1) / rpb;
+      float4* pj = reinterpret_cast<float4*>(ws + kWsHeader);
+      float* blockpart = ws + btcvae_part_offset_floats(B, D);
+      unsigned* counter = reinterpret_cast<unsigned*>(ws);
+#define DV_F3_CALL(DC, EXACT)                                                                                                  \
+  do {                                                                                                                         \
+    static bool attr = false;                                                                                                  \
+    if (!attr) {                                                                                                               \
+      if (cudaFuncSetAttribute(btcvae_fwd3_kernel<DC, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) !=      \
+          cudaSuccess) { g_last_cuda_error = (int)cudaGetLastError(); return DV_ERR_CUDA; }                                    \
+      attr = true;                                                                                                             \
+    }                                                                                                                          \
+    btcvae_fwd3_kernel<DC, EXACT><<<grid, kF3Threads, smem, st>>>(z, mu, logvar, ld, row_stride, B, D, lw, rpb, pj, rowstats, \
+                                                                  terms, blockpart, counter);                                  \
+  } while (0)
+      if (D == 10) DV_F3_CALL(10, true);
+      else if (D == 16) DV_F3_CALL(16, true);
+      else DV_F3_CALL(16, false);
+#undef DV_F3_CALL
+      return check_launch();
+    }
+  }
   btcvae_prep_kernel<<<(B + 3) / 4, 128, 0, st>>>(z, mu, logvar, ld, row_stride, B, D,
                                                   reinterpret_cast<float4*>(ws + kWsHeader), rowstats);
-  int rc = check_launch();
+  rc = check_launch();
   if (rc != DV_OK) return rc;
-  const LogW lw = make_logw(B, n_data, is_mss);
   static int v1 = -1;
   if (v1 < 0) { const char* e = getenv("DV_BTCVAE_V1"); v1 = (e && e[0] == '1') ? 1 : 0; }
   if (v1) {

@@ -67,6 +67,22 @@ __device__ __forceinline__ void split_hi_lo(uint4* hi, uint4* lo4, int t) {
   }
 }
 
+// same, but the hi plane stays the RAW fp32 tile: kind::tf32 reads only the upper 19 bits of a 32-bit operand, i.e.
+// it truncates exactly like the mask above (checked by the fp64-accuracy tests; DV_TC_RAWHI=0 restores the store)
+__device__ __forceinline__ void split_lo_only(const uint4* raw, uint4* lo4, int t) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int idx = t + 128 * k;
+    const uint4 v = raw[idx];
+    uint4 l;
+    l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(v.x & kHiMask));
+    l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(v.y & kHiMask));
+    l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(v.z & kHiMask));
+    l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(v.w & kHiMask));
+    lo4[idx] = l;
+  }
+}
+
 struct DownGeom {
   int B, H, W;          // lo geometry
   int rows_per_tile;    // 128 / W image-rows of lo per tile
@@ -400,6 +416,7 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_mnmajor(uint32_t smem_addr, 
 struct WgGeom {
   int B, H, W, rows_per_tile, num_tiles, tiles_per_cta;
   int prefetch;
+  int rawhi;            // feed the raw fp32 tiles as the hi operand (no hi-plane store)
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -495,7 +512,8 @@ conv_wgrad32_tc_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid
           const uint4 v = hi[t + 128 * k];
           ls[0] += __uint_as_float(v.x); ls[1] += __uint_as_float(v.y); ls[2] += __uint_as_float(v.z); ls[3] += __uint_as_float(v.w);
         }
-        split_hi_lo(hi, reinterpret_cast<uint4*>(Ls + lb * kWgLBytes + kATile), t);
+        if (g.rawhi) split_lo_only(hi, reinterpret_cast<uint4*>(Ls + lb * kWgLBytes + kATile), t);
+        else split_hi_lo(hi, reinterpret_cast<uint4*>(Ls + lb * kWgLBytes + kATile), t);
       }
       fence_proxy_async_smem();
       mbar_arrive(&bars->l_ready[lb]);
@@ -503,8 +521,13 @@ conv_wgrad32_tc_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid
       for (int pr = 0; pr < 8; ++pr) {
         mbar_wait(&bars->raw_full[stage], phase);
         uint8_t* base = St + stage * kWgStageBytes;
-        split_hi_lo(reinterpret_cast<uint4*>(base), reinterpret_cast<uint4*>(base + 2 * kATile), t);
-        split_hi_lo(reinterpret_cast<uint4*>(base + kATile), reinterpret_cast<uint4*>(base + 3 * kATile), t);
+        if (g.rawhi) {
+          split_lo_only(reinterpret_cast<const uint4*>(base), reinterpret_cast<uint4*>(base + 2 * kATile), t);
+          split_lo_only(reinterpret_cast<const uint4*>(base + kATile), reinterpret_cast<uint4*>(base + 3 * kATile), t);
+        } else {
+          split_hi_lo(reinterpret_cast<uint4*>(base), reinterpret_cast<uint4*>(base + 2 * kATile), t);
+          split_hi_lo(reinterpret_cast<uint4*>(base + kATile), reinterpret_cast<uint4*>(base + 3 * kATile), t);
+        }
         fence_proxy_async_smem();
         mbar_arrive(&bars->ready[stage]);
         if (++stage == kWgStages) { stage = 0; phase ^= 1; }
@@ -1527,6 +1550,11 @@ __global__ void conv_pack_tc_kernel(const float* __restrict__ w, float* __restri
 
 // ---- host side ---------------------------------------------------------------------------
 // DV_TC_A=smem selects the variants that keep the A operand in shared memory (A/B testing).
+static int use_rawhi() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DV_TC_RAWHI"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v;
+}
 static int use_prefetch() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("DV_TC_PREFETCH"); v = (e && e[0] == '0') ? 0 : 1; }
@@ -1672,7 +1700,7 @@ int conv_up32_tc(const float* lo, const float* wu_packed, const float* bias, con
 int conv_wgrad32_tc(const float* lo, const float* hi, float* ws, int B, int H, int W, int* nsplit, cudaStream_t st) {
   if (W > 128 || 128 % W != 0) return DV_ERR_BAD_SHAPE;
   WgGeom g;
-  g.B = B; g.H = H; g.W = W; g.prefetch = use_prefetch();
+  g.B = B; g.H = H; g.W = W; g.prefetch = use_prefetch(); g.rawhi = use_rawhi();
   g.rows_per_tile = 128 / W;
   const int TR = g.rows_per_tile < H ? g.rows_per_tile : H;
   if (H % TR != 0 || g.rows_per_tile % TR != 0) return DV_ERR_BAD_SHAPE;
@@ -1773,7 +1801,7 @@ static int launch_wgrad_small(const float* lo, const float* x, float* ws, WgGeom
 int conv_wgrad_small_tc(const float* lo, const float* x, float* ws, int B, int H, int W, int CH, int* nsplit, cudaStream_t st) {
   if (W > 128 || 128 % W != 0) return DV_ERR_BAD_SHAPE;
   WgGeom g;
-  g.B = B; g.H = H; g.W = W; g.prefetch = use_prefetch();
+  g.B = B; g.H = H; g.W = W; g.prefetch = use_prefetch(); g.rawhi = use_rawhi();
   g.rows_per_tile = 128 / W;
   const int TR = g.rows_per_tile < H ? g.rows_per_tile : H;
   if (H % TR != 0 || g.rows_per_tile % TR != 0) return DV_ERR_BAD_SHAPE;
