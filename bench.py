@@ -259,12 +259,15 @@ def kernel_rooflines(trainer, resident, K, B, img, z, n_data, device):
         # algorithmic HBM bytes of one launch: read the hi and lo side once, write the output once
         hi_b, lo_b = 4.0 * B * 4 * H * H * CH, 4.0 * B * H * H * 32
         alg_bytes = hi_b + lo_b + (0 if "wgrad" in name else 0)
-        traffic = None
+        traffic, traffic_src = None, None
         tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-        if os.path.exists(tp):
-            traffic = json.load(open(tp)).get(name)
+        if os.path.exists(tp):                                      # dram__bytes_read+write of one launch (ncu --set full)
+            ent = json.load(open(tp)).get(name)
+            if ent:
+                traffic, traffic_src = ent["dram_bytes"], ent.get("source")
         res["roofline"] = {"kernel": name, "bound": "tensor", "achieved": round(ach, 3), "peak": pk["bf16_sustained"],
                            "unit": "TFLOP/s", "frac": round(ach / pk["bf16_sustained"], 5), "traffic": traffic,
+                           "traffic_source": traffic_src,
                            "algorithmic_flops_per_launch": flops, "algorithmic_hbm_bytes_per_launch": alg_bytes,
                            "us_per_launch": round(per_call_ms * 1e3, 2), "launches_per_step": calls // K,
                            "peak_source": pk["src"] + " bf16 sustained (kernel timed inside a long step)",

@@ -405,7 +405,19 @@ btcvae_finalize_kernel(int B, int D, int JS, const float2* __restrict__ part, fl
 // Every block stages the parameters {c, hiv, mu, z}*[B][D] of ALL columns in shared memory (computing them from
 // z/mu/logvar itself: 3*B*D loads per block instead of a prep launch), so a block owning RPB rows sees whole rows
 // and finishes their logsumexps without any cross-block merge.  16 warps: warp 2r+h sweeps half h of the columns
-// of row r (single sweep, bounded reference exponent as in btcvae_fwd2_kernel; online logsumexp for log q(z)).
+// of row r in a single pass.
+//
+// Instruction diet of the (i,j,d) inner loop -- it is issue bound, not MUFU or memory bound:
+//   * a FIXED reference exponent per dimension, r_d = max_j(c_jd + w_j) (log2 units: an upper bound of every
+//     term), and the column weight w_j are folded into the staged constant once per block:
+//     x''_jd = c_jd + w_j - r_d.  The loop is then
+//     t = z_id - mu_jd;  arg = x'' - hiv*t*t;  a += arg;  s_d += ex2(arg)      (LDS.128 + 6 instructions),
+//     terms are <= 1 (no overflow; the columns that matter have arg near 0, so a keeps full precision), and
+//     sum_d arg = sum_d m + D*w_j - sum_d r_d  feeds log q(z) directly.
+//   * the one irregular weight (row B-2, column 0; math.py:70-72) is a peeled first iteration.
+//   * log q(z): online logsumexp with ONE ex2 per column (rescale-or-add select).
+//   * a row whose terms (nearly) all underflow against the fixed reference (sum < 2^-90: its best term is > 60
+//     nats below the column bound -- an outlier sample) is detected and redone by a slow exact two-pass sweep.
 // Row statistics go straight to `rowstats`; the block's contribution to the three means goes to `blockpart`, and
 // the last block to finish (device counter) adds the contributions in block order -> deterministic.
 // Shared memory: B * (DC+1) float4 (pitch DC+1 keeps the 128-bit row loads conflict free): 176 KB at B=1024, D=10.
@@ -413,35 +425,77 @@ btcvae_finalize_kernel(int B, int D, int JS, const float2* __restrict__ part, fl
 constexpr int kF3Threads = 512;
 constexpr int kF3MaxRows = 8;
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 template <int DC, bool EXACT>
 __global__ void __launch_bounds__(kF3Threads, 1)
 btcvae_fwd3_kernel(const float* __restrict__ z, const float* __restrict__ mu, const float* __restrict__ logvar, int ld,
-                   int row_stride, int B, int D, LogW lw, int rpb, float4* __restrict__ pj_out, float* __restrict__ rowstats,
-                   float* __restrict__ terms, float* __restrict__ blockpart, unsigned* __restrict__ counter) {
+                   int row_stride, int B, int D_rt, LogW lw, int rpb, float4* __restrict__ pj_out, float* __restrict__ rowstats,
+                   float* __restrict__ terms, float* __restrict__ blockpart, unsigned* __restrict__ counter,
+                   float* __restrict__ dbg) {
   extern __shared__ float4 sp[];                               // [B][DP]
   constexpr int DP = DC + 1;
+  // DV_BTCVAE_TIMING=1: block 0 leaves its phase boundaries (SM clocks since kernel entry) in the workspace header
+  const long long t_start = dbg ? clock64() : 0;
+#define DV_F3_MARK(slot) do { if (dbg && blockIdx.x == 0 && threadIdx.x == 0) dbg[slot] = (float)(clock64() - t_start); } while (0)
   __shared__ float s_red[kF3Threads / 32][DC];
-  __shared__ float sbound[DC];
+  __shared__ float s_ref[DC];                                  // r_d
+  __shared__ float s_c[kF3MaxRows][DC];                        // unfolded c*log2e of the block's own rows
   __shared__ float s_sx[kF3MaxRows][DC];
   __shared__ float2 s_q[kF3MaxRows];
+  __shared__ float s_P[kF3MaxRows][DC];                        // log2 units
+  __shared__ float s_lqz[kF3MaxRows];
+  __shared__ int s_bad[kF3MaxRows];
   __shared__ float s_means[kF3MaxRows][3];
   __shared__ bool is_last;
+  const int D = EXACT ? DC : D_rt;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const float Df = (float)D;
+  const int row0 = blockIdx.x * rpb;
+  const float w_gen0 = lw.mss ? lw.ln : 0.f;                   // column 0, every row but B-2
 
-  // ---- phase 1: parameters of every column -> shared memory ----
-  for (int e = tid; e < B * D; e += kF3Threads) {
-    const int j = e / D, k = e - j * D;
-    const float m = mu[(long long)j * row_stride + (long long)k * ld];
-    const float lv = logvar[(long long)j * row_stride + (long long)k * ld];
-    const float zz = z[e];
-    const float cc = -0.5f * (kLog2Pi + lv);
-    const float iv = expf(-lv);
-    sp[j * DP + k] = make_float4(cc * kLog2e, 0.5f * iv * kLog2e, m, zz);
+  // ---- phase 1: parameters of every column -> shared memory (kU independent loads in flight per thread) ----
+  {
+    constexpr int kU = 10;
+    const int total = B * D;
+    const bool paired = (ld == 2) && (logvar == mu + 1) && ((row_stride & 1) == 0) && ((reinterpret_cast<uintptr_t>(mu) & 7) == 0);
+    for (int base = 0; base < total; base += kF3Threads * kU) {
+      float vm[kU], vl[kU], vz[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int e = base + u * kF3Threads + tid;
+        if (e < total) {
+          const int j = e / D, k = e - j * D;
+          const int off = j * row_stride + k * ld;
+          if (paired) {
+            const float2 ml = *reinterpret_cast<const float2*>(mu + off);
+            vm[u] = ml.x; vl[u] = ml.y;
+          } else { vm[u] = mu[off]; vl[u] = logvar[off]; }
+          vz[u] = z[e];
+        } else { vm[u] = 0.f; vl[u] = 0.f; vz[u] = 0.f; }
+      }
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int e = base + u * kF3Threads + tid;
+        if (e < total) {
+          const int j = e / D, k = e - j * D;
+          const float cc = -0.5f * (kLog2Pi + vl[u]);
+          const float iv = expf(-vl[u]);
+          const float4 p = make_float4(cc * kLog2e, 0.5f * iv * kLog2e, vm[u], vz[u]);
+          sp[j * DP + k] = p;
+          const int rl = j - row0;
+          if (rl >= 0 && rl < rpb) { s_c[rl][k] = p.x; pj_out[(long long)k * B + j] = p; }   // the backward pass reads [D][B]
+        }
+      }
+    }
   }
   __syncthreads();
+  DV_F3_MARK(0);
 
-  // ---- phase 2: per-dimension upper bound of (c_j + w_j) over all columns ----
+  // ---- phase 2: r_d = max_j (c_jd + w_j), then fold  x'' = c + w_j - r_d  into the staged constants ----
   {
     float bm[DC];
 #pragma unroll
@@ -464,31 +518,36 @@ btcvae_fwd3_kernel(const float* __restrict__ z, const float* __restrict__ mu, co
       float b = -INFINITY;
 #pragma unroll
       for (int w = 0; w < kF3Threads / 32; ++w) b = fmaxf(b, s_red[w][tid]);
-      sbound[tid] = b;
+      s_ref[tid] = b;
+    }
+    __syncthreads();
+    for (int j = tid; j < B; j += kF3Threads) {
+      const float w = !lw.mss ? 0.f : (j == 0 ? w_gen0 : (j == 1 ? lw.ls : lw.lm));
+#pragma unroll
+      for (int k = 0; k < DC; ++k)
+        if (EXACT || k < D) sp[j * DP + k].x += w - s_ref[k];
     }
     __syncthreads();
   }
 
+  DV_F3_MARK(1);
   // ---- phase 3: warp 2r+h sweeps half h of the columns of row r ----
   const int row_local = warp >> 1, half = warp & 1;
-  const int i_raw = blockIdx.x * rpb + row_local;
+  const int i_raw = row0 + row_local;
   const bool active = row_local < rpb && i_raw < B;
   const int i = min(i_raw, B - 1);
-  float sx[DC], ref[DC], zc[DC];
+  const float dw0 = lw.mss ? (logw2(lw, i, 0) - lw.ln) : 0.f;  // != 0 only for row B-2
+  float sx[DC], zc[DC];
   float am = -INFINITY, as = 0.f;
-  if (active) {
+  float Rsum = 0.f;
 #pragma unroll
-    for (int k = 0; k < DC; ++k) {
-      sx[k] = 0.f;
-      if (EXACT || k < D) {
-        const float4 p = sp[i * DP + k];
-        zc[k] = p.w;
-        const float tt = p.w - p.z;
-        ref[k] = fmaxf(sbound[k] - 60.f, p.x - p.y * (tt * tt) + logw2(lw, i, i));
-      } else { zc[k] = 0.f; ref[k] = 0.f; }
-    }
-    for (int j = lane + 32 * half; j < B; j += 64) {
-      const float wj = logw2(lw, i, j);
+  for (int k = 0; k < DC; ++k) {
+    sx[k] = 0.f;
+    zc[k] = (EXACT || k < D) ? sp[i * DP + k].w : 0.f;
+    if (EXACT || k < D) Rsum += s_ref[k];
+  }
+  if (active) {
+    auto column = [&](int j, float dw) {
       const float4* pr = sp + j * DP;
       float a = 0.f;
 #pragma unroll
@@ -496,15 +555,37 @@ btcvae_fwd3_kernel(const float* __restrict__ z, const float* __restrict__ mu, co
         if (EXACT || k < D) {
           const float4 p = pr[k];
           const float tt = zc[k] - p.z;
-          const float m = p.x - p.y * (tt * tt);
-          a += m;
-          sx[k] += exp2f(m + (wj - ref[k]));
+          const float arg = fmaf(-p.y, tt * tt, p.x) + dw;
+          a += arg;
+          sx[k] += ex2_approx(arg);
         }
       }
-      a += Df * wj;
-      const float nm = fmaxf(am, a);
-      as = as * exp2f(am - nm) + exp2f(a - nm);
-      am = nm;
+      const float d = a - am;
+      const float e = ex2_approx(-fabsf(d));
+      const bool up = d > 0.f;
+      as = up ? fmaf(as, e, 1.f) : as + e;
+      am = up ? a : am;
+    };
+    int j = lane + 32 * half;
+    if (j < B) { column(j, j == 0 ? dw0 : 0.f); j += 64; }     // peeled: the only column whose weight depends on the row
+    for (; j < B; j += 64) {
+      const float4* pr = sp + j * DP;
+      float a = 0.f;
+#pragma unroll
+      for (int k = 0; k < DC; ++k) {
+        if (EXACT || k < D) {
+          const float4 p = pr[k];
+          const float tt = zc[k] - p.z;
+          const float arg = fmaf(-p.y, tt * tt, p.x);
+          a += arg;
+          sx[k] += ex2_approx(arg);
+        }
+      }
+      const float d = a - am;
+      const float e = ex2_approx(-fabsf(d));
+      const bool up = d > 0.f;
+      as = up ? fmaf(as, e, 1.f) : as + e;
+      am = up ? a : am;
     }
 #pragma unroll
     for (int k = 0; k < DC; ++k) sx[k] = warp_sum(sx[k]);
@@ -519,45 +600,87 @@ btcvae_fwd3_kernel(const float* __restrict__ z, const float* __restrict__ mu, co
       s_q[row_local] = make_float2(am, as);
     }
   }
+  if (tid < kF3MaxRows) s_bad[tid] = 0;
   __syncthreads();
+  DV_F3_MARK(2);
+  if (active && half == 0 && lane == 0) {
+    int bad = 0;
+#pragma unroll
+    for (int k = 0; k < DC; ++k) {
+      if (EXACT || k < D) {
+        const float tot = sx[k] + s_sx[row_local][k];
+        // ex2 flushes terms below 2^-126: a total under ~2^-90 could have lost a visible share of them
+        if (!(tot > 1e-27f && tot < INFINITY)) bad = 1;
+        s_P[row_local][k] = log2f(tot) + s_ref[k];
+      }
+    }
+    const float2 q = s_q[row_local];
+    lse_merge2(am, as, q.x, q.y);
+    s_lqz[row_local] = am + log2f(as) + Rsum;
+    s_bad[row_local] = bad;
+  }
+  __syncthreads();
+  {
+    int any_bad = 0;
+    for (int r = 0; r < rpb; ++r) any_bad |= s_bad[r];
+    if (any_bad) {                                             // block-uniform, rare: exact two-pass redo of the flagged rows
+      if (active && half == 0 && s_bad[row_local]) {
+        for (int k = 0; k < D; ++k) {
+          const float zk = sp[i * DP + k].w;
+          float mx = -INFINITY;
+          for (int j = lane; j < B; j += 32) {
+            const float4 p = sp[j * DP + k];
+            const float tt = zk - p.z;
+            mx = fmaxf(mx, fmaf(-p.y, tt * tt, p.x) + (j == 0 ? dw0 : 0.f));
+          }
+          mx = warp_max(mx);
+          float sm = 0.f;
+          for (int j = lane; j < B; j += 32) {
+            const float4 p = sp[j * DP + k];
+            const float tt = zk - p.z;
+            sm += exp2f(fmaf(-p.y, tt * tt, p.x) + (j == 0 ? dw0 : 0.f) - mx);
+          }
+          sm = warp_sum(sm);
+          if (lane == 0) s_P[row_local][k] = mx + log2f(sm) + s_ref[k];
+        }
+      }
+      __syncthreads();
+    }
+  }
   if (active && half == 0) {
-    // this row's own Gaussian terms (what the prep kernel produced): lanes over latent dims
+    // this row's own Gaussian terms: lanes over latent dims
     float lq = 0.f, lp = 0.f;
     for (int d = lane; d < D; d += 32) {
       const float4 p = sp[i * DP + d];
       const float tt = p.w - p.z;
-      lq += (p.x - p.y * (tt * tt)) * kLn2;                    // log N(z; mu, lv)   (math.py:48-51)
+      lq += (s_c[row_local][d] - p.y * (tt * tt)) * kLn2;      // log N(z; mu, lv)   (math.py:48-51)
       lp += -0.5f * kLog2Pi - 0.5f * (p.w * p.w);              // log N(z; 0, 1)     (losses.py:531-532)
-      pj_out[(long long)d * B + i] = p;                        // the backward pass reads [D][B]
     }
     lq = warp_sum(lq); lp = warp_sum(lp);
     if (lane == 0) {
       float lprod = 0.f;
-#pragma unroll
-      for (int k = 0; k < DC; ++k) {
-        if (EXACT || k < D) {
-          const float v = (ref[k] + log2f(sx[k] + s_sx[row_local][k])) * kLn2;
-          rowstats[(long long)(4 + k) * B + i] = v;
-          lprod += v;
-        }
+      for (int k = 0; k < D; ++k) {
+        const float v = s_P[row_local][k] * kLn2;
+        rowstats[(long long)(4 + k) * B + i] = v;
+        lprod += v;
       }
-      const float2 q = s_q[row_local];
-      lse_merge2(am, as, q.x, q.y);
-      const float lqz = (am + log2f(as)) * kLn2;
+      const float lqz = s_lqz[row_local] * kLn2;
       rowstats[i] = lp; rowstats[1LL * B + i] = lqz; rowstats[2LL * B + i] = lprod; rowstats[3LL * B + i] = lq;
       s_means[row_local][0] = lq - lqz; s_means[row_local][1] = lqz - lprod; s_means[row_local][2] = lprod - lp;
     }
   }
   __syncthreads();
+  DV_F3_MARK(3);
   if (tid == 0) {
     float a = 0.f, b = 0.f, c = 0.f;
     for (int r = 0; r < rpb; ++r)
-      if (blockIdx.x * rpb + r < B) { a += s_means[r][0]; b += s_means[r][1]; c += s_means[r][2]; }
+      if (row0 + r < B) { a += s_means[r][0]; b += s_means[r][1]; c += s_means[r][2]; }
     blockpart[4 * blockIdx.x + 0] = a; blockpart[4 * blockIdx.x + 1] = b; blockpart[4 * blockIdx.x + 2] = c;
     __threadfence();
     is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
   }
   __syncthreads();
+  DV_F3_MARK(4);
   if (!is_last || warp != 0) return;
   __threadfence();
   float a = 0.f, b = 0.f, c = 0.f;
@@ -569,6 +692,7 @@ btcvae_fwd3_kernel(const float* __restrict__ z, const float* __restrict__ mu, co
     terms[0] = a / (float)B; terms[1] = b / (float)B; terms[2] = c / (float)B;
     *counter = 0u;
   }
+#undef DV_F3_MARK
 }
 
 // ---- backward ---------------------------------------------------------------------
@@ -754,6 +878,9 @@ int dv_btcvae_fwd(const float* z, const float* mu, const float* logvar, int ld, 
       float4* pj = reinterpret_cast<float4*>(ws + kWsHeader);
       float* blockpart = ws + btcvae_part_offset_floats(B, D);
       unsigned* counter = reinterpret_cast<unsigned*>(ws);
+      static int timing = -1;
+      if (timing < 0) { const char* e = getenv("DV_BTCVAE_TIMING"); timing = (e && e[0] == '1') ? 1 : 0; }
+      float* dbg = timing ? ws + 8 : nullptr;                  // header floats 8..12
 #define DV_F3_CALL(DC, EXACT)                                                                                                  \
   do {                                                                                                                         \
     static bool attr = false;                                                                                                  \
@@ -763,7 +890,7 @@ int dv_btcvae_fwd(const float* z, const float* mu, const float* logvar, int ld, 
       attr = true;                                                                                                             \
     }                                                                                                                          \
     btcvae_fwd3_kernel<DC, EXACT><<<grid, kF3Threads, smem, st>>>(z, mu, logvar, ld, row_stride, B, D, lw, rpb, pj, rowstats, \
-                                                                  terms, blockpart, counter);                                  \
+                                                                  terms, blockpart, counter, dbg);                             \
   } while (0)
       if (D == 10) DV_F3_CALL(10, true);
       else if (D == 16) DV_F3_CALL(16, true);

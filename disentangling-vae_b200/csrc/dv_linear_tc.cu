@@ -330,18 +330,18 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_mnmajor(uint32_t smem_addr, 
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) |
          (1ull << 46) | (1ull << 61);
 }
-__device__ __forceinline__ void split_hi_lo(uint4* hi, uint4* lo4, int t) {
+// residual plane lo = v - trunc_tf32(v).  The hi operand is the RAW fp32 tile itself: kind::tf32 reads only the upper
+// 19 bits of each 32-bit element, which is exactly the truncation the mask performs (the fp64-accuracy tests hold this).
+__device__ __forceinline__ void split_lo_only(const uint4* raw, uint4* lo4, int t) {
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const int idx = t + 128 * k;
-    const uint4 v = hi[idx];
-    uint4 h, l;
-    h.x = v.x & kHiMask; h.y = v.y & kHiMask; h.z = v.z & kHiMask; h.w = v.w & kHiMask;
-    l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x));
-    l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y));
-    l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z));
-    l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w));
-    hi[idx] = h;
+    const uint4 v = raw[idx];
+    uint4 l;
+    l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(v.x & kHiMask));
+    l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(v.y & kHiMask));
+    l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(v.z & kHiMask));
+    l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(v.w & kHiMask));
     lo4[idx] = l;
   }
 }
@@ -426,15 +426,15 @@ linear_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
     int stage = 0; uint32_t phase = 0; int gb = 0; uint32_t gphase = 0;
     for (int tile = t_begin; tile < t_end; ++tile) {
       mbar_wait(&bars->g_raw_full[gb], gphase);
-      split_hi_lo(reinterpret_cast<uint4*>(Gs + gb * kWgGBytes), reinterpret_cast<uint4*>(Gs + gb * kWgGBytes + kATile), t);
+      split_lo_only(reinterpret_cast<const uint4*>(Gs + gb * kWgGBytes), reinterpret_cast<uint4*>(Gs + gb * kWgGBytes + kATile), t);
       fence_proxy_async_smem();
       mbar_arrive(&bars->g_ready[gb]);
       if (++gb == 2) { gb = 0; gphase ^= 1; }
       for (int pr = 0; pr < npairs; ++pr) {
         mbar_wait(&bars->raw_full[stage], phase);
         uint8_t* base = St + stage * kWgStageBytes;
-        split_hi_lo(reinterpret_cast<uint4*>(base), reinterpret_cast<uint4*>(base + 2 * kATile), t);
-        split_hi_lo(reinterpret_cast<uint4*>(base + kATile), reinterpret_cast<uint4*>(base + 3 * kATile), t);
+        split_lo_only(reinterpret_cast<const uint4*>(base), reinterpret_cast<uint4*>(base + 2 * kATile), t);
+        split_lo_only(reinterpret_cast<const uint4*>(base + kATile), reinterpret_cast<uint4*>(base + 3 * kATile), t);
         fence_proxy_async_smem();
         mbar_arrive(&bars->ready[stage]);
         if (++stage == kWgStages) { stage = 0; phase ^= 1; }

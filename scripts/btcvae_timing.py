@@ -1,0 +1,31 @@
+"""Phase boundaries of btcvae_fwd3_kernel (block 0, SM clocks) warm and after an L2 flush.  DV_BTCVAE_TIMING=1."""
+import os, sys, torch
+os.environ["DV_BTCVAE_TIMING"] = "1"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "disentangling-vae_b200"))
+from disvae import _native as N
+from disvae._native import ptr, stream
+dev = torch.device("cuda", 0)
+B, D = 1024, 10
+torch.manual_seed(1)
+mu = torch.randn(B, D, device=dev); lv = torch.randn(B, D, device=dev) * 0.5 - 1
+z = mu + torch.exp(0.5 * lv) * torch.randn(B, D, device=dev)
+L = N.lib()
+ws = torch.zeros((L.dv_btcvae_workspace_bytes(B, D) + 3) // 4, device=dev)
+rs = torch.empty(4 + D, B, device=dev); terms = torch.empty(3, device=dev)
+flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+def run(cold):
+    if cold:
+        flush.fill_(1.0)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    N.call("dv_btcvae_fwd", ptr(z), ptr(mu), ptr(lv), 1, D, B, D, 737280, 1, ptr(rs), ptr(terms), ptr(ws), stream())
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e3, ws[8:13].tolist()
+for i in range(5): run(False)
+for cold in (False, True):
+    rows = [run(cold) for _ in range(9)]
+    rows.sort(key=lambda r: r[0])
+    us, marks = rows[len(rows) // 2]
+    print("cold" if cold else "warm", "event us %.2f" % us, "marks (clk): stage %d | bounds+fold %d | sweep %d | row stats %d | block sum %d"
+          % tuple(marks), " => us @1.9GHz:", [round(m / 1900, 2) for m in marks])
