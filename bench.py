@@ -247,7 +247,11 @@ def kernel_rooflines(trainer, resident, K, B, img, z, n_data, device):
     for k, (t, n) in table.items():
         e = k.split("[")[0]
         by_entry[e] = by_entry.get(e, 0.0) + t
-    res = {"kernel_share": {k: round(v / total, 4) for k, v in sorted(by_entry.items(), key=lambda kv: -kv[1])[:8]}}
+    res = {"kernel_share": {k: round(v / total, 4) for k, v in sorted(by_entry.items(), key=lambda kv: -kv[1])[:8]},
+           # sum of the per-call device times of one eager step (events around every C-ABI call): what is left of
+           # ms_per_step after subtracting it is torch glue kernels + launch gaps
+           "profiled_call_ms_per_step": round(total / K, 4),
+           "profiled_calls_per_step": sum(n for _, n in table.values()) // K}
     conv = [(k, v) for k, v in top if k.startswith("dv_conv_") and "[" in k]
     name, (tms, calls) = conv[0] if conv else top[0]
     if conv:

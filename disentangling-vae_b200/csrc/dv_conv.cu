@@ -570,13 +570,13 @@ namespace dv {
 namespace tc {
 int pack_tc(const float* w, float* wd, float* wu, cudaStream_t st);
 int conv_down32_tc(const float* hi, const float* wd_packed, const float* bias, const float* mask, float* lo,
-                   int B, int H, int W, int act, cudaStream_t st);
+                   int B, int H, int W, int act, cudaStream_t st, float* colsum_part, int* nparts);
 int pack_small_tc(const float* w, float* wd, int CH, cudaStream_t st);
 int pack_up_small_tc(const float* w, float* wu, int CH, cudaStream_t st);
 int conv_up_halo(const float* lo, const float* wu, const float* bias, const float* mask, float* hi,
                  int B, int H, int W, int CH, int act, cudaStream_t st);
 int conv_down_small_tc(const float* x, const float* wd, const float* bias, const float* mask, float* lo,
-                       int B, int H, int W, int CH, int act, cudaStream_t st);
+                       int B, int H, int W, int CH, int act, cudaStream_t st, float* colsum_part, int* nparts);
 int conv_wgrad_small_tc(const float* lo, const float* x, float* ws, int B, int H, int W, int CH, int* nsplit, cudaStream_t st);
 int conv_wgrad32_tc(const float* lo, const float* hi, float* ws, int B, int H, int W, int* nsplit, cudaStream_t st);
 int conv_up32_tc(const float* lo, const float* wu_packed, const float* bias, const float* mask, float* hi,
@@ -639,17 +639,14 @@ int dv_conv_pack_weights(const float* w, float* w_packed, int CH, void* stream) 
   return tc::pack_tc(w, w_packed + kPackFfma, w_packed + kPackFfma + kPackTcSection, as_stream(stream));
 }
 
-int dv_conv_down(const float* hi, const float* w_packed, const float* bias, const float* mask, float* lo,
-                 int B, int H, int W, int CH, int hi_nchw, int act, void* stream) {
-  if (!hi || !w_packed || !lo) return DV_ERR_BAD_ARG;
-  if (!shape_ok(B, H, W, CH)) return DV_ERR_BAD_SHAPE;
-  if (act != DV_ACT_NONE && act != DV_ACT_RELU) return DV_ERR_BAD_ARG;
-  if ((CH == 32) == (hi_nchw != 0)) return DV_ERR_BAD_SHAPE;   // CH==32 <=> NHWC
+static int conv_down_impl(const float* hi, const float* w_packed, const float* bias, const float* mask, float* lo,
+                          int B, int H, int W, int CH, int act, cudaStream_t st, float* colsum_part, int* nparts) {
+  *nparts = 0;
   const long long groups = ((long long)B * H * W + kDownPxPerWarp - 1) / kDownPxPerWarp;
   if (CH == 32 && use_tc("down"))
-    return tc::conv_down32_tc(hi, w_packed + kPackFfma, bias, mask, lo, B, H, W, act, as_stream(stream));
+    return tc::conv_down32_tc(hi, w_packed + kPackFfma, bias, mask, lo, B, H, W, act, st, colsum_part, nparts);
   if (CH != 32 && use_tc("dsmall") && W <= 128 && 128 % W == 0)
-    return tc::conv_down_small_tc(hi, w_packed + 2 * kLoCh * CH * kTaps, bias, mask, lo, B, H, W, CH, act, as_stream(stream));
+    return tc::conv_down_small_tc(hi, w_packed + 2 * kLoCh * CH * kTaps, bias, mask, lo, B, H, W, CH, act, st, colsum_part, nparts);
   if (CH == 32) {
     const int smem = kTaps * 32 * kLoCh * sizeof(float);
     static bool attr_set = false;
@@ -659,12 +656,37 @@ int dv_conv_down(const float* hi, const float* w_packed, const float* bias, cons
       attr_set = true;
     }
     const int grid = grid_for(groups, kDownWarps, 2 * kNumSMs);
-    conv_down32_kernel<<<grid, kDownWarps * 32, smem, as_stream(stream)>>>(hi, w_packed, bias, mask, lo, B, H, W, act);
+    conv_down32_kernel<<<grid, kDownWarps * 32, smem, st>>>(hi, w_packed, bias, mask, lo, B, H, W, act);
   } else {
     const int grid = grid_for(groups, kDownWarps, 8 * kNumSMs);
-    if (CH == 1) conv_down_small_kernel<1><<<grid, kDownWarps * 32, 0, as_stream(stream)>>>(hi, w_packed, bias, mask, lo, B, H, W, act);
-    else         conv_down_small_kernel<3><<<grid, kDownWarps * 32, 0, as_stream(stream)>>>(hi, w_packed, bias, mask, lo, B, H, W, act);
+    if (CH == 1) conv_down_small_kernel<1><<<grid, kDownWarps * 32, 0, st>>>(hi, w_packed, bias, mask, lo, B, H, W, act);
+    else         conv_down_small_kernel<3><<<grid, kDownWarps * 32, 0, st>>>(hi, w_packed, bias, mask, lo, B, H, W, act);
   }
+  return check_launch();
+}
+
+int dv_conv_down(const float* hi, const float* w_packed, const float* bias, const float* mask, float* lo,
+                 int B, int H, int W, int CH, int hi_nchw, int act, float* colsum_out, void* colsum_workspace, void* stream) {
+  if (!hi || !w_packed || !lo) return DV_ERR_BAD_ARG;
+  if (!shape_ok(B, H, W, CH)) return DV_ERR_BAD_SHAPE;
+  if (act != DV_ACT_NONE && act != DV_ACT_RELU) return DV_ERR_BAD_ARG;
+  if ((CH == 32) == (hi_nchw != 0)) return DV_ERR_BAD_SHAPE;   // CH==32 <=> NHWC
+  if (colsum_out && !colsum_workspace) return DV_ERR_WORKSPACE;
+  cudaStream_t st = as_stream(stream);
+  float* part = colsum_out ? reinterpret_cast<float*>(colsum_workspace) : nullptr;
+  static int fuse = -1;
+  if (fuse < 0) { const char* e = getenv("DV_FUSE_COLSUM"); fuse = (e && e[0] == '0') ? 0 : 1; }
+  int nparts = 0;
+  int rc = conv_down_impl(hi, w_packed, bias, mask, lo, B, H, W, CH, act, st, fuse ? part : nullptr, &nparts);
+  if (rc != DV_OK || !colsum_out) return rc;
+  if (nparts == 0) {                                           // this variant does not sum in its epilogue: one more pass over lo
+    const long long rows = (long long)B * H * W;
+    nparts = grid_for(rows, 8, kCsBlocks);
+    channel_sum_nhwc_kernel<<<nparts, 256, 0, st>>>(lo, part, rows, kLoCh);
+    rc = check_launch();
+    if (rc != DV_OK) return rc;
+  }
+  channel_sum_final_kernel<<<1, 1024, 0, st>>>(part, colsum_out, nparts, kLoCh);
   return check_launch();
 }
 

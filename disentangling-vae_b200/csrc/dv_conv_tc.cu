@@ -83,6 +83,23 @@ __device__ __forceinline__ void split_lo_only(const uint4* raw, uint4* lo4, int 
   }
 }
 
+// v[c] of lane l = value of (row l, channel c).  Returns, in lane l, the sum over the 32 rows of channel l
+// (butterfly transpose-reduce: 31 shuffles).  All 32 lanes must call it; v is destroyed.
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#define DV_CS_STEP(BIT, HALF)                                                        \
+  {                                                                                  \
+    const bool up = (lane & BIT) != 0;                                               \
+    _Pragma("unroll") for (int i = 0; i < HALF; ++i) {                               \
+      const float send = up ? v[i] : v[i + HALF];                                    \
+      const float keep = up ? v[i + HALF] : v[i];                                    \
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, BIT);                         \
+    }                                                                                \
+  }
+  DV_CS_STEP(16, 16) DV_CS_STEP(8, 8) DV_CS_STEP(4, 4) DV_CS_STEP(2, 2) DV_CS_STEP(1, 1)
+#undef DV_CS_STEP
+  return v[0];
+}
+
 struct DownGeom {
   int B, H, W;          // lo geometry
   int rows_per_tile;    // 128 / W image-rows of lo per tile
@@ -644,7 +661,7 @@ __device__ __forceinline__ void ts_split_tile(const uint8_t* raw, uint32_t tmem_
 __global__ void __launch_bounds__(kTsThreads, 1)
 conv_down32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                       const float* __restrict__ bias, const float* __restrict__ mask, float* __restrict__ lo,
-                      DownGeom g, int act) {
+                      DownGeom g, int act, float* __restrict__ colsum_part) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* Bs = smem;
@@ -707,6 +724,7 @@ conv_down32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   } else if (warp >= 4 && warp < 8) {
     const int q = warp & 3;
     int acc = 0; uint32_t acc_phase = 0;
+    float csum = 0.f;                                         // lane l: running sum of output channel l over this warp's rows
     for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
       mbar_wait(&bars->acc_full[acc], acc_phase);
       tc_fence_after_sync();
@@ -743,9 +761,22 @@ conv_down32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             v[2] = m4.z > 0.f ? v[2] : 0.f; v[3] = m4.w > 0.f ? v[3] : 0.f;
           }
           *reinterpret_cast<float4*>(dst + c4 * 4) = make_float4(v[0], v[1], v[2], v[3]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) sum[c4 * 4 + e] = v[e];
         }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) sum[c] = 0.f;
       }
+      if (colsum_part) csum += warp_colsum32(sum, lane);      // channel sums of the stored output (next layer's bias gradient)
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (colsum_part) {
+      // the last accumulator was complete -> every MMA and TMA load of this CTA is done: the raw stages are free
+      float* scr = reinterpret_cast<float*>(Raw);
+      scr[q * 32 + lane] = csum;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (q == 0) colsum_part[blockIdx.x * 32 + lane] = (scr[lane] + scr[32 + lane]) + (scr[64 + lane] + scr[96 + lane]);
     }
   } else if (warp >= 8) {
     const int q = warp & 3, grp = (warp - 8) >> 2;
@@ -1226,7 +1257,7 @@ template <int CH>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_down_small_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const float* __restrict__ x,
                           const float* __restrict__ bias, const float* __restrict__ mask, float* __restrict__ lo,
-                          DownGeom g, int act) {
+                          DownGeom g, int act, float* __restrict__ colsum_part) {
   using C = SmallCfg<CH>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -1283,11 +1314,13 @@ conv_down_small_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const floa
   } else if (warp >= 4 && warp < 8) {
     const int q = warp & 3;
     int acc = 0; uint32_t acc_phase = 0;
+    float csum = 0.f;                                         // lane l: running sum of output channel l over this warp's rows
     for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
       mbar_wait(&bars->acc_full[acc], acc_phase);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 64;
       uint32_t r0[32], r1[32];
+      float fin[32];
       tmem_ld_32x32b_x32(taddr, r0);
       tmem_ld_32x32b_x32(taddr + 32, r1);
       tmem_ld_wait();
@@ -1313,9 +1346,22 @@ conv_down_small_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const floa
             v[2] = m4.z > 0.f ? v[2] : 0.f; v[3] = m4.w > 0.f ? v[3] : 0.f;
           }
           *reinterpret_cast<float4*>(dst + c4 * 4) = make_float4(v[0], v[1], v[2], v[3]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) fin[c4 * 4 + e] = v[e];
         }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) fin[c] = 0.f;
       }
+      if (colsum_part) csum += warp_colsum32(fin, lane);      // channel sums of the stored output (next layer's bias gradient)
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (colsum_part) {
+      // all MMAs of this CTA have completed (last accumulator was full): the operand stages are free
+      float* scr = reinterpret_cast<float*>(As);
+      scr[q * 32 + lane] = csum;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (q == 0) colsum_part[blockIdx.x * 32 + lane] = (scr[lane] + scr[32 + lane]) + (scr[64 + lane] + scr[96 + lane]);
     }
   } else if (warp >= 8) {
     // ---- patch builders: thread r owns pixel row r of the tile ----
@@ -1615,8 +1661,11 @@ int pack_tc(const float* w, float* wd, float* wu, cudaStream_t st) {
 }
 
 // lo[B,H,W,32] = act(down(hi[B,2H,2W,32]) + bias) * [mask > 0]
+// colsum_part != NULL: the kernel also leaves per-CTA channel sums of `lo` in colsum_part[grid][32] and sets
+// *nparts = grid (0 when the selected variant cannot do it: the caller then sums `lo` separately).
 int conv_down32_tc(const float* hi, const float* wd_packed, const float* bias, const float* mask, float* lo,
-                   int B, int H, int W, int act, cudaStream_t st) {
+                   int B, int H, int W, int act, cudaStream_t st, float* colsum_part, int* nparts) {
+  if (nparts) *nparts = 0;
   if (W > 128 || 128 % W != 0) return DV_ERR_BAD_SHAPE;
   DownGeom g;
   g.B = B; g.H = H; g.W = W; g.prefetch = use_prefetch();
@@ -1647,7 +1696,8 @@ int conv_down32_tc(const float* hi, const float* wd_packed, const float* bias, c
       }
       attr2 = true;
     }
-    conv_down32_ts_kernel<<<grid, kTsThreads, kTsSmemBytes, st>>>(ta, tb, bias, mask, lo, g, act);
+    conv_down32_ts_kernel<<<grid, kTsThreads, kTsSmemBytes, st>>>(ta, tb, bias, mask, lo, g, act, colsum_part);
+    if (nparts && colsum_part) *nparts = grid;
     return check_launch();
   }
   conv_down32_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(ta, tb, bias, mask, lo, g, act);
@@ -1757,7 +1807,7 @@ static bool make_w_tmap_rows(CUtensorMap* m, const float* base, int rows) {
 
 template <int CH>
 static int launch_down_small(const float* x, const float* wd, const float* bias, const float* mask, float* lo,
-                             DownGeom g, int act, cudaStream_t st) {
+                             DownGeom g, int act, cudaStream_t st, float* colsum_part, int* nparts) {
   CUtensorMap tb;
   if (!make_w_tmap_rows(&tb, wd, SmallCfg<CH>::NKB * 64)) return DV_ERR_CUDA;
   static bool attr = false;
@@ -1769,16 +1819,19 @@ static int launch_down_small(const float* x, const float* wd, const float* bias,
     attr = true;
   }
   const int grid = g.num_tiles < kNumSMs ? g.num_tiles : kNumSMs;
-  conv_down_small_tc_kernel<CH><<<grid, kThreads, SmallCfg<CH>::kSmem, st>>>(tb, x, bias, mask, lo, g, act);
+  conv_down_small_tc_kernel<CH><<<grid, kThreads, SmallCfg<CH>::kSmem, st>>>(tb, x, bias, mask, lo, g, act, colsum_part);
+  if (nparts && colsum_part) *nparts = grid;
   return check_launch();
 }
 int conv_down_small_tc(const float* x, const float* wd, const float* bias, const float* mask, float* lo,
-                       int B, int H, int W, int CH, int act, cudaStream_t st) {
+                       int B, int H, int W, int CH, int act, cudaStream_t st, float* colsum_part, int* nparts) {
+  if (nparts) *nparts = 0;
   DownGeom g;
   g.B = B; g.H = H; g.W = W; g.prefetch = use_prefetch(); g.rows_per_tile = 0;
   g.total_px = (long long)B * H * W;
   g.num_tiles = (int)((g.total_px + 127) / 128);
-  return CH == 1 ? launch_down_small<1>(x, wd, bias, mask, lo, g, act, st) : launch_down_small<3>(x, wd, bias, mask, lo, g, act, st);
+  return CH == 1 ? launch_down_small<1>(x, wd, bias, mask, lo, g, act, st, colsum_part, nparts)
+                 : launch_down_small<3>(x, wd, bias, mask, lo, g, act, st, colsum_part, nparts);
 }
 
 template <int CH>

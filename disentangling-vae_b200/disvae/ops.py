@@ -53,11 +53,16 @@ def conv_pack(w, CH):
     return wp
 
 
-def conv_down(hi, wp, bias, mask, B, H, W, CH, nchw, act):
+def conv_down(hi, wp, bias, mask, B, H, W, CH, nchw, act, want_colsum=False):
+    """-> lo, or (lo, channel sums of lo) with want_colsum (summed in the kernel's epilogue)."""
     lo = _new((B, H, W, LO_CH), hi)
-    call("dv_conv_down", ptr(hi), ptr(wp), ptr(bias), ptr(mask), ptr(lo), B, H, W, CH, nchw, act, stream(),
+    cs = ws = None
+    if want_colsum:
+        cs = _new((LO_CH,), hi)
+        ws = _scratch("chansum", N.lib().dv_channel_sum_workspace_bytes(), hi.device)
+    call("dv_conv_down", ptr(hi), ptr(wp), ptr(bias), ptr(mask), ptr(lo), B, H, W, CH, nchw, act, ptr(cs), ptr(ws), stream(),
          tag="[H=%d,CH=%d]" % (H, CH))
-    return lo
+    return (lo, cs) if want_colsum else lo
 
 
 def conv_up(lo, wp, bias, mask, B, H, W, CH, nchw, act):
@@ -242,17 +247,19 @@ class DecoderFn(Function):
         S = recon.shape[-1]
         g_hi = act_bwd(_c(d_recon), recon, ACT_SIGMOID)                            # NCHW, C channels
         convT_grads = [None] * (2 * n_convT)
+        db = channel_sum(g_hi, B, C, 1, S * S)           # bias gradient of the last convT: sum of its output gradient
         for t in range(n_convT - 1, -1, -1):
             last = (t == n_convT - 1)
             H = 4 << t                                   # input resolution of convT t
             CH, nchw = (C, 1) if last else (LO_CH, 0)
-            if last:
-                db = channel_sum(g_hi, B, C, 1, S * S)
-            else:
-                db = channel_sum(g_hi, B * 4 * H * H, LO_CH, 0, 0)
             dw, _ = conv_wgrad(acts[t], g_hi, B, H, H, CH, nchw, False)
-            g_hi = conv_down(g_hi, packed[t], None, acts[t], B, H, H, CH, nchw, ACT_NONE)   # masked by acts[t] > 0
             convT_grads[2 * t], convT_grads[2 * t + 1] = dw, db
+            # input gradient, masked by acts[t] > 0; for t > 0 it is the output gradient of convT t-1, whose bias
+            # gradient (its sum over pixels) comes out of the same kernel's epilogue
+            if t > 0:
+                g_hi, db = conv_down(g_hi, packed[t], None, acts[t], B, H, H, CH, nchw, ACT_NONE, want_colsum=True)
+            else:
+                g_hi = conv_down(g_hi, packed[t], None, acts[t], B, H, H, CH, nchw, ACT_NONE)
         g3 = flat_transpose(g_hi.view(B, FLAT), B, to_nhwc=False)                  # grad of lin3 pre-activation
         dlw3, dlb3 = linear_wgrad(g3, h2)
         g2 = linear_dgrad(g3, lins[2][0], h2, ACT_RELU)

@@ -72,9 +72,14 @@ long long dv_launch_count(void);
  */
 size_t dv_conv_packed_floats(int CH);                         /* size of w_packed in floats */
 int dv_conv_pack_weights(const float* w, float* w_packed, int CH, void* stream);
-/* lo = act(down(hi) + bias) * [mask>0];  bias may be NULL.  act in {NONE, RELU}. */
+/* lo = act(down(hi) + bias) * [mask>0];  bias may be NULL.  act in {NONE, RELU}.
+ * colsum_out (optional, [32]): sum of the stored `lo` over all pixels, accumulated in the kernel's
+ * epilogue.  In the backward pass `lo` is the gradient reaching the previous ConvTranspose2d's
+ * output, so this IS that layer's bias gradient (no extra pass over the tensor).
+ * colsum_workspace: dv_channel_sum_workspace_bytes() bytes, required with colsum_out. */
 int dv_conv_down(const float* hi, const float* w_packed, const float* bias, const float* mask,
-                 float* lo, int B, int H, int W, int CH, int hi_nchw, int act, void* stream);
+                 float* lo, int B, int H, int W, int CH, int hi_nchw, int act, float* colsum_out,
+                 void* colsum_workspace, void* stream);
 /* hi = act(up(lo) + bias) * [mask>0];  bias[CH] may be NULL.  act in {NONE, RELU, SIGMOID}. */
 int dv_conv_up(const float* lo, const float* w_packed, const float* bias, const float* mask,
                float* hi, int B, int H, int W, int CH, int hi_nchw, int act, void* stream);

@@ -73,6 +73,12 @@ def test_conv_down_matches_conv2d(ops, B, H, CH, act):
     lo2 = ops.conv_down(hi, wp, None, nhwc(mask).to(dev()), B, H, H, CH, int(CH < 32), 0)
     ref2 = F.conv2d(x, w, None, stride=2, padding=1) * (mask > 0)
     assert_close(nchw(lo2.cpu()), ref2, what="down+mask")
+    # channel sums of the output from the same launch (bias gradient of the previous ConvTranspose2d)
+    lo3, cs = ops.conv_down(hi, wp, None, nhwc(mask).to(dev()), B, H, H, CH, int(CH < 32), 0, want_colsum=True)
+    assert torch.equal(lo3, lo2)
+    assert_close(cs.cpu(), ref2.double().sum((0, 2, 3)).float(), tol=2e-5, what="down+mask column sums")
+    _, cs2 = ops.conv_down(hi, wp, None, nhwc(mask).to(dev()), B, H, H, CH, int(CH < 32), 0, want_colsum=True)
+    assert torch.equal(cs, cs2)                                # fixed reduction order
 
 
 @pytest.mark.parametrize("B,H,CH", CONV_CASES)
