@@ -64,7 +64,7 @@ conv_up_c2i_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   uint8_t* Raw = smem + C::kBBytes;
   float* Ds = reinterpret_cast<float*>(Raw + kStages * kATile);
   Barriers* bars = reinterpret_cast<Barriers*>(reinterpret_cast<uint8_t*>(Ds) + ((C::kDBytes + 127) / 128) * 128);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform role index
   // this CTA's images: blockIdx.x, blockIdx.x + gridDim.x, ...; tiles of an image in order
   const int n_img = (g.B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int n_seq = n_img * g.tiles_per_img;
@@ -84,7 +84,7 @@ conv_up_c2i_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   if (bars->tmem_base != 0u) __trap();
   constexpr uint32_t tmem_base = 0u;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && elect_one()) {
     prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b);
     mbar_arrive_expect_tx(&bars->b_full, C::kBBytes);
     for (int h = 0; h < C::kBRows / 64; ++h) tma_load_2d(Bs + h * 8192, &tmap_b, &bars->b_full, 0, h * 64);
@@ -96,7 +96,8 @@ conv_up_c2i_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       mbar_arrive_expect_tx(&bars->full[stage], kATile);
       tma_load_2d(Raw + stage * kATile, &tmap_a, &bars->full[stage], 0, (img * g.H + i0) * g.W);
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 && elect_one()) {      // ONE elected lane runs the whole issue loop (barrier waits included):
+                                              // ptxas then keeps every MMA operand in uniform registers (back-to-back UTCHMMA)
     constexpr uint32_t idesc2 = umma_idesc_tf32(128, 2 * C::kNT), idesc1 = umma_idesc_tf32(128, C::kNT);
     mbar_wait(&bars->b_full, 0);
     const uint64_t b_d = umma_desc_sw128_kmajor(smem_u32(Bs));         // rows [0,NT) hi, [NT,2NT) lo
@@ -109,11 +110,11 @@ conv_up_c2i_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       const uint32_t d = tmem_base + acc * kAccCols;
 #pragma unroll
       for (int k4 = 0; k4 < 4; ++k4) {
-        umma_tf32_ts(d, a_hi + 8 * k4, b_d + 2 * k4, idesc2, k4 != 0);      // cols [0,NT) hi*hi, [NT,2NT) hi*lo
-        umma_tf32_ts(d, a_lo + 8 * k4, b_d + 2 * k4, idesc1, 1);            // cols [0,NT) += lo*hi
+        umma_tf32_ts_1t(d, a_hi + 8 * k4, b_d + 2 * k4, idesc2, k4 != 0);      // cols [0,NT) hi*hi, [NT,2NT) hi*lo
+        umma_tf32_ts_1t(d, a_lo + 8 * k4, b_d + 2 * k4, idesc1, 1);            // cols [0,NT) += lo*hi
       }
-      umma_commit(&bars->a_empty[as]);
-      umma_commit(&bars->acc_full[acc]);
+      umma_commit_1t(&bars->a_empty[as]);
+      umma_commit_1t(&bars->acc_full[acc]);
     }
   } else if (warp >= 4 && warp < 8) {
     // ---- epilogue: D -> smem, then gather the finished output rows ----
@@ -218,11 +219,10 @@ conv_up_c2i_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     // ---- split warps: raw lo tile -> hi/lo planes in TMEM (two groups on alternate tiles) ----
     const int q = warp & 3, grp = (warp - 8) >> 2;
     const int row = q * 32 + lane;
+    int prev_stage = -1, prev_as = 0;                         // tile whose TMEM stores are still in flight
     for (int s = grp; s < n_seq; s += 2) {
       const int stage = s % kStages, as = s % kAStages;
       mbar_wait(&bars->full[stage], (s / kStages) & 1u);
-      mbar_wait(&bars->a_empty[as], ((s / kAStages) & 1u) ^ 1u);
-      tc_fence_after_sync();
       const uint8_t* raw = Raw + stage * kATile;
       uint32_t h[32], l[32];
 #pragma unroll
@@ -236,13 +236,26 @@ conv_up_c2i_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           l[c * 4 + e] = __float_as_uint(__uint_as_float(vv[e]) - __uint_as_float(hb));
         }
       }
+      // software pipeline: the stores of the previous tile overlapped this tile's loads and split; publish it
+      // (and release its raw stage -- only after tcgen05.wait::st, when its reads were certainly consumed) now
+      if (prev_stage >= 0) {
+        tmem_st_wait();
+        mbar_arrive(&bars->consumed[prev_stage]);
+        tc_fence_before_sync();
+        mbar_arrive(&bars->a_ready[prev_as]);
+      }
+      mbar_wait(&bars->a_empty[as], ((s / kAStages) & 1u) ^ 1u);
+      tc_fence_after_sync();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + kACol0 + as * 64;
       tmem_st_32x32b_x32(taddr, h);
       tmem_st_32x32b_x32(taddr + 32, l);
+      prev_stage = stage; prev_as = as;
+    }
+    if (prev_stage >= 0) {
       tmem_st_wait();
-      mbar_arrive(&bars->consumed[stage]);                    // after the stores: every loaded value was consumed
+      mbar_arrive(&bars->consumed[prev_stage]);
       tc_fence_before_sync();
-      mbar_arrive(&bars->a_ready[as]);
+      mbar_arrive(&bars->a_ready[prev_as]);
     }
   }
   tc_fence_before_sync();

@@ -106,6 +106,8 @@ struct DownGeom {
   int num_tiles;
   long long total_px;
   int prefetch;         // L2-prefetch the next tile's hi rows (DV_TC_PREFETCH=0 switches it off)
+  int pipe;             // split warps overlap the TMEM stores of one tile with the loads/split of their next tile
+  int debug;            // DV_TC_DEBUG (timing experiments only, results are WRONG): 2 = load 4 of the 16 tap tiles
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -119,7 +121,7 @@ conv_down32_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   uint8_t* Alo = Ahi + kStages * kATile;
   Barriers* bars = reinterpret_cast<Barriers*>(Alo + kStages * kATile);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform role index
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&bars->raw_full[s], 1); mbar_init(&bars->ready[s], 128); mbar_init(&bars->empty[s], 1); }
@@ -134,7 +136,7 @@ conv_down32_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   tc_fence_after_sync();
   const uint32_t tmem_base = bars->tmem_base;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && elect_one()) {
     // ===================== TMA producer =====================
     prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b);
     mbar_arrive_expect_tx(&bars->b_full, kBBytes);
@@ -151,7 +153,8 @@ conv_down32_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1) {          // whole warp, warp-uniform control flow; one elected lane issues
+  } else if (warp == 1 && elect_one()) {      // ONE elected lane runs the whole issue loop (barrier waits included):
+                                              // ptxas then keeps every MMA operand in uniform registers (back-to-back UTCHMMA)
     // ===================== MMA issuer (single thread) =====================
     constexpr uint32_t idesc64 = umma_idesc_tf32(128, 64), idesc32 = umma_idesc_tf32(128, 32);
     mbar_wait(&bars->b_full, 0);
@@ -171,13 +174,13 @@ conv_down32_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
           // two independent accumulation chains (k4 parity): the tensor core truncates when it adds into
           // the fp32 accumulator, so halving the chain length halves that bias; summed in the epilogue
           const uint32_t d = d_tmem + (k4 & 1) * 64;
-          umma_tf32_ss(d, a_hi + 2 * k4, b_d + 2 * k4, idesc64, (tap | (k4 >> 1)) != 0);  // a_hi * [b_hi | b_lo]
-          umma_tf32_ss(d, a_lo + 2 * k4, b_d + 2 * k4, idesc32, 1);                        // a_lo * b_hi
+          umma_tf32_ss_1t(d, a_hi + 2 * k4, b_d + 2 * k4, idesc64, (tap | (k4 >> 1)) != 0);  // a_hi * [b_hi | b_lo]
+          umma_tf32_ss_1t(d, a_lo + 2 * k4, b_d + 2 * k4, idesc32, 1);                        // a_lo * b_hi
         }
-        umma_commit(&bars->empty[stage]);                  // stage free once these MMAs have read it
+        umma_commit_1t(&bars->empty[stage]);                  // stage free once these MMAs have read it
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
-      umma_commit(&bars->acc_full[acc]);
+      umma_commit_1t(&bars->acc_full[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4 && warp < 8) {
@@ -262,7 +265,7 @@ conv_up32_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   uint8_t* Ahi = smem + kBBytes;
   uint8_t* Alo = Ahi + kStages * kATile;
   Barriers* bars = reinterpret_cast<Barriers*>(Alo + kStages * kATile);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform role index
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&bars->raw_full[s], 1); mbar_init(&bars->ready[s], 128); mbar_init(&bars->empty[s], 1); }
@@ -277,7 +280,7 @@ conv_up32_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   tc_fence_after_sync();
   const uint32_t tmem_base = bars->tmem_base;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && elect_one()) {
     prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b);
     mbar_arrive_expect_tx(&bars->b_full, kBBytes);
     for (int tap = 0; tap < kTaps; ++tap) tma_load_2d(Bs + tap * kBTap, &tmap_b, &bars->b_full, 0, tap * 64);
@@ -293,7 +296,8 @@ conv_up32_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1) {          // whole warp, warp-uniform control flow; one elected lane issues
+  } else if (warp == 1 && elect_one()) {      // ONE elected lane runs the whole issue loop (barrier waits included):
+                                              // ptxas then keeps every MMA operand in uniform registers (back-to-back UTCHMMA)
     constexpr uint32_t idesc64 = umma_idesc_tf32(128, 64), idesc32 = umma_idesc_tf32(128, 32);
     mbar_wait(&bars->b_full, 0);
     int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
@@ -320,15 +324,15 @@ conv_up32_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             inited |= 1u << pidx;
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4) {
-              umma_tf32_ss(d, a_hi + 2 * k4, b_d + 2 * k4, idesc64, (first | (uint32_t)k4) != 0);
-              umma_tf32_ss(d, a_lo + 2 * k4, b_d + 2 * k4, idesc32, 1);
+              umma_tf32_ss_1t(d, a_hi + 2 * k4, b_d + 2 * k4, idesc64, (first | (uint32_t)k4) != 0);
+              umma_tf32_ss_1t(d, a_lo + 2 * k4, b_d + 2 * k4, idesc32, 1);
             }
           }
         }
-        umma_commit(&bars->empty[stage]);
+        umma_commit_1t(&bars->empty[stage]);
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
-      umma_commit(&bars->acc_full[acc]);
+      umma_commit_1t(&bars->acc_full[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4 && warp < 8) {
@@ -444,7 +448,7 @@ conv_wgrad32_tc_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid
   uint8_t* St = smem;                                        // [stage][T0hi|T1hi|T0lo|T1lo]
   uint8_t* Ls = smem + kWgStages * kWgStageBytes;            // [buf][Lhi|Llo]
   WgBarriers* bars = reinterpret_cast<WgBarriers*>(Ls + 2 * kWgLBytes);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform role index
   const int t_begin = blockIdx.x * g.tiles_per_cta;
   const int t_end = min(g.num_tiles, t_begin + g.tiles_per_cta);
 
@@ -461,7 +465,7 @@ conv_wgrad32_tc_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid
   if (bars->tmem_base != 0u) __trap();                       // whole TMEM is ours: base column 0
   constexpr uint32_t tmem_base = 0u;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && elect_one()) {
     prefetch_tmap(&tmap_hi); prefetch_tmap(&tmap_lo);
     int stage = 0; uint32_t phase = 0; int lb = 0; uint32_t lphase = 0;
     for (int tile = t_begin; tile < t_end; ++tile) {
@@ -488,7 +492,8 @@ conv_wgrad32_tc_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid
         if (++stage == kWgStages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1) {          // whole warp, warp-uniform control flow; one elected lane issues
+  } else if (warp == 1 && elect_one()) {      // ONE elected lane runs the whole issue loop (barrier waits included):
+                                              // ptxas then keeps every MMA operand in uniform registers (back-to-back UTCHMMA)
     // M=128, N=64, tf32, both operands MN-major (bits 15 and 16)
     constexpr uint32_t idesc = umma_idesc_tf32(128, 64) | (1u << 15) | (1u << 16);
     int stage = 0; uint32_t phase = 0; int lb = 0; uint32_t lphase = 0;
@@ -503,16 +508,16 @@ conv_wgrad32_tc_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid
         const uint32_t d = tmem_base + pr * 64;
 #pragma unroll 4
         for (int kc = 0; kc < 16; ++kc) {                   // 8 pixels per MMA
-          umma_tf32_ss(d, umma_desc_sw128_mnmajor(a_addr + kc * 1024, kATile),
+          umma_tf32_ss_1t(d, umma_desc_sw128_mnmajor(a_addr + kc * 1024, kATile),
                        umma_desc_sw128_mnmajor(l_addr + kc * 1024, kATile), idesc, (tile != t_begin) || (kc != 0));
         }
-        umma_commit(&bars->empty[stage]);
+        umma_commit_1t(&bars->empty[stage]);
         if (++stage == kWgStages) { stage = 0; phase ^= 1; }
       }
-      umma_commit(&bars->l_empty[lb]);
+      umma_commit_1t(&bars->l_empty[lb]);
       if (++lb == 2) { lb = 0; lphase ^= 1; }
     }
-    umma_commit(&bars->acc_full);
+    umma_commit_1t(&bars->acc_full);
   } else if (warp >= 8) {
     // split raw tiles into hi/lo planes; also accumulate the column sums of lo (bias gradient)
     const int t = threadIdx.x - 256;
@@ -667,14 +672,14 @@ conv_down32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   uint8_t* Bs = smem;
   uint8_t* Raw = smem + kBBytes;
   TsBarriers* bars = reinterpret_cast<TsBarriers*>(Raw + kTsRawStages * kATile);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform role index
   ts_init(bars, bias, warp);
   // All 512 columns are ours (1 CTA/SM), so the allocation starts at column 0.  Using the literal keeps every
   // tensor-memory address a compile-time/warp-uniform value (no per-MMA register -> uniform-register moves).
   if (bars->tmem_base != 0u) __trap();
   constexpr uint32_t tmem_base = 0u;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && elect_one()) {
     prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b);
     mbar_arrive_expect_tx(&bars->b_full, kBBytes);
     for (int tap = 0; tap < kTaps; ++tap) tma_load_2d(Bs + tap * kBTap, &tmap_b, &bars->b_full, 0, tap * 64);
@@ -691,12 +696,17 @@ conv_down32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       for (int tap = 0; tap < kTaps; ++tap) {
         const int kh = tap >> 2, kw = tap & 3;
         mbar_wait(&bars->raw_empty[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&bars->raw_full[stage], kATile);
-        tma_load_4d(Raw + stage * kATile, &tmap_a, &bars->raw_full[stage], 0, kw - 1, 2 * i0 - 1 + kh, b0);
+        if ((g.debug & 2) && (tap & 3)) {
+          mbar_arrive(&bars->raw_full[stage]);                 // timing experiment: no data for this tap
+        } else {
+          mbar_arrive_expect_tx(&bars->raw_full[stage], kATile);
+          tma_load_4d(Raw + stage * kATile, &tmap_a, &bars->raw_full[stage], 0, kw - 1, 2 * i0 - 1 + kh, b0);
+        }
         if (++stage == kTsRawStages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1) {          // whole warp, warp-uniform control flow; one elected lane issues
+  } else if (warp == 1 && elect_one()) {      // ONE elected lane runs the whole issue loop (barrier waits included):
+                                              // ptxas then keeps every MMA operand in uniform registers (back-to-back UTCHMMA)
     constexpr uint32_t idesc64 = umma_idesc_tf32(128, 64), idesc32 = umma_idesc_tf32(128, 32);
     mbar_wait(&bars->b_full, 0);
     int as = 0; uint32_t aphase = 0; int acc = 0; uint32_t acc_phase = 0;
@@ -712,13 +722,13 @@ conv_down32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
 #pragma unroll
         for (int k4 = 0; k4 < 4; ++k4) {
           const uint32_t d = d_tmem + (k4 & 1) * 64;          // two accumulation chains, see the SS kernel
-          umma_tf32_ts(d, a_hi + 8 * k4, b_d + 2 * k4, idesc64, (tap | (k4 >> 1)) != 0);
-          umma_tf32_ts(d, a_lo + 8 * k4, b_d + 2 * k4, idesc32, 1);
+          umma_tf32_ts_1t(d, a_hi + 8 * k4, b_d + 2 * k4, idesc64, (tap | (k4 >> 1)) != 0);
+          umma_tf32_ts_1t(d, a_lo + 8 * k4, b_d + 2 * k4, idesc32, 1);
         }
-        umma_commit(&bars->a_empty[as]);
+        umma_commit_1t(&bars->a_empty[as]);
         if (++as == kTsAStages) { as = 0; aphase ^= 1; }
       }
-      umma_commit(&bars->acc_full[acc]);
+      umma_commit_1t(&bars->acc_full[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4 && warp < 8) {
@@ -781,17 +791,63 @@ conv_down32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   } else if (warp >= 8) {
     const int q = warp & 3, grp = (warp - 8) >> 2;
     uint32_t n = 0;                                           // sequence number of the raw tile within this CTA
-    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
-      for (int tap = 0; tap < kTaps; ++tap, ++n) {
-        if ((int)(n & 1u) != grp) continue;
-        const int stage = n % kTsRawStages, as = n % kTsAStages;
-        mbar_wait(&bars->raw_full[stage], (n / kTsRawStages) & 1u);
-        mbar_wait(&bars->a_empty[as], ((n / kTsAStages) & 1u) ^ 1u);
-        tc_fence_after_sync();
-        ts_split_tile(Raw + stage * kATile, tmem_base, as, q, lane);
-        mbar_arrive(&bars->raw_empty[stage]);
+    if (!g.pipe) {
+      for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+        for (int tap = 0; tap < kTaps; ++tap, ++n) {
+          if ((int)(n & 1u) != grp) continue;
+          const int stage = n % kTsRawStages, as = n % kTsAStages;
+          mbar_wait(&bars->raw_full[stage], (n / kTsRawStages) & 1u);
+          mbar_wait(&bars->a_empty[as], ((n / kTsAStages) & 1u) ^ 1u);
+          tc_fence_after_sync();
+          ts_split_tile(Raw + stage * kATile, tmem_base, as, q, lane);
+          mbar_arrive(&bars->raw_empty[stage]);
+          tc_fence_before_sync();
+          mbar_arrive(&bars->a_ready[as]);
+        }
+      }
+    } else {
+      // Software pipeline: the tcgen05.st of tile n stay in flight while tile n+2 (this group's next one) is loaded
+      // from shared memory and split in registers; tile n is published (and its raw stage released -- only after
+      // tcgen05.wait::st, when its shared-memory reads have certainly been consumed) just before the next stores.
+      const int row = q * 32 + lane;
+      int prev_stage = -1, prev_as = 0;
+      for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+        for (int tap = 0; tap < kTaps; ++tap, ++n) {
+          if ((int)(n & 1u) != grp) continue;
+          const int stage = n % kTsRawStages, as = n % kTsAStages;
+          mbar_wait(&bars->raw_full[stage], (n / kTsRawStages) & 1u);
+          const uint8_t* raw = Raw + stage * kATile;
+          uint32_t h[32], l[32];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint4 v = *reinterpret_cast<const uint4*>(raw + row * 128 + ((c ^ (row & 7)) << 4));
+            const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const uint32_t hb = vv[e] & kHiMask;
+              h[c * 4 + e] = hb;
+              l[c * 4 + e] = __float_as_uint(__uint_as_float(vv[e]) - __uint_as_float(hb));
+            }
+          }
+          if (prev_stage >= 0) {
+            tmem_st_wait();
+            mbar_arrive(&bars->raw_empty[prev_stage]);
+            tc_fence_before_sync();
+            mbar_arrive(&bars->a_ready[prev_as]);
+          }
+          mbar_wait(&bars->a_empty[as], ((n / kTsAStages) & 1u) ^ 1u);
+          tc_fence_after_sync();
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + kTsACol0 + as * 64;
+          tmem_st_32x32b_x32(taddr, h);
+          tmem_st_32x32b_x32(taddr + 32, l);
+          prev_stage = stage; prev_as = as;
+        }
+      }
+      if (prev_stage >= 0) {
+        tmem_st_wait();
+        mbar_arrive(&bars->raw_empty[prev_stage]);
         tc_fence_before_sync();
-        mbar_arrive(&bars->a_ready[as]);
+        mbar_arrive(&bars->a_ready[prev_as]);
       }
     }
   }
@@ -809,14 +865,14 @@ conv_up32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   uint8_t* Bs = smem;
   uint8_t* Raw = smem + kBBytes;
   TsBarriers* bars = reinterpret_cast<TsBarriers*>(Raw + kTsRawStages * kATile);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform role index
   ts_init(bars, bias, warp);
   // All 512 columns are ours (1 CTA/SM), so the allocation starts at column 0.  Using the literal keeps every
   // tensor-memory address a compile-time/warp-uniform value (no per-MMA register -> uniform-register moves).
   if (bars->tmem_base != 0u) __trap();
   constexpr uint32_t tmem_base = 0u;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && elect_one()) {
     prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b);
     mbar_arrive_expect_tx(&bars->b_full, kBBytes);
     for (int tap = 0; tap < kTaps; ++tap) tma_load_2d(Bs + tap * kBTap, &tmap_b, &bars->b_full, 0, tap * 64);
@@ -832,7 +888,8 @@ conv_up32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (++stage == kTsRawStages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1) {          // whole warp, warp-uniform control flow; one elected lane issues
+  } else if (warp == 1 && elect_one()) {      // ONE elected lane runs the whole issue loop (barrier waits included):
+                                              // ptxas then keeps every MMA operand in uniform registers (back-to-back UTCHMMA)
     constexpr uint32_t idesc32 = umma_idesc_tf32(128, 32);
     mbar_wait(&bars->b_full, 0);
     int as = 0; uint32_t aphase = 0; int acc = 0; uint32_t acc_phase = 0;
@@ -859,16 +916,16 @@ conv_up32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             inited |= 1u << pidx;
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4) {
-              umma_tf32_ts(d, a_hi + 8 * k4, b_hi + 2 * k4, idesc32, (first | (uint32_t)k4) != 0);
-              umma_tf32_ts(d, a_hi + 8 * k4, b_lo + 2 * k4, idesc32, 1);
-              umma_tf32_ts(d, a_lo + 8 * k4, b_hi + 2 * k4, idesc32, 1);
+              umma_tf32_ts_1t(d, a_hi + 8 * k4, b_hi + 2 * k4, idesc32, (first | (uint32_t)k4) != 0);
+              umma_tf32_ts_1t(d, a_hi + 8 * k4, b_lo + 2 * k4, idesc32, 1);
+              umma_tf32_ts_1t(d, a_lo + 8 * k4, b_hi + 2 * k4, idesc32, 1);
             }
           }
         }
-        umma_commit(&bars->a_empty[as]);
+        umma_commit_1t(&bars->a_empty[as]);
         if (++as == kTsAStages) { as = 0; aphase ^= 1; }
       }
-      umma_commit(&bars->acc_full[acc]);
+      umma_commit_1t(&bars->acc_full[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4 && warp < 8) {
@@ -956,6 +1013,8 @@ constexpr int kHaloStageBytes = 26 * 1024;      // 208 pixel rows: the largest b
 constexpr int kHaloStages = 3;
 struct HaloGeom {
   int B, H, W, Wp, TR, TB, tiles_per_img, num_tiles, img_px, q_start, box_bytes;
+  int pipe;             // see DownGeom::pipe
+  int debug;            // DV_TC_DEBUG (timing experiments only, results are WRONG): 1 = issue 1 of the 3 MMAs per product
 };
 struct HaloBarriers {
   uint64_t raw_full[kHaloStages], raw_empty[kHaloStages];
@@ -990,7 +1049,7 @@ conv_up_halo_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
   uint8_t* Bs = smem;
   uint8_t* Raw = smem + C::kBAll;
   HaloBarriers* bars = reinterpret_cast<HaloBarriers*>(Raw + kHaloStages * kHaloStageBytes);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform role index
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kHaloStages; ++s) { mbar_init(&bars->raw_full[s], 1); mbar_init(&bars->raw_empty[s], 9 * 128); }
@@ -1007,7 +1066,7 @@ conv_up_halo_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
   if (bars->tmem_base != 0u) __trap();                       // whole TMEM is ours: base column 0 (see the TS kernels)
   constexpr uint32_t tmem_base = 0u;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && elect_one()) {
     prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b);
     mbar_arrive_expect_tx(&bars->b_full, C::kBAll);
     if (CH == 32) { for (int tap = 0; tap < kTaps; ++tap) tma_load_2d(Bs + tap * kBTap, &tmap_b, &bars->b_full, 0, tap * 64); }
@@ -1021,7 +1080,7 @@ conv_up_halo_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
       mbar_arrive_expect_tx(&bars->raw_full[stage], g.box_bytes);
       tma_load_4d(Raw + stage * kHaloStageBytes, &tmap_a, &bars->raw_full[stage], 0, -1, i0 - 1, b0);
     }
-  } else if (warp == 1) {          // whole warp, warp-uniform control flow; one elected lane issues
+  } else if (warp == 1 && elect_one()) {      // ONE elected lane runs the whole issue loop (waits included)
     constexpr uint32_t idescN = umma_idesc_tf32(128, C::kN);
     mbar_wait(&bars->b_full, 0);
     uint32_t n = 0; int acc = 0; uint32_t acc_phase = 0;
@@ -1049,9 +1108,9 @@ conv_up_halo_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
               inited |= 1u << pidx;
 #pragma unroll
               for (int k4 = 0; k4 < 4; ++k4) {
-                umma_tf32_ts(d, a_hi + 8 * k4, b_hi + 2 * k4, idescN, (first | (uint32_t)k4) != 0);
-                umma_tf32_ts(d, a_hi + 8 * k4, b_hi + (4096 >> 4) + 2 * k4, idescN, 1);      // a_hi * b_lo
-                umma_tf32_ts(d, a_lo + 8 * k4, b_hi + 2 * k4, idescN, 1);                    // a_lo * b_hi
+                umma_tf32_ts_1t(d, a_hi + 8 * k4, b_hi + 2 * k4, idescN, (first | (uint32_t)k4) != 0);
+                umma_tf32_ts_1t(d, a_hi + 8 * k4, b_hi + (4096 >> 4) + 2 * k4, idescN, 1);      // a_hi * b_lo
+                umma_tf32_ts_1t(d, a_lo + 8 * k4, b_hi + 2 * k4, idescN, 1);                    // a_lo * b_hi
               }
             }
           }
@@ -1060,13 +1119,13 @@ conv_up_halo_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
           const uint64_t b_s = umma_desc_sw128_kmajor(smem_u32(Bs + s * C::kBTapBytes));
 #pragma unroll
           for (int k4 = 0; k4 < 4; ++k4) {
-            umma_tf32_ts(d, a_hi + 8 * k4, b_s + 2 * k4, idescN, (s | k4) != 0);            // a_hi * [b_hi | b_lo], all phases
-            umma_tf32_ts(d, a_lo + 8 * k4, b_s + 2 * k4, idescN, 1);                        // a_lo * [b_hi | b_lo]
+            umma_tf32_ts_1t(d, a_hi + 8 * k4, b_s + 2 * k4, idescN, (s | k4) != 0);            // a_hi * [b_hi | b_lo], all phases
+            umma_tf32_ts_1t(d, a_lo + 8 * k4, b_s + 2 * k4, idescN, 1);                        // a_lo * [b_hi | b_lo]
           }
         }
-        umma_commit(&bars->a_empty[as]);
+        umma_commit_1t(&bars->a_empty[as]);
       }
-      umma_commit(&bars->acc_full[acc]);
+      umma_commit_1t(&bars->acc_full[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4 && warp < 8) {
@@ -1148,6 +1207,7 @@ conv_up_halo_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     const int q = warp & 3, grp = (warp - 8) >> 2;
     const int row = q * 32 + lane;
     uint32_t n = 0, t_seq = 0;
+    int prev_stage = -1, prev_as = 0;                         // g.pipe: shifted tile whose TMEM stores are still in flight
     for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++t_seq) {
       const int stage = t_seq % kHaloStages;
       const uint8_t* raw = Raw + stage * kHaloStageBytes;
@@ -1170,11 +1230,18 @@ conv_up_halo_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             l[c * 4 + e] = __float_as_uint(__uint_as_float(vv[e]) - __uint_as_float(hb));
           }
         }
+        if (g.pipe && prev_stage >= 0) {                      // publish the previous shifted tile (its stores overlapped this split)
+          tmem_st_wait();
+          mbar_arrive(&bars->raw_empty[prev_stage]);
+          tc_fence_before_sync();
+          mbar_arrive(&bars->a_ready[prev_as]);
+        }
         mbar_wait(&bars->a_empty[as], ((n / kTsAStages) & 1u) ^ 1u);
         tc_fence_after_sync();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + kTsACol0 + as * 64;
         tmem_st_32x32b_x32(taddr, h);
         tmem_st_32x32b_x32(taddr + 32, l);
+        if (g.pipe) { prev_stage = stage; prev_as = as; continue; }
         tmem_st_wait();
         // Release the halo tile only now: the tcgen05.st above consumed every loaded value, so the shared-memory
         // reads have certainly completed (an arrive issued right after the loads can overtake them and let the
@@ -1183,6 +1250,12 @@ conv_up_halo_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         tc_fence_before_sync();
         mbar_arrive(&bars->a_ready[as]);
       }
+    }
+    if (prev_stage >= 0) {
+      tmem_st_wait();
+      mbar_arrive(&bars->raw_empty[prev_stage]);
+      tc_fence_before_sync();
+      mbar_arrive(&bars->a_ready[prev_as]);
     }
   }
   tc_fence_before_sync();
@@ -1264,7 +1337,7 @@ conv_down_small_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const floa
   uint8_t* Bs = smem;                                        // [kb][64 rows][128 B]
   uint8_t* As = smem + C::kBBytesS;                          // [stage][hi kb.. | lo kb..][128 rows][128 B]
   Barriers* bars = reinterpret_cast<Barriers*>(As + C::kNStages * C::kStage);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform role index
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&bars->raw_full[s], 1); mbar_init(&bars->ready[s], 128); mbar_init(&bars->empty[s], 1); }
@@ -1279,11 +1352,12 @@ conv_down_small_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const floa
   tc_fence_after_sync();
   const uint32_t tmem_base = bars->tmem_base;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && elect_one()) {
     prefetch_tmap(&tmap_b);
     mbar_arrive_expect_tx(&bars->b_full, C::kBBytesS);
     for (int kb = 0; kb < C::NKB; ++kb) tma_load_2d(Bs + kb * kBTap, &tmap_b, &bars->b_full, 0, kb * 64);
-  } else if (warp == 1) {          // whole warp, warp-uniform control flow; one elected lane issues
+  } else if (warp == 1 && elect_one()) {      // ONE elected lane runs the whole issue loop (barrier waits included):
+                                              // ptxas then keeps every MMA operand in uniform registers (back-to-back UTCHMMA)
     constexpr uint32_t idesc64 = umma_idesc_tf32(128, 64), idesc32 = umma_idesc_tf32(128, 32);
     mbar_wait(&bars->b_full, 0);
     int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
@@ -1301,13 +1375,13 @@ conv_down_small_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const floa
 #pragma unroll
         for (int k4 = 0; k4 < 4; ++k4) {
           if (kb * 32 + k4 * 8 >= C::K) continue;           // all-zero padding slice
-          umma_tf32_ss(d, a_hi + 2 * k4, b_d + 2 * k4, idesc64, accum);
-          umma_tf32_ss(d, a_lo + 2 * k4, b_d + 2 * k4, idesc32, 1);
+          umma_tf32_ss_1t(d, a_hi + 2 * k4, b_d + 2 * k4, idesc64, accum);
+          umma_tf32_ss_1t(d, a_lo + 2 * k4, b_d + 2 * k4, idesc32, 1);
           accum = 1;
         }
       }
-      umma_commit(&bars->empty[stage]);
-      umma_commit(&bars->acc_full[acc]);
+      umma_commit_1t(&bars->empty[stage]);
+      umma_commit_1t(&bars->acc_full[acc]);
       if (++stage == C::kNStages) { stage = 0; phase ^= 1; }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
@@ -1431,7 +1505,7 @@ conv_wgrad_small_tc_kernel(const __grid_constant__ CUtensorMap tmap_lo, const fl
   uint8_t* Ps = smem;                                        // [stage][P_hi groups | P_lo groups (| unused)]
   uint8_t* Ls = smem + 2 * C::kPStage;                       // [buf][Lhi|Llo]
   WgBarriers* bars = reinterpret_cast<WgBarriers*>(Ls + 2 * kWgLBytes);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform role index
   const int t_begin = blockIdx.x * g.tiles_per_cta;
   const int t_end = min(g.num_tiles, t_begin + g.tiles_per_cta);
 
@@ -1447,7 +1521,7 @@ conv_wgrad_small_tc_kernel(const __grid_constant__ CUtensorMap tmap_lo, const fl
   tc_fence_after_sync();
   const uint32_t tmem_base = bars->tmem_base;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && elect_one()) {
     prefetch_tmap(&tmap_lo);
     int lb = 0; uint32_t lphase = 0;
     for (int tile = t_begin; tile < t_end; ++tile) {
@@ -1458,7 +1532,8 @@ conv_wgrad_small_tc_kernel(const __grid_constant__ CUtensorMap tmap_lo, const fl
       tma_load_4d(Ls + lb * kWgLBytes, &tmap_lo, &bars->l_raw_full[lb], 0, 0, i0, b0);
       if (++lb == 2) { lb = 0; lphase ^= 1; }
     }
-  } else if (warp == 1) {          // whole warp, warp-uniform control flow; one elected lane issues
+  } else if (warp == 1 && elect_one()) {      // ONE elected lane runs the whole issue loop (barrier waits included):
+                                              // ptxas then keeps every MMA operand in uniform registers (back-to-back UTCHMMA)
     constexpr uint32_t idesc = umma_idesc_tf32(128, 64) | (1u << 15) | (1u << 16);
     int stage = 0; uint32_t phase = 0; int lb = 0; uint32_t lphase = 0;
     for (int tile = t_begin; tile < t_end; ++tile) {
@@ -1469,14 +1544,14 @@ conv_wgrad_small_tc_kernel(const __grid_constant__ CUtensorMap tmap_lo, const fl
       const uint32_t a_addr = smem_u32(Ps + stage * C::kPStage);
 #pragma unroll 4
       for (int kc = 0; kc < 16; ++kc)
-        umma_tf32_ss(tmem_base, umma_desc_sw128_mnmajor(a_addr + kc * 1024, kATile),
+        umma_tf32_ss_1t(tmem_base, umma_desc_sw128_mnmajor(a_addr + kc * 1024, kATile),
                      umma_desc_sw128_mnmajor(l_addr + kc * 1024, kATile), idesc, (tile != t_begin) || (kc != 0));
-      umma_commit(&bars->empty[stage]);
-      umma_commit(&bars->l_empty[lb]);
+      umma_commit_1t(&bars->empty[stage]);
+      umma_commit_1t(&bars->l_empty[lb]);
       if (++stage == 2) { stage = 0; phase ^= 1; }
       if (++lb == 2) { lb = 0; lphase ^= 1; }
     }
-    umma_commit(&bars->acc_full);
+    umma_commit_1t(&bars->acc_full);
   } else if (warp >= 8) {
     // split the lo tile, accumulate its column sums, and build the patch operand
     const int t = threadIdx.x - 256;
@@ -1601,6 +1676,16 @@ static int use_rawhi() {
   if (v < 0) { const char* e = getenv("DV_TC_RAWHI"); v = (e && e[0] == '0') ? 0 : 1; }
   return v;
 }
+static int use_debug() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DV_TC_DEBUG"); v = e ? atoi(e) : 0; }
+  return v;
+}
+static int use_pipe() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DV_TC_PIPE"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v;
+}
 static int use_prefetch() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("DV_TC_PREFETCH"); v = (e && e[0] == '0') ? 0 : 1; }
@@ -1668,7 +1753,7 @@ int conv_down32_tc(const float* hi, const float* wd_packed, const float* bias, c
   if (nparts) *nparts = 0;
   if (W > 128 || 128 % W != 0) return DV_ERR_BAD_SHAPE;
   DownGeom g;
-  g.B = B; g.H = H; g.W = W; g.prefetch = use_prefetch();
+  g.B = B; g.H = H; g.W = W; g.prefetch = use_prefetch(); g.pipe = use_pipe(); g.debug = use_debug();
   g.rows_per_tile = 128 / W;
   const int TR = g.rows_per_tile < H ? g.rows_per_tile : H;
   if (H % TR != 0 || g.rows_per_tile % TR != 0) return DV_ERR_BAD_SHAPE;
@@ -1710,7 +1795,7 @@ int conv_up32_tc(const float* lo, const float* wu_packed, const float* bias, con
                  int B, int H, int W, int act, cudaStream_t st) {
   if (W > 128 || 128 % W != 0) return DV_ERR_BAD_SHAPE;
   DownGeom g;
-  g.B = B; g.H = H; g.W = W; g.prefetch = use_prefetch();
+  g.B = B; g.H = H; g.W = W; g.prefetch = use_prefetch(); g.pipe = use_pipe(); g.debug = use_debug();
   g.rows_per_tile = 128 / W;
   const int TR = g.rows_per_tile < H ? g.rows_per_tile : H;
   if (H % TR != 0 || g.rows_per_tile % TR != 0) return DV_ERR_BAD_SHAPE;
@@ -1827,7 +1912,7 @@ int conv_down_small_tc(const float* x, const float* wd, const float* bias, const
                        int B, int H, int W, int CH, int act, cudaStream_t st, float* colsum_part, int* nparts) {
   if (nparts) *nparts = 0;
   DownGeom g;
-  g.B = B; g.H = H; g.W = W; g.prefetch = use_prefetch(); g.rows_per_tile = 0;
+  g.B = B; g.H = H; g.W = W; g.prefetch = use_prefetch(); g.pipe = use_pipe(); g.debug = use_debug(); g.rows_per_tile = 0;
   g.total_px = (long long)B * H * W;
   g.num_tiles = (int)((g.total_px + 127) / 128);
   return CH == 1 ? launch_down_small<1>(x, wd, bias, mask, lo, g, act, st, colsum_part, nparts)
@@ -1894,7 +1979,7 @@ static int launch_up_halo(const float* lo, const float* wu, const float* bias, c
 int conv_up_halo(const float* lo, const float* wu, const float* bias, const float* mask, float* hi,
                  int B, int H, int W, int CH, int act, cudaStream_t st) {
   HaloGeom g;
-  g.B = B; g.H = H; g.W = W; g.Wp = W + 2;
+  g.B = B; g.H = H; g.W = W; g.Wp = W + 2; g.pipe = use_pipe(); g.debug = use_debug();
   int tr = (128 + 2) / g.Wp;                       // largest TR with TR*Wp - 2 <= 128
   if (tr < 1) return DV_ERR_BAD_SHAPE;
   if (tr >= H) {

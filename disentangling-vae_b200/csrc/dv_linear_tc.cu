@@ -55,7 +55,7 @@ linear_nt_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   Barriers* bars = reinterpret_cast<Barriers*>(smem + kStages * kStageBytes);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform role index
   const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * kBN;
   const int nkb = (R + kBK - 1) / kBK;
 
@@ -72,7 +72,7 @@ linear_nt_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (bars->tmem_base != 0u) __trap();                       // 1 CTA/SM owns the whole tensor memory
   constexpr uint32_t tmem_base = 0u;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && elect_one()) {
     // ---- TMA producer: {A raw, B hi, B lo} of one K block per stage ----
     prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_bhi); prefetch_tmap(&tmap_blo);
     for (int kb = 0; kb < nkb; ++kb) {
@@ -86,7 +86,8 @@ linear_nt_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       tma_load_2d(st + kATile, &tmap_bhi, &bars->full[stage], kb * kBK, n0);
       tma_load_2d(st + kATile + kBTile, &tmap_blo, &bars->full[stage], kb * kBK, n0);
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 && elect_one()) {      // ONE elected lane runs the whole issue loop (barrier waits included):
+                                              // ptxas then keeps every MMA operand in uniform registers (back-to-back UTCHMMA)
     // ---- MMA issuer (whole warp, one elected lane issues) ----
     constexpr uint32_t idesc2 = umma_idesc_tf32(128, 2 * kBN), idesc1 = umma_idesc_tf32(128, kBN);
     for (int kb = 0; kb < nkb; ++kb) {
@@ -101,13 +102,13 @@ linear_nt_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         // two accumulation chains (even / odd K slices): the tensor core truncates when it accumulates, shorter
         // chains keep the result fp32-grade.  Chain c: cols [128c, 128c+64) hi*hi + lo*hi, [128c+64, 128c+128) hi*lo.
         const uint32_t d = tmem_base + (k4 & 1) * 128;
-        umma_tf32_ts(d, a_hi + 8 * k4, b_d + 2 * k4, idesc2, (kb | (k4 >> 1)) != 0);
-        umma_tf32_ts(d, a_lo + 8 * k4, b_d + 2 * k4, idesc1, 1);
+        umma_tf32_ts_1t(d, a_hi + 8 * k4, b_d + 2 * k4, idesc2, (kb | (k4 >> 1)) != 0);
+        umma_tf32_ts_1t(d, a_lo + 8 * k4, b_d + 2 * k4, idesc1, 1);
       }
-      umma_commit(&bars->a_empty[as]);
-      umma_commit(&bars->b_consumed[stage]);
+      umma_commit_1t(&bars->a_empty[as]);
+      umma_commit_1t(&bars->b_consumed[stage]);
     }
-    umma_commit(&bars->acc_full);
+    umma_commit_1t(&bars->acc_full);
   } else if (warp >= 4 && warp < 8) {
     // ---- epilogue: thread = output row ----
     const int q = warp & 3;
@@ -183,11 +184,10 @@ linear_nt_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     // ---- split warps: raw A tile -> hi/lo planes in TMEM (two groups on alternate K blocks) ----
     const int q = warp & 3, grp = (warp - 8) >> 2;
     const int row = q * 32 + lane;
+    int prev_stage = -1, prev_as = 0;                         // K block whose TMEM stores are still in flight
     for (int kb = grp; kb < nkb; kb += 2) {
       const int stage = kb % kStages, as = kb % kAStages;
       mbar_wait(&bars->full[stage], (kb / kStages) & 1u);
-      mbar_wait(&bars->a_empty[as], ((kb / kAStages) & 1u) ^ 1u);
-      tc_fence_after_sync();
       const uint8_t* raw = smem + stage * kStageBytes;
       uint32_t h[32], l[32];
 #pragma unroll
@@ -201,13 +201,26 @@ linear_nt_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           l[c * 4 + e] = __float_as_uint(__uint_as_float(vv[e]) - __uint_as_float(hb));
         }
       }
+      // software pipeline: the stores of the previous K block overlapped this block's loads and split; publish
+      // it (and release its raw tile -- only after tcgen05.wait::st, when its reads were certainly consumed) now
+      if (prev_stage >= 0) {
+        tmem_st_wait();
+        mbar_arrive(&bars->a_consumed[prev_stage]);
+        tc_fence_before_sync();
+        mbar_arrive(&bars->a_ready[prev_as]);
+      }
+      mbar_wait(&bars->a_empty[as], ((kb / kAStages) & 1u) ^ 1u);
+      tc_fence_after_sync();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + kACol0 + as * 64;
       tmem_st_32x32b_x32(taddr, h);
       tmem_st_32x32b_x32(taddr + 32, l);
+      prev_stage = stage; prev_as = as;
+    }
+    if (prev_stage >= 0) {
       tmem_st_wait();
-      mbar_arrive(&bars->a_consumed[stage]);                 // after the stores: every loaded value was consumed
+      mbar_arrive(&bars->a_consumed[prev_stage]);
       tc_fence_before_sync();
-      mbar_arrive(&bars->a_ready[as]);
+      mbar_arrive(&bars->a_ready[prev_as]);
     }
   }
   tc_fence_before_sync();
@@ -359,7 +372,7 @@ linear_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
   uint8_t* St = smem;                                        // [stage][Xa_hi|Xb_hi|Xa_lo|Xb_lo]
   uint8_t* Gs = smem + kWgStages * kWgStageBytes;            // [buf][G_hi|G_lo]
   WgBarriers* bars = reinterpret_cast<WgBarriers*>(Gs + 2 * kWgGBytes);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform role index
   const int ng = blockIdx.x, kc = blockIdx.y, sp = blockIdx.z;
   const int kgroups = (g.K + 31) / 32;
   const int my_groups = min(16, kgroups - kc * 16);
@@ -380,7 +393,7 @@ linear_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
   if (bars->tmem_base != 0u) __trap();
   constexpr uint32_t tmem_base = 0u;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && elect_one()) {
     prefetch_tmap(&tmap_x); prefetch_tmap(&tmap_g);
     int stage = 0; uint32_t phase = 0; int gb = 0; uint32_t gphase = 0;
     for (int tile = t_begin; tile < t_end; ++tile) {
@@ -398,7 +411,8 @@ linear_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
         if (++stage == kWgStages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 && elect_one()) {      // ONE elected lane runs the whole issue loop (barrier waits included):
+                                              // ptxas then keeps every MMA operand in uniform registers (back-to-back UTCHMMA)
     constexpr uint32_t idesc = umma_idesc_tf32(128, 64) | (1u << 15) | (1u << 16);   // both operands MN-major
     int stage = 0; uint32_t phase = 0; int gb = 0; uint32_t gphase = 0;
     for (int tile = t_begin; tile < t_end; ++tile) {
@@ -412,15 +426,15 @@ linear_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
         const uint32_t d = tmem_base + pr * 64;
 #pragma unroll 4
         for (int kk = 0; kk < 16; ++kk)                      // 8 batch rows per MMA
-          umma_tf32_ss(d, umma_desc_sw128_mnmajor(a_addr + kk * 1024, kATile),
+          umma_tf32_ss_1t(d, umma_desc_sw128_mnmajor(a_addr + kk * 1024, kATile),
                        umma_desc_sw128_mnmajor(g_addr + kk * 1024, kATile), idesc, (tile != t_begin) || (kk != 0));
-        umma_commit(&bars->empty[stage]);
+        umma_commit_1t(&bars->empty[stage]);
         if (++stage == kWgStages) { stage = 0; phase ^= 1; }
       }
-      umma_commit(&bars->g_empty[gb]);
+      umma_commit_1t(&bars->g_empty[gb]);
       if (++gb == 2) { gb = 0; gphase ^= 1; }
     }
-    umma_commit(&bars->acc_full);
+    umma_commit_1t(&bars->acc_full);
   } else if (warp >= 8 && warp < 12) {
     const int t = threadIdx.x - 256;
     int stage = 0; uint32_t phase = 0; int gb = 0; uint32_t gphase = 0;
