@@ -436,6 +436,7 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_mnmajor(uint32_t smem_addr, 
 
 struct WgGeom {
   int B, H, W, rows_per_tile, num_tiles, tiles_per_cta;
+  int pairs_per_cta;    // conv_wgrad32: blockIdx.y owns tap pairs [y*ppc, (y+1)*ppc) (8 = all taps in one CTA)
   int prefetch;
   int rawhi;            // feed the raw fp32 tiles as the hi operand (no hi-plane store)
 };
@@ -451,6 +452,9 @@ conv_wgrad32_tc_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform role index
   const int t_begin = blockIdx.x * g.tiles_per_cta;
   const int t_end = min(g.num_tiles, t_begin + g.tiles_per_cta);
+  // small layers: the tap pairs are spread over blockIdx.y as well, so that a CTA streams more tiles and writes a
+  // smaller partial (one fixed prologue/epilogue cost per CTA, fewer split-K partials to reduce)
+  const int pr_begin = blockIdx.y * g.pairs_per_cta, pr_end = pr_begin + g.pairs_per_cta;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kWgStages; ++s) { mbar_init(&bars->raw_full[s], 1); mbar_init(&bars->ready[s], 128); mbar_init(&bars->empty[s], 1); }
@@ -481,7 +485,7 @@ conv_wgrad32_tc_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid
       mbar_arrive_expect_tx(&bars->l_raw_full[lb], kATile);
       tma_load_4d(Ls + lb * kWgLBytes, &tmap_lo, &bars->l_raw_full[lb], 0, 0, i0, b0);
       if (++lb == 2) { lb = 0; lphase ^= 1; }
-      for (int pr = 0; pr < 8; ++pr) {
+      for (int pr = pr_begin; pr < pr_end; ++pr) {
         mbar_wait(&bars->empty[stage], phase ^ 1);
         mbar_arrive_expect_tx(&bars->raw_full[stage], 2 * kATile);
 #pragma unroll
@@ -501,11 +505,11 @@ conv_wgrad32_tc_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid
       mbar_wait(&bars->l_ready[lb], lphase);
       tc_fence_after_sync();
       const uint32_t l_addr = smem_u32(Ls + lb * kWgLBytes);
-      for (int pr = 0; pr < 8; ++pr) {
+      for (int pr = pr_begin; pr < pr_end; ++pr) {
         mbar_wait(&bars->ready[stage], phase);
         tc_fence_after_sync();
         const uint32_t a_addr = smem_u32(St + stage * kWgStageBytes);
-        const uint32_t d = tmem_base + pr * 64;
+        const uint32_t d = tmem_base + (pr - pr_begin) * 64;
 #pragma unroll 4
         for (int kc = 0; kc < 16; ++kc) {                   // 8 pixels per MMA
           umma_tf32_ss_1t(d, umma_desc_sw128_mnmajor(a_addr + kc * 1024, kATile),
@@ -540,7 +544,7 @@ conv_wgrad32_tc_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid
       fence_proxy_async_smem();
       mbar_arrive(&bars->l_ready[lb]);
       if (++lb == 2) { lb = 0; lphase ^= 1; }
-      for (int pr = 0; pr < 8; ++pr) {
+      for (int pr = pr_begin; pr < pr_end; ++pr) {
         mbar_wait(&bars->raw_full[stage], phase);
         uint8_t* base = St + stage * kWgStageBytes;
         if (g.rawhi) {
@@ -559,7 +563,7 @@ conv_wgrad32_tc_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid
 #pragma unroll
     for (int e = 0; e < 4; ++e) bars->lscr[t][e] = ls[e];
     asm volatile("bar.sync 2, 128;" ::: "memory");
-    if (t < 32) {
+    if (t < 32 && blockIdx.y == 0) {                        // (every pair group sees the same lo tiles)
       const int want = t >> 2, e = t & 3;
       float acc = 0.f;
       for (int u = 0; u < 128; ++u)
@@ -576,8 +580,8 @@ conv_wgrad32_tc_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid
     tc_fence_after_sync();
     float* red = reinterpret_cast<float*>(St);              // all MMAs have completed: stage buffers are free
     float* out = ws + (long long)blockIdx.x * (kTaps * 32 + 1) * kLoCh;
-    for (int pr = 0; pr < 8; ++pr) {
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + pr * 64;
+    for (int pr = pr_begin; pr < pr_end; ++pr) {
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (pr - pr_begin) * 64;
       uint32_t r0[32], r1[32];
       tmem_ld_32x32b_x32(taddr, r0);
       tmem_ld_32x32b_x32(taddr + 32, r1);
@@ -1860,8 +1864,19 @@ int conv_wgrad32_tc(const float* lo, const float* hi, float* ws, int B, int H, i
   if (H % TR != 0 || g.rows_per_tile % TR != 0) return DV_ERR_BAD_SHAPE;
   const int TB = g.rows_per_tile / TR;
   g.num_tiles = (int)(((long long)B * H * W + 127) / 128);
-  int grid = g.num_tiles < kNumSMs ? g.num_tiles : kNumSMs;
-  g.tiles_per_cta = (g.num_tiles + grid - 1) / grid;
+  // (tile group, tap-pair group) decomposition: big layers keep all 8 pairs in one CTA (one pass over the tiles);
+  // small layers spread the pairs over blockIdx.y so that every CTA still streams >= 8 tiles
+  static int split_pairs = -1;
+  if (split_pairs < 0) { const char* e = getenv("DV_WG_PAIRSPLIT"); split_pairs = (e && e[0] == '0') ? 0 : 1; }
+  int ppc = 8, grid = 1;
+  for (;; ppc >>= 1) {
+    const int pg = 8 / ppc;
+    const int gmax = kNumSMs / pg;
+    grid = g.num_tiles < gmax ? g.num_tiles : gmax;
+    g.tiles_per_cta = (g.num_tiles + grid - 1) / grid;
+    if (g.tiles_per_cta >= 8 || ppc == 1 || !split_pairs) break;
+  }
+  g.pairs_per_cta = ppc;
   grid = (g.num_tiles + g.tiles_per_cta - 1) / g.tiles_per_cta;
   *nsplit = grid;
   CUtensorMap thi, tlo;
@@ -1875,7 +1890,7 @@ int conv_wgrad32_tc(const float* lo, const float* hi, float* ws, int B, int H, i
     }
     attr = true;
   }
-  conv_wgrad32_tc_kernel<<<grid, kThreads, kWgSmemBytes, st>>>(thi, tlo, ws, g);
+  conv_wgrad32_tc_kernel<<<dim3(grid, 8 / ppc), kThreads, kWgSmemBytes, st>>>(thi, tlo, ws, g);
   return check_launch();
 }
 int wgrad32_tc_max_splits() { return kNumSMs; }
