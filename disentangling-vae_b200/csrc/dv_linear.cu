@@ -192,7 +192,7 @@ int dgrad(const float* g, const float* w, const float* mask_src, float* dx, int 
           cudaStream_t st);
 bool wgrad_ok(int M, int N, int K);
 size_t wgrad_workspace_bytes(int M, int N, int K);
-int wgrad(const float* g, const float* x, float* dw, float* ws, int M, int N, int K, int* nsplit, cudaStream_t st);
+int wgrad(const float* g, const float* x, float* dw, float* dbias, float* ws, int M, int N, int K, int* nsplit, cudaStream_t st);
 } }
 
 using namespace dv;
@@ -252,18 +252,21 @@ int dv_linear_wgrad(const float* g, const float* x, float* dw, float* dbias, int
   if (ltc::wgrad_ok(M, N, K)) {
     if (ltc::wgrad_workspace_bytes(M, N, K) > 0 && !workspace) return DV_ERR_WORKSPACE;
     int S = 1;
-    int rc = ltc::wgrad(g, x, dw, reinterpret_cast<float*>(workspace), M, N, K, &S, st);
+    int rc = ltc::wgrad(g, x, dw, dbias, reinterpret_cast<float*>(workspace), M, N, K, &S, st);
     if (rc != DV_OK) return rc;
-    if (S > 1) {
+    if (S > 1) {                                               // fixed-order reduction of the split-K partials (dW, then dbias)
+      const float* part = reinterpret_cast<const float*>(workspace);
       const long long n = (long long)N * K;
       int gr = (int)((n + 255) / 256); if (gr > 4 * kNumSMs) gr = 4 * kNumSMs;
-      splitk_reduce_kernel<<<gr, 256, 0, st>>>(reinterpret_cast<const float*>(workspace), dw, n, S);
+      splitk_reduce_kernel<<<gr, 256, 0, st>>>(part, dw, n, S);
       rc = check_launch();
       if (rc != DV_OK) return rc;
+      if (dbias) {
+        splitk_reduce_kernel<<<(N + 255) / 256, 256, 0, st>>>(part + (size_t)S * n, dbias, N, S);
+        rc = check_launch();
+      }
     }
-    if (!dbias) return rc;
-    colsum_kernel<<<(N + 31) / 32, 1024, 0, st>>>(g, dbias, M, N);
-    return check_launch();
+    return rc;
   }
   const int S = wgrad_splits(M, N, K);
   if (S > 1 && !workspace) return DV_ERR_WORKSPACE;

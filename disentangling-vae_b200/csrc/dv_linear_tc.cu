@@ -335,8 +335,10 @@ struct WgBarriers {
   uint64_t g_raw_full[2], g_ready[2], g_empty[2];
   uint64_t acc_full;
   uint32_t tmem_base;
+  float lscr[128][4];                                    // column sums of G (bias gradient), per split thread
 };
-constexpr int kWgSmemBytes = kWgStages * kWgStageBytes + 2 * kWgGBytes + 1024 + 512;
+constexpr int kWgSmemBytes = kWgStages * kWgStageBytes + 2 * kWgGBytes + 1024 + 3072;
+static_assert(sizeof(WgBarriers) <= 3072, "barriers");
 static_assert(kWgSmemBytes <= 232448, "smem");
 
 __device__ __forceinline__ uint64_t umma_desc_sw128_mnmajor(uint32_t smem_addr, uint32_t lbo_bytes) {
@@ -366,7 +368,8 @@ struct WgGeom {
 
 __global__ void __launch_bounds__(kThreads, 1)
 linear_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_g,
-                       float* __restrict__ out_base, long long split_stride, WgGeom g) {
+                       float* __restrict__ out_base, long long split_stride, float* __restrict__ dbias_base,
+                       long long dbias_stride, WgGeom g) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* St = smem;                                        // [stage][Xa_hi|Xb_hi|Xa_lo|Xb_lo]
@@ -438,8 +441,18 @@ linear_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
   } else if (warp >= 8 && warp < 12) {
     const int t = threadIdx.x - 256;
     int stage = 0; uint32_t phase = 0; int gb = 0; uint32_t gphase = 0;
+    float ls[4] = {0.f, 0.f, 0.f, 0.f};                       // this thread's 16-byte chunk of every G row it touches
+    const bool want_bias = dbias_base != nullptr && kc == 0;   // (every k chunk sees the same G tiles)
     for (int tile = t_begin; tile < t_end; ++tile) {
       mbar_wait(&bars->g_raw_full[gb], gphase);
+      if (want_bias) {
+        const uint4* graw = reinterpret_cast<const uint4*>(Gs + gb * kWgGBytes);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint4 u = graw[t + 128 * k];
+          ls[0] += __uint_as_float(u.x); ls[1] += __uint_as_float(u.y); ls[2] += __uint_as_float(u.z); ls[3] += __uint_as_float(u.w);
+        }
+      }
       split_lo_only(reinterpret_cast<const uint4*>(Gs + gb * kWgGBytes), reinterpret_cast<uint4*>(Gs + gb * kWgGBytes + kATile), t);
       fence_proxy_async_smem();
       mbar_arrive(&bars->g_ready[gb]);
@@ -453,6 +466,19 @@ linear_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
         mbar_arrive(&bars->ready[stage]);
         if (++stage == kWgStages) { stage = 0; phase ^= 1; }
       }
+    }
+    // bias gradient = column sums of G: under the 32-byte-atom swizzle thread t always sees logical 16-byte chunk
+    // `quad` of a row (quad = ((t&7)>>1 ^ (t>>3)&3) << 1 | t&1); 16 threads share a chunk, summed in a fixed order
+#pragma unroll
+    for (int e = 0; e < 4; ++e) bars->lscr[t][e] = ls[e];
+    asm volatile("bar.sync 2, 128;" ::: "memory");
+    if (want_bias && t < 32) {
+      const int want = t >> 2, e = t & 3;
+      float acc = 0.f;
+      for (int u = 0; u < 128; ++u)
+        if ((((((u & 7) >> 1) ^ ((u >> 3) & 3)) << 1) | (u & 1)) == want) acc += bars->lscr[u][e];
+      const int n = ng * 32 + t;
+      if (n < g.N) dbias_base[(long long)sp * dbias_stride + n] = acc;
     }
   }
 
@@ -543,10 +569,11 @@ bool wgrad_ok(int M, int N, int K) { return enabled() && N % 4 == 0 && K % 4 == 
 size_t wgrad_workspace_bytes(int M, int N, int K) {
   int S, per;
   wgrad_plan(M, N, K, &S, &per);
-  return S > 1 ? (size_t)S * N * K * sizeof(float) : 0;
+  return S > 1 ? ((size_t)S * N * K + (size_t)S * N) * sizeof(float) : 0;     // dW partials, then dbias partials
 }
 // returns the number of splits written (1: dw is final) through *nsplit
-int wgrad(const float* g, const float* x, float* dw, float* ws, int M, int N, int K, int* nsplit, cudaStream_t st) {
+// dbias != NULL: the column sums of g come out of the same kernel (partials at ws + S*N*K when S > 1)
+int wgrad(const float* g, const float* x, float* dw, float* dbias, float* ws, int M, int N, int K, int* nsplit, cudaStream_t st) {
   int S, per;
   wgrad_plan(M, N, K, &S, &per);
   CUtensorMap tx, tg;
@@ -562,7 +589,8 @@ int wgrad(const float* g, const float* x, float* dw, float* ws, int M, int N, in
   }
   WgGeom geo{M, N, K, (M + 127) / 128, per};
   dim3 grid((N + 31) / 32, ((K + 31) / 32 + 15) / 16, S);
-  linear_wgrad_tc_kernel<<<grid, kThreads, kWgSmemBytes, st>>>(tx, tg, S > 1 ? ws : dw, (long long)N * K, geo);
+  float* dbias_base = !dbias ? nullptr : (S > 1 ? ws + (size_t)S * N * K : dbias);
+  linear_wgrad_tc_kernel<<<grid, kThreads, kWgSmemBytes, st>>>(tx, tg, S > 1 ? ws : dw, (long long)N * K, dbias_base, (long long)N, geo);
   *nsplit = S;
   return check_launch();
 }
