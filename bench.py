@@ -431,8 +431,11 @@ def run_reference(args):
     out = {"impl": "reference", "metric": "images/sec", "value": v, "unit": "img/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           # same config keys as our own arm (the reference arm runs rank 0 only, on the host cores)
            "config": {"workload": WORKLOAD_NAMES[args.workload],
-                      "loss": loss_name, "img_size": list(img), "batch_per_gpu": B, "latent_dim": z, "n_data": n_data},
+                      "loss": loss_name, "img_size": list(img), "batch_per_gpu": B, "global_batch": B * world,
+                      "latent_dim": z, "n_data": n_data, "rec_dist": "bernoulli", "optimizer": "Adam lr %g" % lr,
+                      "parallelism": "dp%d" % world if world > 1 else "single"},
            "cpu_baseline": {"value": v, "unit": "img/s", "cores": cores, "kind": "port", "sample": sample,
                             "torch": torch.__version__},
            "e2e": {"value": v, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}

@@ -207,3 +207,25 @@ def test_flat_grad_allreduce_world2_gloo(tmp_path):
     mp.spawn(_ddp_worker, args=(2, 29561, out), nprocs=2, join=True)
     r = torch.load(out)
     assert r == dict(same=True, ok=True, views=True, ok_shard=True)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` runs without a GPU (it times the CPU oracle port) and prints ONE JSON line with the
+    keys the bench contract names; its metric/unit/config match our own arm's."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "c1",
+                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "images/sec" and d["unit"] == "img/s" and d["higher_is_better"] is True
+    for k in ("value", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "vs_baseline", "dtype", "data", "config",
+              "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["loss"] == "VAE" and d["config"]["batch_per_gpu"] == 64
