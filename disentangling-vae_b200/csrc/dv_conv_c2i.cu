@@ -227,7 +227,7 @@ conv_up_c2i_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       uint32_t h[32], l[32];
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
-        const uint4 vv4 = *reinterpret_cast<const uint4*>(raw + row * 128 + ((c ^ (row & 7)) << 4));
+        const uint4 vv4 = lds128(raw + row * 128 + ((c ^ (row & 7)) << 4));
         const uint32_t vv[4] = {vv4.x, vv4.y, vv4.z, vv4.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {

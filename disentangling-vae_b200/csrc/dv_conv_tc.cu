@@ -652,7 +652,7 @@ __device__ __forceinline__ void ts_split_tile(const uint8_t* raw, uint32_t tmem_
   uint32_t h[32], l[32];
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
-    const uint4 v = *reinterpret_cast<const uint4*>(raw + row * 128 + ((c ^ (row & 7)) << 4));
+    const uint4 v = lds128(raw + row * 128 + ((c ^ (row & 7)) << 4));
     const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -824,7 +824,7 @@ conv_down32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
           uint32_t h[32], l[32];
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
-            const uint4 v = *reinterpret_cast<const uint4*>(raw + row * 128 + ((c ^ (row & 7)) << 4));
+            const uint4 v = lds128(raw + row * 128 + ((c ^ (row & 7)) << 4));
             const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -1238,7 +1238,7 @@ conv_up_halo_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         uint32_t h[32], l[32];
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-          const uint4 v = *reinterpret_cast<const uint4*>(raw + p * 128 + ((c ^ (p & 7)) << 4));
+          const uint4 v = lds128(raw + p * 128 + ((c ^ (p & 7)) << 4));
           const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {

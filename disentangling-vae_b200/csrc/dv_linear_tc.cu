@@ -192,7 +192,7 @@ linear_nt_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       uint32_t h[32], l[32];
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
-        const uint4 v = *reinterpret_cast<const uint4*>(raw + row * 128 + ((c ^ (row & 7)) << 4));
+        const uint4 v = lds128(raw + row * 128 + ((c ^ (row & 7)) << 4));
         const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {

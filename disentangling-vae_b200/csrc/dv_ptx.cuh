@@ -41,6 +41,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// 16-byte shared-memory load.  The operand tiles live in dynamic shared memory reached through an aligned-up pointer,
+// which the compiler treats as a GENERIC address: it emits LD.E.128 with 64-bit address arithmetic per load (seen in
+// the round-1 SASS of the split loops).  Building with -DDV_SMEM_LDS=1 switches to explicit ld.shared (LDS.128, 32-bit
+// addresses).  Off by default: it has not been measured on hardware yet (no GPU time was left in round 1).
+#ifndef DV_SMEM_LDS
+#define DV_SMEM_LDS 0
+#endif
+__device__ __forceinline__ uint4 lds128(const void* p) {
+#if DV_SMEM_LDS
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_u32(p)) : "memory");
+  return v;
+#else
+  return *reinterpret_cast<const uint4*>(p);
+#endif
+}
+
 // ---- proxy / tcgen05 fences -----------------------------------------------------------
 __device__ __forceinline__ void fence_proxy_async_smem() {   // generic-proxy smem writes -> async proxy (MMA/TMA)
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
