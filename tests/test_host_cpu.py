@@ -174,6 +174,24 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert "sm_100a" in out
 
 
+def test_ctypes_signatures_match_the_header_prototypes():
+    """Every prototype of include/disvae_b200.h has as many parameters as the ctypes binding passes (ABI drift guard:
+    a mismatch would still load and then corrupt the call)."""
+    from disvae import _native
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "include", "disvae_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = dict(re.findall(r"\b(dv_\w+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S))
+    assert set(protos) == set(_native.SIGNATURES)
+    for name, params in protos.items():
+        params = params.strip()
+        n = 0 if params in ("", "void") else len(params.split(","))
+        assert n == len(_native.SIGNATURES[name][1]), (name, n, len(_native.SIGNATURES[name][1]))
+        # pointer parameters are bound as void pointers, sizes/flags as integers
+        for decl, ctype in zip(params.split(",") if n else [], _native.SIGNATURES[name][1]):
+            assert ("*" in decl) == (ctype is ctypes.c_void_p), (name, decl.strip())
+
+
 def _ddp_worker(rank, world, port, out):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
