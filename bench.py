@@ -1,19 +1,26 @@
 #!/usr/bin/env python
-"""bench.py -- disvae training hot path on B200 (contract: see the task statement / DESIGN.md).
+"""bench.py -- disvae training hot path on B200 (contract: see the task statement / DESIGN.md section 6).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c5]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|reference-cuda]
+                  [--workload c1..c5] [--scaling weak|strong]
 
-One "step" = one full optimisation step (forward, loss, backward, gradient all-reduce for N>1,
-Adam) over one synthetic batch.  Workload at every N: BASELINE.json configs[1]
-(btcvae, 1x64x64, batch 1024 PER GPU, z=10, bernoulli, MSS, Adam lr 5e-4) -- weak scaling.
+One "step" = one full optimisation step (forward, loss, backward, gradient all-reduce for N>1, Adam) over one
+synthetic batch.  Default workload at every N: BASELINE.json configs[1] (btcvae, 1x64x64, batch 1024 PER GPU, z=10,
+bernoulli, MSS, Adam lr 5e-4) -- weak scaling.  `--scaling strong` divides the config's batch over the ranks.
 
   value  : images/s with the batches already resident in HBM (CUDA events, max over ranks)
-  e2e    : the same through disvae.Trainer._train_epoch over a loader of PINNED HOST batches: H2D copy of
-           every batch and D2H copy of every step's loss inside the timed region (copies overlap compute)
-  roofline / roofline_logdensity / cpu_baseline / clocks / gpu_launches : see DESIGN.md section 6
+  e2e    : the same through disvae.Trainer._train_epoch over a loader of PINNED HOST batches with a real storer: H2D
+           copy of every batch and D2H copy of every step's loss inside the timed region
+  parity : full-size forward, loss AND every parameter gradient of the timed model against the CPU oracle (fp32, with
+           an fp64 run of the oracle as the arbiter of what fp32 allows)
+  ddp_parity (N>1): rank r's loss == oracle on shard r, rank-averaged gradients == mean of the oracle's shard gradients
+  roofline / roofline_logdensity / cpu_baseline / cuda_eager_baseline / clocks / gpu_launches : DESIGN.md section 6
 
---impl reference times the CPU oracle port (oracle/disvae_oracle.py, validated against the
-reference; the Python reference itself cannot travel to the GPU box) on the host cores.
+--impl reference      : the UNMODIFIED reference (baseline/_ref, shipped by scripts/ship_reference.py) through its own
+                        Trainer._train_iteration on the host cores (kind "reference"); the oracle port if the copy is
+                        not there (kind "port").
+--impl reference-cuda : the same unmodified reference with device=cuda (stock PyTorch eager: cuDNN/cuBLAS, TF32 off) --
+                        the "existing Blackwell kernels" bar of SURVEY.md 8d.
 """
 import argparse
 import json
@@ -24,26 +31,54 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "disentangling-vae_b200")
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "disentangling-vae_b200"))
 
 import torch  # noqa: E402
 
 WORKLOADS = {
-    # name: (loss, img_size, per-GPU batch, latent, n_data, loss kwargs, lr)
-    "c2": ("btcvae", (1, 64, 64), 1024, 10, 737280, dict(btcvae_A=1, btcvae_B=6, btcvae_G=1), 5e-4),
-    "c3": ("betaH", (3, 64, 64), 512, 10, 202599, dict(betaH_B=10), 5e-4),
-    "c5": ("btcvae", (3, 64, 64), 256, 64, 202599, dict(btcvae_A=1, btcvae_B=6, btcvae_G=1), 5e-4),
-    "c1": ("VAE", (1, 32, 32), 64, 10, 60000, dict(), 5e-4),
+    # name: (loss, img_size, per-GPU batch for weak scaling, latent, n_data, loss kwargs, lr, the config's own batch)
+    "c2": ("btcvae", (1, 64, 64), 1024, 10, 737280, dict(btcvae_A=1, btcvae_B=6, btcvae_G=1), 5e-4, 1024),
+    "c3": ("betaH", (3, 64, 64), 512, 10, 202599, dict(betaH_B=10), 5e-4, 512),
+    "c5": ("btcvae", (3, 64, 64), 256, 64, 202599, dict(btcvae_A=1, btcvae_B=6, btcvae_G=1), 5e-4, 2048),
+    "c1": ("VAE", (1, 32, 32), 64, 10, 60000, dict(), 5e-4, 64),
     # FactorVAE: `-b 256` doubled by main.py:191-194 -> loader batch 512 (two halves of 256); factor_celeba gamma 6.4
-    "c4": ("factor", (3, 64, 64), 512, 10, 202599, dict(factor_G=6.4, lr_disc=1e-5), 1e-4),
+    "c4": ("factor", (3, 64, 64), 512, 10, 202599, dict(factor_G=6.4, lr_disc=1e-5), 1e-4, 512),
 }
 WORKLOAD_NAMES = {"c1": "BASELINE.json configs[0]: VAE mnist-shape", "c2": "BASELINE.json configs[1]: btcvae dsprites-shape",
                   "c3": "BASELINE.json configs[2]: betaH celeba-shape", "c4": "BASELINE.json configs[3]: factor celeba-shape",
-                  "c5": "BASELINE.json configs[4]: btcvae celeba-shape z=64 (one GPU's shard of 256)"}
+                  "c5": "BASELINE.json configs[4]: btcvae celeba-shape z=64"}
 # algorithmic work per image, forward + backward: conv FLOPs
 CONV_FLOP_PER_IMG = {(1, 64, 64): 71.30e6, (3, 64, 64): 81.79e6, (1, 32, 32): 17.04e6}
-N_ROTATE = 8            # distinct resident batches cycled through (8 x 16.8 MB > 126 MB L2)
+N_ROTATE = 8            # distinct batches cycled through (8 x 16.8 MB > 126 MB L2)
+
+
+def loss_kwargs(workload, device):
+    loss_name, img, B, z, n_data, lkw, lr, _ = WORKLOADS[workload]
+    kw = dict(rec_dist="bernoulli", reg_anneal=0, betaH_B=4, betaB_initC=0, betaB_finC=25, betaB_G=100, factor_G=6,
+              latent_dim=z, lr_disc=5e-5, btcvae_A=1, btcvae_B=6, btcvae_G=1, device=device, n_data=n_data)
+    kw.update(lkw)
+    return kw
+
+
+def per_gpu_batch(args, world):
+    _, _, B, _, _, _, _, B_cfg = WORKLOADS[args.workload]
+    if args.batch:
+        return args.batch
+    if args.scaling == "strong":
+        assert B_cfg % world == 0
+        return B_cfg // world
+    return B
+
+
+def config_block(args, world, B):
+    """Identical in every arm (ours / reference / reference-cuda): it names the WORKLOAD."""
+    loss_name, img, _, z, n_data, _, lr, _ = WORKLOADS[args.workload]
+    return {"workload": WORKLOAD_NAMES[args.workload], "loss": loss_name, "img_size": list(img), "batch_per_gpu": B,
+            "global_batch": B * world, "latent_dim": z, "n_data": n_data, "rec_dist": "bernoulli",
+            "optimizer": "Adam lr %g" % lr, "parallelism": "dp%d" % world if world > 1 else "single",
+            "l2": "inputs larger than L2: %d distinct batches rotated (%.0f MB)" % (
+                N_ROTATE, N_ROTATE * B * img[0] * img[1] * img[2] * 4 / 1e6)}
 
 
 def peaks():
@@ -101,29 +136,33 @@ class ClockSampler:
         return dict(sm_mhz=load[len(load) // 2], sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
 
 
+# =====================================================================================================
+# our arm
+# =====================================================================================================
 def build_job(workload, device):
+    sys.path.insert(0, PKG)
     import disvae
     from disvae.models.losses import get_loss_f
-    loss_name, img, B, z, n_data, lkw, lr = WORKLOADS[workload]
+    loss_name, img, B, z, n_data, lkw, lr, _ = WORKLOADS[workload]
     torch.manual_seed(1234)
     model = disvae.init_specific_model("Burgess", img, z).to(device)
     from disvae.parallel import broadcast_parameters
     broadcast_parameters(model)
     opt = torch.optim.Adam(model.parameters(), lr=lr)
-    kw = dict(rec_dist="bernoulli", reg_anneal=0, betaH_B=4, betaB_initC=0, betaB_finC=25, betaB_G=100, factor_G=6,
-              latent_dim=z, lr_disc=5e-5, btcvae_A=1, btcvae_B=6, btcvae_G=1, device=device, n_data=n_data)
-    kw.update(lkw)
-    loss_f = get_loss_f(loss_name, **kw)
+    loss_f = get_loss_f(loss_name, **loss_kwargs(workload, device))
+    if loss_name == "factor":
+        broadcast_parameters(loss_f.discriminator)
     import logging
     import tempfile
     trainer = disvae.Trainer(model, opt, loss_f, device=device, logger=logging.getLogger("bench"),
                              save_dir=tempfile.mkdtemp(prefix="dvbench"), is_progress_bar=False)
     model.train()
-    return trainer, (loss_name, img, B, z, n_data, lr)
+    return trainer
 
 
 def run_ours(args):
     import torch.distributed as dist
+    from collections import defaultdict
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -133,15 +172,18 @@ def run_ours(args):
     device = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
+    sys.path.insert(0, PKG)
     from disvae import _native
     L = _native.lib()
     assert L.dv_device_check() == 0, "not an sm_100 device"
 
-    trainer, (loss_name, img, B, z, n_data, lr) = build_job(args.workload, device)
+    loss_name, img, _, z, n_data, lkw, lr, _ = WORKLOADS[args.workload]
+    B = per_gpu_batch(args, world)
+    trainer = build_job(args.workload, device)
     g = torch.Generator().manual_seed(1234 + rank)
     host = [torch.rand(B, *img, generator=g).pin_memory() for _ in range(N_ROTATE)]
     resident = [h.to(device) for h in host]
-    K, Wm = args.steps, max(args.warmup, 6)     # >= 6: the Trainer captures its CUDA graph on the 4th eligible step
+    K, W = args.steps, args.warmup     # the Trainer captures its CUDA graph on the 3rd eligible step: W >= 3 keeps it untimed
 
     def barrier():
         if world > 1:
@@ -163,11 +205,12 @@ def run_ours(args):
 
     step_res = lambda i: trainer._step(resident[i % N_ROTATE], None)            # noqa: E731
     # end to end: the Trainer's epoch loop over a loader of PINNED HOST batches (H2D of every batch on the Trainer's
-    # copy stream one step ahead, async D2H of every step's loss, one blocking read of the epoch mean at the end)
+    # copy stream one step ahead, async D2H of every step's loss, one blocking read of the epoch mean at the end) with a
+    # real storer, so the steps that log scalars (every 50th, losses.py:105-114) run their eager + host-sync path
     loader = [(host[i % N_ROTATE], None) for i in range(K)]
-    epoch_e2e = lambda: trainer._train_epoch(loader, None, 0)                    # noqa: E731
+    epoch_e2e = lambda: trainer._train_epoch(loader, defaultdict(list), 0)       # noqa: E731
 
-    for i in range(Wm):
+    for i in range(W):
         step_res(i)
     clk = ClockSampler(local)
     if rank == 0:
@@ -187,54 +230,82 @@ def run_ours(args):
         e2e_v = imgs / (ms_e2e / 1e3)
         conv_flop = CONV_FLOP_PER_IMG[img]
         out = {
-            "metric": "images/sec", "value": round(value, 1), "unit": "img/s", "n_gpus": world, "steps": K, "warmup": Wm,
-            "ms_per_step": round(ms / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": "images/sec", "value": round(value, 1), "unit": "img/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": round(ms / K, 4), "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic (torch.rand, seed 1234+rank); random-init weights (seed 1234)",
-            "config": {"workload": WORKLOAD_NAMES[args.workload],
-                       "loss": loss_name, "img_size": list(img), "batch_per_gpu": B, "global_batch": B * world,
-                       "latent_dim": z, "n_data": n_data, "rec_dist": "bernoulli", "optimizer": "Adam lr %g" % lr,
-                       "parallelism": "dp%d" % world if world > 1 else "single",
-                       "l2": "inputs larger than L2: %d distinct resident batches rotated (%.0f MB)" % (
-                           N_ROTATE, N_ROTATE * B * img[0] * img[1] * img[2] * 4 / 1e6)},
+            "config": config_block(args, world, B),
             "e2e": {"value": round(e2e_v, 1), "unit": "img/s", "h2d_bytes_per_step": B * img[0] * img[1] * img[2] * 4,
                     "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / K, 4),
-                    "api": "disvae.Trainer._train_epoch(loader of pinned host batches) -> mean loss (float)"},
+                    "api": "disvae.Trainer._train_epoch(loader of pinned host batches, storer) -> mean loss (float)"},
             "cuda_graph": bool(trainer._graphs),
             "gpu_launches": int(launches),
+            "launches_per_step": round(launches / K, 1),
             "conv_flop_fraction_of_bf16_peak": round(value / world * conv_flop / (pk["bf16_sustained"] * 1e12), 5),
             "clocks": clocks,
         }
     # ---- roofline of the dominant kernel + the named log-density kernel ----
     # Every rank runs the profiled steps (they contain the gradient all-reduce); only rank 0 reports.
     try:
-        roof = kernel_rooflines(trainer, resident, K, B, img, z, n_data, device)
+        roof = kernel_rooflines(trainer, resident, min(K, 20), B, img, z, n_data, device, detail=args.detail and rank == 0)
     except Exception as e:                                     # never lose the headline line
         roof = {"roofline_error": repr(e)}
     if rank == 0:
         out.update(roof)
+    if not args.no_parity:
+        try:
+            par = parity_check(trainer, args.workload, B, device, rank, world)
+        except Exception as e:
+            import traceback
+            traceback.print_exc()
+            par = {"error": repr(e), "ok": False}
+        if rank == 0:
+            out["ddp_parity" if world > 1 else "parity"] = par
+    if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
-            try:
-                out["parity"] = parity_check(trainer, args.workload, device)
-            except Exception as e:
-                out["parity_error"] = repr(e)
-            try:
-                out["cpu_baseline"] = cpu_baseline(args.workload, budget_s=20.0)
-            except Exception as e:
-                out["cpu_baseline_error"] = repr(e)
+            out["cpu_baseline"] = sub_arm("reference", args, steps=8, warmup=1, key="cpu_baseline")
+        if world == 1 and not args.no_eager_baseline:
+            torch.cuda.synchronize()
+            eager = sub_arm("reference-cuda", args, steps=min(K, 30), warmup=5)
+            if isinstance(eager, dict) and "value" in eager:
+                out["cuda_eager_baseline"] = {
+                    "value": eager["value"], "unit": "img/s", "ms_per_step": eager["ms_per_step"],
+                    "what": eager.get("what"), "torch": torch.__version__,
+                    "ours_over_eager": round(out["value"] / eager["value"], 3)}
+            else:
+                out["cuda_eager_baseline"] = eager
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
-def kernel_rooflines(trainer, resident, K, B, img, z, n_data, device):
+def sub_arm(impl, args, steps, warmup, key=None):
+    """Run another arm of this script in a child process (the reference's `disvae` package cannot share a process with
+    ours: same module name) and return its JSON line (or `key` of it)."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", impl, "--workload", args.workload, "--steps", str(steps),
+           "--warmup", str(warmup)]
+    if args.batch:
+        cmd += ["--batch", str(args.batch)]
+    env = dict(os.environ)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
+        line = [l for l in r.stdout.strip().splitlines() if l.startswith("{")][-1]
+        d = json.loads(line)
+        return d[key] if key else d
+    except Exception as e:
+        return {"error": repr(e)}
+
+
+def kernel_rooflines(trainer, resident, K, B, img, z, n_data, device, detail=False):
     """Per-entry-point device time inside K more steps (CUDA events around every C-ABI call on the
     launching stream), then the roofline of the dominant one and of the beta-TCVAE kernel."""
     from disvae import _native, ops
     pk = peaks()
     graph_was = trainer.use_cuda_graph
     trainer.use_cuda_graph = False               # per-call events need direct launches (the graph replays them opaquely)
-    prof = _native.enable_profiling()
+    _native.enable_profiling()
     for i in range(K):
         trainer._step(resident[i % len(resident)], None)
     torch.cuda.synchronize()
@@ -242,6 +313,10 @@ def kernel_rooflines(trainer, resident, K, B, img, z, n_data, device):
     trainer.use_cuda_graph = graph_was
     total = sum(t for t, _ in table.values())
     top = sorted(table.items(), key=lambda kv: -kv[1][0])
+    if detail:
+        for k, (t, n) in top:
+            sys.stderr.write("%-44s %4d calls/step  %8.2f us/call  %8.2f us/step  %5.1f%%\n" % (
+                k, n // K, t / n * 1e3, t / K * 1e3, 100 * t / total))
     # share per entry point (all layers) and the single heaviest (entry point, layer geometry)
     by_entry = {}
     for k, (t, n) in table.items():
@@ -252,6 +327,10 @@ def kernel_rooflines(trainer, resident, K, B, img, z, n_data, device):
            # ms_per_step after subtracting it is torch glue kernels + launch gaps
            "profiled_call_ms_per_step": round(total / K, 4),
            "profiled_calls_per_step": sum(n for _, n in table.values()) // K}
+    traffic_table = {}
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tp):                                          # dram__bytes_read+write of one launch (ncu --set full)
+        traffic_table = json.load(open(tp))
     conv = [(k, v) for k, v in top if k.startswith("dv_conv_") and "[" in k]
     name, (tms, calls) = conv[0] if conv else top[0]
     if conv:
@@ -260,19 +339,16 @@ def kernel_rooflines(trainer, resident, K, B, img, z, n_data, device):
         per_call_ms = tms / calls
         flops = 2.0 * B * H * H * 32 * 16 * CH                      # algorithmic MACs*2 of one launch (counted once,
         ach = flops / (per_call_ms / 1e3) / 1e12                    # the kernels issue 3 tf32 passes per product)
-        # algorithmic HBM bytes of one launch: read the hi and lo side once, write the output once
+        # algorithmic HBM bytes of one launch: read/write the hi and the lo side once
         hi_b, lo_b = 4.0 * B * 4 * H * H * CH, 4.0 * B * H * H * 32
-        alg_bytes = hi_b + lo_b + (0 if "wgrad" in name else 0)
-        traffic, traffic_src = None, None
-        tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-        if os.path.exists(tp):                                      # dram__bytes_read+write of one launch (ncu --set full)
-            ent = json.load(open(tp)).get(name)
-            if ent:
-                traffic, traffic_src = ent["dram_bytes"], ent.get("source")
+        alg_bytes = hi_b + lo_b
+        ent = traffic_table.get(name) or {}
         res["roofline"] = {"kernel": name, "bound": "tensor", "achieved": round(ach, 3), "peak": pk["bf16_sustained"],
-                           "unit": "TFLOP/s", "frac": round(ach / pk["bf16_sustained"], 5), "traffic": traffic,
-                           "traffic_source": traffic_src,
+                           "unit": "TFLOP/s", "frac": round(ach / pk["bf16_sustained"], 5),
+                           "traffic": ent.get("dram_bytes"), "traffic_source": ent.get("source"),
                            "algorithmic_flops_per_launch": flops, "algorithmic_hbm_bytes_per_launch": alg_bytes,
+                           "hbm_achieved_gbs": round(alg_bytes / (per_call_ms / 1e3) / 1e9, 1),
+                           "hbm_frac": round(alg_bytes / (per_call_ms / 1e3) / 1e9 / pk["hbm"], 4),
                            "us_per_launch": round(per_call_ms * 1e3, 2), "launches_per_step": calls // K,
                            "peak_source": pk["src"] + " bf16 sustained (kernel timed inside a long step)",
                            "note": "tcgen05 kind::tf32, error-compensated 3xTF32 (three tensor passes per algorithmic "
@@ -292,9 +368,8 @@ def kernel_rooflines(trainer, resident, K, B, img, z, n_data, device):
     ts = []
     for _ in range(20):
         flush.fill_(1.0)                                         # L2 flush between timed iterations
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         _native.PROFILE_ONLY = "dv_btcvae_fwd"
-        prof = _native.enable_profiling()
+        _native.enable_profiling()
         ops.btcvae_rowstats(zz, mu, lv, n_data, True)
         torch.cuda.synchronize()
         t = _native.disable_profiling()
@@ -304,71 +379,188 @@ def kernel_rooflines(trainer, resident, K, B, img, z, n_data, device):
     t_med = ts[len(ts) // 2]
     vbytes = 4 * Bk * Bk * Dk + 12 * Bk * Dk + 16 * Bk
     ach = vbytes / (t_med / 1e3) / 1e9
+    ent = traffic_table.get("dv_btcvae_fwd[B=1024,D=10]") or {}
     res["roofline_logdensity"] = {"kernel": "dv_btcvae_fwd (one launch: parameters + B x B x D sweep + means)", "bound": "hbm", "B": Bk, "D": Dk,
                                   "achieved": round(ach, 1), "peak": pk["hbm"], "unit": "GB/s (virtual bytes of the "
                                   "reference's B*B*D matrix)", "frac": round(ach / pk["hbm"], 4), "us": round(t_med * 1e3, 2),
-                                  "virtual_bytes": vbytes, "compulsory_bytes": 12 * Bk * Dk + 16 * Bk, "traffic": None,
+                                  "virtual_bytes": vbytes, "compulsory_bytes": 12 * Bk * Dk + 16 * Bk,
+                                  "traffic": ent.get("dram_bytes"), "traffic_source": ent.get("source"),
                                   "l2": "256 MB flush before every timed launch"}
     return res
 
 
-def parity_check(trainer, workload, device):
-    """Full-size forward + loss of the trained-so-far model on one seeded batch: CUDA path vs the CPU oracle
-    (same weights, same input, same injected noise).  Guards the timed numbers against silently wrong kernels."""
+def _flat(ts):
+    return torch.cat([t.detach().double().flatten().cpu() for t in ts])
+
+
+def _grad_errs(ours, ref):
+    """(max over tensors of max|a-b| / max|b|, min cosine) over parameter-gradient dicts with the same keys."""
+    worst, cos_min, worst_key = 0.0, 1.0, None
+    for k, b in ref.items():
+        a = ours[k].detach().double().cpu().flatten()
+        b = b.detach().double().cpu().flatten()
+        e = ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+        c = (torch.dot(a, b) / (a.norm() * b.norm()).clamp_min(1e-30)).item()
+        if e > worst:
+            worst, worst_key = e, k
+        cos_min = min(cos_min, c)
+    return worst, cos_min, worst_key
+
+
+def parity_check(trainer, workload, B, device, rank, world):
+    """Full-size check of the timed model on one seeded batch per rank: forward, loss and EVERY parameter gradient
+    (after the rank average for N>1) of the CUDA path against the CPU oracle -- same weights, input and injected
+    noise/permutations.  The oracle also runs in fp64: two correct fp32 evaluation orders differ by what fp32 allows,
+    which is measured (oracle fp32 vs oracle fp64) instead of assumed.  N>1 ("ddp_parity"): rank r's loss is checked
+    against the oracle on shard r and the rank-averaged gradients against the mean of the oracle's shard gradients
+    (SURVEY.md 8e); for FactorVAE that covers Trainer._factor_grads_distributed and the discriminator."""
     from collections import OrderedDict
-    from disvae.models.losses import get_loss_f
+    import torch.distributed as dist
     from oracle import disvae_oracle as O
-    loss_name, img, B, z, n_data, lkw, lr = WORKLOADS[workload]
-    g = torch.Generator().manual_seed(4321)
+    loss_name, img, _, z, n_data, lkw, lr, _ = WORKLOADS[workload]
+    g = torch.Generator().manual_seed(4321 + rank)
     x = torch.rand(B, *img, generator=g)
-    eps = torch.randn(B, z, generator=g)
-    model = trainer.model
-    was_training = model.training
+    model, lf = trainer.model, trainer.loss_f
     model.train()
-    kw = dict(rec_dist="bernoulli", reg_anneal=0, betaH_B=4, betaB_initC=0, betaB_finC=25, betaB_G=100, factor_G=6,
-              latent_dim=z, lr_disc=5e-5, btcvae_A=1, btcvae_B=6, btcvae_G=1, device=device, n_data=n_data)
-    kw.update(lkw)
-    cmp_loss = "VAE" if loss_name == "factor" else loss_name      # factor: compare the VAE part (rec + KL) of the step
-    lf = get_loss_f(cmp_loss, **kw)
+    kw = loss_kwargs(workload, device)
+    p32 = OrderedDict((k, v.detach().cpu().clone()) for k, v in model.state_dict().items())
+    factor = loss_name == "factor"
+    steps_before = lf.n_train_steps
+    if factor:
+        h = B // 2
+        e1, e2 = torch.randn(h, z, generator=g), torch.randn(h, z, generator=g)
+        perms = torch.stack([torch.randperm(h, generator=g) for _ in range(z)])
+        d32 = OrderedDict((k, v.detach().cpu().clone()) for k, v in lf.discriminator.state_dict().items())
+        loss = trainer._grads_only(x.to(device), None, eps1=e1.to(device), eps2=e2.to(device), perms=perms).item()
+    else:
+        eps = torch.randn(B, z, generator=g)
+        model.inject_noise([eps])
+        loss = trainer._grads_only(x.to(device), None).item()
+    lf.n_train_steps = steps_before
+    ours = {k: p.grad for k, p in model.named_parameters()}
+    if factor:
+        ours.update({"disc." + k: p.grad for k, p in lf.discriminator.named_parameters()})
     with torch.no_grad():
-        xd = x.to(device)
-        recon, (mu, lv), zz = model(xd, eps=eps.to(device))
-        loss = lf(xd, recon, (mu, lv), True, None, latent_sample=zz).item()
-        p = OrderedDict((k, v.detach().cpu()) for k, v in model.state_dict().items())
-        ro, (mo, lo), zo = O.vae_forward(p, x, eps)
-        if cmp_loss == "btcvae":
-            lo_, _ = O.loss_btcvae(x, ro, mo, lo, zo, n_data, kw["btcvae_A"], kw["btcvae_B"], kw["btcvae_G"], "bernoulli", 1, 0)
+        if factor:
+            recon = model(x[:h].to(device), eps=e1.to(device))[0].cpu()
         else:
-            lo_, _ = O.loss_betaH(x, ro, mo, lo, kw["betaH_B"] if cmp_loss == "betaH" else 1, "bernoulli", 1, 0)
-    model.train(was_training)
-    rel = abs(loss - lo_.item()) / abs(lo_.item())
-    rerr = (recon.cpu() - ro).abs().max().item()
-    return {"loss_cuda": loss, "loss_oracle": lo_.item(), "loss_rel_err": rel, "recon_max_abs_err": rerr,
-            "batch": B, "ok": bool(rel < 1e-4 and rerr < 1e-4)}
+            recon = model(x.to(device), eps=eps.to(device))[0].cpu()
+
+    def oracle(dtype):
+        p = O.make_leaf_params(OrderedDict((k, v.to(dtype)) for k, v in p32.items()))
+        xx = x.to(dtype)
+        if factor:
+            dp = O.make_leaf_params(OrderedDict((k, v.to(dtype)) for k, v in d32.items()))
+            cfg = dict(rec_dist="bernoulli", reg_anneal=0, factor_G=kw["factor_G"])
+            l, _, ro = O.factor_step(p, dp, O.make_adam(p, 0.0), O.make_adam(dp, 0.0, betas=(0.5, 0.9)), xx, cfg, step=1,
+                                     eps1=e1.to(dtype), eps2=e2.to(dtype), perms=perms)
+            gr = {k: v.grad for k, v in p.items()}
+            gr.update({"disc." + k: v.grad for k, v in dp.items()})
+            return l.item(), ro, gr
+        ro, (mo, lo), zo = O.vae_forward(p, xx, eps.to(dtype))
+        if loss_name == "btcvae":
+            l, _ = O.loss_btcvae(xx, ro, mo, lo, zo, n_data, kw["btcvae_A"], kw["btcvae_B"], kw["btcvae_G"], "bernoulli", 1, 0)
+        else:
+            l, _ = O.loss_betaH(xx, ro, mo, lo, kw["betaH_B"] if loss_name == "betaH" else 1, "bernoulli", 1, 0)
+        l.backward()
+        return l.item(), ro.detach(), {k: v.grad for k, v in p.items()}
+
+    l32, r32, g32 = oracle(torch.float32)
+    l64, r64, g64 = oracle(torch.float64)
+    if world > 1:                                              # mean of the shard gradients over ranks, like ours
+        for gd in (g32, g64):
+            for k in gd:
+                t = gd[k].to(device)
+                dist.all_reduce(t, op=dist.ReduceOp.SUM)
+                gd[k] = (t / world).cpu()
+    rel = abs(loss - l32) / abs(l32)
+    rerr = (recon - r32).abs().max().item()
+    e_ours32, cos32, key32 = _grad_errs(ours, g32)
+    e_ours64, cos64, key64 = _grad_errs(ours, g64)
+    e_cpu64, _, _ = _grad_errs(g32, g64)
+    # gradients: within 1e-4 of the fp32 oracle, or as close to the fp64 truth as the fp32 oracle itself is (x3)
+    grad_ok = e_ours32 <= 1e-4 or (e_ours64 <= max(1e-4, 3.0 * e_cpu64) and cos64 > 1 - 1e-6)
+    ok = bool(rel < 1e-4 and rerr < 1e-4 and grad_ok)
+    res = {"loss_cuda": loss, "loss_oracle": l32, "loss_rel_err": rel, "loss_rel_err_vs_fp64": abs(loss - l64) / abs(l64),
+           "recon_max_abs_err": rerr, "grad_rel_err_vs_oracle_fp32": e_ours32, "grad_rel_err_vs_oracle_fp64": e_ours64,
+           "oracle_fp32_vs_fp64_grad_rel_err": e_cpu64, "grad_cos_min_vs_fp64": cos64, "grad_worst_tensor": key64,
+           "n_grad_tensors": len(ours), "batch": B, "ok": ok}
+    if world > 1:
+        flags = torch.tensor([float(ok), rel, e_ours64, e_cpu64], device=device, dtype=torch.float64)
+        allf = [torch.zeros_like(flags) for _ in range(world)]
+        dist.all_gather(allf, flags)
+        res = {"world": world, "ok": bool(all(f[0].item() > 0.5 for f in allf)),
+               "loss_rel_err_max": max(f[1].item() for f in allf),
+               "avg_grad_rel_err_vs_oracle_fp64": max(f[2].item() for f in allf),
+               "oracle_fp32_vs_fp64_grad_rel_err": max(f[3].item() for f in allf),
+               "rank0": res,
+               "what": "rank r loss vs oracle on shard r (max over ranks); rank-averaged gradients of every parameter "
+                       "vs the mean of the oracle's shard gradients"}
+    return res
 
 
-def oracle_job(workload, batch=None):
+# =====================================================================================================
+# reference arms
+# =====================================================================================================
+def oracle_job(workload, batch):
     from oracle import disvae_oracle as O
-    loss_name, img, B, z, n_data, lkw, lr = WORKLOADS[workload]
-    B = batch or B
+    loss_name, img, _, z, n_data, lkw, lr, _ = WORKLOADS[workload]
     torch.manual_seed(1234)
     p = O.make_leaf_params(O.init_vae_params(img, z))
     opt = O.make_adam(p, lr)
     cfg = dict(rec_dist="bernoulli", reg_anneal=0, n_data=n_data, betaH_B=4, btcvae_A=1, btcvae_B=6, btcvae_G=1)
     cfg.update(lkw)
-    x = torch.rand(B, *img)
+    xs = [torch.rand(batch, *img) for _ in range(N_ROTATE)]
     state = dict(step=0)
     if loss_name == "factor":
         dp = O.make_leaf_params(O.init_disc_params(z))
         opt_d = O.make_adam(dp, cfg["lr_disc"], betas=(0.5, 0.9))
 
     def step():
+        x = xs[state["step"] % N_ROTATE]
         state["step"] += 1
         if loss_name == "factor":
             O.factor_step(p, dp, opt, opt_d, x, cfg, state["step"])
         else:
             O.train_step(p, opt, x, loss_name, cfg, state["step"])
-    return step, B
+    return step
+
+
+def reference_job(workload, batch, device):
+    """The unmodified reference's own training step: disvae.Trainer._train_iteration (training.py:137-164) of
+    baseline/_ref.  None if the copy is not there."""
+    from oracle import reference_env
+    ref = reference_env.find_reference()
+    if ref is None:
+        return None
+    reference_env.activate(ref)
+    import logging
+    import tempfile
+    from collections import defaultdict
+    import disvae
+    from disvae.models.losses import get_loss_f
+    from disvae.training import Trainer
+    assert os.path.realpath(disvae.__file__).startswith(os.path.realpath(ref)), disvae.__file__
+    loss_name, img, _, z, n_data, lkw, lr, _ = WORKLOADS[workload]
+    torch.manual_seed(1234)
+    model = disvae.init_specific_model("Burgess", img, z)
+    opt = torch.optim.Adam(model.parameters(), lr=lr)
+    model = model.to(device)
+    loss_f = get_loss_f(loss_name, **loss_kwargs(workload, device))
+    trainer = Trainer(model, opt, loss_f, device=device, logger=logging.getLogger("refbench"),
+                      save_dir=tempfile.mkdtemp(prefix="dvref"), is_progress_bar=False)
+    model.train()
+    xs = [torch.rand(batch, *img) for _ in range(N_ROTATE)]
+    if device.type == "cuda":
+        xs = [x.to(device) for x in xs]                      # resident, like our `value`
+    state = dict(step=0)
+    storer = defaultdict(list)
+
+    def step():
+        x = xs[state["step"] % N_ROTATE]
+        state["step"] += 1
+        return trainer._train_iteration(x, storer)
+    return step
 
 
 def pick_threads(step):
@@ -388,39 +580,29 @@ def pick_threads(step):
     return best
 
 
-def cpu_baseline(workload, budget_s=20.0):
-    """Oracle port (plain PyTorch CPU ops == what the reference executes) on the host cores."""
-    step, B = oracle_job(workload)
-    cores = pick_threads(step)
-    step()                                                   # warm-up
-    t0 = time.perf_counter()
-    n = 0
-    while n < 3 or (time.perf_counter() - t0 < budget_s and n < 50):
-        step()
-        n += 1
-    dt = time.perf_counter() - t0
-    return {"value": round(B * n / dt, 1), "unit": "img/s", "cores": cores, "kind": "port",
-            "sample": "%d full steps of the same workload (batch %d) after warm-up, %.1f s; thread count picked as the "
-                      "fastest of {16,32,64,all} (host has %d logical cores)" % (n, B, dt, os.cpu_count() or 1),
-            "torch": torch.__version__}
-
-
 def run_reference(args):
+    """CPU arm (rank 0 only): the reference's own implementation of the path on the host cores."""
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    loss_name, img, B, z, n_data, lkw, lr = WORKLOADS[args.workload]
-    step, Bs = oracle_job(args.workload)
+    B = per_gpu_batch(args, world)
+    Bs = B
+    step = reference_job(args.workload, Bs, torch.device("cpu"))
+    kind = "reference" if step is not None else "port"
+    if step is None:
+        step = oracle_job(args.workload, Bs)
     cores = pick_threads(step)
     t0 = time.perf_counter()
     step()
     t_one = time.perf_counter() - t0
-    sample = "full batch %d per step" % Bs
+    sample = "full per-GPU batch of %d images per step" % Bs
     if t_one * (args.steps + args.warmup) > 240.0:                     # keep the arm within a few minutes
         Bs = max(64, B // 4)
-        step, Bs = oracle_job(args.workload, batch=Bs)
+        step = reference_job(args.workload, Bs, torch.device("cpu")) or oracle_job(args.workload, Bs)
         sample = "bounded sample: batch %d per step (of %d) -- the B^2 term of the loss is 1/16 per step" % (Bs, B)
+    if world > 1:
+        sample += "; rank 0 only: %d of the %d images of the global batch per step on ONE host process" % (Bs, B * world)
     for _ in range(max(args.warmup - 1, 1)):
         step()
     t0 = time.perf_counter()
@@ -428,31 +610,78 @@ def run_reference(args):
         step()
     dt = time.perf_counter() - t0
     v = round(Bs * args.steps / dt, 1)
+    what = ("unmodified reference (baseline/_ref) disvae.Trainer._train_iteration on CPU" if kind == "reference"
+            else "oracle port (oracle/disvae_oracle.py) on CPU")
     out = {"impl": "reference", "metric": "images/sec", "value": v, "unit": "img/s", "n_gpus": world, "steps": args.steps,
-           "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
-           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           # same config keys as our own arm (the reference arm runs rank 0 only, on the host cores)
-           "config": {"workload": WORKLOAD_NAMES[args.workload],
-                      "loss": loss_name, "img_size": list(img), "batch_per_gpu": B, "global_batch": B * world,
-                      "latent_dim": z, "n_data": n_data, "rec_dist": "bernoulli", "optimizer": "Adam lr %g" % lr,
-                      "parallelism": "dp%d" % world if world > 1 else "single"},
-           "cpu_baseline": {"value": v, "unit": "img/s", "cores": cores, "kind": "port", "sample": sample,
-                            "torch": torch.__version__},
+           "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3), "higher_is_better": True,
+           "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic (torch.rand); random-init weights (seed 1234)",
+           "config": config_block(args, world, B), "sample_images_per_step": Bs, "what": what,
+           "cpu_baseline": {"value": v, "unit": "img/s", "cores": cores, "kind": kind, "sample": sample,
+                            "host_logical_cores": os.cpu_count(), "torch": torch.__version__},
            "e2e": {"value": v, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def run_reference_cuda(args):
+    """The unmodified reference on the B200 through stock PyTorch eager (cuDNN / cuBLAS), TF32 disabled so that it
+    computes in the same fp32 as the CPU path -- SURVEY.md 8d's "existing Blackwell kernels" bar."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    if not torch.cuda.is_available():
+        print(json.dumps({"impl": "reference-cuda", "unavailable": "no CUDA device"}), flush=True)
+        return
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cudnn.benchmark = True
+    device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(device)
+    B = per_gpu_batch(args, world)
+    step = reference_job(args.workload, B, device)
+    if step is None:
+        print(json.dumps({"impl": "reference-cuda", "unavailable": "baseline/_ref not shipped"}), flush=True)
+        return
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    v = round(B * args.steps / (ms / 1e3), 1)
+    out = {"impl": "reference-cuda", "metric": "images/sec", "value": v, "unit": "img/s", "n_gpus": 1, "steps": args.steps,
+           "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
+           "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic (torch.rand); random-init weights",
+           "config": config_block(args, 1, B),
+           "what": "unmodified reference (baseline/_ref) disvae.Trainer._train_iteration, device=cuda, stock PyTorch %s eager "
+                   "(cuDNN %s), allow_tf32=False, cudnn.benchmark=True, batches resident" % (
+                       torch.__version__, torch.backends.cudnn.version())}
     print(json.dumps(out), flush=True)
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cuda"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch (experiments)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--detail", action="store_true", help="per-entry-point table on stderr")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "reference-cuda":
+        run_reference_cuda(args)
     else:
         run_ours(args)
 

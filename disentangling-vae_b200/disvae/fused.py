@@ -3,7 +3,8 @@
 `FusedAdam` drives `dv_adam_multi` (one launch for every parameter tensor of a model) with the
 hyper-parameters and the state dictionary of the `torch.optim.Adam` instance that `main.py`
 constructed (main.py:208, losses.py:238): `optimizer.state[p]` holds the very buffers the kernel
-updates, so `optimizer.state_dict()` stays meaningful.  Anything other than a plain Adam (amsgrad,
+updates, so `optimizer.state_dict()` stays meaningful (the step
+counter is mirrored back by `flush_state`, which the Trainer calls at every epoch end).  Anything other than a plain Adam (amsgrad,
 weight decay, maximize, non-CUDA parameters) is not taken over: `FusedAdam.supports` says no and the
 caller keeps using `optimizer.step()`.
 """
@@ -45,7 +46,7 @@ class FusedAdam:
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                 step0 = float(st["step"])
-            self.groups.append(dict(group=g, params=params,
+            self.groups.append(dict(group=g, params=params, step0=step0,
                                     step_dev=torch.full((1,), step0, dtype=torch.float32, device=params[0].device)))
 
     def step(self, grad_scale=1.0):
@@ -69,7 +70,9 @@ class FusedAdam:
         self.host_steps += 1
 
     def flush_state(self):
-        """Write the step counters back into optimizer.state (cheap; call before state_dict())."""
+        """Write the step counters back into optimizer.state: the count the optimizer was constructed/loaded with
+        plus the steps taken here (host mirror of the device counter; no sync).  The Trainer calls this at every
+        epoch end, so `optimizer.state_dict()` saved at a checkpoint resumes with the right bias correction."""
         for G in self.groups:
             for p in G["params"]:
-                self.optimizer.state[p]["step"].fill_(float(self.host_steps))
+                self.optimizer.state[p]["step"].fill_(float(G["step0"] + self.host_steps))

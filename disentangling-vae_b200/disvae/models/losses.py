@@ -164,13 +164,16 @@ class FactorKLoss(BaseLoss):
 
     def _perm_state(self, device):
         if self._perm_offset is None or self._perm_offset.device != device:
-            self._perm_seed = (int(torch.initial_seed()) ^ 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+            from disvae.parallel import rank_salt
+            self._perm_seed = ((int(torch.initial_seed()) ^ 0x9E3779B97F4A7C15) + rank_salt()) & 0xFFFFFFFFFFFFFFFF
             self._perm_offset = torch.zeros(1, dtype=torch.int64, device=device)
         return self._perm_seed, self._perm_offset
 
-    def call_optimize(self, data, model, optimizer, storer, eps1=None, eps2=None, perms=None):
+    def call_optimize(self, data, model, optimizer, storer, eps1=None, eps2=None, perms=None, step_optimizers=True):
         """losses.py:243-313.  `eps1`/`eps2`/`perms` optionally inject the noise of the two
-        halves and the per-dimension permutations ([D, B/2] int64) for parity tests."""
+        halves and the per-dimension permutations ([D, B/2] int64) for parity tests.
+        `step_optimizers=False` (data parallel): both backward passes run, neither optimizer steps -- the
+        Trainer steps them after the gradients of all ranks are averaged."""
         storer = self._pre_call(model.training, storer)
         half = data.size(0) // 2
         parts = data.split(half)
@@ -204,10 +207,8 @@ class FactorKLoss(BaseLoss):
 
         self.optimizer_d.zero_grad()
         d_tc_loss.backward()                                     # also reaches the encoder through d_z (trap T5)
-        optimizer.step()
-        if type(self.optimizer_d).__name__ == "_Deferred":
-            self.optimizer_d.step()                               # data-parallel: the Trainer steps after the all-reduce
-        else:
+        if step_optimizers:
+            optimizer.step()
             self._step_d()
 
         _record(storer, ['recon_loss', 'kl_loss', _kl_names(kl_dims.numel()), 'loss', 'tc_loss', 'discrim_loss'],

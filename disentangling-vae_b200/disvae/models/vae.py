@@ -40,7 +40,9 @@ class VAE(nn.Module):
     # -- device noise stream ------------------------------------------------------------
     def _noise_state(self, device):
         if self._rng_offset is None or self._rng_offset.device != device:
-            self._rng_seed = int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF
+            from disvae.parallel import rank_salt
+            # identically seeded replicas (main.py's set_seed) must still draw different noise for their shards
+            self._rng_seed = (int(torch.initial_seed()) + rank_salt()) & 0xFFFFFFFFFFFFFFFF
             self._rng_offset = torch.zeros(1, dtype=torch.int64, device=device)
         return self._rng_seed, self._rng_offset
 

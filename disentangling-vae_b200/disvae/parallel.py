@@ -10,6 +10,14 @@ def is_distributed():
     return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
 
 
+def rank_salt():
+    """Folded into the device Philox keys (reparameterisation noise, latent permutations): 0 for a single process,
+    a rank-dependent odd multiplier otherwise, so replicas seeded identically draw independent streams."""
+    if not is_distributed():
+        return 0
+    return (dist.get_rank() * 0xD1342543DE82EF95) & 0xFFFFFFFFFFFFFFFF
+
+
 class FlatGradSync:
     """Packs the gradients of `params` into one contiguous buffer, all-reduces it (sum) and
     scatters the mean back.  The buffer is allocated once; `.grad` tensors are re-pointed to

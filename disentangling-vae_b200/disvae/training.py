@@ -68,20 +68,24 @@ class Trainer():
 
     def _train_epoch(self, data_loader, storer, epoch):
         """training.py:104-135; the epoch loss is accumulated on the device."""
-        epoch_loss = None
         kwargs = dict(desc="Epoch {}".format(epoch + 1), leave=False, disable=not self.is_progress_bar)
         on_gpu = self.device.type == "cuda"
+        # own accumulator, updated in place: `loss` may be the CUDA graph's static output tensor, which the next
+        # replay overwrites -- never keep a reference to it across steps
+        epoch_loss = torch.zeros((), dtype=torch.float32, device=self.device)
         batches = _Prefetcher(data_loader, self.device) if on_gpu else data_loader
         ring = self._loss_ring() if on_gpu else None
         with trange(len(data_loader), **kwargs) as t:
             for i, (data, _) in enumerate(batches):
                 loss = self._step(data, storer)
-                epoch_loss = loss if epoch_loss is None else epoch_loss + loss
+                epoch_loss += loss
                 if ring is not None:
                     ring.push(loss)                           # async D2H of this step's loss (4 bytes)
                 if self.is_progress_bar and i % self.sync_every == 0:
                     t.set_postfix(loss=ring.latest() if ring is not None else loss.item())
                 t.update()
+        if self._fused:
+            self._fused.flush_state()                         # optimizer.state[p]["step"] follows the device counter
         return epoch_loss.item() / len(data_loader)
 
     def _loss_ring(self):
@@ -172,22 +176,27 @@ class Trainer():
         """One optimisation step; returns the loss as a detached 0-dim device tensor."""
         if self._graph_eligible(data, storer):
             self._eligible_steps += 1
-            if self._eligible_steps > 3 or (tuple(data.shape), str(data.dtype)) in self._graphs:   # 3 eager warm-up steps first
+            if self._eligible_steps > 2 or (tuple(data.shape), str(data.dtype)) in self._graphs:   # 2 eager warm-up steps first
                 return self._graph_step(data)
         data = data.to(self.device, non_blocking=True)
+        recon_batch, latent_dist, latent_sample = self.model(data)
         try:
-            recon_batch, latent_dist, latent_sample = self.model(data)
             loss = self.loss_f(data, recon_batch, latent_dist, self.model.training, storer, latent_sample=latent_sample)
-            self.optimizer.zero_grad()
-            loss.backward()
-            self._sync_grads()
-            self._optimizer_step()
         except ValueError:
-            # losses with several optimizers (FactorVAE): training.py:160-162
+            # losses with several optimizers (FactorVAE) announce themselves by raising from __call__
+            # (training.py:160-162, losses.py:240-241).  Only the loss call is inside the `try`: a ValueError from
+            # anywhere else in the step (a kernel-side shape check, the optimizer) must surface, not be rerouted.
+            if not hasattr(self.loss_f, "call_optimize"):
+                raise
             if is_distributed():
                 loss = self._factor_step_distributed(data, storer)
             else:
                 loss = self.loss_f.call_optimize(data, self.model, _StepProxy(self.optimizer, self._optimizer_step), storer)
+            return loss.detach()
+        self.optimizer.zero_grad()
+        loss.backward()
+        self._sync_grads()
+        self._optimizer_step()
         return loss.detach()
 
     def _train_iteration(self, data, storer):
@@ -204,27 +213,41 @@ class Trainer():
 
     def _factor_step_distributed(self, data, storer):
         """FactorVAE step with the optimizer updates deferred until gradients are averaged."""
-        class _Deferred:
-            def __init__(self, opt):
-                self.opt = opt
-            def zero_grad(self, *a, **k):
-                return self.opt.zero_grad(*a, **k)
-            def step(self):
-                return None
-        lf = self.loss_f
-        real_d = lf.optimizer_d
-        lf.optimizer_d = _Deferred(real_d)
-        try:
-            loss = lf.call_optimize(data, self.model, _Deferred(self.optimizer), storer)
-        finally:
-            lf.optimizer_d = real_d
-        self._sync_grads()
-        if self._grad_sync_d is None:
-            self._grad_sync_d = FlatGradSync(list(lf.discriminator.parameters()))
-        self._grad_sync_d.sync()
+        loss = self._factor_grads_distributed(data, storer)
         self._optimizer_step()
-        lf._step_d()
+        self.loss_f._step_d()
         return loss
+
+    def _factor_grads_distributed(self, data, storer, **inject):
+        """Both backward passes of losses.py:243-313 on this rank's shard, then the rank-average of the VAE and the
+        discriminator gradients (two flat all-reduces); no optimizer steps."""
+        lf = self.loss_f
+        if self._grad_sync_d is None:
+            from disvae.parallel import broadcast_parameters
+            broadcast_parameters(lf.discriminator)                # replicas must start from identical discriminators
+            self._grad_sync_d = FlatGradSync(list(lf.discriminator.parameters()))
+        loss = lf.call_optimize(data, self.model, self.optimizer, storer, step_optimizers=False, **inject)
+        self._sync_grads()
+        self._grad_sync_d.sync()
+        return loss
+
+    def _grads_only(self, data, storer=None, **inject):
+        """Forward + loss + backward (+ the data-parallel gradient average) of one batch WITHOUT an optimizer step:
+        afterwards every `p.grad` (and, for FactorVAE, the discriminator's) holds exactly what the optimizers would
+        consume.  Used by the parity checks (bench.py `parity` / `ddp_parity`, tests); `inject` forwards
+        eps1/eps2/perms to FactorKLoss.call_optimize."""
+        data = data.to(self.device, non_blocking=True)
+        lf = self.loss_f
+        if hasattr(lf, "call_optimize"):
+            if is_distributed():
+                return self._factor_grads_distributed(data, storer, **inject).detach()
+            return lf.call_optimize(data, self.model, self.optimizer, storer, step_optimizers=False, **inject).detach()
+        recon_batch, latent_dist, latent_sample = self.model(data)
+        loss = lf(data, recon_batch, latent_dist, self.model.training, storer, latent_sample=latent_sample)
+        self.optimizer.zero_grad()
+        loss.backward()
+        self._sync_grads()
+        return loss.detach()
 
 
 class _Prefetcher:

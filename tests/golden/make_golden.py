@@ -219,8 +219,18 @@ def gen_train_steps():
             steps.append(dict(loss=lv, storer={k: list(v) for k, v in storer.items()}))
         rec = dict(img_size=img_size, batch=b, n_data=n_data, over=over, xs_digest=[tensor_digest(x) for x in xs],
                    steps=steps, params=state_digest(model.state_dict()))
+        # Adam moments after the 3 steps: linear / quadratic in the gradients, so -- unlike the parameters, which
+        # move by ~lr whatever the gradient is -- they pin the gradients' magnitudes through the optimizer
+        names = {id(p): k for k, p in model.named_parameters()}
+        rec["opt_state"] = {names[id(p)]: dict(exp_avg=tensor_digest(st["exp_avg"]), exp_avg_sq=tensor_digest(st["exp_avg_sq"]),
+                                               step=float(st["step"]))
+                            for p, st in optimizer.state.items()}
         if loss_name == "factor":
             rec["disc_params"] = state_digest(loss_f.discriminator.state_dict())
+            dnames = {id(p): k for k, p in loss_f.discriminator.named_parameters()}
+            rec["disc_opt_state"] = {dnames[id(p)]: dict(exp_avg=tensor_digest(st["exp_avg"]),
+                                                          exp_avg_sq=tensor_digest(st["exp_avg_sq"]), step=float(st["step"]))
+                                     for p, st in loss_f.optimizer_d.state.items()}
         out[loss_name] = rec
         shutil.rmtree(tmp, ignore_errors=True)
     torch.save(out, os.path.join(HERE, "train_steps.pt"))

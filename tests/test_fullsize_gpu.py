@@ -1,0 +1,162 @@
+"""Parity AT THE SHAPES bench.py TIMES (ADVICE medium #1): every conv layer geometry of BASELINE
+configs[1..4] at its full batch (the persistent kernels' many-tiles-per-CTA regime, the all-tap-pairs plan of
+conv_wgrad32_tc above 1184 tiles, ...), the MLP shapes at M = 1024 / 512, and whole-model gradients at the full
+batch.  References are PyTorch CPU ops in fp64, so the tolerance is an accuracy statement (<= 4e-6 of the output scale,
+the bar the small-shape tests hold the 3xTF32 kernels to), not a comparison of two fp32 roundings."""
+from collections import OrderedDict
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import disvae_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def rel_err(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+def assert_close(a, b, tol, what=""):
+    assert tuple(a.shape) == tuple(b.shape), (what, a.shape, b.shape)
+    e = rel_err(a, b)
+    assert e <= tol, "%s: rel err %.3e > %.1e" % (what, e, tol)
+
+
+def nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+def nchw(t):
+    return t.permute(0, 3, 1, 2).contiguous()
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from disvae import ops as _ops
+    return _ops
+
+
+# (B, H of the low-resolution side, CH of the high-resolution side): c2's four layers at B=1024, c3/c4's image layer at
+# B=512/256, c5's shard at 256
+FULL_CASES = [(1024, 32, 1), (1024, 16, 32), (1024, 8, 32), (1024, 4, 32), (512, 32, 3), (256, 32, 3), (512, 16, 32),
+              (256, 16, 32)]
+
+
+@pytest.mark.parametrize("B,H,CH", FULL_CASES)
+def test_conv_layer_full_size_down_up_wgrad(ops, B, H, CH):
+    torch.manual_seed(B + 10 * H + CH)
+    x = torch.randn(B, CH, 2 * H, 2 * H)
+    lo = torch.randn(B, 32, H, H)
+    w = torch.randn(32, CH, 4, 4) * 0.1
+    b32, bch = torch.randn(32), torch.randn(CH)
+    wp = ops.conv_pack(w.to(DEV), CH)
+    small = int(CH < 32)
+    hi_d = x.to(DEV) if small else nhwc(x).to(DEV)
+    lo_d = nhwc(lo).to(DEV)
+    xd, lod, wd = x.double(), lo.double(), w.double()
+    # down: Conv2d forward with ReLU (encoders.py:72-77) ...
+    ref = torch.relu(F.conv2d(xd, wd, b32.double(), stride=2, padding=1))
+    got = ops.conv_down(hi_d, wp, b32.to(DEV), None, B, H, H, CH, small, 1)
+    assert_close(nchw(got.cpu()), ref, 4e-6, "down+relu")
+    # ... and as ConvTranspose2d's input gradient with the ReLU mask and the fused bias gradient (channel sums)
+    mask = torch.randn(B, 32, H, H)
+    ref2 = F.conv2d(xd, wd, None, stride=2, padding=1) * (mask > 0)
+    got2, cs = ops.conv_down(hi_d, wp, None, nhwc(mask).to(DEV), B, H, H, CH, small, 0, want_colsum=True)
+    assert_close(nchw(got2.cpu()), ref2, 4e-6, "down+mask")
+    assert_close(cs.cpu(), ref2.sum((0, 2, 3)), 1e-5, "column sums")
+    # up: ConvTranspose2d forward (ReLU inside the decoder, sigmoid on the image layer; decoders.py:76-82)
+    act = 2 if small else 1
+    refu = F.conv_transpose2d(lod, wd, bch.double(), stride=2, padding=1)
+    refu = torch.sigmoid(refu) if small else torch.relu(refu)
+    gotu = ops.conv_up(lo_d, wp, bch.to(DEV), None, B, H, H, CH, small, act)
+    assert_close(gotu.cpu() if small else nchw(gotu.cpu()), refu, 4e-6, "up")
+    if not small:           # Conv2d's input gradient with the ReLU mask of the layer below
+        masku = torch.randn(B, 32, 2 * H, 2 * H)
+        refm = F.conv_transpose2d(lod, wd, None, stride=2, padding=1) * (masku > 0)
+        gotm = ops.conv_up(lo_d, wp, None, nhwc(masku).to(DEV), B, H, H, CH, 0, 0)
+        assert_close(nchw(gotm.cpu()), refm, 4e-6, "up+mask")
+    # wgrad (both Conv2d's and ConvTranspose2d's weight gradient) + bias gradient, deterministic
+    wz = torch.zeros(32, CH, 4, 4, dtype=torch.float64, requires_grad=True)
+    (F.conv2d(xd, wz, None, stride=2, padding=1) * lod).sum().backward()
+    dw, db = ops.conv_wgrad(lo_d, hi_d, B, H, H, CH, small, True)
+    assert_close(dw.cpu(), wz.grad, 4e-6, "wgrad")
+    assert_close(db.cpu(), lod.sum((0, 2, 3)), 4e-6, "dbias")
+    dw2, db2 = ops.conv_wgrad(lo_d, hi_d, B, H, H, CH, small, True)
+    assert torch.equal(dw, dw2) and torch.equal(db, db2)
+
+
+@pytest.mark.parametrize("M,N,K", [(1024, 256, 512), (1024, 256, 256), (1024, 20, 256), (1024, 256, 10), (1024, 512, 256),
+                                   (512, 256, 512), (512, 512, 256), (256, 128, 256), (256, 256, 64),
+                                   (256, 1000, 1000), (256, 1000, 10), (256, 2, 1000)])
+def test_linear_full_size(ops, M, N, K):
+    torch.manual_seed(M + N + K)
+    x = torch.randn(M, K)
+    w = torch.randn(N, K) / K ** 0.5
+    b = torch.randn(N)
+    g = torch.randn(M, N)
+    y = ops.linear_fwd(x.to(DEV), w.to(DEV), b.to(DEV), 1)
+    assert_close(y.cpu(), torch.relu(F.linear(x.double(), w.double(), b.double())), 4e-6, "fwd")
+    prev = torch.randn(M, K)
+    dx = ops.linear_dgrad(g.to(DEV), w.to(DEV), torch.relu(prev).to(DEV), 1)
+    assert_close(dx.cpu(), (g.double() @ w.double()) * (prev > 0), 4e-6, "dgrad+mask")
+    dw, db = ops.linear_wgrad(g.to(DEV), x.to(DEV))
+    assert_close(dw.cpu(), g.double().t() @ x.double(), 4e-6, "wgrad")
+    assert_close(db.cpu(), g.double().sum(0), 4e-6, "dbias")
+
+
+def _model(img, z):
+    import disvae
+    torch.manual_seed(1234)
+    return disvae.init_specific_model("Burgess", img, z).to(DEV)
+
+
+@pytest.mark.parametrize("loss_name,img,z,B", [("btcvae", (1, 64, 64), 10, 1024), ("betaH", (3, 64, 64), 10, 512),
+                                               ("btcvae", (3, 64, 64), 64, 256)])
+def test_model_gradients_full_batch_fp64_arbitrated(loss_name, img, z, B):
+    """All parameter gradients of one full-size training batch (BASELINE configs[1], [2], [4]-shard).  Two fp32
+    evaluation orders of this network differ by more than 1e-4 on a few weight-gradient entries (ReLU pre-activations
+    that round to opposite sides of zero switch whole back-propagated paths), so the fp32 oracle cannot referee that
+    alone: the oracle also runs in fp64, and the CUDA path must be as close to the fp64 truth as the CPU fp32 oracle
+    is (x3 slack) -- or within 1e-4 of the fp32 oracle outright."""
+    from disvae.models.losses import get_loss_f
+    m = _model(img, z)
+    m.train()
+    n_data = 737280
+    p32 = OrderedDict((k, v.detach().cpu().clone()) for k, v in m.state_dict().items())
+    torch.manual_seed(B + z)
+    x, eps = torch.rand(B, *img), torch.randn(B, z)
+
+    def oracle(dt):
+        p = O.make_leaf_params(OrderedDict((k, v.to(dt)) for k, v in p32.items()))
+        ro, (mo, lo), zo = O.vae_forward(p, x.to(dt), eps.to(dt))
+        if loss_name == "btcvae":
+            l, _ = O.loss_btcvae(x.to(dt), ro, mo, lo, zo, n_data, 1, 6, 1, "bernoulli", 1, 0)
+        else:
+            l, _ = O.loss_betaH(x.to(dt), ro, mo, lo, 10, "bernoulli", 1, 0)
+        l.backward()
+        return l.item(), ro.detach(), {k: v.grad for k, v in p.items()}
+
+    l32, r32, g32 = oracle(torch.float32)
+    l64, r64, g64 = oracle(torch.float64)
+    lf = get_loss_f(loss_name, rec_dist="bernoulli", reg_anneal=0, betaH_B=10, btcvae_A=1, btcvae_B=6, btcvae_G=1, n_data=n_data)
+    xd = x.to(DEV)
+    recon, (mu, lv), zz = m(xd, eps=eps.to(DEV))
+    loss = lf(xd, recon, (mu, lv), True, None, latent_sample=zz)
+    m.zero_grad()
+    loss.backward()
+    assert abs(loss.item() - l32) <= 1e-4 * abs(l32)
+    assert abs(loss.item() - l64) <= 1e-4 * abs(l64)
+    assert_close(recon.cpu(), r64, 1e-4, "recon vs fp64")
+    worst_ours = worst_cpu = 0.0
+    for k, prm in m.named_parameters():
+        e_ours, e_cpu = rel_err(prm.grad, g64[k]), rel_err(g32[k], g64[k])
+        worst_ours, worst_cpu = max(worst_ours, e_ours), max(worst_cpu, e_cpu)
+        assert e_ours <= max(1e-4, 3.0 * e_cpu) or rel_err(prm.grad, g32[k]) <= 1e-4, \
+            "grad %s: ours vs fp64 %.2e, oracle fp32 vs fp64 %.2e" % (k, e_ours, e_cpu)
+        a, b = prm.grad.double().cpu().flatten(), g64[k].flatten()
+        assert torch.dot(a, b) / (a.norm() * b.norm()).clamp_min(1e-30) > 1 - 1e-6, k
+    print("max grad rel err vs fp64: ours %.2e, CPU fp32 oracle %.2e" % (worst_ours, worst_cpu))

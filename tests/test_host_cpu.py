@@ -228,8 +228,9 @@ def test_flat_grad_allreduce_world2_gloo(tmp_path):
 
 
 def test_bench_reference_arm_contract():
-    """`bench.py --impl reference` runs without a GPU (it times the CPU oracle port) and prints ONE JSON line with the
-    keys the bench contract names; its metric/unit/config match our own arm's."""
+    """`bench.py --impl reference` runs without a GPU (it times the unmodified reference shipped to baseline/_ref, or
+    the CPU oracle port when that copy is absent) and prints ONE JSON line with the keys the bench contract names; its
+    metric/unit/config match our own arm's."""
     import json
     import subprocess
     import sys
@@ -244,6 +245,9 @@ def test_bench_reference_arm_contract():
     for k in ("value", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "vs_baseline", "dtype", "data", "config",
               "cpu_baseline", "e2e"):
         assert k in d, k
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"]
+    shipped = os.path.isfile(os.path.join(root, "baseline", "_ref", "main.py")) or os.path.isdir("/root/reference")
+    assert d["cpu_baseline"]["kind"] == ("reference" if shipped else "port") and d["cpu_baseline"]["value"] == d["value"]
+    assert set(d["config"]) == {"workload", "loss", "img_size", "batch_per_gpu", "global_batch", "latent_dim", "n_data",
+                                "rec_dist", "optimizer", "parallelism", "l2"}          # == our own arm's keys
     assert d["e2e"] == {"value": d["value"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["loss"] == "VAE" and d["config"]["batch_per_gpu"] == 64
