@@ -19,6 +19,7 @@
 // multiply.  Each logsumexp is an exact two-sweep (max, then sum of exp2) reduction; cross-lane
 // merges are warp shuffles, cross-warp merges go through a few hundred bytes of shared memory.
 #include <stdlib.h>
+#include <cooperative_groups.h>
 #include "dv_common.cuh"
 
 namespace dv {
@@ -251,13 +252,14 @@ constexpr int kRG = 32;            // rows per block
 // terms are < 2^-66 of the block bound and far below the diagonal term.  One MUFU.EX2, ~8 FP32 ops per (i,j,d).
 template <int DC, bool EXACT>
 __global__ void __launch_bounds__(kBtWarps * 32)
-btcvae_fwd2_kernel(int B, int D, LogW lw, const float4* __restrict__ pj, float2* __restrict__ part) {
+btcvae_fwd2_kernel(int B, int D, int row0, int nrows, LogW lw, const float4* __restrict__ pj, float2* __restrict__ part) {
   __shared__ float4 sp[DC][kJT];
   __shared__ float sbound[DC];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int r = lane >> 3, jl = lane & 7;
-  const int i_raw = blockIdx.x * kRG + warp * kRows + r;
-  const int i = min(i_raw, B - 1);
+  const int i_raw = row0 + blockIdx.x * kRG + warp * kRows + r;       // rows [row0, row0 + nrows) of the global batch
+  const int row_end = row0 + nrows;
+  const int i = min(i_raw, row_end - 1);
   const int js = blockIdx.y;
   const int j0 = js * kJT;
   const float Df = (float)D;
@@ -328,7 +330,7 @@ btcvae_fwd2_kernel(int B, int D, LogW lw, const float4* __restrict__ pj, float2*
     for (int k = 0; k < DC; ++k) {
 #pragma unroll
       for (int o = 1; o < kJL; o <<= 1) sx[k] += __shfl_xor_sync(0xffffffffu, sx[k], o);
-      if (jl == 0 && i_raw < B && (EXACT || k < nd))
+      if (jl == 0 && i_raw < row_end && (EXACT || k < nd))
         part[((long long)js * (D + 1) + d0 + k) * B + i] = make_float2(ref[k], sx[k]);
     }
   }
@@ -348,19 +350,20 @@ btcvae_fwd2_kernel(int B, int D, LogW lw, const float4* __restrict__ pj, float2*
     const float m2 = __shfl_xor_sync(0xffffffffu, am, o), s2 = __shfl_xor_sync(0xffffffffu, as, o);
     lse_merge2(am, as, m2, s2);
   }
-  if (jl == 0 && i_raw < B) part[((long long)js * (D + 1) + D) * B + i] = make_float2(am, as);
+  if (jl == 0 && i_raw < row_end) part[((long long)js * (D + 1) + D) * B + i] = make_float2(am, as);
 }
 
 // merge the column ranges in a fixed order: 16 lanes per row (lane l owns dims l, l+16, ... and lane
 // D%16.. the log_qz slot), rowstats rows 1, 2, 4.. written per row; the last block forms the three means.
 __global__ void __launch_bounds__(256)
-btcvae_finalize_kernel(int B, int D, int JS, const float2* __restrict__ part, float* __restrict__ rowstats,
-                       float* __restrict__ terms, unsigned* __restrict__ counter) {
+btcvae_finalize_kernel(int B, int D, int row0, int nrows, int JS, const float2* __restrict__ part,
+                       float* __restrict__ rowstats, float* __restrict__ terms, unsigned* __restrict__ counter) {
   __shared__ bool is_last;
   const int gl = threadIdx.x & 15;
-  const int i = blockIdx.x * 16 + (threadIdx.x >> 4);
+  const int i = row0 + blockIdx.x * 16 + (threadIdx.x >> 4);
+  const int row_end = row0 + nrows;
   float lprod = 0.f;
-  if (i < B) {
+  if (i < row_end) {
     for (int d = gl; d <= D; d += 16) {
       float2 st = part[(long long)d * B + i];
       float m = st.x, s = st.y;
@@ -375,7 +378,7 @@ btcvae_finalize_kernel(int B, int D, int JS, const float2* __restrict__ part, fl
   }
 #pragma unroll
   for (int o = 8; o > 0; o >>= 1) lprod += __shfl_xor_sync(0xffffffffu, lprod, o);
-  if (i < B && gl == 0) rowstats[2LL * B + i] = lprod;
+  if (i < row_end && gl == 0) rowstats[2LL * B + i] = lprod;
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
@@ -384,7 +387,7 @@ btcvae_finalize_kernel(int B, int D, int JS, const float2* __restrict__ part, fl
   __threadfence();
   __shared__ float red[3][8];
   float mi = 0.f, tc = 0.f, dw = 0.f;
-  for (int r = threadIdx.x; r < B; r += blockDim.x) {
+  for (int r = row0 + threadIdx.x; r < row_end; r += blockDim.x) {     // means over THIS window's rows
     const float lpz = rowstats[r], lqz = rowstats[1LL * B + r], lp = rowstats[2LL * B + r], lqc = rowstats[3LL * B + r];
     mi += lqc - lqz; tc += lqz - lp; dw += lp - lpz;
   }
@@ -395,7 +398,7 @@ btcvae_finalize_kernel(int B, int D, int JS, const float2* __restrict__ part, fl
   if (threadIdx.x == 0) {
     float a = 0.f, b2 = 0.f, c = 0.f;
     for (int w = 0; w < 8; ++w) { a += red[0][w]; b2 += red[1][w]; c += red[2][w]; }
-    terms[0] = a / (float)B; terms[1] = b2 / (float)B; terms[2] = c / (float)B;
+    terms[0] = a / (float)nrows; terms[1] = b2 / (float)nrows; terms[2] = c / (float)nrows;
     *counter = 0u;
   }
 }
@@ -695,14 +698,307 @@ btcvae_fwd3_kernel(const float* __restrict__ z, const float* __restrict__ mu, co
 #undef DV_F3_MARK
 }
 
+// ------------------------------------------------------------------------------------------
+// Forward, version 4 (D <= 16): ONE launch, thread-block CLUSTERS of 4.
+// What held version 3 at 24 us: every CTA staged the parameters of ALL B columns (148 x 176 KB = 26 MB of L2->smem
+// traffic, 176 KB smem CTAs) and every lane of a warp read a different column (LDS.128 with 32 distinct addresses =
+// 4 shared-memory wavefronts per 32 evaluations: the sweep was shared-memory-bandwidth bound).  Here
+//   * a cluster of 4 CTAs owns R rows; CTA c of the cluster stages only ITS QUARTER of the columns (40 KB at
+//     (1024,10)) and sweeps those columns for all R rows; the four partial logsumexp states of every (row, dim) are
+//     merged through distributed shared memory after one cluster barrier -- no global-memory round trip, no second
+//     launch, nothing but the O(B*D) outputs touches HBM;
+//   * a warp is 4 rows x 8 column lanes: one LDS.128 request fetches 8 distinct columns (128 B = ONE wavefront)
+//     and broadcasts each to the 4 rows -- 4x less shared-memory traffic per evaluation; a thread keeps its row's
+//     z_d and the D running sums in registers;
+//   * the reference exponent is per CTA and per dimension (r_cd = max over the CTA's columns of c_jd + w_j, an
+//     upper bound of every term it sums), folded with the column weight into the staged constant as before
+//     (t = z - mu; arg = x'' - hiv*t*t; a += arg; s_d += ex2(arg)); partial sums of different CTAs are brought to
+//     the common exponent max_c r_cd in the merge.  log q(z): online logsumexp with one ex2 per column.
+//   * rows whose merged sum (nearly) underflows against the reference (outlier samples: best term > 60 nats below
+//     the column bound) are redone exactly (two passes straight from global memory) by the finalising warp.
+// Rows of a cluster are finalised by its 4 CTAs round-robin (one warp per row: lanes = latent dims); the block's
+// contribution to the three means goes to `blockpart`, the last block adds them in block order (deterministic).
+// Cluster size 4 leaves 132 of the 148 SMs usable (GPC sizes 16/18/20): 32 clusters x 4 at B = 1024.
+// ------------------------------------------------------------------------------------------
+constexpr int kF4Threads = 512;
+constexpr int kF4Warps = kF4Threads / 32;
+constexpr int kF4Clus = 4;
+constexpr int kF4MaxTasks = 32;      // (row group of 4) x (column split) pairs per CTA
+constexpr int kF4MaxRows = 128;      // rows per cluster
+
+template <int DC, bool EXACT>
+__global__ void __launch_bounds__(kF4Threads, 1)
+btcvae_fwd4_kernel(const float* __restrict__ z, const float* __restrict__ mu, const float* __restrict__ logvar, int ld,
+                   int row_stride, int B, int D_rt, LogW lw, int R, int S, int NC, float4* __restrict__ pj_out,
+                   float* __restrict__ rowstats, float* __restrict__ terms, float* __restrict__ blockpart,
+                   unsigned* __restrict__ counter) {
+  extern __shared__ float4 sp[];                               // [NC][DC]: {x'', hiv*log2e, mu, z} of this CTA's columns
+  __shared__ float s_red[kF4Warps][DC];
+  __shared__ float s_ref[DC];                                  // r_cd (log2 units); -inf if the CTA owns no column
+  __shared__ float s_rsum;                                     // sum_d r_cd
+  __shared__ float s_tsx[kF4MaxTasks * kRows][DC];             // per (task, row) partial sums
+  __shared__ float2 s_tq[kF4MaxTasks * kRows];
+  __shared__ float s_sx[kF4MaxRows][DC];                       // per row: this CTA's sum_j ex2(arg)  (read by the peers)
+  __shared__ float2 s_q[kF4MaxRows];                           // per row: this CTA's log q(z) state, relative to s_rsum
+  __shared__ float s_means[kF4MaxRows / kF4Clus][3];
+  __shared__ bool is_last;
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int D = EXACT ? DC : D_rt;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int crank = (int)cluster.block_rank();
+  const int clus = blockIdx.x / kF4Clus;
+  const int c0 = crank * NC;
+  const int ncols = max(0, min(B, c0 + NC) - c0);
+
+  // ---- phase 1: this CTA's columns -> shared memory (weight folded in), unfolded copy for the backward pass ----
+  for (int e = tid; e < ncols * D; e += kF4Threads) {
+    const int jl = e / D, k = e - jl * D;
+    const int j = c0 + jl;
+    const long long off = (long long)j * row_stride + (long long)k * ld;
+    const float m = mu[off], lv = logvar[off], zz = z[(long long)j * D + k];
+    const float cc = -0.5f * (kLog2Pi + lv) * kLog2e;
+    const float hiv = 0.5f * expf(-lv) * kLog2e;
+    const float w = !lw.mss ? 0.f : (j == 0 ? lw.ln : (j == 1 ? lw.ls : lw.lm));
+    sp[jl * DC + k] = make_float4(cc + w, hiv, m, zz);
+    if (clus == 0) pj_out[(long long)k * B + j] = make_float4(cc, hiv, m, zz);   // the backward pass reads [D][B]
+  }
+  __syncthreads();
+  // ---- phase 2: r_cd = max_j (c_jd + w_j) over the CTA's columns (column 0: the larger of its two weights) ----
+  {
+    float bm[DC];
+#pragma unroll
+    for (int k = 0; k < DC; ++k) bm[k] = -INFINITY;
+    const float col0_extra = lw.mss ? fmaxf(lw.ls - lw.ln, 0.f) : 0.f;
+    for (int jl = tid; jl < ncols; jl += kF4Threads) {
+      const float extra = (c0 + jl == 0) ? col0_extra : 0.f;
+#pragma unroll
+      for (int k = 0; k < DC; ++k)
+        if (EXACT || k < D) bm[k] = fmaxf(bm[k], sp[jl * DC + k].x + extra);
+    }
+#pragma unroll
+    for (int k = 0; k < DC; ++k) {
+      bm[k] = warp_max(bm[k]);
+      if (lane == 0) s_red[warp][k] = bm[k];
+    }
+    __syncthreads();
+    if (tid < DC) {
+      float b = -INFINITY;
+#pragma unroll
+      for (int w = 0; w < kF4Warps; ++w) b = fmaxf(b, s_red[w][tid]);
+      s_ref[tid] = (EXACT || tid < D) ? b : 0.f;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      float rs = 0.f;
+      for (int k = 0; k < D; ++k) rs += s_ref[k];
+      s_rsum = rs;
+    }
+    for (int e = tid; e < ncols * D; e += kF4Threads) {
+      const int jl = e / D, k = e - jl * D;
+      sp[jl * DC + k].x -= s_ref[k];
+    }
+    __syncthreads();
+  }
+
+  // ---- phase 3: tasks = (group of 4 rows) x (column split); warp = 4 rows x 8 column lanes ----
+  {
+    const int G = (R + kRows - 1) / kRows;
+    const int ntasks = G * S;
+    const int CS = (((NC + S - 1) / S) + kJL - 1) / kJL * kJL;
+    const int r = lane >> 3, cl = lane & 7;
+    for (int task = warp; task < ntasks; task += kF4Warps) {
+      const int g = task / S, s = task - g * S;
+      const int i = min(clus * R + g * kRows + r, B - 1);      // rows past the end recompute row B-1 (never finalised)
+      const float dw0 = (lw.mss && i == B - 2) ? (lw.ls - lw.ln) : 0.f;
+      float sx[DC], zc[DC];
+#pragma unroll
+      for (int k = 0; k < DC; ++k) {
+        sx[k] = 0.f;
+        zc[k] = (EXACT || k < D) ? __ldg(z + (long long)i * D + k) : 0.f;
+      }
+      float am = -INFINITY, as = 0.f;
+      const int jend = min(ncols, (s + 1) * CS);
+      int jl = s * CS + cl;
+      auto column = [&](int jj, float dw) {
+        const float4* pr = sp + jj * DC;
+        float a = 0.f;
+#pragma unroll
+        for (int k = 0; k < DC; ++k) {
+          if (EXACT || k < D) {
+            const float4 p = pr[k];
+            const float tt = zc[k] - p.z;
+            const float arg = fmaf(-p.y, tt * tt, p.x) + dw;
+            a += arg;
+            sx[k] += ex2_approx(arg);
+          }
+        }
+        const float d = a - am;
+        const float e = ex2_approx(-fabsf(d));
+        const bool up = d > 0.f;
+        as = up ? fmaf(as, e, 1.f) : as + e;
+        am = up ? a : am;
+      };
+      if (jl < jend) { column(jl, (c0 + jl == 0) ? dw0 : 0.f); jl += kJL; }   // peeled: the only row-dependent weight
+      for (; jl < jend; jl += kJL) {
+        const float4* pr = sp + jl * DC;
+        float a = 0.f;
+#pragma unroll
+        for (int k = 0; k < DC; ++k) {
+          if (EXACT || k < D) {
+            const float4 p = pr[k];
+            const float tt = zc[k] - p.z;
+            const float arg = fmaf(-p.y, tt * tt, p.x);
+            a += arg;
+            sx[k] += ex2_approx(arg);
+          }
+        }
+        const float d = a - am;
+        const float e = ex2_approx(-fabsf(d));
+        const bool up = d > 0.f;
+        as = up ? fmaf(as, e, 1.f) : as + e;
+        am = up ? a : am;
+      }
+#pragma unroll
+      for (int o = 1; o < kJL; o <<= 1) {
+#pragma unroll
+        for (int k = 0; k < DC; ++k) sx[k] += __shfl_xor_sync(0xffffffffu, sx[k], o);
+        const float m2 = __shfl_xor_sync(0xffffffffu, am, o), s2 = __shfl_xor_sync(0xffffffffu, as, o);
+        lse_merge2(am, as, m2, s2);
+      }
+      if (cl == 0) {
+#pragma unroll
+        for (int k = 0; k < DC; ++k) s_tsx[task * kRows + r][k] = sx[k];
+        s_tq[task * kRows + r] = make_float2(am, as);
+      }
+    }
+    __syncthreads();
+    // merge the column splits of every row in a fixed order -> this CTA's partial state
+    for (int e = tid; e < R * (DC + 1); e += kF4Threads) {
+      const int rr = e / (DC + 1), k = e - rr * (DC + 1);
+      const int g = rr / kRows, r2 = rr - g * kRows;
+      if (k < DC) {
+        float a = 0.f;
+        for (int s = 0; s < S; ++s) a += s_tsx[(g * S + s) * kRows + r2][k];
+        s_sx[rr][k] = a;
+      } else {
+        float m = -INFINITY, a = 0.f;
+        for (int s = 0; s < S; ++s) { const float2 q = s_tq[(g * S + s) * kRows + r2]; lse_merge2(m, a, q.x, q.y); }
+        s_q[rr] = make_float2(m, a);
+      }
+    }
+  }
+  cluster.sync();                                              // every CTA's s_sx / s_q / s_ref / s_rsum are final
+
+  // ---- phase 4: cluster rows round-robin over the 4 CTAs; one warp per row, lanes = latent dims ----
+  for (int slot = warp; slot * kF4Clus + crank < R; slot += kF4Warps) {
+    const int rr = slot * kF4Clus + crank;
+    const int i = clus * R + rr;
+    if (i >= B) { if (lane == 0) { s_means[slot][0] = 0.f; s_means[slot][1] = 0.f; s_means[slot][2] = 0.f; } continue; }
+    float P2 = 0.f;
+    bool bad = false;
+    if (lane < D) {
+      float rc[kF4Clus], sc[kF4Clus], Rm = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < kF4Clus; ++c) {
+        sc[c] = *cluster.map_shared_rank(&s_sx[rr][lane], c);
+        rc[c] = *cluster.map_shared_rank(&s_ref[lane], c);
+        if (sc[c] > 0.f) Rm = fmaxf(Rm, rc[c]);
+      }
+      float tot = 0.f;
+#pragma unroll
+      for (int c = 0; c < kF4Clus; ++c)
+        if (sc[c] > 0.f) tot += sc[c] * exp2f(rc[c] - Rm);
+      // ex2 flushes terms below 2^-126 of a CTA's reference: a total under ~2^-90 could have lost a visible share
+      bad = !(tot > 1e-27f && tot < INFINITY);
+      P2 = Rm + log2f(tot);
+    }
+    float lqz2 = 0.f;
+    if (lane == 31) {
+      float m = -INFINITY, a = 0.f;
+#pragma unroll
+      for (int c = 0; c < kF4Clus; ++c) {
+        const float2 q = *cluster.map_shared_rank(&s_q[rr], c);
+        const float rs = *cluster.map_shared_rank(&s_rsum, c);
+        if (q.y > 0.f) lse_merge2(m, a, q.x + rs, q.y);
+      }
+      lqz2 = m + log2f(a);
+    }
+    const unsigned badmask = __ballot_sync(0xffffffffu, bad);
+    if (badmask) {                                             // rare: exact two-pass logsumexp from global memory
+      for (int k = 0; k < D; ++k) {
+        if (!((badmask >> k) & 1u)) continue;
+        const float zk = z[(long long)i * D + k];
+        float mx = -INFINITY;
+        for (int j = lane; j < B; j += 32) {
+          const long long off = (long long)j * row_stride + (long long)k * ld;
+          const float tt = zk - mu[off], lv = logvar[off];
+          mx = fmaxf(mx, (-0.5f * (kLog2Pi + lv) - 0.5f * (tt * tt) * expf(-lv)) * kLog2e + logw2(lw, i, j));
+        }
+        mx = warp_max(mx);
+        float sm = 0.f;
+        for (int j = lane; j < B; j += 32) {
+          const long long off = (long long)j * row_stride + (long long)k * ld;
+          const float tt = zk - mu[off], lv = logvar[off];
+          sm += exp2f((-0.5f * (kLog2Pi + lv) - 0.5f * (tt * tt) * expf(-lv)) * kLog2e + logw2(lw, i, j) - mx);
+        }
+        sm = warp_sum(sm);
+        if (lane == k) P2 = mx + log2f(sm);
+      }
+    }
+    // this row's own Gaussian terms: lanes over latent dims (same arithmetic as btcvae_prep_kernel)
+    float lq = 0.f, lp = 0.f;
+    for (int d = lane; d < D; d += 32) {
+      const long long off = (long long)i * row_stride + (long long)d * ld;
+      const float m = mu[off], lv = logvar[off], zz = z[(long long)i * D + d];
+      const float tt = zz - m;
+      lq += -0.5f * (kLog2Pi + lv) - 0.5f * (tt * tt * expf(-lv));   // log N(z; mu, lv)   (math.py:48-51)
+      lp += -0.5f * kLog2Pi - 0.5f * (zz * zz);                      // log N(z; 0, 1)     (losses.py:531-532)
+    }
+    lq = warp_sum(lq); lp = warp_sum(lp);
+    const float Pn = (lane < D) ? P2 * kLn2 : 0.f;
+    if (lane < D) rowstats[(long long)(4 + lane) * B + i] = Pn;
+    const float lprod = warp_sum(Pn);
+    const float lqz = __shfl_sync(0xffffffffu, lqz2, 31) * kLn2;
+    if (lane == 0) {
+      rowstats[i] = lp; rowstats[1LL * B + i] = lqz; rowstats[2LL * B + i] = lprod; rowstats[3LL * B + i] = lq;
+      s_means[slot][0] = lq - lqz; s_means[slot][1] = lqz - lprod; s_means[slot][2] = lprod - lp;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float a = 0.f, b = 0.f, c = 0.f;
+    for (int slot = 0; slot * kF4Clus + crank < R; ++slot) { a += s_means[slot][0]; b += s_means[slot][1]; c += s_means[slot][2]; }
+    blockpart[4 * blockIdx.x + 0] = a; blockpart[4 * blockIdx.x + 1] = b; blockpart[4 * blockIdx.x + 2] = c;
+    __threadfence();
+    is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  }
+  cluster.sync();                                              // no CTA leaves while a peer may still read its shared memory
+  if (!is_last || warp != 0) return;
+  __threadfence();
+  float a = 0.f, b = 0.f, c = 0.f;
+  for (int g = lane; g < (int)gridDim.x; g += 32) {             // lane-strided, then a fixed shuffle tree
+    a += __ldcg(blockpart + 4 * g); b += __ldcg(blockpart + 4 * g + 1); c += __ldcg(blockpart + 4 * g + 2);
+  }
+  a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
+  if (lane == 0) {
+    terms[0] = a / (float)B; terms[1] = b / (float)B; terms[2] = c / (float)B;
+    *counter = 0u;
+  }
+}
+
 // ---- backward ---------------------------------------------------------------------
 // G[i,j,d] = cq * S[i,j] + cp * T[i,j,d],  S = exp(A[i,j] - log_qz[i]),  T = exp(M[i,j,d] - P[i,d])
 // role 0 (rows):    g_z[i,d]  = sum_j G * (-(z_i - mu_j) * iv_j)            + direct terms
 // role 1 (columns): g_mu[j,d] = sum_i G * ( (z_i - mu_j) * iv_j)            + direct terms
 //                   g_lv[j,d] = sum_i G * (-0.5 + 0.5 (z_i - mu_j)^2 iv_j)  + direct terms
 // The thread owns a "line" (i for role 0, j for role 1) and sweeps the other index.
+// Row window [row0, row0 + nrows) of the global batch (the whole batch, or one rank's rows when the estimator runs
+// over an all-gathered batch): role 0 lines are the window's rows and sweep all B columns (g_z is [nrows, D]);
+// role 1 lines are ALL B columns and sweep the window's rows (g_mu / g_lv are [B, D] partial sums, to be
+// reduce-scattered over the ranks); the diagonal terms belong to the rank that owns the row.
 template <int ROLE, int DC, bool FUSE, bool EXACT>
-__device__ __forceinline__ void btcvae_bwd_body(int B, int D, const LogW& lw, const float* __restrict__ ws,
+__device__ __forceinline__ void btcvae_bwd_body(int B, int D, int row0, int nrows, const LogW& lw, const float* __restrict__ ws,
                                                 const float* __restrict__ rowstats, float cq, float cp, float cqc, float cpz,
                                                 float* __restrict__ g_z, float* __restrict__ g_mu, float* __restrict__ g_lv,
                                                 int block) {
@@ -713,11 +1009,13 @@ __device__ __forceinline__ void btcvae_bwd_body(int B, int D, const LogW& lw, co
   const float* __restrict__ P = rowstats + 4LL * B;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int r = lane >> 3, ol = lane & 7;
-  const int line = min(block * kRows + r, B - 1);
-  const int slice = ((B + kBtWarps - 1) / kBtWarps + kJL - 1) / kJL * kJL;
-  const int o_begin = warp * slice, o_end = min(B, o_begin + slice);
+  const int row_end = row0 + nrows;
+  const int line = (ROLE == 0) ? min(row0 + block * kRows + r, row_end - 1) : min(block * kRows + r, B - 1);
+  const int sweep0 = (ROLE == 0) ? 0 : row0, sweep1 = (ROLE == 0) ? B : row_end;
+  const int slice = ((sweep1 - sweep0 + kBtWarps - 1) / kBtWarps + kJL - 1) / kJL * kJL;
+  const int o_begin = sweep0 + warp * slice, o_end = min(sweep1, o_begin + slice);
   const float Df = (float)D;
-  const float own_lqz2 = lqz[line] * kLog2e;
+  const float own_lqz2 = (ROLE == 0) ? lqz[line] * kLog2e : 0.f;
 
   for (int d0 = 0; d0 < D; d0 += DC) {
     const int nd = EXACT ? DC : min(DC, D - d0);
@@ -784,8 +1082,8 @@ __device__ __forceinline__ void btcvae_bwd_body(int B, int D, const LogW& lw, co
     if (warp == 0) {
       for (int e = lane; e < kRows * DC; e += 32) {
         const int rr = e / DC, k = e % DC;
-        const int ln = block * kRows + rr;
-        if (k < nd && ln < B) {
+        const int ln = (ROLE == 0 ? row0 : 0) + block * kRows + rr;
+        if (k < nd && ln < (ROLE == 0 ? row_end : B)) {
           float a = 0.f, b = 0.f;
           for (int w2 = 0; w2 < kBtWarps; ++w2) { a += sm_a[w2][rr][k]; if (ROLE == 1) b += sm_b[w2][rr][k]; }
           const float4 q = __ldg(pj + (long long)(d0 + k) * B + ln);
@@ -793,10 +1091,11 @@ __device__ __forceinline__ void btcvae_bwd_body(int B, int D, const LogW& lw, co
           const float tiv = (2.f * kLn2) * q.y * t;              // (z-mu) iv  of the diagonal pair
           if (ROLE == 0) {
             // d log_q_zCx / dz = -(z-mu) iv ; d log_pz / dz = -z
-            if (g_z) g_z[(long long)ln * D + d0 + k] = a - cqc * tiv - cpz * q.w;
+            if (g_z) g_z[(long long)(ln - row0) * D + d0 + k] = a - cqc * tiv - cpz * q.w;
           } else {
-            if (g_mu) g_mu[(long long)ln * D + d0 + k] = a + cqc * tiv;
-            if (g_lv) g_lv[(long long)ln * D + d0 + k] = b + cqc * (kLn2 * q.y * (t * t) - 0.5f);
+            const float own = (ln >= row0 && ln < row_end) ? cqc : 0.f;   // the diagonal pair lives with its row
+            if (g_mu) g_mu[(long long)ln * D + d0 + k] = a + own * tiv;
+            if (g_lv) g_lv[(long long)ln * D + d0 + k] = b + own * (kLn2 * q.y * (t * t) - 0.5f);
           }
         }
       }
@@ -807,19 +1106,19 @@ __device__ __forceinline__ void btcvae_bwd_body(int B, int D, const LogW& lw, co
 
 template <int DC, bool FUSE, bool EXACT>
 __global__ void __launch_bounds__(kBtWarps * 32)
-btcvae_bwd_kernel(int B, int D, LogW lw, const float* __restrict__ ws, const float* __restrict__ rowstats,
+btcvae_bwd_kernel(int B, int D, int row0, int nrows, LogW lw, const float* __restrict__ ws, const float* __restrict__ rowstats,
                   const float* __restrict__ g_terms, float* __restrict__ g_z, float* __restrict__ g_mu, float* __restrict__ g_lv) {
-  const float invB = 1.f / (float)B;
+  const float invB = 1.f / (float)nrows;       // the three terms are means over the window's rows
   const float g_mi = g_terms[0], g_tc = g_terms[1], g_dw = g_terms[2];
   const float cq = (g_tc - g_mi) * invB;       // d loss / d log_qz[i]
   const float cp = (g_dw - g_tc) * invB;       // d loss / d log_prod_qzi[i]
   const float cqc = g_mi * invB;               // d loss / d log_q_zCx[i]
   const float cpz = -g_dw * invB;              // d loss / d log_pz[i]
-  const int nblk = (B + kRows - 1) / kRows;
+  const int nblk = (nrows + kRows - 1) / kRows;
   if ((int)blockIdx.x < nblk)
-    btcvae_bwd_body<0, DC, FUSE, EXACT>(B, D, lw, ws, rowstats, cq, cp, cqc, cpz, g_z, g_mu, g_lv, blockIdx.x);
+    btcvae_bwd_body<0, DC, FUSE, EXACT>(B, D, row0, nrows, lw, ws, rowstats, cq, cp, cqc, cpz, g_z, g_mu, g_lv, blockIdx.x);
   else
-    btcvae_bwd_body<1, DC, FUSE, EXACT>(B, D, lw, ws, rowstats, cq, cp, cqc, cpz, g_z, g_mu, g_lv, blockIdx.x - nblk);
+    btcvae_bwd_body<1, DC, FUSE, EXACT>(B, D, row0, nrows, lw, ws, rowstats, cq, cp, cqc, cpz, g_z, g_mu, g_lv, blockIdx.x - nblk);
 }
 
 static LogW make_logw(int B, long long n_data, int is_mss) {
@@ -859,13 +1158,64 @@ size_t dv_btcvae_workspace_bytes(int B, int D) {
 
 int dv_btcvae_fwd(const float* z, const float* mu, const float* logvar, int ld, int row_stride, int B, int D,
                   long long n_data, int is_mss, float* rowstats, float* terms, void* workspace, void* stream) {
+  return dv_btcvae_fwd_rows(z, mu, logvar, ld, row_stride, B, D, 0, B, n_data, is_mss, rowstats, terms, workspace, stream);
+}
+
+int dv_btcvae_fwd_rows(const float* z, const float* mu, const float* logvar, int ld, int row_stride, int B, int D,
+                       int row0, int nrows, long long n_data, int is_mss, float* rowstats, float* terms, void* workspace,
+                       void* stream) {
   if (!z || !mu || !logvar || !rowstats || !terms || !workspace) return DV_ERR_BAD_ARG;
   if (B < 2 || D < 1 || n_data < 1) return DV_ERR_BAD_SHAPE;
+  if (row0 < 0 || nrows < 1 || row0 + nrows > B) return DV_ERR_BAD_SHAPE;
+  const bool whole = (row0 == 0 && nrows == B);
   if ((uintptr_t)workspace & 15) return DV_ERR_BAD_ARG;
   float* ws = reinterpret_cast<float*>(workspace);
   cudaStream_t st = as_stream(stream);
   const LogW lw = make_logw(B, n_data, is_mss);
   int rc;
+  {
+    // single-launch cluster path (D <= 16): columns split over the 4 CTAs of a cluster, rows over the clusters
+    static int v4 = -1;
+    if (v4 < 0) { const char* e = getenv("DV_BTCVAE_V4"); v4 = (e && e[0] == '0') ? 0 : 1; }
+    const int dc = D == 10 ? 10 : 16;
+    const int max_clusters = 33;                               // cluster size 4 packs 132 of the 148 SMs
+    int R = ((B + max_clusters - 1) / max_clusters + kRows - 1) / kRows * kRows;
+    const int NC = ((B + kF4Clus - 1) / kF4Clus + kJL - 1) / kJL * kJL;
+    const size_t smem = (size_t)NC * dc * sizeof(float4);
+    const int G = R / kRows;
+    int S = G >= kF4Warps ? 1 : kF4Warps / G;
+    if (S > NC / kJL) S = NC / kJL;
+    if (whole && v4 && D <= 16 && smem <= 200 * 1024 && R <= kF4MaxRows && G * S <= kF4MaxTasks) {
+      const int nclus = (B + R - 1) / R;
+      float4* pj = reinterpret_cast<float4*>(ws + kWsHeader);
+      float* blockpart = ws + btcvae_part_offset_floats(B, D);
+      unsigned* counter = reinterpret_cast<unsigned*>(ws);
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(nclus * kF4Clus); cfg.blockDim = dim3(kF4Threads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = kF4Clus; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      cudaError_t err = cudaSuccess;
+#define DV_F4_CALL(DC, EXACT)                                                                                                  \
+  do {                                                                                                                         \
+    static bool attr_set = false;                                                                                              \
+    if (!attr_set) {                                                                                                           \
+      if (cudaFuncSetAttribute(btcvae_fwd4_kernel<DC, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) !=      \
+          cudaSuccess) { g_last_cuda_error = (int)cudaGetLastError(); return DV_ERR_CUDA; }                                    \
+      attr_set = true;                                                                                                         \
+    }                                                                                                                          \
+    err = cudaLaunchKernelEx(&cfg, btcvae_fwd4_kernel<DC, EXACT>, z, mu, logvar, ld, row_stride, B, D, lw, R, S, NC, pj,       \
+                             rowstats, terms, blockpart, counter);                                                             \
+  } while (0)
+      if (D == 10) DV_F4_CALL(10, true);
+      else if (D == 16) DV_F4_CALL(16, true);
+      else DV_F4_CALL(16, false);
+#undef DV_F4_CALL
+      if (err != cudaSuccess) { g_last_cuda_error = (int)err; cudaGetLastError(); return DV_ERR_CUDA; }
+      return check_launch();
+    }
+  }
   {
     // single-launch path: all columns' parameters fit in one block's shared memory
     static int v3 = -1;
@@ -873,7 +1223,7 @@ int dv_btcvae_fwd(const float* z, const float* mu, const float* logvar, int ld, 
     const int dc = D == 10 ? 10 : 16;
     const size_t smem = (size_t)B * (dc + 1) * sizeof(float4);
     const int rpb = (B + kNumSMs - 1) / kNumSMs;
-    if (v3 && D <= 16 && smem <= 200 * 1024 && rpb <= kF3MaxRows) {
+    if (whole && v3 && D <= 16 && smem <= 200 * 1024 && rpb <= kF3MaxRows) {
       const int grid = (B + rpb - 1) / rpb;
       float4* pj = reinterpret_cast<float4*>(ws + kWsHeader);
       float* blockpart = ws + btcvae_part_offset_floats(B, D);
@@ -905,7 +1255,7 @@ int dv_btcvae_fwd(const float* z, const float* mu, const float* logvar, int ld, 
   if (rc != DV_OK) return rc;
   static int v1 = -1;
   if (v1 < 0) { const char* e = getenv("DV_BTCVAE_V1"); v1 = (e && e[0] == '1') ? 1 : 0; }
-  if (v1) {
+  if (v1 && whole) {
     const int grid = (B + kRows - 1) / kRows;
 #define DV_FWD_CALL(DC, FUSE, EXACT) \
   btcvae_fwd_kernel<DC, FUSE, EXACT><<<grid, kBtWarps * 32, 0, st>>>(B, D, lw, ws, rowstats, terms)
@@ -916,27 +1266,34 @@ int dv_btcvae_fwd(const float* z, const float* mu, const float* logvar, int ld, 
   const int JS = (B + kJT - 1) / kJT;
   float2* part = reinterpret_cast<float2*>(ws + btcvae_part_offset_floats(B, D));
   const float4* pjc = reinterpret_cast<const float4*>(ws + kWsHeader);
-  dim3 grid((B + kRG - 1) / kRG, JS);
-  if (D == 10)          btcvae_fwd2_kernel<10, true><<<grid, kBtWarps * 32, 0, st>>>(B, D, lw, pjc, part);
-  else if (D % 16 == 0) btcvae_fwd2_kernel<16, true><<<grid, kBtWarps * 32, 0, st>>>(B, D, lw, pjc, part);
-  else if (D <= 8)      btcvae_fwd2_kernel<8, false><<<grid, kBtWarps * 32, 0, st>>>(B, D, lw, pjc, part);
-  else                  btcvae_fwd2_kernel<16, false><<<grid, kBtWarps * 32, 0, st>>>(B, D, lw, pjc, part);
+  dim3 grid((nrows + kRG - 1) / kRG, JS);
+  if (D == 10)          btcvae_fwd2_kernel<10, true><<<grid, kBtWarps * 32, 0, st>>>(B, D, row0, nrows, lw, pjc, part);
+  else if (D % 16 == 0) btcvae_fwd2_kernel<16, true><<<grid, kBtWarps * 32, 0, st>>>(B, D, row0, nrows, lw, pjc, part);
+  else if (D <= 8)      btcvae_fwd2_kernel<8, false><<<grid, kBtWarps * 32, 0, st>>>(B, D, row0, nrows, lw, pjc, part);
+  else                  btcvae_fwd2_kernel<16, false><<<grid, kBtWarps * 32, 0, st>>>(B, D, row0, nrows, lw, pjc, part);
   rc = check_launch();
   if (rc != DV_OK) return rc;
-  btcvae_finalize_kernel<<<(B + 15) / 16, 256, 0, st>>>(B, D, JS, part, rowstats, terms, reinterpret_cast<unsigned*>(ws));
+  btcvae_finalize_kernel<<<(nrows + 15) / 16, 256, 0, st>>>(B, D, row0, nrows, JS, part, rowstats, terms,
+                                                            reinterpret_cast<unsigned*>(ws));
   return check_launch();
 }
 
 int dv_btcvae_bwd(int B, int D, long long n_data, int is_mss, const float* rowstats, const void* workspace,
                   const float* g_terms, float* g_z, float* g_mu, float* g_logvar, void* stream) {
+  return dv_btcvae_bwd_rows(B, D, 0, B, n_data, is_mss, rowstats, workspace, g_terms, g_z, g_mu, g_logvar, stream);
+}
+
+int dv_btcvae_bwd_rows(int B, int D, int row0, int nrows, long long n_data, int is_mss, const float* rowstats,
+                       const void* workspace, const float* g_terms, float* g_z, float* g_mu, float* g_logvar, void* stream) {
   if (!rowstats || !g_terms || !workspace) return DV_ERR_BAD_ARG;
   if (B < 2 || D < 1) return DV_ERR_BAD_SHAPE;
+  if (row0 < 0 || nrows < 1 || row0 + nrows > B) return DV_ERR_BAD_SHAPE;
   const float* ws = reinterpret_cast<const float*>(workspace);
   cudaStream_t st = as_stream(stream);
   const LogW lw = make_logw(B, n_data, is_mss);
-  const int grid = 2 * ((B + kRows - 1) / kRows);
+  const int grid = (nrows + kRows - 1) / kRows + (B + kRows - 1) / kRows;
 #define DV_BWD_CALL(DC, FUSE, EXACT) \
-  btcvae_bwd_kernel<DC, FUSE, EXACT><<<grid, kBtWarps * 32, 0, st>>>(B, D, lw, ws, rowstats, g_terms, g_z, g_mu, g_logvar)
+  btcvae_bwd_kernel<DC, FUSE, EXACT><<<grid, kBtWarps * 32, 0, st>>>(B, D, row0, nrows, lw, ws, rowstats, g_terms, g_z, g_mu, g_logvar)
   DV_BT_DISPATCH(D, DV_BWD_CALL);
 #undef DV_BWD_CALL
   return check_launch();

@@ -49,6 +49,10 @@ SIGNATURES = {
     "dv_btcvae_workspace_bytes": (SZ, [I, I]),
     "dv_btcvae_fwd": (I, [P, P, P, I, I, I, I, LL, I, P, P, P, P]),
     "dv_btcvae_bwd": (I, [I, I, LL, I, P, P, P, P, P, P, P]),
+    "dv_btcvae_fwd_rows": (I, [P, P, P, I, I, I, I, I, I, LL, I, P, P, P, P]),
+    "dv_btcvae_bwd_rows": (I, [I, I, I, I, LL, I, P, P, P, P, P, P, P]),
+    "dv_latent_entropy_workspace_bytes": (SZ, [I, I, I]),
+    "dv_latent_entropy": (I, [P, P, P, I, I, I, I, I, P, P, P, P]),
     "dv_permute_dims": (I, [P, P, ULL, P, P, I, I, P]),
     "dv_factor_tc_fwd": (I, [P, I, P, P]),
     "dv_factor_tc_bwd": (I, [P, I, P, P]),

@@ -227,11 +227,21 @@ class BtcvaeLoss(BaseLoss):
         self.alpha = alpha
         self.gamma = gamma
         self.is_mss = is_mss
+        # Data parallel only (no meaning for one process): False = every rank applies the estimator to its own shard
+        # (the reference handed that shard as its batch); True = the estimator of the GLOBAL batch
+        # (all-gather of z/mu/logvar, row-block kernel, reduce-scatter of the column gradients), whose
+        # value no longer depends on the number of ranks.  DISVAE_GLOBAL_BTCVAE=1 turns it on without touching main.py.
+        import os
+        self.global_batch = os.environ.get("DISVAE_GLOBAL_BTCVAE", "0") == "1"
 
     def __call__(self, data, recon_batch, latent_dist, is_train, storer, latent_sample=None):
         storer = self._pre_call(is_train, storer)
         rec_loss, kl_loss, kl_dims = self._rec_kl(data, recon_batch, latent_dist)
-        terms = ops.BtcvaeFn.apply(latent_sample, latent_dist[0], latent_dist[1], self.n_data, self.is_mss)
+        from disvae.parallel import is_distributed
+        if self.global_batch and is_train and is_distributed():
+            terms = ops.BtcvaeGlobalFn.apply(latent_sample, latent_dist[0], latent_dist[1], self.n_data, self.is_mss, None)
+        else:
+            terms = ops.BtcvaeFn.apply(latent_sample, latent_dist[0], latent_dist[1], self.n_data, self.is_mss)
         mi_loss, tc_loss, dw_kl_loss = terms[0], terms[1], terms[2]
         anneal_reg = linear_annealing(0, 1, self.n_train_steps, self.steps_anneal) if is_train else 1
         loss = rec_loss + (self.alpha * mi_loss + self.beta * tc_loss + anneal_reg * self.gamma * dw_kl_loss)

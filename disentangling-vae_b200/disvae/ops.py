@@ -44,6 +44,29 @@ def _new(shape, like):
     return torch.empty(shape, dtype=torch.float32, device=like.device)
 
 
+# Activation trace for the parity checks (same_branch.py next to the CPU reference restatement): while a list is installed, the three network nodes append
+# (name, tensor) for every (Leaky)ReLU output they produce -- the on/off pattern a flip-robust gradient comparison needs.
+# None in production: one `is not None` test per layer.
+_trace = None
+
+
+def start_trace():
+    global _trace
+    _trace = []
+    return _trace
+
+
+def stop_trace():
+    global _trace
+    t, _trace = _trace, None
+    return t
+
+
+def _note(name, t):
+    if _trace is not None:
+        _trace.append((name, t))
+
+
 # ---------------------------------------------------------------------------------------
 # thin functional layer (one C call each) -- also what the per-kernel parity tests use
 # ---------------------------------------------------------------------------------------
@@ -156,6 +179,7 @@ class EncoderFn(Function):
         for w, b in convs:
             wp = conv_pack(w, CH)
             lo = conv_down(hi, wp, b, None, B, H, H, CH, nchw, ACT_RELU)
+            _note("encoder.conv%d" % len(acts), lo)
             acts.append(lo)
             packed.append(wp)
             hi, CH, nchw, H = lo, LO_CH, 0, H // 2
@@ -163,6 +187,8 @@ class EncoderFn(Function):
         h1 = linear_fwd(flat, lins[0][0], lins[0][1], ACT_RELU)
         h2 = linear_fwd(h1, lins[1][0], lins[1][1], ACT_RELU)
         ml = linear_fwd(h2, lins[2][0], lins[2][1], ACT_NONE)
+        _note("encoder.lin1", h1)
+        _note("encoder.lin2", h2)
         ctx.n_conv = n_conv
         ctx.save_for_backward(x, flat, h1, h2, *acts, *packed, *params)
         return ml
@@ -217,6 +243,9 @@ class DecoderFn(Function):
         h1 = linear_fwd(z, lins[0][0], lins[0][1], ACT_RELU)
         h2 = linear_fwd(h1, lins[1][0], lins[1][1], ACT_RELU)
         h3 = linear_fwd(h2, lins[2][0], lins[2][1], ACT_RELU)                    # [B,512] == view(B,32,4,4)
+        _note("decoder.lin1", h1)
+        _note("decoder.lin2", h2)
+        _note("decoder.lin3", h3)
         lo = flat_transpose(h3, B, to_nhwc=True).view(B, 4, 4, LO_CH)
         acts, packed = [lo], []
         H = 4
@@ -227,6 +256,7 @@ class DecoderFn(Function):
             packed.append(wp)
             hi = conv_up(lo, wp, b, None, B, H, H, CH, 1 if last else 0, ACT_SIGMOID if last else ACT_RELU)
             if not last:
+                _note("decoder.convT%d" % t, hi)
                 acts.append(hi)
             lo, H = hi, 2 * H
         recon = lo
@@ -286,6 +316,8 @@ class MlpFn(Function):
         h = x
         for i in range(n):
             h = linear_fwd(h, params[2 * i], params[2 * i + 1], ACT_LEAKY if i < n - 1 else ACT_NONE, slope)
+            if i < n - 1:
+                _note("mlp.lin%d" % (i + 1), h)
             hs.append(h)
         ctx.slope, ctx.n = slope, n
         ctx.save_for_backward(*hs[:-1], *params)
@@ -424,6 +456,50 @@ class BtcvaeFn(Function):
         call("dv_btcvae_bwd", B, D, n_data, is_mss, ptr(rowstats), ptr(ws), ptr(g_terms), ptr(g_z), ptr(g_mu),
              ptr(g_lv), stream())
         return g_z, g_mu, g_lv, None, None
+
+
+class BtcvaeGlobalFn(Function):
+    """beta-TCVAE terms of THIS rank's rows against the batch all-gathered from every rank:
+    the B x B log-density matrix of losses.py:523-544 is that of the GLOBAL batch B = world * b, each rank evaluates its
+    row block [rank*b, (rank+1)*b) with dv_btcvae_fwd_rows, and -> terms[3] = means over its rows, so the mean of the
+    ranks' terms is exactly the single-process value (equal shards).  Backward: the row side (g_z) is local and
+    complete; the column side (g_mu, g_logvar) is a [B, D] partial sum over this rank's rows -> reduce-scatter.
+    One all-gather of [b, 3D] forward, one reduce-scatter of [B, 2D] backward."""
+
+    @staticmethod
+    def forward(ctx, z, mu, logvar, n_data, is_mss, group):
+        from . import parallel
+        N.require_cuda_f32(z, mu, logvar)
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        b, D = z.shape
+        B = b * world
+        gathered = parallel.all_gather_rows(torch.cat([z, mu, logvar], dim=1), group)       # [B, 3D]
+        zg = gathered[:, :D].contiguous()
+        mug, lvg = gathered[:, D:2 * D], gathered[:, 2 * D:]                                 # ld 1, row stride 3D
+        nbytes = N.lib().dv_btcvae_workspace_bytes(B, D)
+        ws = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=z.device)
+        ws[:16].zero_()
+        rowstats = _new((4 + D, B), z)
+        terms = _new((3,), z)
+        call("dv_btcvae_fwd_rows", ptr(zg), ptr(mug), ptr(lvg), 1, 3 * D, B, D, rank * b, b, int(n_data), int(bool(is_mss)),
+             ptr(rowstats), ptr(terms), ptr(ws), stream())
+        ctx.meta = (B, D, b, rank, int(n_data), int(bool(is_mss)), group)
+        ctx.save_for_backward(rowstats, ws)
+        return terms
+
+    @staticmethod
+    def backward(ctx, g_terms):
+        from . import parallel
+        rowstats, ws = ctx.saved_tensors
+        B, D, b, rank, n_data, is_mss, group = ctx.meta
+        g_terms = _c(g_terms)
+        g_z = _new((b, D), rowstats)
+        g_cols = _new((2, B, D), rowstats)
+        call("dv_btcvae_bwd_rows", B, D, rank * b, b, n_data, is_mss, ptr(rowstats), ptr(ws), ptr(g_terms), ptr(g_z),
+             ptr(g_cols[0]), ptr(g_cols[1]), stream())
+        mine = parallel.reduce_scatter_rows(torch.cat([g_cols[0], g_cols[1]], dim=1), group)   # [b, 2D]
+        return g_z, mine[:, :D].contiguous(), mine[:, D:].contiguous(), None, None, None
 
 
 def btcvae_rowstats(z, mu, logvar, n_data, is_mss=True):

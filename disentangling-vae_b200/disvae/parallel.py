@@ -69,3 +69,41 @@ def broadcast_parameters(module, src=0):
         return
     for p in module.parameters():
         dist.broadcast(p.data, src=src)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Row collectives for the global-batch beta-TCVAE estimator (SURVEY.md 8f-1): every rank contributes the same number
+# of rows.  NCCL: one all_gather_into_tensor / reduce_scatter_tensor.  gloo (CPU tests; CUDA tensors of ranks that
+# share one GPU in tests/ddp_worker.py) has neither for CUDA tensors nor reduce_scatter at all: staged through an
+# all_gather / all_reduce on the host, same results.
+# ---------------------------------------------------------------------------------------------------------
+def _backend(group=None):
+    return dist.get_backend(group)
+
+
+def all_gather_rows(t, group=None):
+    """[b, n] on every rank -> [world * b, n], rank-major (rank r's rows at [r*b, (r+1)*b))."""
+    world = dist.get_world_size(group)
+    t = t.contiguous()
+    if _backend(group) == "nccl":
+        out = torch.empty((world * t.size(0),) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, t, group=group)
+        return out
+    host = t.detach().cpu()
+    parts = [torch.empty_like(host) for _ in range(world)]
+    dist.all_gather(parts, host, group=group)
+    return torch.cat(parts, dim=0).to(t.device)
+
+
+def reduce_scatter_rows(t, group=None):
+    """[world * b, n] partial sums on every rank -> this rank's [b, n] block of the sum over ranks."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    t = t.contiguous()
+    b = t.size(0) // world
+    if _backend(group) == "nccl":
+        out = torch.empty((b,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        dist.reduce_scatter_tensor(out, t, op=dist.ReduceOp.SUM, group=group)
+        return out
+    host = t.detach().cpu().clone()
+    dist.all_reduce(host, op=dist.ReduceOp.SUM, group=group)
+    return host[rank * b:(rank + 1) * b].to(t.device)

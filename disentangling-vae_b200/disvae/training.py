@@ -111,6 +111,8 @@ class Trainer():
             return False
         if hasattr(lf, "call_optimize") or getattr(self.model, "_eps_queue", None):
             return False
+        if getattr(lf, "global_batch", False) and is_distributed():
+            return False                                      # collectives inside the loss node: run eagerly
         if lf.steps_anneal != 0 and lf.n_train_steps < lf.steps_anneal:
             return False                                      # host-side annealing coefficient still moving
         if storer is not None and (lf.n_train_steps + 1) % lf.record_loss_every == 1:

@@ -172,6 +172,30 @@ int dv_btcvae_fwd(const float* z, const float* mu, const float* logvar, int ld, 
 int dv_btcvae_bwd(int B, int D, long long n_data, int is_mss, const float* rowstats,
                   const void* workspace, const float* g_terms, float* g_z, float* g_mu,
                   float* g_logvar, void* stream);
+/* Row-window form (the estimator over a batch all-gathered from several GPUs, each rank
+ * evaluating its own rows of the B x B matrix -- losses.py:523-544 semantics of the GLOBAL batch).
+ * z / mu / logvar hold all B rows; only rows [row0, row0 + nrows) are evaluated: their rowstats entries are
+ * written (global row index), terms = means over the window.  Backward: g_z is [nrows, D] (the window's rows);
+ * g_mu / g_logvar are [B, D] PARTIAL sums over the window's rows for every column -- summing them over the
+ * windows of all ranks (reduce-scatter) gives the gradient of the mean-over-ranks loss.
+ * dv_btcvae_fwd / dv_btcvae_bwd are the (0, B) window. */
+int dv_btcvae_fwd_rows(const float* z, const float* mu, const float* logvar, int ld, int row_stride,
+                       int B, int D, int row0, int nrows, long long n_data, int is_mss, float* rowstats,
+                       float* terms, void* workspace, void* stream);
+int dv_btcvae_bwd_rows(int B, int D, int row0, int nrows, long long n_data, int is_mss,
+                       const float* rowstats, const void* workspace, const float* g_terms, float* g_z,
+                       float* g_mu, float* g_logvar, void* stream);
+
+/* ---- disentanglement metrics: marginal-entropy estimator ---------------------
+ * Replaces Evaluator._estimate_latent_entropies (disvae/evaluate.py:233-297), the inner loop of the MIG / AAM metrics
+ * (:119-161, :299-317): for S samples zs[D][S] (row d = samples of latent dimension d) and the N posteriors
+ * mean/logvar[n][d] (element (n,d) at n*row_stride + d*ld),
+ *   H[d] = -(1/S) sum_s ( -log N + logsumexp_n log N(zs[d][s]; mean[n][d], exp(logvar[n][d])) ).
+ * logq_out (optional, [D][S]) receives the per-sample log q(z).  Deterministic (fixed merge order).
+ */
+size_t dv_latent_entropy_workspace_bytes(int N, int D, int S);
+int dv_latent_entropy(const float* zs, const float* mean, const float* logvar, int ld, int row_stride,
+                      int N, int D, int S, float* H, float* logq_out, void* workspace, void* stream);
 
 /* ---- FactorVAE pieces ---------------------------------------------------------------------
  * dv_permute_dims replaces _permute_dims (losses.py:483-508): out[b][d] = z[perm[d][b]][d].

@@ -126,16 +126,46 @@ def _has(p, key):
     return (key + ".weight") in p
 
 
+# Test hook for FLIP-ROBUST gradient parity (oracle/same_branch.py).  Two correct fp32 evaluations of this network round
+# a few (Leaky)ReLU pre-activations of a large batch to opposite sides of zero; every such unit switches a whole
+# back-propagated path on or off, so full-batch gradients of two correct implementations differ by far more than their
+# arithmetic error.  With `_ACT = dict(record={}, masks={...}, calls={})` the forward passes below (a) record every
+# pre-activation and (b) apply GIVEN on/off patterns instead of their own sign test (`pre * mask`), which makes the
+# backward pass a smooth function of the inputs again.  None (the default) = plain reference semantics.
+_ACT = None
+
+
+def _call_index(prefix):
+    if _ACT is None:
+        return 0
+    c = _ACT.setdefault("calls", {})
+    c[prefix] = c.get(prefix, -1) + 1
+    return c[prefix]
+
+
+def _act(pre, name, slope=0.0):
+    if _ACT is None:
+        return torch.relu(pre) if slope == 0.0 else F.leaky_relu(pre, slope)
+    if _ACT.get("record") is not None:
+        _ACT["record"][name] = pre.detach()
+    m = (_ACT.get("masks") or {}).get(name)
+    if m is None:
+        return torch.relu(pre) if slope == 0.0 else F.leaky_relu(pre, slope)
+    m = m.to(pre.dtype)
+    return pre * (m if slope == 0.0 else m + slope * (1 - m))
+
+
 def encoder_forward(p, x):
     """encoders.py:69-89.  Returns (mu, logvar), interleaved split (trap T1)."""
     h = x
+    tag = "encoder#%d." % _call_index("encoder")
     for name in ("conv1", "conv2", "conv3", "conv_64"):
         k = "encoder." + name
         if _has(p, k):
-            h = torch.relu(F.conv2d(h, p[k + ".weight"], p[k + ".bias"], stride=2, padding=1))
+            h = _act(F.conv2d(h, p[k + ".weight"], p[k + ".bias"], stride=2, padding=1), tag + name)
     h = h.reshape(x.size(0), -1)
-    h = torch.relu(F.linear(h, p["encoder.lin1.weight"], p["encoder.lin1.bias"]))
-    h = torch.relu(F.linear(h, p["encoder.lin2.weight"], p["encoder.lin2.bias"]))
+    h = _act(F.linear(h, p["encoder.lin1.weight"], p["encoder.lin1.bias"]), tag + "lin1")
+    h = _act(F.linear(h, p["encoder.lin2.weight"], p["encoder.lin2.bias"]), tag + "lin2")
     ml = F.linear(h, p["encoder.mu_logvar_gen.weight"], p["encoder.mu_logvar_gen.bias"])
     ml = ml.view(x.size(0), -1, 2)
     return ml[..., 0], ml[..., 1]
@@ -143,14 +173,15 @@ def encoder_forward(p, x):
 
 def decoder_forward(p, z):
     """decoders.py:67-84."""
-    h = torch.relu(F.linear(z, p["decoder.lin1.weight"], p["decoder.lin1.bias"]))
-    h = torch.relu(F.linear(h, p["decoder.lin2.weight"], p["decoder.lin2.bias"]))
-    h = torch.relu(F.linear(h, p["decoder.lin3.weight"], p["decoder.lin3.bias"]))
+    tag = "decoder#%d." % _call_index("decoder")
+    h = _act(F.linear(z, p["decoder.lin1.weight"], p["decoder.lin1.bias"]), tag + "lin1")
+    h = _act(F.linear(h, p["decoder.lin2.weight"], p["decoder.lin2.bias"]), tag + "lin2")
+    h = _act(F.linear(h, p["decoder.lin3.weight"], p["decoder.lin3.bias"]), tag + "lin3")
     h = h.view(z.size(0), HID_CH, KSIZE, KSIZE)
     for name in ("convT_64", "convT1", "convT2"):
         k = "decoder." + name
         if _has(p, k):
-            h = torch.relu(F.conv_transpose2d(h, p[k + ".weight"], p[k + ".bias"], stride=2, padding=1))
+            h = _act(F.conv_transpose2d(h, p[k + ".weight"], p[k + ".bias"], stride=2, padding=1), tag + name)
     k = "decoder.convT3"
     return torch.sigmoid(F.conv_transpose2d(h, p[k + ".weight"], p[k + ".bias"], stride=2, padding=1))
 
@@ -175,8 +206,9 @@ def vae_forward(p, x, eps=None, training=True):
 def discriminator_forward(dp, z):
     """discriminator.py:60-70."""
     h = z
+    tag = "disc#%d." % _call_index("disc")
     for i in range(1, 6):
-        h = F.leaky_relu(F.linear(h, dp["lin%d.weight" % i], dp["lin%d.bias" % i]), DISC_SLOPE)
+        h = _act(F.linear(h, dp["lin%d.weight" % i], dp["lin%d.bias" % i]), tag + "lin%d" % i, DISC_SLOPE)
     return F.linear(h, dp["lin6.weight"], dp["lin6.bias"])
 
 
@@ -364,3 +396,55 @@ def factor_step(p, dp, opt, opt_d, x, cfg, step, eps_full=None, eps1=None, eps2=
 def make_adam(params, lr, betas=(0.9, 0.999)):
     """main.py:208 / losses.py:238."""
     return torch.optim.Adam(list(params.values()), lr=lr, betas=betas)
+
+
+# --------------------------------------------------------------------------
+# disentanglement metrics (Evaluator.compute_metrics, evaluate.py:119-317)
+# --------------------------------------------------------------------------
+def estimate_latent_entropies(samples_zCx, mean, logvar, samples_x, chunk=50):
+    """evaluate.py:233-297 with the drawn indices `samples_x` given ([n_samples] int64; the reference draws
+    torch.randperm(len_dataset)[:n_samples], :267).  Includes the reference's reshape-not-transpose of the selected
+    block (:270).  -> H_z [latent_dim].  `chunk` samples at a time (the reference uses 10, :272): a sum over samples in
+    a different grouping, not different arithmetic."""
+    len_dataset, latent_dim = samples_zCx.shape
+    n_samples = samples_x.numel()
+    zs = samples_zCx.index_select(0, samples_x).view(latent_dim, n_samples)
+    log_N = math.log(len_dataset)
+    H_z = torch.zeros(latent_dim, dtype=samples_zCx.dtype)
+    for k in range(0, n_samples, chunk):
+        zk = zs[:, k:k + chunk].unsqueeze(0)                            # [1, D, c]
+        log_q_zCx = log_density_gaussian(zk, mean.unsqueeze(-1), logvar.unsqueeze(-1))   # [N, D, c]
+        log_q_z = -log_N + torch.logsumexp(log_q_zCx, dim=0)            # :284
+        H_z += (-log_q_z).sum(1)                                        # :287
+    return H_z / n_samples                                              # :291
+
+
+def estimate_H_zCv(samples_zCx, mean, logvar, lat_sizes, perms):
+    """evaluate.py:299-317; `perms` = iterator over the index draws of the successive estimator calls."""
+    latent_dim = samples_zCx.size(-1)
+    lat_sizes = [int(v) for v in lat_sizes]
+    len_dataset = 1
+    for v in lat_sizes:
+        len_dataset *= v
+    s = samples_zCx.view(*lat_sizes, latent_dim)
+    m, lv = mean.view(*lat_sizes, latent_dim), logvar.view(*lat_sizes, latent_dim)
+    H_zCv = torch.zeros(len(lat_sizes), latent_dim, dtype=samples_zCx.dtype)
+    for f, lat_size in enumerate(lat_sizes):
+        idcs = [slice(None)] * len(lat_sizes)
+        for i in range(lat_size):
+            idcs[f] = i
+            sub = [t[tuple(idcs)].contiguous().view(len_dataset // lat_size, latent_dim) for t in (s, m, lv)]
+            H_zCv[f] += estimate_latent_entropies(sub[0], sub[1], sub[2], next(perms)) / lat_size
+    return H_zCv
+
+
+def mig_aam(H_z, H_zCv, lat_sizes):
+    """evaluate.py:148-158, 163-198 -> (MIG, AAM, mig_k, aam_k)."""
+    mut_info = -H_zCv + H_z
+    sorted_mut_info = torch.sort(mut_info, dim=1, descending=True)[0].clamp(min=0)
+    delta = sorted_mut_info[:, 0] - sorted_mut_info[:, 1]
+    mig_k = delta / torch.as_tensor([float(v) for v in lat_sizes]).log()
+    numerator = (sorted_mut_info[:, 0] - sorted_mut_info[:, 1:].sum(dim=1)).clamp(min=0)
+    aam_k = numerator / sorted_mut_info[:, 0]
+    aam_k[torch.isnan(aam_k)] = 0
+    return mig_k.mean(), aam_k.mean(), mig_k, aam_k

@@ -244,6 +244,75 @@ def gen_permute():
     torch.save(dict(z=z, z_perm=zp), os.path.join(HERE, "permute.pt"))
 
 
+def gen_metrics():
+    """MIG / AAM metrics (evaluate.py:119-317) from the reference Evaluator.
+    (A) direct calls of Evaluator._estimate_latent_entropies on seeded statistics with explicit n_samples;
+    (B) the whole Evaluator.__call__(loader, is_metrics=True) on a procedural dataset with 4 known factors
+        (tests/synthetic_factors.py) through the shipped VAE_mnist checkpoint.  The estimator's default n_samples=10000
+        needs >= 10000 examples in every factor slice (>= 10^5 images); the fixture lowers the DEFAULT ARGUMENT to 1000
+        (`__defaults__`, no code change) so that 10^4 images suffice.  The index draws (`torch.randperm`, :267) are
+        recorded so the CUDA path -- whose device generator draws differently -- can replay them."""
+    import logging
+    import tempfile
+    from disvae.evaluate import Evaluator
+    sys.path.insert(0, os.path.dirname(HERE))
+    from synthetic_factors import FactorRectangles, loader
+    out = {}
+    drawn = []
+    real_randperm = torch.randperm
+
+    def recording_randperm(n, *a, **k):
+        p = real_randperm(n, *a, **k)
+        drawn.append(p.clone())
+        return p
+
+    torch.manual_seed(SEED)
+    model = disvae.init_specific_model("Burgess", (1, 32, 32), 10)
+    model.load_state_dict(torch.load(os.path.join(REF, "results", "VAE_mnist", "model.pt")))
+    tmp = tempfile.mkdtemp()
+    ev = Evaluator(model, None, device=torch.device("cpu"), logger=logging.getLogger("golden"), save_dir=tmp,
+                   is_progress_bar=True)       # (evaluate.py:276 disables its bar when this is True)
+    torch.randperm = recording_randperm
+    try:
+        # (A)
+        for name, (n, d, s) in dict(n3000_d10_s500=(3000, 10, 500), n1200_d6_s1200=(1200, 6, 1200)).items():
+            torch.manual_seed(SEED + 8)
+            mean = torch.randn(n, d)
+            logvar = torch.randn(n, d) * 0.7 - 1.5
+            samples = mean + torch.exp(0.5 * logvar) * torch.randn(n, d)
+            drawn.clear()
+            H = ev._estimate_latent_entropies(samples, (mean, logvar), n_samples=s)
+            out[name] = dict(n=n, d=d, s=s, mean=mean, logvar=logvar, samples=samples, perm=drawn[0][:s].clone(), H=H.clone())
+        # (B)
+        old_defaults = Evaluator._estimate_latent_entropies.__defaults__
+        Evaluator._estimate_latent_entropies.__defaults__ = (1000,)
+        ds = FactorRectangles()
+        drawn.clear()
+        torch.manual_seed(SEED + 9)
+        ev(loader(ds), is_metrics=True, is_losses=False)
+        Evaluator._estimate_latent_entropies.__defaults__ = old_defaults
+        import json
+        metrics = json.load(open(os.path.join(tmp, "metrics.log")))
+        helpers = torch.load(os.path.join(tmp, "metric_helpers.pth"), weights_only=False)
+        out["full"] = dict(n_samples=1000, k=10, metrics=metrics, helpers={k: v.clone() for k, v in helpers.items()},
+                           perms=[p[:1000].clone() for p in drawn], imgs_digest=tensor_digest(ds.imgs))
+        # (C) the two metric formulas on a table where they are not clamped away (evaluate.py:163-198)
+        torch.manual_seed(SEED + 10)
+        mi_table = torch.rand(4, 10) * 0.05
+        mi_table[0, 2], mi_table[1, 7], mi_table[3, 0], mi_table[3, 5] = 1.5, 0.9, 0.6, 0.5
+        mi_table[2] = 0.0                                  # a factor no latent informs: AAM's 0/0 -> 0 branch
+        smi = torch.sort(mi_table, dim=1, descending=True)[0].clamp(min=0)
+        st = {}
+        mig = ev._mutual_information_gap(smi, np.array([10, 10, 10, 10]), storer=st)
+        aam = ev._axis_aligned_metric(smi, storer=st)
+        out["formulas"] = dict(sorted_mut_info=smi, mig=mig.clone(), aam=aam.clone(), mig_k=st["mig_k"].clone(),
+                               aam_k=st["aam_k"].clone())
+    finally:
+        torch.randperm = real_randperm
+    shutil.rmtree(tmp, ignore_errors=True)
+    torch.save(out, os.path.join(HERE, "metrics.pt"))
+
+
 def copy_checkpoints():
     dst = os.path.join(HERE, "ckpt")
     os.makedirs(dst, exist_ok=True)
@@ -259,6 +328,7 @@ if __name__ == "__main__":
     gen_btcvae_density()
     gen_train_steps()
     gen_permute()
+    gen_metrics()
     copy_checkpoints()
     for f in sorted(os.listdir(HERE)):
         p = os.path.join(HERE, f)

@@ -23,7 +23,10 @@ def _free_port():
 
 
 @pytest.mark.parametrize("loss,extra", [("btcvae", []), ("factor", ["--img", "3,64,64", "--per", "32"]),
-                                        ("btcvae", ["--img", "3,64,64", "--z", "64", "--per", "24"])])
+                                        ("btcvae", ["--img", "3,64,64", "--z", "64", "--per", "24"]),
+                                        # global-batch-exact estimator == ONE process on the whole batch
+                                        ("btcvae", ["--img", "3,64,64", "--z", "64", "--per", "24", "--global-btcvae"]),
+                                        ("btcvae", ["--per", "40", "--global-btcvae"])])
 def test_two_rank_data_parallel_parity(loss, extra):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "ddp_worker.py"), "--loss", loss] + extra

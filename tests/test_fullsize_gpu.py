@@ -13,6 +13,9 @@ from oracle import disvae_oracle as O
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
+import os
+import sys
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 
 def rel_err(a, b):
@@ -116,12 +119,13 @@ def _model(img, z):
 
 @pytest.mark.parametrize("loss_name,img,z,B", [("btcvae", (1, 64, 64), 10, 1024), ("betaH", (3, 64, 64), 10, 512),
                                                ("btcvae", (3, 64, 64), 64, 256)])
-def test_model_gradients_full_batch_fp64_arbitrated(loss_name, img, z, B):
-    """All parameter gradients of one full-size training batch (BASELINE configs[1], [2], [4]-shard).  Two fp32
-    evaluation orders of this network differ by more than 1e-4 on a few weight-gradient entries (ReLU pre-activations
-    that round to opposite sides of zero switch whole back-propagated paths), so the fp32 oracle cannot referee that
-    alone: the oracle also runs in fp64, and the CUDA path must be as close to the fp64 truth as the CPU fp32 oracle
-    is (x3 slack) -- or within 1e-4 of the fp32 oracle outright."""
+def test_model_gradients_full_batch_same_branch(loss_name, img, z, B):
+    """All parameter gradients of one full-size training batch (BASELINE configs[1], [2], [4]-shard) against the fp64
+    oracle ON THE SAME BRANCH of the network (oracle/same_branch.py): 1e-4 of every tensor's scale, and every ReLU whose
+    on/off state differs from the fp64 sign must be numerically ambiguous.  The plain fp32 oracle is also compared --
+    informationally: at these sizes two correct fp32 evaluations differ by 1e-3..1e-1 through ReLU flips (printed)."""
+    from oracle import same_branch as PU
+    from disvae import ops
     from disvae.models.losses import get_loss_f
     m = _model(img, z)
     m.train()
@@ -130,33 +134,39 @@ def test_model_gradients_full_batch_fp64_arbitrated(loss_name, img, z, B):
     torch.manual_seed(B + z)
     x, eps = torch.rand(B, *img), torch.randn(B, z)
 
-    def oracle(dt):
-        p = O.make_leaf_params(OrderedDict((k, v.to(dt)) for k, v in p32.items()))
-        ro, (mo, lo), zo = O.vae_forward(p, x.to(dt), eps.to(dt))
+    def oracle_loss(p, xx, ee):
+        ro, (mo, lo), zo = O.vae_forward(p, xx, ee)
         if loss_name == "btcvae":
-            l, _ = O.loss_btcvae(x.to(dt), ro, mo, lo, zo, n_data, 1, 6, 1, "bernoulli", 1, 0)
+            l, _ = O.loss_btcvae(xx, ro, mo, lo, zo, n_data, 1, 6, 1, "bernoulli", 1, 0)
         else:
-            l, _ = O.loss_betaH(x.to(dt), ro, mo, lo, 10, "bernoulli", 1, 0)
-        l.backward()
-        return l.item(), ro.detach(), {k: v.grad for k, v in p.items()}
+            l, _ = O.loss_betaH(xx, ro, mo, lo, 10, "bernoulli", 1, 0)
+        return l, ro
 
-    l32, r32, g32 = oracle(torch.float32)
-    l64, r64, g64 = oracle(torch.float64)
     lf = get_loss_f(loss_name, rec_dist="bernoulli", reg_anneal=0, betaH_B=10, btcvae_A=1, btcvae_B=6, btcvae_G=1, n_data=n_data)
     xd = x.to(DEV)
+    ops.start_trace()
     recon, (mu, lv), zz = m(xd, eps=eps.to(DEV))
+    trace = ops.stop_trace()
     loss = lf(xd, recon, (mu, lv), True, None, latent_sample=zz)
     m.zero_grad()
     loss.backward()
-    assert abs(loss.item() - l32) <= 1e-4 * abs(l32)
-    assert abs(loss.item() - l64) <= 1e-4 * abs(l64)
-    assert_close(recon.cpu(), r64, 1e-4, "recon vs fp64")
-    worst_ours = worst_cpu = 0.0
-    for k, prm in m.named_parameters():
-        e_ours, e_cpu = rel_err(prm.grad, g64[k]), rel_err(g32[k], g64[k])
-        worst_ours, worst_cpu = max(worst_ours, e_ours), max(worst_cpu, e_cpu)
-        assert e_ours <= max(1e-4, 3.0 * e_cpu) or rel_err(prm.grad, g32[k]) <= 1e-4, \
-            "grad %s: ours vs fp64 %.2e, oracle fp32 vs fp64 %.2e" % (k, e_ours, e_cpu)
-        a, b = prm.grad.double().cpu().flatten(), g64[k].flatten()
-        assert torch.dot(a, b) / (a.norm() * b.norm()).clamp_min(1e-30) > 1 - 1e-6, k
-    print("max grad rel err vs fp64: ours %.2e, CPU fp32 oracle %.2e" % (worst_ours, worst_cpu))
+    ours = {k: prm.grad for k, prm in m.named_parameters()}
+
+    def run64(p, dp):
+        l, _ = oracle_loss(p, x.double(), eps.double())
+        l.backward()
+        return l.item()
+    ref = PU.same_branch_reference(trace, p32, run64)
+    assert abs(loss.item() - ref["loss"]) <= 1e-4 * abs(ref["loss"])
+    assert ref["flip_max_rel"] <= 1e-3, "a ReLU flipped at |pre-activation| = %.2e of its layer's scale" % ref["flip_max_rel"]
+    err, key = PU.grad_errors(ours, ref["grads"])
+    # informational: the plain fp32 oracle (its own branch)
+    p = O.make_leaf_params(p32)
+    l32, r32 = oracle_loss(p, x, eps)
+    l32.backward()
+    e32, _ = PU.grad_errors(ours, {k: v.grad for k, v in p.items()})
+    assert abs(loss.item() - l32.item()) <= 1e-4 * abs(l32.item())
+    assert_close(recon.cpu(), r32.detach(), 1e-4, "recon")
+    print("B=%d: %d of %d ReLU units flipped vs fp64 (largest |pre| %.1e of layer scale); gradients vs fp64 on the same branch "
+          "%.2e (worst %s); vs the fp32 oracle on ITS branch %.2e" % (B, ref["flips"], ref["units"], ref["flip_max_rel"], err, key, e32))
+    assert err <= 1e-4, "grad %s: %.2e vs fp64 on the same branch" % (key, err)

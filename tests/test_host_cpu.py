@@ -251,3 +251,37 @@ def test_bench_reference_arm_contract():
                                 "rec_dist", "optimizer", "parallelism", "l2"}          # == our own arm's keys
     assert d["e2e"] == {"value": d["value"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["loss"] == "VAE" and d["config"]["batch_per_gpu"] == 64
+
+
+def _row_collectives_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from disvae import parallel
+    b, n = 3, 4
+    mine = torch.arange(b * n, dtype=torch.float32).view(b, n) + 100 * rank
+    g = parallel.all_gather_rows(mine)
+    ok = tuple(g.shape) == (world * b, n) and all(torch.equal(g[r * b:(r + 1) * b], torch.arange(b * n, dtype=torch.float32).view(b, n) + 100 * r) for r in range(world))
+    part = torch.full((world * b, n), float(rank + 1)) * torch.arange(world * b).view(-1, 1)
+    rs = parallel.reduce_scatter_rows(part)
+    expect = (sum(range(1, world + 1)) * torch.arange(world * b).view(-1, 1).float()).expand(-1, n)[rank * b:(rank + 1) * b]
+    ok = ok and torch.equal(rs, expect)
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_row_collectives_world2_gloo():
+    """all_gather_rows / reduce_scatter_rows (the two collectives of the global-batch beta-TCVAE estimator, SURVEY.md
+    8f-1) on the gloo fallback path, world size 2: rank-major row order, sum semantics, this rank's block."""
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_row_collectives_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(60)
+    assert sorted(res) == [(0, True), (1, True)]

@@ -475,3 +475,57 @@ def test_fused_adam_multi_matches_torch_adam():
         assert_close(opt.state[b]["exp_avg_sq"].cpu(), opt_ref.state[a]["exp_avg_sq"], tol=1e-6)
     fused.flush_state()
     assert float(opt.state[ps[0]]["step"]) == 4.0
+
+
+@pytest.mark.parametrize("B,D,world", [(256, 64, 2), (96, 10, 3), (2048, 64, 8), (130, 5, 2)])
+def test_btcvae_row_windows_compose_to_the_full_batch(ops, B, D, world):
+    """SURVEY.md 8f-1 kernels: the estimator over row windows of one (all-gathered) batch.  Window r evaluates rows
+    [r*b, (r+1)*b) against ALL B columns; rowstats of the windows == the oracle's full-batch values; the mean of the
+    windows' terms == the full-batch terms; g_z windows stack to the full g_z and the column-side partial sums add up to
+    the full g_mu / g_logvar (what the reduce-scatter over ranks computes)."""
+    from disvae import _native as N
+    torch.manual_seed(B + D + world)
+    b = B // world
+    B = b * world
+    mu = torch.randn(B, D)
+    lv = torch.randn(B, D) * 0.5 - 1
+    z = mu + torch.exp(0.5 * lv) * torch.randn(B, D)
+    n_data = 202599
+    big = B * B * D > 5e7
+    zo, muo, lvo = [t.clone().requires_grad_(not big) for t in (z, mu, lv)]
+    with torch.set_grad_enabled(not big):
+        ref = O.btcvae_log_densities(zo, muo, lvo, n_data)
+    coef = (1.0, 6.0, -2.5)
+    if not big:
+        mi, tc, dw = (ref[3] - ref[1]).mean(), (ref[1] - ref[2]).mean(), (ref[2] - ref[0]).mean()
+        (coef[0] * mi + coef[1] * tc + coef[2] * dw).backward()
+    zd, mud, lvd = z.to(dev()), mu.to(dev()), lv.to(dev())
+    nbytes = N.lib().dv_btcvae_workspace_bytes(B, D)
+    g_terms = torch.tensor(coef, device=dev())
+    terms_mean = torch.zeros(3)
+    g_z, g_mu, g_lv = torch.zeros(B, D), torch.zeros(B, D), torch.zeros(B, D)
+    for r in range(world):
+        ws = torch.zeros((nbytes + 3) // 4, device=dev())
+        rowstats = torch.full((4 + D, B), float("nan"), device=dev())
+        terms = torch.empty(3, device=dev())
+        N.call("dv_btcvae_fwd_rows", N.ptr(zd), N.ptr(mud), N.ptr(lvd), 1, D, B, D, r * b, b, n_data, 1, N.ptr(rowstats),
+               N.ptr(terms), N.ptr(ws), N.stream())
+        for got, rf, name in zip(rowstats[:4], ref, ["log_pz", "log_qz", "log_prod_qzi", "log_q_zCx"]):
+            assert_close(got[r * b:(r + 1) * b].cpu(), rf.detach()[r * b:(r + 1) * b], tol=2e-5, what="%s window %d" % (name, r))
+        if r * b > 0:
+            assert torch.isnan(rowstats[1:3, :r * b]).all()          # rows outside the window are not touched
+        terms_mean += terms.cpu() / world
+        gz = torch.empty(b, D, device=dev())
+        gm, gl = torch.empty(B, D, device=dev()), torch.empty(B, D, device=dev())
+        N.call("dv_btcvae_bwd_rows", B, D, r * b, b, n_data, 1, N.ptr(rowstats), N.ptr(ws), N.ptr(g_terms), N.ptr(gz), N.ptr(gm),
+               N.ptr(gl), N.stream())
+        g_z[r * b:(r + 1) * b] = gz.cpu()
+        g_mu += gm.cpu()
+        g_lv += gl.cpu()
+    full = ops.BtcvaeFn.apply(zd, mud, lvd, n_data, True)
+    assert_close(terms_mean, full.cpu(), tol=2e-5, what="mean of window terms")
+    if not big:
+        # gradients of the MEAN-over-windows loss: each window's backward used 1/b, the full batch uses 1/B
+        assert_close(g_z / world, zo.grad, what="g_z")
+        assert_close(g_mu / world, muo.grad, what="g_mu")
+        assert_close(g_lv / world, lvo.grad, what="g_logvar")

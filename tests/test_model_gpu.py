@@ -96,28 +96,35 @@ def test_forward_backward_matches_oracle_larger_batches(img_size, z, B):
     recon_o, (mu_o, lv_o), z_o = O.vae_forward(p, x, eps)
     loss_o, _ = O.loss_betaH(x, recon_o, mu_o, lv_o, 4, "bernoulli", 1, 0)
     loss_o.backward()
-    recon, (mu, lv), zz = m(x.to(DEV), eps=eps.to(DEV))
+    from disvae import ops
     from disvae.models.losses import get_loss_f
+    from oracle import same_branch as SB
+    ops.start_trace()
+    recon, (mu, lv), zz = m(x.to(DEV), eps=eps.to(DEV))
+    trace = ops.stop_trace()
     lf = get_loss_f("betaH", rec_dist="bernoulli", reg_anneal=0, betaH_B=4)
     loss = lf(x.to(DEV), recon, (mu, lv), True, None)
     assert_close(recon.cpu(), recon_o.detach(), what="recon")
     assert abs(loss.item() - loss_o.item()) <= RTOL * abs(loss_o.item())
     m.zero_grad()
     loss.backward()
-    # Gradients: two fp32 evaluation orders (MKL/oneDNN on CPU vs 3xTF32 tensor cores) round a handful of ReLU
-    # pre-activations to opposite sides of zero; each such unit switches a whole back-propagated path on or off.  How
-    # much that moves a gradient is MEASURED, not assumed: the oracle is re-run in fp64 and the CUDA path must be as
-    # close to that truth as the CPU fp32 oracle is (x3), or within 1e-4 of the fp32 oracle outright.
-    p64 = O.make_leaf_params(OrderedDict((k, v.detach().cpu().double()) for k, v in m.state_dict().items()))
-    r64, (m64, l64), _ = O.vae_forward(p64, x.double(), eps.double())
-    O.loss_betaH(x.double(), r64, m64, l64, 4, "bernoulli", 1, 0)[0].backward()
-    for k, prm in m.named_parameters():
-        e32, e64, ecpu = rel_err(prm.grad, p[k].grad), rel_err(prm.grad, p64[k].grad), rel_err(p[k].grad, p64[k].grad)
-        assert e32 <= RTOL or e64 <= max(RTOL, 3.0 * ecpu), \
-            "grad %s: vs fp32 oracle %.2e, vs fp64 %.2e, fp32 oracle vs fp64 %.2e" % (k, e32, e64, ecpu)
-        a, b = prm.grad.double().cpu().flatten(), p64[k].grad.flatten()
-        cos = torch.dot(a, b) / (a.norm() * b.norm()).clamp_min(1e-30)
-        assert cos > 1 - 1e-6, ("grad direction " + k, cos.item())
+    # Gradients: two fp32 evaluation orders (MKL/oneDNN on CPU vs 3xTF32 tensor cores) may round a ReLU pre-activation
+    # to opposite sides of zero, which switches a whole back-propagated path.  Referee = the fp64 oracle on the SAME
+    # branch of the network as the CUDA path (oracle/same_branch.py), held to 1e-4; every flipped unit must be
+    # numerically ambiguous.  Where no unit flipped, the plain fp32 oracle must agree to 1e-4 as well.
+    def run64(pp, dd):
+        r64, (m64, l64), _ = O.vae_forward(pp, x.double(), eps.double())
+        l = O.loss_betaH(x.double(), r64, m64, l64, 4, "bernoulli", 1, 0)[0]
+        l.backward()
+        return l.item()
+    ref = SB.same_branch_reference(trace, OrderedDict((k, v.detach().cpu()) for k, v in m.state_dict().items()), run64)
+    assert ref["flip_max_rel"] <= 1e-3, ref
+    ours = {k: prm.grad for k, prm in m.named_parameters()}
+    err, key = SB.grad_errors(ours, ref["grads"])
+    assert err <= RTOL, "grad %s: %.2e vs fp64 on the same branch (%d flipped units)" % (key, err, ref["flips"])
+    if ref["flips"] == 0:
+        e32, k32 = SB.grad_errors(ours, {k: v.grad for k, v in p.items()})
+        assert e32 <= RTOL, (k32, e32)
 
 
 @pytest.mark.parametrize("loss_name", ["VAE", "betaH", "betaB", "btcvae"])

@@ -187,3 +187,23 @@ def test_train_steps_match_reference(golden, loss_name):
             digest_close(v, g["disc_params"][k], rtol=2e-5)
             digest_close(opt_d.state[v]["exp_avg"], g["disc_opt_state"][k]["exp_avg"], rtol=2e-5)
             digest_close(opt_d.state[v]["exp_avg_sq"], g["disc_opt_state"][k]["exp_avg_sq"], rtol=2e-5)
+
+
+@pytest.mark.parametrize("key", ["n3000_d10_s500", "n1200_d6_s1200"])
+def test_latent_entropy_estimator_matches_reference(golden, key):
+    """oracle.estimate_latent_entropies == reference Evaluator._estimate_latent_entropies (evaluate.py:233-297) on the
+    recorded index draw, including the reshape-not-transpose of the selected samples."""
+    g = golden("metrics.pt")[key]
+    H = O.estimate_latent_entropies(g["samples"], g["mean"], g["logvar"], g["perm"])
+    assert torch.allclose(H, g["H"], rtol=2e-5, atol=1e-6), (H, g["H"])
+
+
+def test_metrics_tables_match_reference(golden):
+    """Conditional entropies + MIG / AAM of the full fixture from the recorded marginal statistics is a GPU test (it needs
+    the encoder); here: the two metric formulas (evaluate.py:163-198) incl. the 0/0 -> 0 branch."""
+    g = golden("metrics.pt")["formulas"]
+    smi = g["sorted_mut_info"]
+    # feed a table whose sort/clamp is the identity: H_z - H_zCv == smi
+    mig, aam, mig_k, aam_k = O.mig_aam(torch.zeros(10), -smi, [10, 10, 10, 10])
+    assert torch.allclose(mig, g["mig"], rtol=1e-6) and torch.allclose(aam, g["aam"], rtol=1e-6)
+    assert torch.allclose(mig_k, g["mig_k"], rtol=1e-6) and torch.allclose(aam_k, g["aam_k"], rtol=1e-6)
