@@ -471,7 +471,8 @@ def parity_check(trainer, workload, B, device, rank, world):
     if factor:
         g32.update({"disc." + k: v.grad for k, v in dp.items()})
     # fp64 oracle on the CUDA path's branch: gradient referee
-    ref = SB.same_branch_reference(trace, p32, lambda pp, dd: oracle(pp, dd, torch.float64)[0], disc32=d32)
+    ref = SB.same_branch_reference(trace, p32, lambda pp, dd: oracle(pp, dd, torch.float64)[0], disc32=d32,
+                                   run_oracle32=lambda pp, dd: oracle(pp, dd, torch.float32)[0])
     g64 = ref["grads"]
     if world > 1:                                              # mean of the shard gradients over ranks, like ours
         for gd in (g32, g64):
@@ -483,9 +484,14 @@ def parity_check(trainer, workload, B, device, rank, world):
     rerr = (recon - r32).abs().max().item()
     e_same, key = SB.grad_errors(ours, g64)
     e_own, _ = SB.grad_errors(ours, g32)
-    ok = bool(rel < 1e-4 and rerr < 1e-4 and e_same <= 1e-4 and ref["flip_max_rel"] <= 1e-3)
+    e_cpu = ref["cpu_fp32_same_branch_err"]
+    # 1e-4 where fp32 allows it; where the CPU fp32 oracle itself is further than 1e-4/8 from fp64 on this branch (long
+    # cancelling sums: bias gradients over 10^4..10^6 positions), 8x its error (3xTF32 vs an fp32 FMA chain), capped
+    grad_tol = min(max(1e-4, 8.0 * e_cpu), 1e-3)
+    ok = bool(rel < 1e-4 and rerr < 1e-4 and e_same <= grad_tol and ref["flip_max_rel"] <= 1e-3)
     res = {"loss_cuda": loss, "loss_oracle": l32, "loss_rel_err": rel, "loss_rel_err_vs_fp64": abs(loss - ref["loss"]) / abs(ref["loss"]),
            "recon_max_abs_err": rerr, "grad_rel_err_vs_fp64_same_branch": e_same, "grad_worst_tensor": key,
+           "cpu_fp32_oracle_grad_rel_err_vs_fp64_same_branch": e_cpu, "grad_tol": grad_tol,
            "relu_units": ref["units"], "relu_flips_vs_fp64": ref["flips"], "flip_max_rel_preact": ref["flip_max_rel"],
            "grad_rel_err_vs_oracle_fp32_own_branch": e_own, "grad_cos_min_vs_oracle_fp32": _cos_min(ours, g32),
            "n_grad_tensors": len(ours), "batch": B, "ok": ok}

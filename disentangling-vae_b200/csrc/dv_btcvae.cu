@@ -731,8 +731,11 @@ __global__ void __launch_bounds__(kF4Threads, 1)
 btcvae_fwd4_kernel(const float* __restrict__ z, const float* __restrict__ mu, const float* __restrict__ logvar, int ld,
                    int row_stride, int B, int D_rt, LogW lw, int R, int S, int NC, float4* __restrict__ pj_out,
                    float* __restrict__ rowstats, float* __restrict__ terms, float* __restrict__ blockpart,
-                   unsigned* __restrict__ counter) {
+                   unsigned* __restrict__ counter, float* __restrict__ dbg) {
   extern __shared__ float4 sp[];                               // [NC][DC]: {x'', hiv*log2e, mu, z} of this CTA's columns
+  // DV_BTCVAE_TIMING=1: block 0 leaves its phase boundaries (SM clocks since kernel entry) in the workspace header
+  const long long t_start = dbg ? clock64() : 0;
+#define DV_F4_MARK(slot) do { if (dbg && blockIdx.x == 0 && threadIdx.x == 0) dbg[slot] = (float)(clock64() - t_start); } while (0)
   __shared__ float s_red[kF4Warps][DC];
   __shared__ float s_ref[DC];                                  // r_cd (log2 units); -inf if the CTA owns no column
   __shared__ float s_rsum;                                     // sum_d r_cd
@@ -764,6 +767,7 @@ btcvae_fwd4_kernel(const float* __restrict__ z, const float* __restrict__ mu, co
     if (clus == 0) pj_out[(long long)k * B + j] = make_float4(cc, hiv, m, zz);   // the backward pass reads [D][B]
   }
   __syncthreads();
+  DV_F4_MARK(0);
   // ---- phase 2: r_cd = max_j (c_jd + w_j) over the CTA's columns (column 0: the larger of its two weights) ----
   {
     float bm[DC];
@@ -801,6 +805,7 @@ btcvae_fwd4_kernel(const float* __restrict__ z, const float* __restrict__ mu, co
     __syncthreads();
   }
 
+  DV_F4_MARK(1);
   // ---- phase 3: tasks = (group of 4 rows) x (column split); warp = 4 rows x 8 column lanes ----
   {
     const int G = (R + kRows - 1) / kRows;
@@ -873,6 +878,7 @@ btcvae_fwd4_kernel(const float* __restrict__ z, const float* __restrict__ mu, co
       }
     }
     __syncthreads();
+    DV_F4_MARK(2);
     // merge the column splits of every row in a fixed order -> this CTA's partial state
     for (int e = tid; e < R * (DC + 1); e += kF4Threads) {
       const int rr = e / (DC + 1), k = e - rr * (DC + 1);
@@ -889,6 +895,7 @@ btcvae_fwd4_kernel(const float* __restrict__ z, const float* __restrict__ mu, co
     }
   }
   cluster.sync();                                              // every CTA's s_sx / s_q / s_ref / s_rsum are final
+  DV_F4_MARK(3);
 
   // ---- phase 4: cluster rows round-robin over the 4 CTAs; one warp per row, lanes = latent dims ----
   for (int slot = warp; slot * kF4Clus + crank < R; slot += kF4Warps) {
@@ -966,6 +973,7 @@ btcvae_fwd4_kernel(const float* __restrict__ z, const float* __restrict__ mu, co
     }
   }
   __syncthreads();
+  DV_F4_MARK(4);
   if (tid == 0) {
     float a = 0.f, b = 0.f, c = 0.f;
     for (int slot = 0; slot * kF4Clus + crank < R; ++slot) { a += s_means[slot][0]; b += s_means[slot][1]; c += s_means[slot][2]; }
@@ -974,6 +982,8 @@ btcvae_fwd4_kernel(const float* __restrict__ z, const float* __restrict__ mu, co
     is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
   }
   cluster.sync();                                              // no CTA leaves while a peer may still read its shared memory
+  DV_F4_MARK(5);
+#undef DV_F4_MARK
   if (!is_last || warp != 0) return;
   __threadfence();
   float a = 0.f, b = 0.f, c = 0.f;
@@ -1197,6 +1207,9 @@ int dv_btcvae_fwd_rows(const float* z, const float* mu, const float* logvar, int
       attr[0].val.clusterDim.x = kF4Clus; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr; cfg.numAttrs = 1;
       cudaError_t err = cudaSuccess;
+      static int timing4 = -1;
+      if (timing4 < 0) { const char* e = getenv("DV_BTCVAE_TIMING"); timing4 = (e && e[0] == '1') ? 1 : 0; }
+      float* dbg = timing4 ? ws + 8 : nullptr;                 // header floats 8..13
 #define DV_F4_CALL(DC, EXACT)                                                                                                  \
   do {                                                                                                                         \
     static bool attr_set = false;                                                                                              \
@@ -1206,7 +1219,7 @@ int dv_btcvae_fwd_rows(const float* z, const float* mu, const float* logvar, int
       attr_set = true;                                                                                                         \
     }                                                                                                                          \
     err = cudaLaunchKernelEx(&cfg, btcvae_fwd4_kernel<DC, EXACT>, z, mu, logvar, ld, row_stride, B, D, lw, R, S, NC, pj,       \
-                             rowstats, terms, blockpart, counter);                                                             \
+                             rowstats, terms, blockpart, counter, dbg);                                                        \
   } while (0)
       if (D == 10) DV_F4_CALL(10, true);
       else if (D == 16) DV_F4_CALL(16, true);

@@ -582,6 +582,13 @@ int conv_wgrad32_tc(const float* lo, const float* hi, float* ws, int B, int H, i
 int conv_up32_tc(const float* lo, const float* wu_packed, const float* bias, const float* mask, float* hi,
                  int B, int H, int W, int act, cudaStream_t st);
 }  // namespace tc
+namespace img {       // dv_conv_img.cu: exact-fp32 CUDA-core kernels for the image-boundary layers (CH in {1,3})
+bool shape_ok(int B, int H, int W, int CH);
+int conv_down(const float* hi, const float* wd, const float* bias, const float* mask, float* lo, int B, int H, int W, int CH,
+              int act, cudaStream_t st, float* colsum_part, int* nparts, int max_parts);
+int conv_wgrad(const float* lo, const float* hi, float* ws, int B, int H, int W, int CH, int max_split, int* nsplit, cudaStream_t st);
+int conv_up(const float* lo, const float* wu, const float* bias, float* hi, int B, int H, int W, int CH, int act, cudaStream_t st);
+}  // namespace img
 namespace c2i {
 size_t packed_floats(int CH);
 int pack(const float* w, float* wp, int CH, cudaStream_t st);
@@ -596,6 +603,12 @@ constexpr int kPackTcSection = kTaps * 64 * 32;
 
 // DV_CONV_IMPL=ffma forces the CUDA-core kernels for the 32-channel layers (A/B testing)
 // DV_TC_DISABLE=down,up,wgrad switches individual tensor-core kernels off.
+// DV_IMG=0 switches the dv_conv_img.cu kernels off (A/B against the tcgen05 image-boundary kernels).
+static bool use_img() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DV_IMG"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
 static bool use_tc(const char* which = nullptr) {
   static int v = -1;
   static const char* dis = nullptr;
@@ -645,6 +658,8 @@ static int conv_down_impl(const float* hi, const float* w_packed, const float* b
   const long long groups = ((long long)B * H * W + kDownPxPerWarp - 1) / kDownPxPerWarp;
   if (CH == 32 && use_tc("down"))
     return tc::conv_down32_tc(hi, w_packed + kPackFfma, bias, mask, lo, B, H, W, act, st, colsum_part, nparts);
+  if (CH != 32 && use_img() && img::shape_ok(B, H, W, CH))
+    return img::conv_down(hi, w_packed, bias, mask, lo, B, H, W, CH, act, st, colsum_part, nparts, kCsBlocks);
   if (CH != 32 && use_tc("dsmall") && W <= 128 && 128 % W == 0)
     return tc::conv_down_small_tc(hi, w_packed + 2 * kLoCh * CH * kTaps, bias, mask, lo, B, H, W, CH, act, st, colsum_part, nparts);
   if (CH == 32) {
@@ -697,6 +712,8 @@ int dv_conv_up(const float* lo, const float* w_packed, const float* bias, const 
   if (act != DV_ACT_NONE && act != DV_ACT_RELU && act != DV_ACT_SIGMOID) return DV_ERR_BAD_ARG;
   if ((CH == 32) == (hi_nchw != 0)) return DV_ERR_BAD_SHAPE;
   const float* wu = w_packed + kLoCh * CH * kTaps;
+  if (CH != 32 && !mask && use_img() && img::shape_ok(B, H, W, CH))
+    return img::conv_up(lo, wu, bias, hi, B, H, W, CH, act, as_stream(stream));
   if (CH != 32 && !mask && use_tc("c2i") && c2i::shape_ok(B, H, W, CH))
     return c2i::conv_up(lo, w_packed + 2 * kLoCh * CH * kTaps + small_tc_floats(CH) + kPackUpSmall, bias, hi, B, H, W, CH, act,
                         as_stream(stream));
@@ -742,6 +759,15 @@ int dv_conv_wgrad(const float* lo, const float* hi, float* dw, float* dbias_lo, 
   const int ns = wgrad_nsplit(B, H, W, &chunk);
   float* ws = reinterpret_cast<float*>(workspace);
   cudaStream_t st = as_stream(stream);
+  if (CH != 32 && use_img() && img::shape_ok(B, H, W, CH)) {
+    int nsplit_img = 0;
+    const int max_split = (int)(dv_conv_wgrad_workspace_bytes(B, H, W, CH) / ((size_t)(kTaps * CH + 1) * kLoCh * sizeof(float)));
+    int rc = img::conv_wgrad(lo, hi, ws, B, H, W, CH, max_split, &nsplit_img, st);
+    if (rc != DV_OK) return rc;
+    const int n = (kTaps * CH + 1) * kLoCh;
+    conv_wgrad_reduce_kernel<<<(n + 31) / 32, 256, 0, st>>>(ws, dw, dbias_lo, CH, nsplit_img);
+    return check_launch();
+  }
   if ((CH == 32 && use_tc("wgrad")) || (CH != 32 && use_tc("wsmall"))) {
     int nsplit_tc = 0;
     int rc = CH == 32 ? tc::conv_wgrad32_tc(lo, hi, ws, B, H, W, &nsplit_tc, st)

@@ -1,0 +1,413 @@
+// Image-boundary layers of the Burgess networks on the CUDA cores: the first Conv2d of the encoder and the last
+// ConvTranspose2d of the decoder (encoders.py:54-55,72; decoders.py:58-59,82), whose "hi" side is the image itself
+// (CH = 1 or 3 channels, NCHW) and whose "lo" side is the 32-channel NHWC activation.
+//
+// With K = 16*CH these layers have ~1/30 of the arithmetic intensity of the 32->32 layers: 2*512*CH FLOP per lo
+// pixel against 128 B (lo) + 16*CH B (hi) of compulsory traffic, i.e. they are pure HBM streaming problems (151 MB per
+// launch at B = 1024, 1x64x64) whose whole arithmetic (1.07 GFLOP) fits in ~15 us of FP32 FMA issue.  The tcgen05
+// variants (dv_conv_tc.cu conv_*_small_tc_kernel, dv_conv_c2i.cu) pay for operand staging they cannot amortise
+// (im2col gather by 4 builder warps, hi/lo splitting, three tensor passes) and ran at 15-22 % of HBM bandwidth; these
+// kernels do exact fp32 FMAs from shared-memory tiles with register blocking instead:
+//
+//   down  (Conv2d fwd, ConvTranspose2d dgrad): thread = PX output pixels x 32 channels; the image tile (with halo and
+//         zero padding) in shared memory, 4x4 patches fetched as conflict-free LDS.64, weights as broadcast LDS.128
+//         (8 per tap for 64 FMAs); bias / ReLU / ReLU-mask epilogue, 128 B pixel lines stored as float4; optional
+//         channel sums of the stored tile (the previous ConvTranspose2d's bias gradient) by the 31-shuffle butterfly.
+//   up    (ConvTranspose2d fwd, NCHW + sigmoid): thread = a block of PY x 2 lo positions -> (2PY) x 4 output pixels per
+//         channel; the 32-channel lo tile (pixel pitch 36 floats: conflict-free LDS.128) with a 1-pixel halo in shared
+//         memory; per 4-channel chunk (PY+2) x 4 neighbour float4 serve 2*PY*16*4*CH FMAs; float4 row stores.
+//   wgrad (both weight gradients + the lo-side bias gradient): a "stream" of 16 threads owns the whole 32 x 16*CH
+//         output (thread = 4 lo channels x 8 taps x CH) in registers and walks over pixels (1 LDS.128 + 4*CH LDS.64 per
+//         32*CH FMAs); 16 streams per CTA, persistent CTAs, one ordered cross-stream reduction at the end, partials in
+//         the layout conv_wgrad_reduce_kernel already consumes (deterministic).
+//
+// Geometry handled here: square images of 32 or 64 pixels (lo W = H in {16, 32}), CH in {1, 3}; everything else keeps
+// the older paths.
+#include "dv_common.cuh"
+
+namespace dv {
+namespace img {
+
+constexpr int kThreads = 256;
+constexpr int kLoPitch = 36;                 // floats per lo pixel in shared memory (32 + 4: 16-byte groups rotate)
+
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#define DV_CS_STEP(BIT, HALF)                                                        \
+  {                                                                                  \
+    const bool up = (lane & BIT) != 0;                                               \
+    _Pragma("unroll") for (int i = 0; i < HALF; ++i) {                               \
+      const float send = up ? v[i] : v[i + HALF];                                    \
+      const float keep = up ? v[i + HALF] : v[i];                                    \
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, BIT);                         \
+    }                                                                                \
+  }
+  DV_CS_STEP(16, 16) DV_CS_STEP(8, 8) DV_CS_STEP(4, 4) DV_CS_STEP(2, 2) DV_CS_STEP(1, 1)
+#undef DV_CS_STEP
+  return v[0];
+}
+
+// hi tile: rows 2*i0-1 .. 2*i0+2*TR of image b, columns -1 .. 2W (in-tile column = x + 1), zero outside the image
+template <int CH, int W, int TR>
+__device__ __forceinline__ void load_hi_tile(float* __restrict__ s_hi, const float* __restrict__ hi, int b, int i0, int H) {
+  constexpr int IN_ROWS = 2 * TR + 2, COLS = 2 * W + 2, PITCH = 2 * W + 4;
+  const int HH = 2 * H, WW = 2 * W;
+  for (int e = threadIdx.x; e < CH * IN_ROWS * COLS; e += kThreads) {
+    const int xx = e % COLS, rr = (e / COLS) % IN_ROWS, c = e / (COLS * IN_ROWS);
+    const int iy = 2 * i0 - 1 + rr, ix = xx - 1;
+    float v = 0.f;
+    if ((unsigned)iy < (unsigned)HH && (unsigned)ix < (unsigned)WW)
+      v = __ldg(hi + ((long long)(b * CH + c) * HH + iy) * WW + ix);
+    s_hi[(c * IN_ROWS + rr) * PITCH + xx] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// down
+// ------------------------------------------------------------------------------------------------------------
+template <int CH, int W>
+__global__ void __launch_bounds__(kThreads, 2)
+img_down_kernel(const float* __restrict__ hi, const float* __restrict__ wd, const float* __restrict__ bias,
+                const float* __restrict__ mask, float* __restrict__ lo, int B, int H, int act,
+                float* __restrict__ colsum_part) {
+  constexpr int PX = (W == 32) ? 2 : 1;
+  constexpr int RPT = kThreads / W;            // thread rows per tile
+  constexpr int TR = RPT * PX;                 // output rows per tile (16)
+  constexpr int IN_ROWS = 2 * TR + 2, PITCH = 2 * W + 4;
+  __shared__ __align__(16) float s_w[kTaps * CH * kLoCh];
+  __shared__ __align__(16) float s_hi[CH * IN_ROWS * PITCH];
+  __shared__ __align__(16) float s_bias[kLoCh];
+  __shared__ float s_cs[kThreads / 32][kLoCh];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < kTaps * CH * kLoCh; i += kThreads) s_w[i] = wd[i];
+  if (tid < kLoCh) s_bias[tid] = bias ? bias[tid] : 0.f;
+  const int c_out = tid % W, r_thr = tid / W;
+  const int tiles_per_img = H / TR;
+  const int num_tiles = B * tiles_per_img;
+  float csum = 0.f;
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int b = tile / tiles_per_img, i0 = (tile % tiles_per_img) * TR;
+    __syncthreads();                                           // previous tile fully consumed (and weights staged)
+    load_hi_tile<CH, W, TR>(s_hi, hi, b, i0, H);
+    __syncthreads();
+    float acc[PX][kLoCh];
+#pragma unroll
+    for (int q = 0; q < PX; ++q)
+#pragma unroll
+      for (int k = 0; k < kLoCh; ++k) acc[q][k] = 0.f;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      float pt[PX][4][4];
+#pragma unroll
+      for (int q = 0; q < PX; ++q)
+#pragma unroll
+        for (int kh = 0; kh < 4; ++kh) {
+          const float* row = s_hi + (c * IN_ROWS + 2 * (r_thr + RPT * q) + kh) * PITCH + 2 * c_out;
+          const float2 a = *reinterpret_cast<const float2*>(row), d = *reinterpret_cast<const float2*>(row + 2);
+          pt[q][kh][0] = a.x; pt[q][kh][1] = a.y; pt[q][kh][2] = d.x; pt[q][kh][3] = d.y;
+        }
+#pragma unroll
+      for (int tap = 0; tap < kTaps; ++tap) {
+        const float4* wv = reinterpret_cast<const float4*>(s_w + (tap * CH + c) * kLoCh);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 w4 = wv[j];
+#pragma unroll
+          for (int q = 0; q < PX; ++q) {
+            const float x = pt[q][tap >> 2][tap & 3];
+            acc[q][4 * j + 0] = fmaf(x, w4.x, acc[q][4 * j + 0]);
+            acc[q][4 * j + 1] = fmaf(x, w4.y, acc[q][4 * j + 1]);
+            acc[q][4 * j + 2] = fmaf(x, w4.z, acc[q][4 * j + 2]);
+            acc[q][4 * j + 3] = fmaf(x, w4.w, acc[q][4 * j + 3]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < PX; ++q) {
+      const long long p = ((long long)b * H + i0 + r_thr + RPT * q) * W + c_out;
+      float* dst = lo + p * kLoCh;
+      const float* mk = mask ? mask + p * kLoCh : nullptr;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 b4 = *reinterpret_cast<const float4*>(s_bias + 4 * j);
+        float v0 = acc[q][4 * j] + b4.x, v1 = acc[q][4 * j + 1] + b4.y, v2 = acc[q][4 * j + 2] + b4.z, v3 = acc[q][4 * j + 3] + b4.w;
+        if (act == DV_ACT_RELU) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
+        if (mk) {
+          const float4 m4 = ldg4(mk + 4 * j);
+          v0 = m4.x > 0.f ? v0 : 0.f; v1 = m4.y > 0.f ? v1 : 0.f; v2 = m4.z > 0.f ? v2 : 0.f; v3 = m4.w > 0.f ? v3 : 0.f;
+        }
+        *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(v0, v1, v2, v3);
+        acc[q][4 * j] = v0; acc[q][4 * j + 1] = v1; acc[q][4 * j + 2] = v2; acc[q][4 * j + 3] = v3;
+      }
+      if (colsum_part) csum += warp_colsum32(acc[q], lane);    // lane l: channel l summed over the warp's 32 pixels
+    }
+  }
+  if (colsum_part) {
+    s_cs[warp][lane] = csum;
+    __syncthreads();
+    if (warp == 0) {
+      float t = 0.f;
+#pragma unroll
+      for (int w2 = 0; w2 < kThreads / 32; ++w2) t += s_cs[w2][lane];
+      colsum_part[blockIdx.x * kLoCh + lane] = t;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// wgrad:  ws[block][k][cl], k = tap*CH + c (k == 16*CH: the lo-side bias gradient)
+// ------------------------------------------------------------------------------------------------------------
+template <int CH, int W>
+__global__ void __launch_bounds__(kThreads, (CH == 1) ? 2 : 1)
+img_wgrad_kernel(const float* __restrict__ lo, const float* __restrict__ hi, float* __restrict__ ws, int B, int H) {
+  constexpr int TR = (W == 32) ? 16 : 16;
+  constexpr int IN_ROWS = 2 * TR + 2, PITCH = 2 * W + 4;
+  constexpr int NPX = TR * W;                                  // lo pixels per tile
+  constexpr int NSTREAM = kThreads / 16;
+  extern __shared__ __align__(16) float smem[];
+  float* s_lo = smem;                                          // [NPX][kLoPitch]
+  float* s_hi = smem + NPX * kLoPitch;                         // [CH][IN_ROWS][PITCH]
+  const int tid = threadIdx.x;
+  const int stream = tid >> 4, st = tid & 15;
+  const int cl4 = st & 7, half = st >> 3;                      // 4 lo channels x taps of rows {2*half, 2*half+1}
+  float acc[CH][8][4];
+  float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int c = 0; c < CH; ++c)
+#pragma unroll
+    for (int t = 0; t < 8; ++t)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[c][t][e] = 0.f;
+  const int tiles_per_img = H / TR;
+  const int num_tiles = B * tiles_per_img;
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int b = tile / tiles_per_img, i0 = (tile % tiles_per_img) * TR;
+    __syncthreads();
+    load_hi_tile<CH, W, TR>(s_hi, hi, b, i0, H);
+    {
+      const float4* src = reinterpret_cast<const float4*>(lo + ((long long)b * H + i0) * W * kLoCh);
+      for (int e = tid; e < NPX * 8; e += kThreads) {
+        const int px = e >> 3, j = e & 7;
+        *reinterpret_cast<float4*>(s_lo + px * kLoPitch + 4 * j) = __ldg(src + e);
+      }
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int px = stream; px < NPX; px += NSTREAM) {
+      const int r = px / W, cc = px % W;
+      const float4 l4 = *reinterpret_cast<const float4*>(s_lo + px * kLoPitch + 4 * cl4);
+      if (half == 0) { bsum[0] += l4.x; bsum[1] += l4.y; bsum[2] += l4.z; bsum[3] += l4.w; }
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+          const float* row = s_hi + (c * IN_ROWS + 2 * r + 2 * half + rr) * PITCH + 2 * cc;
+          const float2 a = *reinterpret_cast<const float2*>(row), d = *reinterpret_cast<const float2*>(row + 2);
+          const float xv[4] = {a.x, a.y, d.x, d.y};
+#pragma unroll
+          for (int kw = 0; kw < 4; ++kw) {
+            acc[c][rr * 4 + kw][0] = fmaf(xv[kw], l4.x, acc[c][rr * 4 + kw][0]);
+            acc[c][rr * 4 + kw][1] = fmaf(xv[kw], l4.y, acc[c][rr * 4 + kw][1]);
+            acc[c][rr * 4 + kw][2] = fmaf(xv[kw], l4.z, acc[c][rr * 4 + kw][2]);
+            acc[c][rr * 4 + kw][3] = fmaf(xv[kw], l4.w, acc[c][rr * 4 + kw][3]);
+          }
+        }
+      }
+    }
+  }
+  // ordered reduction over the 16 streams through shared memory (the tiles are free now)
+  __syncthreads();
+  constexpr int K = kTaps * CH;
+  float* red = smem;                                           // [NSTREAM][(K + 1) * 32]
+  {
+    float* mine = red + stream * (K + 1) * kLoCh;
+#pragma unroll
+    for (int c = 0; c < CH; ++c)
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const int tap = (2 * half + (t >> 2)) * 4 + (t & 3);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) mine[(tap * CH + c) * kLoCh + 4 * cl4 + e] = acc[c][t][e];
+      }
+    if (half == 0) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) mine[K * kLoCh + 4 * cl4 + e] = bsum[e];
+    }
+  }
+  __syncthreads();
+  float* out = ws + (long long)blockIdx.x * (K + 1) * kLoCh;
+  for (int idx = tid; idx < (K + 1) * kLoCh; idx += kThreads) {
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < NSTREAM; ++q) s += red[q * (K + 1) * kLoCh + idx];
+    out[idx] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// up: hi[b][c][2m+py][2n+px] = bias[c] + sum_{cl} sum_{(dm, kh) valid for py} sum_{(dn, kw) valid for px}
+//                                        lo[b][m+dm][n+dn][cl] * w[cl][c][kh][kw]
+//     py = 0: (dm, kh) in {(0,1), (-1,3)};  py = 1: (dm, kh) in {(+1,0), (0,2)}   (same for px / dn / kw)
+// weights wu[(tap*CH + c)*32 + cl] (the "up" section of conv_pack_kernel for CH < 32)
+// ------------------------------------------------------------------------------------------------------------
+template <int CH, int W>
+__global__ void __launch_bounds__(128, 2)
+img_up_kernel(const float* __restrict__ lo, const float* __restrict__ wu, const float* __restrict__ bias,
+              float* __restrict__ hi, int B, int H, int act) {
+  constexpr int NT = 128;
+  constexpr int PY = 2;                                        // lo rows per thread
+  constexpr int TCOLS = W / 2;                                 // thread columns (2 lo positions each)
+  constexpr int TROWS = NT / TCOLS;                            // thread rows
+  constexpr int TR = TROWS * PY;                               // lo rows per tile: 16 (W = 32), 32 -> capped below (W = 16)
+  constexpr int SW = W + 2;                                    // tile width incl. halo
+  extern __shared__ __align__(16) float smem[];
+  // [(TR + 2)][SW][32]; the 16-byte chunk j of the pixel in tile column xx sits at chunk j ^ ((xx >> 1) & 7): a thread
+  // reads columns 2*tn .. 2*tn+3, so the 8 lanes of a quarter-warp hit 8 different 16-byte bank groups (pitch padding
+  // cannot do that for a 2-pixel lane stride)
+  float* s_lo = smem;
+  float* s_w = smem + (TR + 2) * SW * kLoCh;                   // [16*CH][32]
+  const int tid = threadIdx.x;
+  for (int i = tid; i < kTaps * CH * kLoCh; i += NT) s_w[i] = wu[i];
+  const int tn = tid % TCOLS, tm = tid / TCOLS;
+  const int tiles_per_img = (H + TR - 1) / TR;
+  const int num_tiles = B * tiles_per_img;
+  const int HH = 2 * H, WW = 2 * W;
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int b = tile / tiles_per_img, m0 = (tile % tiles_per_img) * TR;
+    __syncthreads();
+    // lo rows m0-1 .. m0+TR, columns -1 .. W (zero outside the image)
+    for (int e = tid; e < (TR + 2) * SW * 8; e += NT) {
+      const int j = e & 7, xx = (e >> 3) % SW, rr = (e >> 3) / SW;
+      const int m = m0 - 1 + rr, n = xx - 1;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if ((unsigned)m < (unsigned)H && (unsigned)n < (unsigned)W)
+        v = __ldg(reinterpret_cast<const float4*>(lo + (((long long)b * H + m) * W + n) * kLoCh) + j);
+      *reinterpret_cast<float4*>(s_lo + (rr * SW + xx) * kLoCh + 4 * (j ^ ((xx >> 1) & 7))) = v;
+    }
+    __syncthreads();
+    if (m0 + PY * tm < H) {
+      float out[CH][2 * PY][4];
+#pragma unroll
+      for (int c = 0; c < CH; ++c)
+#pragma unroll
+        for (int y = 0; y < 2 * PY; ++y)
+#pragma unroll
+          for (int x = 0; x < 4; ++x) out[c][y][x] = 0.f;
+      // neighbourhood rows PY*tm .. PY*tm + PY + 1 (tile rows; +1 halo offset folded in), columns 2*tn .. 2*tn + 3
+      const float* base = s_lo + ((PY * tm) * SW + 2 * tn) * kLoCh;
+#pragma unroll 1
+      for (int j = 0; j < 8; ++j) {                            // 4-channel chunk of the lo side
+        float4 nb[PY + 2][4];
+#pragma unroll
+        for (int rr = 0; rr < PY + 2; ++rr)
+#pragma unroll
+          for (int xx = 0; xx < 4; ++xx)
+            nb[rr][xx] = *reinterpret_cast<const float4*>(base + (rr * SW + xx) * kLoCh + 4 * (j ^ ((tn + (xx >> 1)) & 7)));
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+#pragma unroll
+          for (int tap = 0; tap < kTaps; ++tap) {
+            const int kh = tap >> 2, kw = tap & 3;
+            const float4 w4 = *reinterpret_cast<const float4*>(s_w + (tap * CH + c) * kLoCh + 4 * j);
+            // kh -> (py, dm): kh=1:(0,0) kh=3:(0,-1) kh=0:(1,+1) kh=2:(1,0); tile row of lo row m is (m - m0 + 1)
+            const int py = (kh & 1) ? 0 : 1, dm = (kh == 1 || kh == 2) ? 0 : ((kh == 3) ? -1 : 1);
+            const int px = (kw & 1) ? 0 : 1, dn = (kw == 1 || kw == 2) ? 0 : ((kw == 3) ? -1 : 1);
+#pragma unroll
+            for (int a = 0; a < PY; ++a)
+#pragma unroll
+              for (int d = 0; d < 2; ++d) {
+                const float4 v = nb[a + 1 + dm][d + 1 + dn];
+                out[c][2 * a + py][2 * d + px] += (v.x * w4.x + v.y * w4.y) + (v.z * w4.z + v.w * w4.w);
+              }
+          }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        const float bv = bias ? __ldg(bias + c) : 0.f;
+#pragma unroll
+        for (int y = 0; y < 2 * PY; ++y) {
+          const int oy = 2 * (m0 + PY * tm) + y;
+          if (oy < HH) {
+            float v[4];
+#pragma unroll
+            for (int x = 0; x < 4; ++x) v[x] = apply_act(out[c][y][x] + bv, act, 0.f);
+            *reinterpret_cast<float4*>(hi + ((long long)(b * CH + c) * HH + oy) * WW + 4 * tn) = make_float4(v[0], v[1], v[2], v[3]);
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int W> constexpr int up_tile_rows() { return (128 / (W / 2)) * 2; }
+template <int CH, int W> constexpr size_t up_smem() {
+  return (size_t)((up_tile_rows<W>() + 2) * (W + 2) * kLoCh + kTaps * CH * kLoCh) * sizeof(float);
+}
+template <int CH, int W> constexpr size_t wgrad_smem() {
+  constexpr size_t tiles = (size_t)16 * W * kLoPitch + (size_t)CH * 34 * (2 * W + 4);
+  constexpr size_t red = (size_t)(kThreads / 16) * (kTaps * CH + 1) * kLoCh;
+  return (tiles > red ? tiles : red) * sizeof(float);
+}
+
+bool shape_ok(int B, int H, int W, int CH) {
+  return B > 0 && H == W && (W == 16 || W == 32) && (CH == 1 || CH == 3);
+}
+
+template <typename K>
+static bool set_smem(K kernel, size_t bytes) {
+  return bytes <= 48 * 1024 || cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) == cudaSuccess;
+}
+
+int conv_down(const float* hi, const float* wd, const float* bias, const float* mask, float* lo, int B, int H, int W, int CH,
+              int act, cudaStream_t st, float* colsum_part, int* nparts, int max_parts) {
+  const int tiles = B * (H / 16);
+  int grid = tiles < 2 * kNumSMs ? tiles : 2 * kNumSMs;
+  if (colsum_part && grid > max_parts) grid = max_parts;
+#define DV_IMG_DOWN(CHV, WV) img_down_kernel<CHV, WV><<<grid, kThreads, 0, st>>>(hi, wd, bias, mask, lo, B, H, act, colsum_part)
+  if (CH == 1 && W == 32) DV_IMG_DOWN(1, 32);
+  else if (CH == 3 && W == 32) DV_IMG_DOWN(3, 32);
+  else if (CH == 1 && W == 16) DV_IMG_DOWN(1, 16);
+  else DV_IMG_DOWN(3, 16);
+#undef DV_IMG_DOWN
+  *nparts = colsum_part ? grid : 0;
+  return check_launch();
+}
+
+int conv_wgrad(const float* lo, const float* hi, float* ws, int B, int H, int W, int CH, int max_split, int* nsplit, cudaStream_t st) {
+  const int tiles = B * (H / 16);
+  const int per_sm = (CH == 1) ? 2 : 1;
+  int grid = tiles < per_sm * kNumSMs ? tiles : per_sm * kNumSMs;
+  if (grid > max_split) grid = max_split;
+#define DV_IMG_WG(CHV, WV)                                                                     \
+  do {                                                                                         \
+    if (!set_smem(img_wgrad_kernel<CHV, WV>, wgrad_smem<CHV, WV>())) return DV_ERR_CUDA;       \
+    img_wgrad_kernel<CHV, WV><<<grid, kThreads, wgrad_smem<CHV, WV>(), st>>>(lo, hi, ws, B, H); \
+  } while (0)
+  if (CH == 1 && W == 32) DV_IMG_WG(1, 32);
+  else if (CH == 3 && W == 32) DV_IMG_WG(3, 32);
+  else if (CH == 1 && W == 16) DV_IMG_WG(1, 16);
+  else DV_IMG_WG(3, 16);
+#undef DV_IMG_WG
+  *nsplit = grid;
+  return check_launch();
+}
+
+int conv_up(const float* lo, const float* wu, const float* bias, float* hi, int B, int H, int W, int CH, int act, cudaStream_t st) {
+#define DV_IMG_UP(CHV, WV)                                                                     \
+  do {                                                                                         \
+    const int tiles = B * ((H + up_tile_rows<WV>() - 1) / up_tile_rows<WV>());                \
+    const int grid = tiles < 2 * kNumSMs ? tiles : 2 * kNumSMs;                                \
+    if (!set_smem(img_up_kernel<CHV, WV>, up_smem<CHV, WV>())) return DV_ERR_CUDA;             \
+    img_up_kernel<CHV, WV><<<grid, 128, up_smem<CHV, WV>(), st>>>(lo, wu, bias, hi, B, H, act); \
+  } while (0)
+  if (CH == 1 && W == 32) DV_IMG_UP(1, 32);
+  else if (CH == 3 && W == 32) DV_IMG_UP(3, 32);
+  else if (CH == 1 && W == 16) DV_IMG_UP(1, 16);
+  else DV_IMG_UP(3, 16);
+#undef DV_IMG_UP
+  return check_launch();
+}
+
+}  // namespace img
+}  // namespace dv

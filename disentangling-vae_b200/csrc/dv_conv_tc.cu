@@ -108,6 +108,8 @@ struct DownGeom {
   int prefetch;         // L2-prefetch the next tile's hi rows (DV_TC_PREFETCH=0 switches it off)
   int pipe;             // split warps overlap the TMEM stores of one tile with the loads/split of their next tile
   int debug;            // DV_TC_DEBUG (timing experiments only, results are WRONG): 2 = load 4 of the 16 tap tiles
+  int rawhi;            // down32_ts: the hi operand is the RAW TMA tile in shared memory (SS MMA; kind::tf32 reads only the
+                        // upper 19 bits = the hi/lo truncation), the split warps produce only the lo plane (DV_TC_RAWHI=0: off)
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -631,9 +633,9 @@ constexpr int kTsSmemBytes = kBBytes + kTsRawStages * kATile + 1024 + 512;
 static_assert(sizeof(TsBarriers) <= 512, "barrier block too large");
 static_assert(kTsSmemBytes <= 232448, "smem");
 
-__device__ __forceinline__ void ts_init(TsBarriers* bars, const float* bias, int warp) {
+__device__ __forceinline__ void ts_init(TsBarriers* bars, const float* bias, int warp, int raw_readers = 128) {
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kTsRawStages; ++s) { mbar_init(&bars->raw_full[s], 1); mbar_init(&bars->raw_empty[s], 128); }
+    for (int s = 0; s < kTsRawStages; ++s) { mbar_init(&bars->raw_full[s], 1); mbar_init(&bars->raw_empty[s], raw_readers); }
     for (int s = 0; s < kTsAStages; ++s) { mbar_init(&bars->a_ready[s], 128); mbar_init(&bars->a_empty[s], 1); }
     mbar_init(&bars->b_full, 1);
     for (int a = 0; a < 2; ++a) { mbar_init(&bars->acc_full[a], 1); mbar_init(&bars->acc_empty[a], 128); }
@@ -667,6 +669,22 @@ __device__ __forceinline__ void ts_split_tile(const uint8_t* raw, uint32_t tmem_
   tmem_st_wait();
 }
 
+// rawhi variant: only the residual plane goes to TMEM (the MMA reads the hi part straight from the raw tile)
+__device__ __forceinline__ void ts_split_tile_lo(const uint8_t* raw, uint32_t tmem_base, int as, int q, int lane) {
+  const int row = q * 32 + lane;
+  uint32_t l[32];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const uint4 v = lds128(raw + row * 128 + ((c ^ (row & 7)) << 4));
+    const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      l[c * 4 + e] = __float_as_uint(__uint_as_float(vv[e]) - __uint_as_float(vv[e] & kHiMask));
+  }
+  tmem_st_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + kTsACol0 + as * 64 + 32, l);
+  tmem_st_wait();
+}
+
 __global__ void __launch_bounds__(kTsThreads, 1)
 conv_down32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                       const float* __restrict__ bias, const float* __restrict__ mask, float* __restrict__ lo,
@@ -677,7 +695,7 @@ conv_down32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   uint8_t* Raw = smem + kBBytes;
   TsBarriers* bars = reinterpret_cast<TsBarriers*>(Raw + kTsRawStages * kATile);
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform role index
-  ts_init(bars, bias, warp);
+  ts_init(bars, bias, warp, g.rawhi ? 129 : 128);           // rawhi: the MMA's commit is a reader of the raw stage too
   // All 512 columns are ours (1 CTA/SM), so the allocation starts at column 0.  Using the literal keeps every
   // tensor-memory address a compile-time/warp-uniform value (no per-MMA register -> uniform-register moves).
   if (bars->tmem_base != 0u) __trap();
@@ -714,20 +732,38 @@ conv_down32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     constexpr uint32_t idesc64 = umma_idesc_tf32(128, 64), idesc32 = umma_idesc_tf32(128, 32);
     mbar_wait(&bars->b_full, 0);
     int as = 0; uint32_t aphase = 0; int acc = 0; uint32_t acc_phase = 0;
+    int rs = 0; uint32_t rphase = 0;
     for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
       mbar_wait(&bars->acc_empty[acc], acc_phase ^ 1);
       tc_fence_after_sync();
       const uint32_t d_tmem = tmem_base + acc * 128;
       for (int tap = 0; tap < kTaps; ++tap) {
-        mbar_wait(&bars->a_ready[as], aphase);
-        tc_fence_after_sync();
         const uint32_t a_hi = tmem_base + kTsACol0 + as * 64, a_lo = a_hi + 32;
         const uint64_t b_d = umma_desc_sw128_kmajor(smem_u32(Bs + tap * kBTap));
+        if (g.rawhi) {
+          // a_hi * [b_hi | b_lo] straight from the TMA tile: needs only the load, not the split warps
+          mbar_wait(&bars->raw_full[rs], rphase);
+          tc_fence_after_sync();
+          const uint64_t a_d = umma_desc_sw128_kmajor(smem_u32(Raw + rs * kATile));
 #pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4) {
-          const uint32_t d = d_tmem + (k4 & 1) * 64;          // two accumulation chains, see the SS kernel
-          umma_tf32_ts_1t(d, a_hi + 8 * k4, b_d + 2 * k4, idesc64, (tap | (k4 >> 1)) != 0);
-          umma_tf32_ts_1t(d, a_lo + 8 * k4, b_d + 2 * k4, idesc32, 1);
+          for (int k4 = 0; k4 < 4; ++k4)
+            umma_tf32_ss_1t(d_tmem + (k4 & 1) * 64, a_d + 2 * k4, b_d + 2 * k4, idesc64, (tap | (k4 >> 1)) != 0);
+          mbar_wait(&bars->a_ready[as], aphase);              // residual plane of the same tile (split warps -> TMEM)
+          tc_fence_after_sync();
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4)
+            umma_tf32_ts_1t(d_tmem + (k4 & 1) * 64, a_lo + 8 * k4, b_d + 2 * k4, idesc32, 1);
+          umma_commit_1t(&bars->raw_empty[rs]);               // the raw stage is free once these MMAs have read it
+          if (++rs == kTsRawStages) { rs = 0; rphase ^= 1; }
+        } else {
+          mbar_wait(&bars->a_ready[as], aphase);
+          tc_fence_after_sync();
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const uint32_t d = d_tmem + (k4 & 1) * 64;        // two accumulation chains, see the SS kernel
+            umma_tf32_ts_1t(d, a_hi + 8 * k4, b_d + 2 * k4, idesc64, (tap | (k4 >> 1)) != 0);
+            umma_tf32_ts_1t(d, a_lo + 8 * k4, b_d + 2 * k4, idesc32, 1);
+          }
         }
         umma_commit_1t(&bars->a_empty[as]);
         if (++as == kTsAStages) { as = 0; aphase ^= 1; }
@@ -803,7 +839,8 @@ conv_down32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
           mbar_wait(&bars->raw_full[stage], (n / kTsRawStages) & 1u);
           mbar_wait(&bars->a_empty[as], ((n / kTsAStages) & 1u) ^ 1u);
           tc_fence_after_sync();
-          ts_split_tile(Raw + stage * kATile, tmem_base, as, q, lane);
+          if (g.rawhi) ts_split_tile_lo(Raw + stage * kATile, tmem_base, as, q, lane);
+          else ts_split_tile(Raw + stage * kATile, tmem_base, as, q, lane);
           mbar_arrive(&bars->raw_empty[stage]);
           tc_fence_before_sync();
           mbar_arrive(&bars->a_ready[as]);
@@ -842,7 +879,7 @@ conv_down32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
           mbar_wait(&bars->a_empty[as], ((n / kTsAStages) & 1u) ^ 1u);
           tc_fence_after_sync();
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + kTsACol0 + as * 64;
-          tmem_st_32x32b_x32(taddr, h);
+          if (!g.rawhi) tmem_st_32x32b_x32(taddr, h);
           tmem_st_32x32b_x32(taddr + 32, l);
           prev_stage = stage; prev_as = as;
         }

@@ -59,6 +59,11 @@ entropy_partial_kernel(const float* __restrict__ zs, const float* __restrict__ m
       sp[threadIdx.x] = make_float4(-0.5f * (kLog2Pi + lv) * kLog2e, 0.5f * expf(-lv) * kLog2e, mu, 0.f);
     }
     __syncthreads();
+    // two-level accumulation: an online (max, sum) over THIS chunk, merged into the running state afterwards -- a
+    // single running fp32 sum over 10^5..10^6 terms loses ~sqrt(n)*eps (1e-4 in log q at dSprites size)
+    float mc[kSPT], ac[kSPT];
+#pragma unroll
+    for (int u = 0; u < kSPT; ++u) { mc[u] = -INFINITY; ac[u] = 0.f; }
 #pragma unroll 4
     for (int k = 0; k < cnt; ++k) {
       const float4 p = sp[k];
@@ -66,11 +71,20 @@ entropy_partial_kernel(const float* __restrict__ zs, const float* __restrict__ m
       for (int u = 0; u < kSPT; ++u) {
         const float t = zv[u] - p.z;
         const float v = fmaf(-p.y, t * t, p.x);
-        const float dd = v - m[u];
+        const float dd = v - mc[u];
         const float e = ex2a(-fabsf(dd));                      // first element: dd = +inf -> e = 0 -> a = 1, m = v
         const bool up = dd > 0.f;
-        a[u] = up ? fmaf(a[u], e, 1.f) : a[u] + e;
-        m[u] = up ? v : m[u];
+        ac[u] = up ? fmaf(ac[u], e, 1.f) : ac[u] + e;
+        mc[u] = up ? v : mc[u];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kSPT; ++u) {
+      if (a[u] == 0.f) { m[u] = mc[u]; a[u] = ac[u]; }
+      else {
+        const float nm = fmaxf(m[u], mc[u]);
+        a[u] = a[u] * exp2f(m[u] - nm) + ac[u] * exp2f(mc[u] - nm);
+        m[u] = nm;
       }
     }
   }

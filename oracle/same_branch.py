@@ -56,7 +56,7 @@ def _to_oracle_names(trace, params):
     return masks
 
 
-def same_branch_reference(trace, params32, run_oracle, disc32=None):
+def same_branch_reference(trace, params32, run_oracle, disc32=None, run_oracle32=None):
     """`run_oracle(p, dp)` evaluates the oracle's loss in fp64 on leaf params `p` (and discriminator `dp`, or None),
     runs its backward pass(es) and returns the loss.
     -> dict(loss, grads {name: fp64 grad}, flips, units, flip_max_rel = largest |pre-activation| among the units where
@@ -88,7 +88,23 @@ def same_branch_reference(trace, params32, run_oracle, disc32=None):
     grads = OrderedDict((k, v.grad) for k, v in p.items())
     if dp is not None:
         grads.update(("disc." + k, v.grad) for k, v in dp.items())
-    return dict(loss=float(loss), grads=grads, flips=flips, units=units, flip_max_rel=worst)
+    out = dict(loss=float(loss), grads=grads, flips=flips, units=units, flip_max_rel=worst)
+    if run_oracle32 is not None:
+        # calibration: the CPU fp32 oracle on the SAME branch -- what plain fp32 arithmetic (MKL/oneDNN) loses against
+        # fp64 when no unit flips; the CUDA path (error-compensated 3xTF32, ~5x the rounding of an fp32 FMA chain per
+        # kernel) is judged relative to it
+        O._ACT = dict(record=None, masks=masks, calls={})
+        try:
+            q = O.make_leaf_params(OrderedDict((k, v.detach().cpu().float()) for k, v in params32.items()))
+            dq = O.make_leaf_params(OrderedDict((k, v.detach().cpu().float()) for k, v in disc32.items())) if disc32 is not None else None
+            run_oracle32(q, dq)
+        finally:
+            O._ACT = None
+        g32 = OrderedDict((k, v.grad) for k, v in q.items())
+        if dq is not None:
+            g32.update(("disc." + k, v.grad) for k, v in dq.items())
+        out["cpu_fp32_same_branch_err"], out["cpu_fp32_worst_tensor"] = grad_errors(g32, grads)
+    return out
 
 
 def grad_errors(ours, ref):

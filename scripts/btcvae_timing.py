@@ -1,4 +1,5 @@
-"""Phase boundaries of btcvae_fwd3_kernel (block 0, SM clocks) warm and after an L2 flush.  DV_BTCVAE_TIMING=1."""
+"""Phase boundaries of the single-launch beta-TCVAE forward kernel (block 0, SM clocks) warm and after an L2 flush.
+DV_BTCVAE_TIMING=1; DV_BTCVAE_V4=0 times the previous generation (fwd3)."""
 import os, sys, torch
 os.environ["DV_BTCVAE_TIMING"] = "1"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -21,11 +22,13 @@ def run(cold):
     e0.record()
     N.call("dv_btcvae_fwd", ptr(z), ptr(mu), ptr(lv), 1, D, B, D, 737280, 1, ptr(rs), ptr(terms), ptr(ws), stream())
     e1.record(); torch.cuda.synchronize()
-    return e0.elapsed_time(e1) * 1e3, ws[8:13].tolist()
+    return e0.elapsed_time(e1) * 1e3, ws[8:14].tolist()
 for i in range(5): run(False)
 for cold in (False, True):
     rows = [run(cold) for _ in range(9)]
     rows.sort(key=lambda r: r[0])
     us, marks = rows[len(rows) // 2]
-    print("cold" if cold else "warm", "event us %.2f" % us, "marks (clk): stage %d | bounds+fold %d | sweep %d | row stats %d | block sum %d"
-          % tuple(marks), " => us @1.9GHz:", [round(m / 1900, 2) for m in marks])
+    v4 = os.environ.get("DV_BTCVAE_V4", "1") != "0"
+    names = ("stage | fold | sweep | cluster.sync | finalise | exit sync" if v4 else "stage | bounds+fold | sweep | row stats | block sum | -")
+    print("cold" if cold else "warm", "event us %.2f" % us, "marks (clk since entry): %s =" % names, [int(m) for m in marks],
+          " => us @1.9GHz:", [round(m / 1900, 2) for m in marks])

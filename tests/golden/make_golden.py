@@ -213,15 +213,30 @@ def gen_train_steps():
         model.train()
         steps = []
         torch.manual_seed(SEED + 5)               # noise stream of the training iterations
+        names = {id(p): k for k, p in model.named_parameters()}
+        opt_state_step1 = None
         for x in xs:
             storer = defaultdict(list)
             lv = trainer._train_iteration(x, storer)
             steps.append(dict(loss=lv, storer={k: list(v) for k, v in storer.items()}))
+            if opt_state_step1 is None:
+                # after the FIRST step exp_avg = (1 - beta1) * grad and exp_avg_sq = (1 - beta2) * grad^2 exactly: the
+                # gradient seen THROUGH the optimizer.  (Later steps depend on which way Adam moved the entries whose
+                # first gradient is numerically zero -- +-lr regardless of magnitude -- and are only loosely comparable.)
+                opt_state_step1 = {names[id(p)]: dict(exp_avg=tensor_digest(st["exp_avg"]),
+                                                      exp_avg_sq=tensor_digest(st["exp_avg_sq"]))
+                                   for p, st in optimizer.state.items()}
+                if loss_name == "factor":
+                    dn = {id(p): k for k, p in loss_f.discriminator.named_parameters()}
+                    disc_step1 = {dn[id(p)]: dict(exp_avg=tensor_digest(st["exp_avg"]), exp_avg_sq=tensor_digest(st["exp_avg_sq"]))
+                                  for p, st in loss_f.optimizer_d.state.items()}
         rec = dict(img_size=img_size, batch=b, n_data=n_data, over=over, xs_digest=[tensor_digest(x) for x in xs],
                    steps=steps, params=state_digest(model.state_dict()))
         # Adam moments after the 3 steps: linear / quadratic in the gradients, so -- unlike the parameters, which
         # move by ~lr whatever the gradient is -- they pin the gradients' magnitudes through the optimizer
-        names = {id(p): k for k, p in model.named_parameters()}
+        rec["opt_state_step1"] = opt_state_step1
+        if loss_name == "factor":
+            rec["disc_opt_state_step1"] = disc_step1
         rec["opt_state"] = {names[id(p)]: dict(exp_avg=tensor_digest(st["exp_avg"]), exp_avg_sq=tensor_digest(st["exp_avg_sq"]),
                                                step=float(st["step"]))
                             for p, st in optimizer.state.items()}

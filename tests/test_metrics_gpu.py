@@ -117,6 +117,8 @@ def test_metrics_need_known_factors(tmp_path):
     ev = _evaluator(save_dir=str(tmp_path))
 
     class NoFactors(list):
-        dataset = list(range(4))
+        pass
+    loader = NoFactors()
+    loader.dataset = list(range(4))               # the reference reads dataloader.__dict__["dataset"] for its message
     with pytest.raises(ValueError):
-        ev.compute_metrics(NoFactors())
+        ev.compute_metrics(loader)
