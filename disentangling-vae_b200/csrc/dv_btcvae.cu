@@ -707,9 +707,10 @@ btcvae_fwd3_kernel(const float* __restrict__ z, const float* __restrict__ mu, co
 //     (1024,10)) and sweeps those columns for all R rows; the four partial logsumexp states of every (row, dim) are
 //     merged through distributed shared memory after one cluster barrier -- no global-memory round trip, no second
 //     launch, nothing but the O(B*D) outputs touches HBM;
-//   * a warp is 4 rows x 8 column lanes: one LDS.128 request fetches 8 distinct columns (128 B = ONE wavefront)
-//     and broadcasts each to the 4 rows -- 4x less shared-memory traffic per evaluation; a thread keeps its row's
-//     z_d and the D running sums in registers;
+//   * register blocking over ROWS: a lane owns columns (conflict-free LDS.128, odd float4 pitch) and applies each loaded
+//     column to RPT = 4 rows whose z_d and running sums it keeps in registers -- 4x less shared-memory traffic per
+//     evaluation (an LDS.128 is four shared-memory cycles whatever the addresses: broadcasting ACROSS lanes, the first
+//     attempt, bought nothing and its even pitch cost 2-way conflicts: 11.7 us for the sweep);
 //   * the reference exponent is per CTA and per dimension (r_cd = max over the CTA's columns of c_jd + w_j, an
 //     upper bound of every term it sums), folded with the column weight into the staged constant as before
 //     (t = z - mu; arg = x'' - hiv*t*t; a += arg; s_d += ex2(arg)); partial sums of different CTAs are brought to
@@ -726,17 +727,23 @@ constexpr int kF4Clus = 4;
 constexpr int kF4MaxTasks = 32;      // (row group of 4) x (column split) pairs per CTA
 constexpr int kF4MaxRows = 128;      // rows per cluster
 
-template <int DC, bool EXACT>
+__device__ __forceinline__ void atomic_max_float(float* addr, float v) {   // shared memory; works for mixed signs
+  if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else atomicMin(reinterpret_cast<unsigned*>(addr), __float_as_uint(v));
+}
+
+// RPT = rows per thread (register blocking over rows: one LDS.128 of a column's parameters serves RPT evaluations)
+template <int DC, bool EXACT, int RPT>
 __global__ void __launch_bounds__(kF4Threads, 1)
 btcvae_fwd4_kernel(const float* __restrict__ z, const float* __restrict__ mu, const float* __restrict__ logvar, int ld,
                    int row_stride, int B, int D_rt, LogW lw, int R, int S, int NC, float4* __restrict__ pj_out,
                    float* __restrict__ rowstats, float* __restrict__ terms, float* __restrict__ blockpart,
                    unsigned* __restrict__ counter, float* __restrict__ dbg) {
-  extern __shared__ float4 sp[];                               // [NC][DC]: {x'', hiv*log2e, mu, z} of this CTA's columns
+  extern __shared__ float4 sp[];                               // [NC][DC+1]: {x'', hiv*log2e, mu, z} of this CTA's columns
+  constexpr int DP = DC + 1;                                   // odd pitch: lanes over consecutive columns are conflict free
   // DV_BTCVAE_TIMING=1: block 0 leaves its phase boundaries (SM clocks since kernel entry) in the workspace header
   const long long t_start = dbg ? clock64() : 0;
 #define DV_F4_MARK(slot) do { if (dbg && blockIdx.x == 0 && threadIdx.x == 0) dbg[slot] = (float)(clock64() - t_start); } while (0)
-  __shared__ float s_red[kF4Warps][DC];
   __shared__ float s_ref[DC];                                  // r_cd (log2 units); -inf if the CTA owns no column
   __shared__ float s_rsum;                                     // sum_d r_cd
   __shared__ float s_tsx[kF4MaxTasks * kRows][DC];             // per (task, row) partial sums
@@ -754,127 +761,114 @@ btcvae_fwd4_kernel(const float* __restrict__ z, const float* __restrict__ mu, co
   const int c0 = crank * NC;
   const int ncols = max(0, min(B, c0 + NC) - c0);
 
-  // ---- phase 1: this CTA's columns -> shared memory (weight folded in), unfolded copy for the backward pass ----
-  for (int e = tid; e < ncols * D; e += kF4Threads) {
-    const int jl = e / D, k = e - jl * D;
-    const int j = c0 + jl;
-    const long long off = (long long)j * row_stride + (long long)k * ld;
-    const float m = mu[off], lv = logvar[off], zz = z[(long long)j * D + k];
-    const float cc = -0.5f * (kLog2Pi + lv) * kLog2e;
-    const float hiv = 0.5f * expf(-lv) * kLog2e;
-    const float w = !lw.mss ? 0.f : (j == 0 ? lw.ln : (j == 1 ? lw.ls : lw.lm));
-    sp[jl * DC + k] = make_float4(cc + w, hiv, m, zz);
-    if (clus == 0) pj_out[(long long)k * B + j] = make_float4(cc, hiv, m, zz);   // the backward pass reads [D][B]
-  }
-  __syncthreads();
-  DV_F4_MARK(0);
-  // ---- phase 2: r_cd = max_j (c_jd + w_j) over the CTA's columns (column 0: the larger of its two weights) ----
+  // ---- phase 1: this CTA's columns -> shared memory with the weight and the reference exponent folded in ----
+  // thread = (latent dim k, every CPT-th column): its running max is ONE register, the block-wide r_cd one shared-memory
+  // atomic per thread; the (cheap, L1/L2-resident) inputs are then read a second time to store x'' = c + w - r_cd.
   {
-    float bm[DC];
-#pragma unroll
-    for (int k = 0; k < DC; ++k) bm[k] = -INFINITY;
-    const float col0_extra = lw.mss ? fmaxf(lw.ls - lw.ln, 0.f) : 0.f;
-    for (int jl = tid; jl < ncols; jl += kF4Threads) {
-      const float extra = (c0 + jl == 0) ? col0_extra : 0.f;
-#pragma unroll
-      for (int k = 0; k < DC; ++k)
-        if (EXACT || k < D) bm[k] = fmaxf(bm[k], sp[jl * DC + k].x + extra);
-    }
-#pragma unroll
-    for (int k = 0; k < DC; ++k) {
-      bm[k] = warp_max(bm[k]);
-      if (lane == 0) s_red[warp][k] = bm[k];
+    if (tid < DC) s_ref[tid] = -INFINITY;
+    __syncthreads();
+    const int CPT = kF4Threads / D;
+    const bool worker = tid < CPT * D;
+    const int k = tid % D, jl0 = tid / D;
+    const float col0_extra = lw.mss ? fmaxf(lw.ls - lw.ln, 0.f) : 0.f;    // column 0: the larger of its two weights
+    if (worker) {
+      float bm = -INFINITY;
+      for (int jl = jl0; jl < ncols; jl += CPT) {
+        const int j = c0 + jl;
+        const float lv = logvar[(long long)j * row_stride + (long long)k * ld];
+        const float w = !lw.mss ? 0.f : (j == 0 ? lw.ln + col0_extra : (j == 1 ? lw.ls : lw.lm));
+        bm = fmaxf(bm, -0.5f * (kLog2Pi + lv) * kLog2e + w);
+      }
+      if (bm > -INFINITY) atomic_max_float(&s_ref[k], bm);
     }
     __syncthreads();
-    if (tid < DC) {
-      float b = -INFINITY;
-#pragma unroll
-      for (int w = 0; w < kF4Warps; ++w) b = fmaxf(b, s_red[w][tid]);
-      s_ref[tid] = (EXACT || tid < D) ? b : 0.f;
+    if (worker) {
+      const float ref = s_ref[k];
+      for (int jl = jl0; jl < ncols; jl += CPT) {
+        const int j = c0 + jl;
+        const long long off = (long long)j * row_stride + (long long)k * ld;
+        const float m = mu[off], lv = logvar[off], zz = z[(long long)j * D + k];
+        const float cc = -0.5f * (kLog2Pi + lv) * kLog2e;
+        const float hiv = 0.5f * expf(-lv) * kLog2e;
+        const float w = !lw.mss ? 0.f : (j == 0 ? lw.ln : (j == 1 ? lw.ls : lw.lm));
+        sp[jl * DP + k] = make_float4(cc + w - ref, hiv, m, zz);
+        if (clus == 0) pj_out[(long long)k * B + j] = make_float4(cc, hiv, m, zz);   // the backward pass reads [D][B]
+      }
     }
-    __syncthreads();
     if (tid == 0) {
       float rs = 0.f;
-      for (int k = 0; k < D; ++k) rs += s_ref[k];
+      for (int kk = 0; kk < D; ++kk) rs += s_ref[kk];
       s_rsum = rs;
-    }
-    for (int e = tid; e < ncols * D; e += kF4Threads) {
-      const int jl = e / D, k = e - jl * D;
-      sp[jl * DC + k].x -= s_ref[k];
     }
     __syncthreads();
   }
-
   DV_F4_MARK(1);
-  // ---- phase 3: tasks = (group of 4 rows) x (column split); warp = 4 rows x 8 column lanes ----
+
+  // ---- phase 2: tasks = (group of RPT rows) x (column split); lanes = columns, RPT rows in registers ----
   {
-    const int G = (R + kRows - 1) / kRows;
+    const int G = (R + RPT - 1) / RPT;
     const int ntasks = G * S;
-    const int CS = (((NC + S - 1) / S) + kJL - 1) / kJL * kJL;
-    const int r = lane >> 3, cl = lane & 7;
+    const int CS = (((NC + S - 1) / S) + 31) / 32 * 32;
     for (int task = warp; task < ntasks; task += kF4Warps) {
       const int g = task / S, s = task - g * S;
-      const int i = min(clus * R + g * kRows + r, B - 1);      // rows past the end recompute row B-1 (never finalised)
-      const float dw0 = (lw.mss && i == B - 2) ? (lw.ls - lw.ln) : 0.f;
-      float sx[DC], zc[DC];
+      float zc[RPT][DC], sx[RPT][DC], am[RPT], as[RPT], dw0[RPT];
 #pragma unroll
-      for (int k = 0; k < DC; ++k) {
-        sx[k] = 0.f;
-        zc[k] = (EXACT || k < D) ? __ldg(z + (long long)i * D + k) : 0.f;
+      for (int r = 0; r < RPT; ++r) {
+        const int i = min(clus * R + g * RPT + r, B - 1);      // rows past the end recompute row B-1 (never finalised)
+        dw0[r] = (lw.mss && i == B - 2) ? (lw.ls - lw.ln) : 0.f;
+        am[r] = -INFINITY; as[r] = 0.f;
+#pragma unroll
+        for (int k = 0; k < DC; ++k) {
+          sx[r][k] = 0.f;
+          zc[r][k] = (EXACT || k < D) ? __ldg(z + (long long)i * D + k) : 0.f;
+        }
       }
-      float am = -INFINITY, as = 0.f;
       const int jend = min(ncols, (s + 1) * CS);
-      int jl = s * CS + cl;
-      auto column = [&](int jj, float dw) {
-        const float4* pr = sp + jj * DC;
-        float a = 0.f;
+      int jl = s * CS + lane;
+      bool first = (c0 + jl == 0);                             // the only (row-dependent) weight: row B-2, column 0
+      for (; jl < jend; jl += 32) {
+        const float4* pr = sp + jl * DP;
+        float a[RPT];
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) a[r] = 0.f;
 #pragma unroll
         for (int k = 0; k < DC; ++k) {
           if (EXACT || k < D) {
             const float4 p = pr[k];
-            const float tt = zc[k] - p.z;
-            const float arg = fmaf(-p.y, tt * tt, p.x) + dw;
-            a += arg;
-            sx[k] += ex2_approx(arg);
+#pragma unroll
+            for (int r = 0; r < RPT; ++r) {
+              const float tt = zc[r][k] - p.z;
+              float arg = fmaf(-p.y, tt * tt, p.x);
+              if (first) arg += dw0[r];
+              a[r] += arg;
+              sx[r][k] += ex2_approx(arg);
+            }
           }
         }
-        const float d = a - am;
-        const float e = ex2_approx(-fabsf(d));
-        const bool up = d > 0.f;
-        as = up ? fmaf(as, e, 1.f) : as + e;
-        am = up ? a : am;
-      };
-      if (jl < jend) { column(jl, (c0 + jl == 0) ? dw0 : 0.f); jl += kJL; }   // peeled: the only row-dependent weight
-      for (; jl < jend; jl += kJL) {
-        const float4* pr = sp + jl * DC;
-        float a = 0.f;
 #pragma unroll
-        for (int k = 0; k < DC; ++k) {
-          if (EXACT || k < D) {
-            const float4 p = pr[k];
-            const float tt = zc[k] - p.z;
-            const float arg = fmaf(-p.y, tt * tt, p.x);
-            a += arg;
-            sx[k] += ex2_approx(arg);
-          }
+        for (int r = 0; r < RPT; ++r) {
+          const float d = a[r] - am[r];
+          const float e = ex2_approx(-fabsf(d));
+          const bool up = d > 0.f;
+          as[r] = up ? fmaf(as[r], e, 1.f) : as[r] + e;
+          am[r] = up ? a[r] : am[r];
         }
-        const float d = a - am;
-        const float e = ex2_approx(-fabsf(d));
-        const bool up = d > 0.f;
-        as = up ? fmaf(as, e, 1.f) : as + e;
-        am = up ? a : am;
+        first = false;
       }
 #pragma unroll
-      for (int o = 1; o < kJL; o <<= 1) {
+      for (int r = 0; r < RPT; ++r) {
 #pragma unroll
-        for (int k = 0; k < DC; ++k) sx[k] += __shfl_xor_sync(0xffffffffu, sx[k], o);
-        const float m2 = __shfl_xor_sync(0xffffffffu, am, o), s2 = __shfl_xor_sync(0xffffffffu, as, o);
-        lse_merge2(am, as, m2, s2);
-      }
-      if (cl == 0) {
+        for (int k = 0; k < DC; ++k) sx[r][k] = warp_sum(sx[r][k]);
 #pragma unroll
-        for (int k = 0; k < DC; ++k) s_tsx[task * kRows + r][k] = sx[k];
-        s_tq[task * kRows + r] = make_float2(am, as);
+        for (int o = 16; o > 0; o >>= 1) {
+          const float m2 = __shfl_xor_sync(0xffffffffu, am[r], o), s2 = __shfl_xor_sync(0xffffffffu, as[r], o);
+          lse_merge2(am[r], as[r], m2, s2);
+        }
+        if (lane == 0) {
+#pragma unroll
+          for (int k = 0; k < DC; ++k) s_tsx[task * RPT + r][k] = sx[r][k];
+          s_tq[task * RPT + r] = make_float2(am[r], as[r]);
+        }
       }
     }
     __syncthreads();
@@ -882,14 +876,14 @@ btcvae_fwd4_kernel(const float* __restrict__ z, const float* __restrict__ mu, co
     // merge the column splits of every row in a fixed order -> this CTA's partial state
     for (int e = tid; e < R * (DC + 1); e += kF4Threads) {
       const int rr = e / (DC + 1), k = e - rr * (DC + 1);
-      const int g = rr / kRows, r2 = rr - g * kRows;
+      const int g = rr / RPT, r2 = rr - g * RPT;
       if (k < DC) {
         float a = 0.f;
-        for (int s = 0; s < S; ++s) a += s_tsx[(g * S + s) * kRows + r2][k];
+        for (int s = 0; s < S; ++s) a += s_tsx[(g * S + s) * RPT + r2][k];
         s_sx[rr][k] = a;
       } else {
         float m = -INFINITY, a = 0.f;
-        for (int s = 0; s < S; ++s) { const float2 q = s_tq[(g * S + s) * kRows + r2]; lse_merge2(m, a, q.x, q.y); }
+        for (int s = 0; s < S; ++s) { const float2 q = s_tq[(g * S + s) * RPT + r2]; lse_merge2(m, a, q.x, q.y); }
         s_q[rr] = make_float2(m, a);
       }
     }
@@ -1191,10 +1185,12 @@ int dv_btcvae_fwd_rows(const float* z, const float* mu, const float* logvar, int
     const int max_clusters = 33;                               // cluster size 4 packs 132 of the 148 SMs
     int R = ((B + max_clusters - 1) / max_clusters + kRows - 1) / kRows * kRows;
     const int NC = ((B + kF4Clus - 1) / kF4Clus + kJL - 1) / kJL * kJL;
-    const size_t smem = (size_t)NC * dc * sizeof(float4);
-    const int G = R / kRows;
+    const size_t smem = (size_t)NC * (dc + 1) * sizeof(float4);
+    const int rpt = (dc == 10) ? 4 : 2;                        // rows per thread (register budget)
+    const int G = R / rpt;
     int S = G >= kF4Warps ? 1 : kF4Warps / G;
-    if (S > NC / kJL) S = NC / kJL;
+    if (S > NC / 32) S = NC / 32;
+    if (S < 1) S = 1;
     if (whole && v4 && D <= 16 && smem <= 200 * 1024 && R <= kF4MaxRows && G * S <= kF4MaxTasks) {
       const int nclus = (B + R - 1) / R;
       float4* pj = reinterpret_cast<float4*>(ws + kWsHeader);
@@ -1210,20 +1206,20 @@ int dv_btcvae_fwd_rows(const float* z, const float* mu, const float* logvar, int
       static int timing4 = -1;
       if (timing4 < 0) { const char* e = getenv("DV_BTCVAE_TIMING"); timing4 = (e && e[0] == '1') ? 1 : 0; }
       float* dbg = timing4 ? ws + 8 : nullptr;                 // header floats 8..13
-#define DV_F4_CALL(DC, EXACT)                                                                                                  \
+#define DV_F4_CALL(DC, EXACT, RPT)                                                                                             \
   do {                                                                                                                         \
     static bool attr_set = false;                                                                                              \
     if (!attr_set) {                                                                                                           \
-      if (cudaFuncSetAttribute(btcvae_fwd4_kernel<DC, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) !=      \
+      if (cudaFuncSetAttribute(btcvae_fwd4_kernel<DC, EXACT, RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != \
           cudaSuccess) { g_last_cuda_error = (int)cudaGetLastError(); return DV_ERR_CUDA; }                                    \
       attr_set = true;                                                                                                         \
     }                                                                                                                          \
-    err = cudaLaunchKernelEx(&cfg, btcvae_fwd4_kernel<DC, EXACT>, z, mu, logvar, ld, row_stride, B, D, lw, R, S, NC, pj,       \
+    err = cudaLaunchKernelEx(&cfg, btcvae_fwd4_kernel<DC, EXACT, RPT>, z, mu, logvar, ld, row_stride, B, D, lw, R, S, NC, pj,  \
                              rowstats, terms, blockpart, counter, dbg);                                                        \
   } while (0)
-      if (D == 10) DV_F4_CALL(10, true);
-      else if (D == 16) DV_F4_CALL(16, true);
-      else DV_F4_CALL(16, false);
+      if (D == 10) DV_F4_CALL(10, true, 4);
+      else if (D == 16) DV_F4_CALL(16, true, 2);
+      else DV_F4_CALL(16, false, 2);
 #undef DV_F4_CALL
       if (err != cudaSuccess) { g_last_cuda_error = (int)err; cudaGetLastError(); return DV_ERR_CUDA; }
       return check_launch();

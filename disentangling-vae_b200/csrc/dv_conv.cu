@@ -568,7 +568,7 @@ static int wgrad_nsplit(int B, int H, int W, long long* chunk) {
 
 namespace dv {
 namespace tc {
-int pack_tc(const float* w, float* wd, float* wu, cudaStream_t st);
+int pack_tc(const float* w, float* wd, float* wu, float* wf, cudaStream_t st);
 int conv_down32_tc(const float* hi, const float* wd_packed, const float* bias, const float* mask, float* lo,
                    int B, int H, int W, int act, cudaStream_t st, float* colsum_part, int* nparts);
 int pack_small_tc(const float* w, float* wd, int CH, cudaStream_t st);
@@ -639,9 +639,12 @@ int dv_conv_pack_weights(const float* w, float* w_packed, int CH, void* stream) 
   if (!w || !w_packed) return DV_ERR_BAD_ARG;
   if (CH != 1 && CH != 3 && CH != 32) return DV_ERR_BAD_SHAPE;
   const int n = kLoCh * CH * kTaps;
+  if (CH == 32)                                     // ONE launch: both tcgen05 operand layouts + the two CUDA-core layouts
+    return tc::pack_tc(w, w_packed + kPackFfma, w_packed + kPackFfma + kPackTcSection, w_packed, as_stream(stream));
   conv_pack_kernel<<<(n + 255) / 256, 256, 0, as_stream(stream)>>>(w, w_packed, CH);
   int rc = check_launch();
   if (rc != DV_OK) return rc;
+  if (use_img()) return DV_OK;                      // image-boundary layers run on dv_conv_img.cu: nothing else reads a pack
   if (CH != 32) {
     rc = tc::pack_small_tc(w, w_packed + 2 * kLoCh * CH * kTaps, CH, as_stream(stream));
     if (rc != DV_OK) return rc;
@@ -649,7 +652,7 @@ int dv_conv_pack_weights(const float* w, float* w_packed, int CH, void* stream) 
     if (rc != DV_OK) return rc;
     return c2i::pack(w, w_packed + 2 * kLoCh * CH * kTaps + small_tc_floats(CH) + kPackUpSmall, CH, as_stream(stream));
   }
-  return tc::pack_tc(w, w_packed + kPackFfma, w_packed + kPackFfma + kPackTcSection, as_stream(stream));
+  return DV_OK;
 }
 
 static int conv_down_impl(const float* hi, const float* w_packed, const float* bias, const float* mask, float* lo,
@@ -660,7 +663,7 @@ static int conv_down_impl(const float* hi, const float* w_packed, const float* b
     return tc::conv_down32_tc(hi, w_packed + kPackFfma, bias, mask, lo, B, H, W, act, st, colsum_part, nparts);
   if (CH != 32 && use_img() && img::shape_ok(B, H, W, CH))
     return img::conv_down(hi, w_packed, bias, mask, lo, B, H, W, CH, act, st, colsum_part, nparts, kCsBlocks);
-  if (CH != 32 && use_tc("dsmall") && W <= 128 && 128 % W == 0)
+  if (CH != 32 && !use_img() && use_tc("dsmall") && W <= 128 && 128 % W == 0)
     return tc::conv_down_small_tc(hi, w_packed + 2 * kLoCh * CH * kTaps, bias, mask, lo, B, H, W, CH, act, st, colsum_part, nparts);
   if (CH == 32) {
     const int smem = kTaps * 32 * kLoCh * sizeof(float);
@@ -714,10 +717,10 @@ int dv_conv_up(const float* lo, const float* w_packed, const float* bias, const 
   const float* wu = w_packed + kLoCh * CH * kTaps;
   if (CH != 32 && !mask && use_img() && img::shape_ok(B, H, W, CH))
     return img::conv_up(lo, wu, bias, hi, B, H, W, CH, act, as_stream(stream));
-  if (CH != 32 && !mask && use_tc("c2i") && c2i::shape_ok(B, H, W, CH))
+  if (CH != 32 && !mask && !use_img() && use_tc("c2i") && c2i::shape_ok(B, H, W, CH))
     return c2i::conv_up(lo, w_packed + 2 * kLoCh * CH * kTaps + small_tc_floats(CH) + kPackUpSmall, bias, hi, B, H, W, CH, act,
                         as_stream(stream));
-  if (use_tc("halo") && (CH != 32 || act != DV_ACT_SIGMOID) && W + 2 <= 40)
+  if (use_tc("halo") && (CH == 32 ? act != DV_ACT_SIGMOID : !use_img()) && W + 2 <= 40)
     return tc::conv_up_halo(lo, CH == 32 ? w_packed + kPackFfma + kPackTcSection
                                           : w_packed + 2 * kLoCh * CH * kTaps + small_tc_floats(CH),
                             bias, mask, hi, B, H, W, CH, act, as_stream(stream));
@@ -768,7 +771,7 @@ int dv_conv_wgrad(const float* lo, const float* hi, float* dw, float* dbias_lo, 
     conv_wgrad_reduce_kernel<<<(n + 31) / 32, 256, 0, st>>>(ws, dw, dbias_lo, CH, nsplit_img);
     return check_launch();
   }
-  if ((CH == 32 && use_tc("wgrad")) || (CH != 32 && use_tc("wsmall"))) {
+  if ((CH == 32 && use_tc("wgrad")) || (CH != 32 && !use_img() && use_tc("wsmall"))) {
     int nsplit_tc = 0;
     int rc = CH == 32 ? tc::conv_wgrad32_tc(lo, hi, ws, B, H, W, &nsplit_tc, st)
                       : tc::conv_wgrad_small_tc(lo, hi, ws, B, H, W, CH, &nsplit_tc, st);

@@ -14,8 +14,10 @@
 //         (8 per tap for 64 FMAs); bias / ReLU / ReLU-mask epilogue, 128 B pixel lines stored as float4; optional
 //         channel sums of the stored tile (the previous ConvTranspose2d's bias gradient) by the 31-shuffle butterfly.
 //   up    (ConvTranspose2d fwd, NCHW + sigmoid): thread = a block of PY x 2 lo positions -> (2PY) x 4 output pixels per
-//         channel; the 32-channel lo tile (pixel pitch 36 floats: conflict-free LDS.128) with a 1-pixel halo in shared
-//         memory; per 4-channel chunk (PY+2) x 4 neighbour float4 serve 2*PY*16*4*CH FMAs; float4 row stores.
+//         channel; the 32-channel lo tile (16-byte chunks XOR-swizzled by the column: conflict-free LDS.128 for a
+//         2-pixel lane stride) with a 1-pixel halo in shared memory; per 4-channel chunk (PY+2) x 4 neighbour float4
+//         serve 2*PY*16*4*CH FMAs; float4 row stores.
+//   All tiles arrive by cp.async (every copy of a tile in flight at once).
 //   wgrad (both weight gradients + the lo-side bias gradient): a "stream" of 16 threads owns the whole 32 x 16*CH
 //         output (thread = 4 lo channels x 8 taps x CH) in registers and walks over pixels (1 LDS.128 + 4*CH LDS.64 per
 //         32*CH FMAs); 16 streams per CTA, persistent CTAs, one ordered cross-stream reduction at the end, partials in
@@ -46,18 +48,33 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
   return v[0];
 }
 
+// Tiles are brought in with cp.async (global -> shared without a register round trip): a thread issues ALL its copies
+// back to back, so the whole tile is in flight at once.  (A plain "load, then store" loop kept ONE load per thread in
+// flight: 16-38 dependent round trips to HBM per tile, 4x the time of everything else in these kernels.)
+// src-size 0 = zero fill (padding / halo outside the image); the source pointer is then any valid address.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  const int sz = valid ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // hi tile: rows 2*i0-1 .. 2*i0+2*TR of image b, columns -1 .. 2W (in-tile column = x + 1), zero outside the image
 template <int CH, int W, int TR>
 __device__ __forceinline__ void load_hi_tile(float* __restrict__ s_hi, const float* __restrict__ hi, int b, int i0, int H) {
   constexpr int IN_ROWS = 2 * TR + 2, COLS = 2 * W + 2, PITCH = 2 * W + 4;
   const int HH = 2 * H, WW = 2 * W;
+#pragma unroll 4
   for (int e = threadIdx.x; e < CH * IN_ROWS * COLS; e += kThreads) {
     const int xx = e % COLS, rr = (e / COLS) % IN_ROWS, c = e / (COLS * IN_ROWS);
     const int iy = 2 * i0 - 1 + rr, ix = xx - 1;
-    float v = 0.f;
-    if ((unsigned)iy < (unsigned)HH && (unsigned)ix < (unsigned)WW)
-      v = __ldg(hi + ((long long)(b * CH + c) * HH + iy) * WW + ix);
-    s_hi[(c * IN_ROWS + rr) * PITCH + xx] = v;
+    const bool ok = (unsigned)iy < (unsigned)HH && (unsigned)ix < (unsigned)WW;
+    cp_async4(s_hi + (c * IN_ROWS + rr) * PITCH + xx, ok ? hi + ((long long)(b * CH + c) * HH + iy) * WW + ix : hi, ok);
   }
 }
 
@@ -88,6 +105,24 @@ img_down_kernel(const float* __restrict__ hi, const float* __restrict__ wd, cons
     const int b = tile / tiles_per_img, i0 = (tile % tiles_per_img) * TR;
     __syncthreads();                                           // previous tile fully consumed (and weights staged)
     load_hi_tile<CH, W, TR>(s_hi, hi, b, i0, H);
+    // ReLU-backward mask of this thread's pixels as one bit per channel, requested BEFORE the FMAs: the 8 x 16-byte
+    // loads per pixel complete behind the arithmetic instead of sitting between it and the stores
+    uint32_t mbits[PX];
+#pragma unroll
+    for (int q = 0; q < PX; ++q) {
+      mbits[q] = 0xffffffffu;
+      if (mask) {
+        const float* mk = mask + (((long long)b * H + i0 + r_thr + RPT * q) * W + c_out) * kLoCh;
+        uint32_t bits = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 m4 = ldg4(mk + 4 * j);
+          bits |= ((m4.x > 0.f ? 1u : 0u) | (m4.y > 0.f ? 2u : 0u) | (m4.z > 0.f ? 4u : 0u) | (m4.w > 0.f ? 8u : 0u)) << (4 * j);
+        }
+        mbits[q] = bits;
+      }
+    }
+    cp_async_wait_all();
     __syncthreads();
     float acc[PX][kLoCh];
 #pragma unroll
@@ -126,16 +161,14 @@ img_down_kernel(const float* __restrict__ hi, const float* __restrict__ wd, cons
     for (int q = 0; q < PX; ++q) {
       const long long p = ((long long)b * H + i0 + r_thr + RPT * q) * W + c_out;
       float* dst = lo + p * kLoCh;
-      const float* mk = mask ? mask + p * kLoCh : nullptr;
+      const uint32_t bits = mbits[q];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float4 b4 = *reinterpret_cast<const float4*>(s_bias + 4 * j);
         float v0 = acc[q][4 * j] + b4.x, v1 = acc[q][4 * j + 1] + b4.y, v2 = acc[q][4 * j + 2] + b4.z, v3 = acc[q][4 * j + 3] + b4.w;
         if (act == DV_ACT_RELU) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
-        if (mk) {
-          const float4 m4 = ldg4(mk + 4 * j);
-          v0 = m4.x > 0.f ? v0 : 0.f; v1 = m4.y > 0.f ? v1 : 0.f; v2 = m4.z > 0.f ? v2 : 0.f; v3 = m4.w > 0.f ? v3 : 0.f;
-        }
+        v0 = ((bits >> (4 * j)) & 1u) ? v0 : 0.f; v1 = ((bits >> (4 * j + 1)) & 1u) ? v1 : 0.f;
+        v2 = ((bits >> (4 * j + 2)) & 1u) ? v2 : 0.f; v3 = ((bits >> (4 * j + 3)) & 1u) ? v3 : 0.f;
         *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(v0, v1, v2, v3);
         acc[q][4 * j] = v0; acc[q][4 * j + 1] = v1; acc[q][4 * j + 2] = v2; acc[q][4 * j + 3] = v3;
       }
@@ -186,11 +219,13 @@ img_wgrad_kernel(const float* __restrict__ lo, const float* __restrict__ hi, flo
     load_hi_tile<CH, W, TR>(s_hi, hi, b, i0, H);
     {
       const float4* src = reinterpret_cast<const float4*>(lo + ((long long)b * H + i0) * W * kLoCh);
+#pragma unroll 4
       for (int e = tid; e < NPX * 8; e += kThreads) {
         const int px = e >> 3, j = e & 7;
-        *reinterpret_cast<float4*>(s_lo + px * kLoPitch + 4 * j) = __ldg(src + e);
+        cp_async16(s_lo + px * kLoPitch + 4 * j, src + e, true);
       }
     }
+    cp_async_wait_all();
     __syncthreads();
 #pragma unroll 2
     for (int px = stream; px < NPX; px += NSTREAM) {
@@ -276,14 +311,15 @@ img_up_kernel(const float* __restrict__ lo, const float* __restrict__ wu, const 
     const int b = tile / tiles_per_img, m0 = (tile % tiles_per_img) * TR;
     __syncthreads();
     // lo rows m0-1 .. m0+TR, columns -1 .. W (zero outside the image)
+#pragma unroll 4
     for (int e = tid; e < (TR + 2) * SW * 8; e += NT) {
       const int j = e & 7, xx = (e >> 3) % SW, rr = (e >> 3) / SW;
       const int m = m0 - 1 + rr, n = xx - 1;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if ((unsigned)m < (unsigned)H && (unsigned)n < (unsigned)W)
-        v = __ldg(reinterpret_cast<const float4*>(lo + (((long long)b * H + m) * W + n) * kLoCh) + j);
-      *reinterpret_cast<float4*>(s_lo + (rr * SW + xx) * kLoCh + 4 * (j ^ ((xx >> 1) & 7))) = v;
+      const bool ok = (unsigned)m < (unsigned)H && (unsigned)n < (unsigned)W;
+      cp_async16(s_lo + (rr * SW + xx) * kLoCh + 4 * (j ^ ((xx >> 1) & 7)),
+                 ok ? lo + (((long long)b * H + m) * W + n) * kLoCh + 4 * j : lo, ok);
     }
+    cp_async_wait_all();
     __syncthreads();
     if (m0 + PY * tm < H) {
       float out[CH][2 * PY][4];

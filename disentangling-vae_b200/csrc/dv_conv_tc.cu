@@ -1715,11 +1715,18 @@ conv_wgrad_small_tc_kernel(const __grid_constant__ CUtensorMap tmap_lo, const fl
 // ---- weight packing for the tensor-core kernels ------------------------------------------
 // w[cl][c][tap] ->  down: Wd[tap][row][c],  row <  32: tf32-exact hi of w[row][c][tap], row >= 32: lo
 //                   up  : Wu[tap][row][cl], row <  32: hi of w[cl][row][tap],          row >= 32: lo
-__global__ void conv_pack_tc_kernel(const float* __restrict__ w, float* __restrict__ wd, float* __restrict__ wu) {
+// wf != NULL: the same launch also writes the two CUDA-core layouts of conv_pack_kernel (dv_conv.cu): Wd[tap*32+c][cl]
+// and Wu[tap][cl][c] -- the fallbacks for geometries the tensor-core kernels do not take.
+__global__ void conv_pack_tc_kernel(const float* __restrict__ w, float* __restrict__ wd, float* __restrict__ wu,
+                                    float* __restrict__ wf) {
   const int n = kLoCh * 32 * kTaps;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
     const int tap = idx % kTaps, c = (idx / kTaps) % 32, cl = idx / (kTaps * 32);
     const float v = w[idx];
+    if (wf) {
+      wf[(tap * 32 + c) * kLoCh + cl] = v;
+      wf[n + (tap * kLoCh + cl) * 32 + c] = v;
+    }
     const float hi = __uint_as_float(__float_as_uint(v) & kHiMask);
     const float lo = v - hi;
     wd[(tap * 64 + cl) * 32 + c] = hi;
@@ -1734,6 +1741,14 @@ __global__ void conv_pack_tc_kernel(const float* __restrict__ w, float* __restri
 static int use_rawhi() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("DV_TC_RAWHI"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v;
+}
+// conv_down32_ts: hi operand straight from the raw TMA tile (SS MMA) instead of a TMEM copy.  OFF by default: measured
+// 87.5 us vs 75.6 us at (1024,16,32) -- the SS operand fetch (16 KB per tap) competes with the weight tile for the
+// tensor core's shared-memory read bandwidth, which costs more than the halved tcgen05.st traffic saves.  DV_TC_RAWHI_DOWN=1.
+static int use_rawhi_down() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DV_TC_RAWHI_DOWN"); v = (e && e[0] == '1') ? 1 : 0; }
   return v;
 }
 static int use_debug() {
@@ -1800,8 +1815,8 @@ static bool make_w_tmap(CUtensorMap* m, const float* base) {
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-int pack_tc(const float* w, float* wd, float* wu, cudaStream_t st) {
-  conv_pack_tc_kernel<<<64, 256, 0, st>>>(w, wd, wu);
+int pack_tc(const float* w, float* wd, float* wu, float* wf, cudaStream_t st) {
+  conv_pack_tc_kernel<<<64, 256, 0, st>>>(w, wd, wu, wf);
   return check_launch();
 }
 
@@ -1812,8 +1827,8 @@ int conv_down32_tc(const float* hi, const float* wd_packed, const float* bias, c
                    int B, int H, int W, int act, cudaStream_t st, float* colsum_part, int* nparts) {
   if (nparts) *nparts = 0;
   if (W > 128 || 128 % W != 0) return DV_ERR_BAD_SHAPE;
-  DownGeom g;
-  g.B = B; g.H = H; g.W = W; g.prefetch = use_prefetch(); g.pipe = use_pipe(); g.debug = use_debug();
+  DownGeom g = {};
+  g.B = B; g.H = H; g.W = W; g.prefetch = use_prefetch(); g.pipe = use_pipe(); g.debug = use_debug(); g.rawhi = use_rawhi_down();
   g.rows_per_tile = 128 / W;
   const int TR = g.rows_per_tile < H ? g.rows_per_tile : H;
   if (H % TR != 0 || g.rows_per_tile % TR != 0) return DV_ERR_BAD_SHAPE;
@@ -1854,7 +1869,7 @@ int conv_down32_tc(const float* hi, const float* wd_packed, const float* bias, c
 int conv_up32_tc(const float* lo, const float* wu_packed, const float* bias, const float* mask, float* hi,
                  int B, int H, int W, int act, cudaStream_t st) {
   if (W > 128 || 128 % W != 0) return DV_ERR_BAD_SHAPE;
-  DownGeom g;
+  DownGeom g = {};
   g.B = B; g.H = H; g.W = W; g.prefetch = use_prefetch(); g.pipe = use_pipe(); g.debug = use_debug();
   g.rows_per_tile = 128 / W;
   const int TR = g.rows_per_tile < H ? g.rows_per_tile : H;
@@ -1894,7 +1909,7 @@ int conv_up32_tc(const float* lo, const float* wu_packed, const float* bias, con
 // partial sums of dw (and of lo, last row) per CTA into ws[grid][16*32+1][32]; returns the grid size in *nsplit
 int conv_wgrad32_tc(const float* lo, const float* hi, float* ws, int B, int H, int W, int* nsplit, cudaStream_t st) {
   if (W > 128 || 128 % W != 0) return DV_ERR_BAD_SHAPE;
-  WgGeom g;
+  WgGeom g = {};
   g.B = B; g.H = H; g.W = W; g.prefetch = use_prefetch(); g.rawhi = use_rawhi();
   g.rows_per_tile = 128 / W;
   const int TR = g.rows_per_tile < H ? g.rows_per_tile : H;
@@ -1982,7 +1997,7 @@ static int launch_down_small(const float* x, const float* wd, const float* bias,
 int conv_down_small_tc(const float* x, const float* wd, const float* bias, const float* mask, float* lo,
                        int B, int H, int W, int CH, int act, cudaStream_t st, float* colsum_part, int* nparts) {
   if (nparts) *nparts = 0;
-  DownGeom g;
+  DownGeom g = {};
   g.B = B; g.H = H; g.W = W; g.prefetch = use_prefetch(); g.pipe = use_pipe(); g.debug = use_debug(); g.rows_per_tile = 0;
   g.total_px = (long long)B * H * W;
   g.num_tiles = (int)((g.total_px + 127) / 128);
@@ -2009,7 +2024,7 @@ static int launch_wgrad_small(const float* lo, const float* x, float* ws, WgGeom
 }
 int conv_wgrad_small_tc(const float* lo, const float* x, float* ws, int B, int H, int W, int CH, int* nsplit, cudaStream_t st) {
   if (W > 128 || 128 % W != 0) return DV_ERR_BAD_SHAPE;
-  WgGeom g;
+  WgGeom g = {};
   g.B = B; g.H = H; g.W = W; g.prefetch = use_prefetch(); g.rawhi = use_rawhi();
   g.rows_per_tile = 128 / W;
   const int TR = g.rows_per_tile < H ? g.rows_per_tile : H;
@@ -2049,7 +2064,7 @@ static int launch_up_halo(const float* lo, const float* wu, const float* bias, c
 // hi = act(up(lo) + bias) * [mask > 0]; hi is NHWC for CH == 32, NCHW for CH in {1,3}
 int conv_up_halo(const float* lo, const float* wu, const float* bias, const float* mask, float* hi,
                  int B, int H, int W, int CH, int act, cudaStream_t st) {
-  HaloGeom g;
+  HaloGeom g = {};
   g.B = B; g.H = H; g.W = W; g.Wp = W + 2; g.pipe = use_pipe(); g.debug = use_debug();
   int tr = (128 + 2) / g.Wp;                       // largest TR with TR*Wp - 2 <= 128
   if (tr < 1) return DV_ERR_BAD_SHAPE;

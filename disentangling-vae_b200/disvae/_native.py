@@ -51,6 +51,10 @@ SIGNATURES = {
     "dv_btcvae_bwd": (I, [I, I, LL, I, P, P, P, P, P, P, P]),
     "dv_btcvae_fwd_rows": (I, [P, P, P, I, I, I, I, I, I, LL, I, P, P, P, P]),
     "dv_btcvae_bwd_rows": (I, [I, I, I, I, LL, I, P, P, P, P, P, P, P]),
+    "dv_u8_to_f32": (I, [P, P, LL, P]),
+    "dv_loss_combine_fwd": (I, [P, P, I, P, P, I, P, P]),
+    "dv_loss_combine_bwd": (I, [P, P, I, I, P, I, P, P, P]),
+    "dv_act_bwd_chansum": (I, [P, P, P, I, I, I, I, F, P, P, P]),
     "dv_latent_entropy_workspace_bytes": (SZ, [I, I, I]),
     "dv_latent_entropy": (I, [P, P, P, I, I, I, I, I, P, P, P, P]),
     "dv_permute_dims": (I, [P, P, ULL, P, P, I, I, P]),

@@ -95,8 +95,12 @@ class BaseLoss(abc.ABC):
 
     def _rec_kl(self, data, recon_data, latent_dist):
         """(recon_loss, kl_total, per-dim kl vector) from the fused kernel."""
-        out = ops.VaeLossFn.apply(recon_data, data, latent_dist[0], latent_dist[1], _dist_id(self.rec_dist))
+        out = self._rec_kl_vec(data, recon_data, latent_dist)
         return out[0], out[1], out[2:]
+
+    def _rec_kl_vec(self, data, recon_data, latent_dist):
+        """The fused kernel's whole output [2 + D] = (recon_loss, kl_total, kl_dim_0 ..): for ops.LossCombineFn."""
+        return ops.VaeLossFn.apply(recon_data, data, latent_dist[0], latent_dist[1], _dist_id(self.rec_dist))
 
 
 class BetaHLoss(BaseLoss):
@@ -108,9 +112,10 @@ class BetaHLoss(BaseLoss):
 
     def __call__(self, data, recon_data, latent_dist, is_train, storer, **kwargs):
         storer = self._pre_call(is_train, storer)
-        rec_loss, kl_loss, kl_dims = self._rec_kl(data, recon_data, latent_dist)
+        out = self._rec_kl_vec(data, recon_data, latent_dist)
+        rec_loss, kl_loss, kl_dims = out[0], out[1], out[2:]
         anneal_reg = linear_annealing(0, 1, self.n_train_steps, self.steps_anneal) if is_train else 1
-        loss = rec_loss + anneal_reg * (self.beta * kl_loss)
+        loss = ops.LossCombineFn.apply(out, None, [1.0, anneal_reg * self.beta], None)     # rec + anneal * (beta * kl)
         _record(storer, ['recon_loss', 'kl_loss', _kl_names(kl_dims.numel()), 'loss'],
                 [rec_loss, kl_loss, kl_dims, loss])
         return loss
@@ -180,11 +185,12 @@ class FactorKLoss(BaseLoss):
         data1, data2 = parts[0], parts[1]
 
         recon_batch, latent_dist, latent_sample1 = model(data1, eps=eps1)
-        rec_loss, kl_loss, kl_dims = self._rec_kl(data1, recon_batch, latent_dist)
+        out = self._rec_kl_vec(data1, recon_batch, latent_dist)
+        rec_loss, kl_loss, kl_dims = out[0], out[1], out[2:]
         d_z = self.discriminator(latent_sample1)
         tc_loss = ops.FactorTcFn.apply(d_z)                      # mean(d_z[:,0] - d_z[:,1])
         anneal_reg = linear_annealing(0, 1, self.n_train_steps, self.steps_anneal) if model.training else 1
-        vae_loss = rec_loss + kl_loss + anneal_reg * self.gamma * tc_loss
+        vae_loss = ops.LossCombineFn.apply(out, tc_loss, [1.0, 1.0], [anneal_reg * self.gamma])   # rec + kl + anneal*gamma*tc
 
         if not model.training:
             _record(storer, ['recon_loss', 'kl_loss', _kl_names(kl_dims.numel()), 'loss', 'tc_loss'],
@@ -236,7 +242,8 @@ class BtcvaeLoss(BaseLoss):
 
     def __call__(self, data, recon_batch, latent_dist, is_train, storer, latent_sample=None):
         storer = self._pre_call(is_train, storer)
-        rec_loss, kl_loss, kl_dims = self._rec_kl(data, recon_batch, latent_dist)
+        out = self._rec_kl_vec(data, recon_batch, latent_dist)
+        rec_loss, kl_loss, kl_dims = out[0], out[1], out[2:]
         from disvae.parallel import is_distributed
         if self.global_batch and is_train and is_distributed():
             terms = ops.BtcvaeGlobalFn.apply(latent_sample, latent_dist[0], latent_dist[1], self.n_data, self.is_mss, None)
@@ -244,7 +251,8 @@ class BtcvaeLoss(BaseLoss):
             terms = ops.BtcvaeFn.apply(latent_sample, latent_dist[0], latent_dist[1], self.n_data, self.is_mss)
         mi_loss, tc_loss, dw_kl_loss = terms[0], terms[1], terms[2]
         anneal_reg = linear_annealing(0, 1, self.n_train_steps, self.steps_anneal) if is_train else 1
-        loss = rec_loss + (self.alpha * mi_loss + self.beta * tc_loss + anneal_reg * self.gamma * dw_kl_loss)
+        # rec + (alpha*mi + beta*tc + anneal*gamma*dw_kl) as one launch (the kl entries of `out` only feed the log)
+        loss = ops.LossCombineFn.apply(out, terms, [1.0], [self.alpha, self.beta, anneal_reg * self.gamma])
         _record(storer, ['recon_loss', 'loss', 'mi_loss', 'tc_loss', 'dw_kl_loss', 'kl_loss', _kl_names(kl_dims.numel())],
                 [rec_loss, loss, mi_loss, tc_loss, dw_kl_loss, kl_loss, kl_dims])
         return loss

@@ -119,6 +119,28 @@ def flat_transpose(src, B, to_nhwc):
     return dst
 
 
+def act_bwd_chansum(dy, y, act, slope=0.0):
+    """g = dy * act'(y) over an NCHW tensor and, from the same pass, the per-channel sums of g."""
+    B, C = y.shape[0], y.shape[1]
+    hw = y.numel() // (B * C)
+    g = torch.empty_like(y)
+    cs = _new((C,), y)
+    ws = _scratch("chansum", N.lib().dv_channel_sum_workspace_bytes(), y.device)
+    call("dv_act_bwd_chansum", ptr(dy), ptr(y), ptr(g), B, C, hw, act, slope, ptr(cs), ptr(ws), stream())
+    return g, cs
+
+
+def u8_to_f32(src, out=None):
+    """uint8 CUDA tensor -> float32 / 255 (ToTensor on the device); `out` = preallocated float32 tensor of the same shape."""
+    if not src.is_cuda or src.dtype != torch.uint8:
+        raise RuntimeError("disvae_b200.u8_to_f32 expects a CUDA uint8 tensor, got %s on %s" % (src.dtype, src.device))
+    src = _c(src)
+    if out is None:
+        out = torch.empty(src.shape, dtype=torch.float32, device=src.device)
+    call("dv_u8_to_f32", src.data_ptr(), ptr(out), src.numel(), stream())
+    return out
+
+
 def act_bwd(dy, y, act, slope=0.0):
     g = torch.empty_like(y)
     call("dv_act_bwd", ptr(dy), ptr(y), ptr(g), y.numel(), act, slope, stream())
@@ -275,9 +297,9 @@ class DecoderFn(Function):
         lins = [(params[2 * i], params[2 * i + 1]) for i in range(3)]
         B = z.shape[0]
         S = recon.shape[-1]
-        g_hi = act_bwd(_c(d_recon), recon, ACT_SIGMOID)                            # NCHW, C channels
+        # sigmoid backward of the output layer fused with its bias gradient (the sum of the result over pixels)
+        g_hi, db = act_bwd_chansum(_c(d_recon), recon, ACT_SIGMOID)                # NCHW, C channels
         convT_grads = [None] * (2 * n_convT)
-        db = channel_sum(g_hi, B, C, 1, S * S)           # bias gradient of the last convT: sum of its output gradient
         for t in range(n_convT - 1, -1, -1):
             last = (t == n_convT - 1)
             H = 4 << t                                   # input resolution of convT t
@@ -422,6 +444,32 @@ class VaeLossFn(Function):
 # ---------------------------------------------------------------------------------------
 # beta-TCVAE decomposition (losses.py:523-544 + 369-373)
 # ---------------------------------------------------------------------------------------
+# beta-TCVAE workspaces: the kernel leaves the header (its "last block" counter) zero, and the body carries the column
+# parameters from forward to backward -- so one buffer per (B, D, device) serves every step WITHOUT a per-step zero-fill,
+# as long as its previous forward has been consumed by its backward ("busy" flag; anything else gets a fresh buffer).
+_bt_pool = {}
+
+
+def _bt_workspace(B, D, device):
+    key = (B, D, device.index)
+    ent = _bt_pool.get(key)
+    if ent is not None and not ent[1]:
+        ent[1] = True
+        return ent[0], key
+    nbytes = N.lib().dv_btcvae_workspace_bytes(B, D)
+    ws = torch.zeros((nbytes + 3) // 4, dtype=torch.float32, device=device)
+    if ent is None:
+        _bt_pool[key] = [ws, True]
+        return ws, key
+    return ws, None                                            # pool buffer in flight: private, zero-filled
+
+
+def _bt_release(key, ws):
+    ent = _bt_pool.get(key) if key is not None else None
+    if ent is not None and ent[0] is ws:
+        ent[1] = False
+
+
 class BtcvaeFn(Function):
     """-> terms[3] = (mi, tc, dw_kl).  ctx keeps the [4+D][B] row statistics."""
 
@@ -434,27 +482,29 @@ class BtcvaeFn(Function):
             mu, logvar = mu.contiguous(), logvar.contiguous()
             st = _strides(mu, logvar)
         B, D = z.shape
-        nbytes = N.lib().dv_btcvae_workspace_bytes(B, D)
-        ws = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=z.device)
-        ws[:16].zero_()
+        ws, key = _bt_workspace(B, D, z.device)
         rowstats = _new((4 + D, B), z)
         terms = _new((3,), z)
         call("dv_btcvae_fwd", ptr(z), ptr(mu), ptr(logvar), st[0], st[1], B, D, int(n_data), int(bool(is_mss)),
              ptr(rowstats), ptr(terms), ptr(ws), stream())
-        ctx.meta = (B, D, int(n_data), int(bool(is_mss)))
+        if not (z.requires_grad or mu.requires_grad or logvar.requires_grad) or not torch.is_grad_enabled():
+            _bt_release(key, ws)                               # no backward will come for it
+            key = None
+        ctx.meta = (B, D, int(n_data), int(bool(is_mss)), key)
         ctx.save_for_backward(rowstats, ws)
         return terms
 
     @staticmethod
     def backward(ctx, g_terms):
         rowstats, ws = ctx.saved_tensors
-        B, D, n_data, is_mss = ctx.meta
+        B, D, n_data, is_mss, key = ctx.meta
         g_terms = _c(g_terms)
         g_z = _new((B, D), rowstats) if ctx.needs_input_grad[0] else None
         g_mu = _new((B, D), rowstats) if ctx.needs_input_grad[1] else None
         g_lv = _new((B, D), rowstats) if ctx.needs_input_grad[2] else None
         call("dv_btcvae_bwd", B, D, n_data, is_mss, ptr(rowstats), ptr(ws), ptr(g_terms), ptr(g_z), ptr(g_mu),
              ptr(g_lv), stream())
+        _bt_release(key, ws)
         return g_z, g_mu, g_lv, None, None
 
 
@@ -500,6 +550,36 @@ class BtcvaeGlobalFn(Function):
              ptr(g_cols[0]), ptr(g_cols[1]), stream())
         mine = parallel.reduce_scatter_rows(torch.cat([g_cols[0], g_cols[1]], dim=1), group)   # [b, 2D]
         return g_z, mine[:, :D].contiguous(), mine[:, D:].contiguous(), None, None, None
+
+
+class LossCombineFn(Function):
+    """loss = sum_i coef_a[i]*a[i] + sum_j coef_b[j]*b[j] with a = the fused loss kernel's output (rec, kl, per-dim kl..:
+    only the first len(coef_a) entries are weighted) and b = a short vector or 0-dim tensor (beta-TCVAE terms, the
+    FactorVAE tc) or None.  One launch forward, one backward (writes the FULL gradient of `a`, zeros included) -- instead
+    of the scalar select/mul/add kernels of `rec + (alpha*mi + beta*tc + ...)` and their zero-filled backward buffers."""
+
+    @staticmethod
+    def forward(ctx, a, b, coef_a, coef_b):
+        import ctypes
+        N.require_cuda_f32(a, b)
+        a = _c(a)
+        b = _c(b) if b is not None else None
+        na, nb = len(coef_a), (len(coef_b) if b is not None else 0)
+        ca = (ctypes.c_float * max(na, 1))(*coef_a)
+        cb = (ctypes.c_float * max(nb, 1))(*(coef_b if nb else [0.0]))
+        loss = _new((), a)
+        call("dv_loss_combine_fwd", ptr(a), ca, na, ptr(b), cb, nb, ptr(loss), stream())
+        ctx.meta = (ca, cb, na, nb, a.numel(), tuple(b.shape) if b is not None else None)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        ca, cb, na, nb, na_total, b_shape = ctx.meta
+        g = _c(g)
+        g_a = _new((na_total,), g)
+        g_b = _new(b_shape, g) if nb else None
+        call("dv_loss_combine_bwd", ptr(g), ca, na, na_total, cb, nb, ptr(g_a), ptr(g_b), stream())
+        return g_a, g_b, None, None
 
 
 def btcvae_rowstats(z, mu, logvar, n_data, is_mss=True):

@@ -63,6 +63,39 @@ def shard_batch(data, rank=None, world_size=None):
     return data[rank * per:(rank + 1) * per]
 
 
+class ShardSampler(torch.utils.data.Sampler):
+    """Index sampler for one rank of a data-parallel job -- the role torch's DistributedSampler plays for the reference's
+    DataLoader (utils/datasets.py:67-71 has `shuffle=True`, one process): every epoch ONE permutation of the dataset,
+    identical on all ranks (seed + epoch), padded by wrapping around to a multiple of the world size, dealt out
+    round-robin; `set_epoch` like DistributedSampler.  Without shuffling: the identity order."""
+
+    def __init__(self, dataset_len, rank=None, world_size=None, shuffle=True, seed=0, drop_last=False):
+        if rank is None:
+            rank = dist.get_rank() if is_distributed() else 0
+        if world_size is None:
+            world_size = dist.get_world_size() if is_distributed() else 1
+        self.n, self.rank, self.world, self.shuffle, self.seed, self.epoch = int(dataset_len), rank, world_size, shuffle, seed, 0
+        self.per_rank = self.n // world_size if drop_last else -(-self.n // world_size)
+        self.total = self.per_rank * world_size
+
+    def set_epoch(self, epoch):
+        self.epoch = int(epoch)
+
+    def __iter__(self):
+        if self.shuffle:
+            g = torch.Generator().manual_seed(self.seed + self.epoch)
+            order = torch.randperm(self.n, generator=g).tolist()
+        else:
+            order = list(range(self.n))
+        if self.total > self.n:
+            order += order[:self.total - self.n]
+        order = order[:self.total]
+        return iter(order[self.rank:self.total:self.world])
+
+    def __len__(self):
+        return self.per_rank
+
+
 def broadcast_parameters(module, src=0):
     """Make every rank start from rank `src`'s parameters."""
     if not is_distributed():

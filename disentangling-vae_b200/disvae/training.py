@@ -131,7 +131,7 @@ class Trainer():
         ddp = is_distributed()
         if entry is None:
             static_x = torch.empty(data.shape, dtype=torch.float32, device=self.device)
-            static_x.copy_(data, non_blocking=True)
+            self._fill_static(static_x, data)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             steps_before = self.loss_f.n_train_steps
@@ -159,7 +159,7 @@ class Trainer():
             entry = (g, static_x, static_loss, _native.lib().dv_launch_count() - launches_before, flat)
             self._graphs[key] = entry
         g, static_x, static_loss, n_kernels, flat = entry
-        static_x.copy_(data, non_blocking=True)
+        self._fill_static(static_x, data)
         g.replay()
         _native.GRAPH_LAUNCHES += n_kernels
         if flat is not None:
@@ -174,6 +174,15 @@ class Trainer():
         self._fused.host_steps += 1
         return static_loss
 
+    def _fill_static(self, static_x, data):
+        """The graph's input buffer <- this step's batch.  uint8 batches are uploaded as bytes and
+        converted by dv_u8_to_f32 straight into the buffer (ToTensor's /255), float batches are copied."""
+        if data.dtype == torch.uint8:
+            from disvae import ops
+            ops.u8_to_f32(data.to(self.device, non_blocking=True), out=static_x)
+        else:
+            static_x.copy_(data, non_blocking=True)
+
     def _step(self, data, storer):
         """One optimisation step; returns the loss as a detached 0-dim device tensor."""
         if self._graph_eligible(data, storer):
@@ -181,6 +190,9 @@ class Trainer():
             if self._eligible_steps > 2 or (tuple(data.shape), str(data.dtype)) in self._graphs:   # 2 eager warm-up steps first
                 return self._graph_step(data)
         data = data.to(self.device, non_blocking=True)
+        if data.dtype == torch.uint8:                         # bytes over PCIe, ToTensor's /255 on the device
+            from disvae import ops
+            data = ops.u8_to_f32(data)
         recon_batch, latent_dist, latent_sample = self.model(data)
         try:
             loss = self.loss_f(data, recon_batch, latent_dist, self.model.training, storer, latent_sample=latent_sample)

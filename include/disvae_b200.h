@@ -186,6 +186,24 @@ int dv_btcvae_bwd_rows(int B, int D, int row0, int nrows, long long n_data, int 
                        const float* rowstats, const void* workspace, const float* g_terms, float* g_z,
                        float* g_mu, float* g_logvar, void* stream);
 
+/* ---- input pipeline and step glue -----------------------------
+ * dv_u8_to_f32: dst[i] = src[i] / 255 (true division) -- torchvision ToTensor on the device, so host batches can be
+ * uploaded as bytes (training.py:150; utils/datasets.py:182,247,364-367).  Both pointers 16-byte aligned.
+ */
+int dv_u8_to_f32(const unsigned char* src, float* dst, long long n, void* stream);
+/* loss[0] = sum_{i<na} coef_a[i]*a[i] + sum_{j<nb} coef_b[j]*b[j]; a, b device vectors, coef_* HOST arrays (<= 8 each,
+ * passed to the kernel by value).  The scalar combinations of losses.py:151 (rec + anneal*beta*kl), :199-200 is not
+ * covered (|kl - C|), :381-382 (rec + alpha*mi + beta*tc + anneal*gamma*dw_kl).  Backward: g_a[0..na_total) (zeros past
+ * na), g_b[0..nb) from the upstream scalar g[0]. */
+int dv_loss_combine_fwd(const float* a, const float* coef_a, int na, const float* b, const float* coef_b, int nb,
+                        float* loss, void* stream);
+int dv_loss_combine_bwd(const float* g, const float* coef_a, int na, int na_total, const float* coef_b, int nb,
+                        float* g_a, float* g_b, void* stream);
+/* g = dy * act'(y) over an NCHW tensor [B, C <= 4, hw] fused with chansum[c] = sum_{b,hw} g (the bias gradient of the
+ * ConvTranspose2d that produced y; decoders.py:82).  workspace: dv_channel_sum_workspace_bytes(). */
+int dv_act_bwd_chansum(const float* dy, const float* y, float* g, int B, int C, int hw, int act, float slope,
+                       float* chansum, void* workspace, void* stream);
+
 /* ---- disentanglement metrics: marginal-entropy estimator ---------------------
  * Replaces Evaluator._estimate_latent_entropies (disvae/evaluate.py:233-297), the inner loop of the MIG / AAM metrics
  * (:119-161, :299-317): for S samples zs[D][S] (row d = samples of latent dimension d) and the N posteriors

@@ -29,6 +29,6 @@ for cold in (False, True):
     rows.sort(key=lambda r: r[0])
     us, marks = rows[len(rows) // 2]
     v4 = os.environ.get("DV_BTCVAE_V4", "1") != "0"
-    names = ("stage | fold | sweep | cluster.sync | finalise | exit sync" if v4 else "stage | bounds+fold | sweep | row stats | block sum | -")
+    names = ("(unused) | stage+fold | sweep | cluster.sync | finalise | exit sync" if v4 else "stage | bounds+fold | sweep | row stats | block sum | -")
     print("cold" if cold else "warm", "event us %.2f" % us, "marks (clk since entry): %s =" % names, [int(m) for m in marks],
           " => us @1.9GHz:", [round(m / 1900, 2) for m in marks])

@@ -285,3 +285,26 @@ def test_row_collectives_world2_gloo():
     for p in procs:
         p.join(60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_shard_sampler_partitions_every_epoch():
+    """disvae.parallel.ShardSampler: the ranks' index lists are disjoint, equally long and cover the
+    dataset (padding by wrap-around), identical permutation on every rank, a new one per epoch, deterministic."""
+    from disvae.parallel import ShardSampler
+    n, world = 1003, 4
+    samplers = [ShardSampler(n, rank=r, world_size=world, shuffle=True, seed=7) for r in range(world)]
+    for epoch in range(3):
+        for s in samplers:
+            s.set_epoch(epoch)
+        parts = [list(s) for s in samplers]
+        assert all(len(p) == len(samplers[0]) == 251 for p in parts)
+        flat = [i for p in parts for i in p]
+        assert set(flat) == set(range(n)) and len(flat) == 1004                 # one wrapped-around duplicate
+        assert parts == [list(s) for s in samplers]                               # deterministic
+        if epoch:
+            assert parts[0] != prev
+        prev = parts[0]
+    assert list(ShardSampler(10, rank=1, world_size=2, shuffle=False)) == [1, 3, 5, 7, 9]
+    assert len(ShardSampler(10, rank=0, world_size=4, drop_last=True)) == 2
+    loader = torch.utils.data.DataLoader(list(range(20)), batch_size=4, sampler=ShardSampler(20, rank=0, world_size=2, seed=1))
+    assert sum(len(b) for b in loader) == 10

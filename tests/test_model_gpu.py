@@ -264,17 +264,66 @@ def test_first_step_adam_moments_match_reference_golden(golden, loss_name, tmp_p
         lf._perm_queue = [perms]
     else:
         m.inject_noise([noise])
+    from disvae import ops
+    from oracle import same_branch as SB
+    p32 = OrderedDict((k, v.detach().cpu().clone()) for k, v in m.state_dict().items())
+    d32 = (OrderedDict((k, v.detach().cpu().clone()) for k, v in lf.discriminator.state_dict().items())
+           if loss_name == "factor" else None)
+    ops.start_trace()
     lv = trainer._train_iteration(x, None)
+    trace = ops.stop_trace()
     assert abs(lv - g["steps"][0]["loss"]) <= RTOL * abs(g["steps"][0]["loss"])
-    for k, prm in m.named_parameters():
-        st, ref = opt.state[prm], g["opt_state_step1"][k]
-        digest_close(st["exp_avg"], ref["exp_avg"], rtol=RTOL)
-        digest_close(st["exp_avg_sq"], ref["exp_avg_sq"], rtol=2 * RTOL)
+
+    def moments_match_golden():
+        try:
+            for k, prm in m.named_parameters():
+                st, ref = opt.state[prm], g["opt_state_step1"][k]
+                digest_close(st["exp_avg"], ref["exp_avg"], rtol=RTOL)
+                digest_close(st["exp_avg_sq"], ref["exp_avg_sq"], rtol=2 * RTOL)
+            if loss_name == "factor":
+                for k, prm in lf.discriminator.named_parameters():
+                    st, ref = lf.optimizer_d.state[prm], g["disc_opt_state_step1"][k]
+                    digest_close(st["exp_avg"], ref["exp_avg"], rtol=RTOL)
+                    digest_close(st["exp_avg_sq"], ref["exp_avg_sq"], rtol=2 * RTOL)
+            return True
+        except AssertionError:
+            return False
+
+    if moments_match_golden():
+        return
+    # The reference run and this one may sit on different sides of a (Leaky)ReLU for a unit whose pre-activation is
+    # numerically zero (oracle/same_branch.py).  Then -- and only then -- the referee is the fp64 oracle on THIS run's
+    # branch: the trace must show at least one flipped, numerically ambiguous unit, and exp_avg = (1 - beta1) * grad must
+    # match that oracle to 1e-4.
     if loss_name == "factor":
-        for k, prm in lf.discriminator.named_parameters():
-            st, ref = lf.optimizer_d.state[prm], g["disc_opt_state_step1"][k]
-            digest_close(st["exp_avg"], ref["exp_avg"], rtol=RTOL)
-            digest_close(st["exp_avg_sq"], ref["exp_avg_sq"], rtol=2 * RTOL)
+        # the Trainer's discarded full-batch forward (training.py:153) is the first encoder/decoder pass of the trace
+        second_enc = [i for i, (n, _) in enumerate(trace) if n == "encoder.conv0"][1]
+        trace = trace[second_enc:]
+    cfg = dict(rec_dist="bernoulli", reg_anneal=kw["reg_anneal"], factor_G=kw["factor_G"])
+
+    def run64(pp, dd):
+        xx = x.double()
+        if loss_name == "factor":
+            l, _, _ = O.factor_step(pp, dd, O.make_adam(pp, 0.0), O.make_adam(dd, 0.0, betas=(0.5, 0.9)), xx, cfg, step=1,
+                                    eps1=e1.double(), eps2=e2.double(), perms=perms)
+            return l.item()
+        ro, (mo, lo), zo = O.vae_forward(pp, xx, noise.double())
+        if loss_name in ("VAE", "betaH"):
+            l, _ = O.loss_betaH(xx, ro, mo, lo, 1 if loss_name == "VAE" else kw["betaH_B"], "bernoulli", 1, kw["reg_anneal"])
+        elif loss_name == "betaB":
+            l, _ = O.loss_betaB(xx, ro, mo, lo, kw["betaB_initC"], kw["betaB_finC"], kw["betaB_G"], "bernoulli", 1, kw["reg_anneal"])
+        else:
+            l, _ = O.loss_btcvae(xx, ro, mo, lo, zo, g["n_data"], kw["btcvae_A"], kw["btcvae_B"], kw["btcvae_G"], "bernoulli", 1,
+                                 kw["reg_anneal"])
+        l.backward()
+        return l.item()
+    ref = SB.same_branch_reference(trace, p32, run64, disc32=d32)
+    assert ref["flips"] > 0 and ref["flip_max_rel"] <= 1e-3, ref
+    ours = {k: opt.state[prm]["exp_avg"] / 0.1 for k, prm in m.named_parameters()}
+    if loss_name == "factor":
+        ours.update({"disc." + k: lf.optimizer_d.state[prm]["exp_avg"] / 0.5 for k, prm in lf.discriminator.named_parameters()})
+    err, key = SB.grad_errors(ours, ref["grads"])
+    assert err <= RTOL, "exp_avg/(1-beta1) of %s: %.2e vs fp64 on the same branch (%d flips)" % (key, err, ref["flips"])
 
 
 def test_factor_step_matches_oracle_including_encoder_leak():
@@ -419,3 +468,31 @@ def test_train_epoch_mean_identical_in_graph_and_eager_mode(tmp_path):
         assert abs(a - b) <= 1e-6 * abs(a), (means_e, means_g)
     assert means_g[0] > means_g[1] > means_g[2]
     assert steps_e == steps_g == 15.0                  # FusedAdam.flush_state at every epoch end
+
+
+def test_uint8_batches_train_like_float_batches(tmp_path):
+    """a uint8 host batch (bytes over PCIe, /255 on the device by dv_u8_to_f32 -- in graph mode straight
+    into the captured input buffer) walks exactly the trajectory of the same batch converted by ToTensor on the host."""
+    import disvae
+    from disvae.models.losses import get_loss_f
+
+    def run(as_u8):
+        torch.manual_seed(SEED)
+        m = disvae.init_specific_model("Burgess", (1, 32, 32), 10)
+        opt = torch.optim.Adam(m.parameters(), lr=5e-4)
+        lf = get_loss_f("betaH", rec_dist="bernoulli", reg_anneal=0, betaH_B=4)
+        tr = disvae.Trainer(m, opt, lf, device=torch.device(DEV), logger=logging.getLogger("t"), save_dir=str(tmp_path),
+                            is_progress_bar=False)
+        m.train()
+        g = torch.Generator().manual_seed(5)
+        us = [torch.randint(0, 256, (64, 1, 32, 32), generator=g, dtype=torch.uint8) for _ in range(6)]
+        loader = [((u.pin_memory() if as_u8 else u.float().div(255).pin_memory()), None) for u in us]
+        means = [tr._train_epoch(loader, None, e) for e in range(2)]
+        return means, m, tr
+
+    mf, m_f, _ = run(False)
+    mu8, m_u, tr_u = run(True)
+    assert len(tr_u._graphs) == 1
+    assert mf == mu8
+    for (k, a), (_, b) in zip(m_f.state_dict().items(), m_u.state_dict().items()):
+        assert torch.equal(a, b), k
