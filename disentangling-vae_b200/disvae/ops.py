@@ -84,14 +84,14 @@ def conv_down(hi, wp, bias, mask, B, H, W, CH, nchw, act, want_colsum=False):
         cs = _new((LO_CH,), hi)
         ws = _scratch("chansum", N.lib().dv_channel_sum_workspace_bytes(), hi.device)
     call("dv_conv_down", ptr(hi), ptr(wp), ptr(bias), ptr(mask), ptr(lo), B, H, W, CH, nchw, act, ptr(cs), ptr(ws), stream(),
-         tag="[H=%d,CH=%d]" % (H, CH))
+         tag="[H=%d,CH=%d]%s" % (H, CH, "+mask" if mask is not None else ""))
     return (lo, cs) if want_colsum else lo
 
 
 def conv_up(lo, wp, bias, mask, B, H, W, CH, nchw, act):
     hi = _new((B, CH, 2 * H, 2 * W) if nchw else (B, 2 * H, 2 * W, CH), lo)
     call("dv_conv_up", ptr(lo), ptr(wp), ptr(bias), ptr(mask), ptr(hi), B, H, W, CH, nchw, act, stream(),
-         tag="[H=%d,CH=%d]" % (H, CH))
+         tag="[H=%d,CH=%d]%s" % (H, CH, "+mask" if mask is not None else ""))
     return hi
 
 
@@ -183,6 +183,46 @@ def _c(t):
 
 
 # ---------------------------------------------------------------------------------------
+# Weight-gradient lane: in a backward pass the weight gradient of a layer and the input gradient that continues the
+# chain are independent.  The MLP layers and the 4x4 / 8x8 conv layers occupy a fraction of the 148 SMs for ~15 us each
+# (launch-latency bound), so their weight-gradient kernels run on a second stream beside the dgrad chain and are joined
+# at the end of the node's backward.  Works inside CUDA-graph capture (fork/join from the capturing stream become graph
+# dependencies).  Tensors read on the side stream are kept alive until the join, so the caching allocator cannot hand
+# their memory to the main stream meanwhile.  DISVAE_SIDE_STREAM=0 switches it off (same kernels, same results).
+# ---------------------------------------------------------------------------------------
+import os as _os
+
+_side_streams = {}
+
+
+class _WgradLane:
+    def __init__(self, device):
+        self.enabled = _os.environ.get("DISVAE_SIDE_STREAM", "1") != "0"
+        self.keep = []
+        if self.enabled:
+            self.main = torch.cuda.current_stream(device)
+            side = _side_streams.get(device.index)
+            if side is None:
+                side = _side_streams[device.index] = torch.cuda.Stream(device)
+            self.side = side
+
+    def run(self, fn, *reads):
+        """fn() on the side stream after everything enqueued on the main stream so far; `reads` = its input tensors."""
+        if not self.enabled:
+            return fn()
+        self.side.wait_stream(self.main)
+        with torch.cuda.stream(self.side):
+            out = fn()
+        self.keep.extend(reads)
+        return out
+
+    def join(self):
+        if self.enabled:
+            self.main.wait_stream(self.side)
+            self.keep.clear()
+
+
+# ---------------------------------------------------------------------------------------
 # Burgess encoder (disvae/models/encoders.py:69-89) as ONE autograd node
 # ---------------------------------------------------------------------------------------
 class EncoderFn(Function):
@@ -226,11 +266,12 @@ class EncoderFn(Function):
         lins = [(params[2 * n_conv + 2 * i], params[2 * n_conv + 2 * i + 1]) for i in range(3)]
         B, C, S, _ = x.shape
         g = _c(g_ml)
-        dlw3, dlb3 = linear_wgrad(g, h2)
+        lane = _WgradLane(g.device)
+        dlw3, dlb3 = lane.run(lambda: linear_wgrad(g, h2), g, h2)
         g2 = linear_dgrad(g, lins[2][0], h2, ACT_RELU)
-        dlw2, dlb2 = linear_wgrad(g2, h1)
+        dlw2, dlb2 = lane.run(lambda: linear_wgrad(g2, h1), g2, h1)
         g1 = linear_dgrad(g2, lins[1][0], h1, ACT_RELU)
-        dlw1, dlb1 = linear_wgrad(g1, flat)
+        dlw1, dlb1 = lane.run(lambda: linear_wgrad(g1, flat), g1, flat)
         gflat = linear_dgrad(g1, lins[0][0], flat, ACT_RELU)                     # masked by the last conv's ReLU
         g_lo = flat_transpose(gflat, B, to_nhwc=True)
         conv_grads = [None] * (2 * n_conv)
@@ -238,13 +279,14 @@ class EncoderFn(Function):
         for l in range(n_conv - 1, -1, -1):
             H = S >> (l + 1)
             if l > 0:
-                dw, db = conv_wgrad(g_lo, acts[l - 1], B, H, H, LO_CH, 0, True)
+                dw, db = lane.run(lambda gl=g_lo, a=acts[l - 1], H=H: conv_wgrad(gl, a, B, H, H, LO_CH, 0, True), g_lo, acts[l - 1])
                 g_lo = conv_up(g_lo, packed[l], None, acts[l - 1], B, H, H, LO_CH, 0, ACT_NONE)
             else:
-                dw, db = conv_wgrad(g_lo, x, B, H, H, C, 1, True)
+                dw, db = lane.run(lambda gl=g_lo, H=H: conv_wgrad(gl, x, B, H, H, C, 1, True), g_lo, x)
                 if ctx.needs_input_grad[0]:
                     dx = conv_up(g_lo, packed[0], None, None, B, H, H, C, 1, ACT_NONE)
             conv_grads[2 * l], conv_grads[2 * l + 1] = dw, db
+        lane.join()
         return (dx, None, *conv_grads, dlw1, dlb1, dlw2, dlb2, dlw3, dlb3)
 
 
@@ -300,11 +342,13 @@ class DecoderFn(Function):
         # sigmoid backward of the output layer fused with its bias gradient (the sum of the result over pixels)
         g_hi, db = act_bwd_chansum(_c(d_recon), recon, ACT_SIGMOID)                # NCHW, C channels
         convT_grads = [None] * (2 * n_convT)
+        lane = _WgradLane(g_hi.device)
         for t in range(n_convT - 1, -1, -1):
             last = (t == n_convT - 1)
             H = 4 << t                                   # input resolution of convT t
             CH, nchw = (C, 1) if last else (LO_CH, 0)
-            dw, _ = conv_wgrad(acts[t], g_hi, B, H, H, CH, nchw, False)
+            dw, _ = lane.run(lambda a=acts[t], gh=g_hi, H=H, CH=CH, nchw=nchw: conv_wgrad(a, gh, B, H, H, CH, nchw, False),
+                             acts[t], g_hi)
             convT_grads[2 * t], convT_grads[2 * t + 1] = dw, db
             # input gradient, masked by acts[t] > 0; for t > 0 it is the output gradient of convT t-1, whose bias
             # gradient (its sum over pixels) comes out of the same kernel's epilogue
@@ -313,12 +357,13 @@ class DecoderFn(Function):
             else:
                 g_hi = conv_down(g_hi, packed[t], None, acts[t], B, H, H, CH, nchw, ACT_NONE)
         g3 = flat_transpose(g_hi.view(B, FLAT), B, to_nhwc=False)                  # grad of lin3 pre-activation
-        dlw3, dlb3 = linear_wgrad(g3, h2)
+        dlw3, dlb3 = lane.run(lambda: linear_wgrad(g3, h2), g3, h2)
         g2 = linear_dgrad(g3, lins[2][0], h2, ACT_RELU)
-        dlw2, dlb2 = linear_wgrad(g2, h1)
+        dlw2, dlb2 = lane.run(lambda: linear_wgrad(g2, h1), g2, h1)
         g1 = linear_dgrad(g2, lins[1][0], h1, ACT_RELU)
-        dlw1, dlb1 = linear_wgrad(g1, z)
+        dlw1, dlb1 = lane.run(lambda: linear_wgrad(g1, z), g1, z)
         dz = linear_dgrad(g1, lins[0][0], None, ACT_NONE) if ctx.needs_input_grad[0] else None
+        lane.join()
         return (dz, None, None, dlw1, dlb1, dlw2, dlb2, dlw3, dlb3, *convT_grads)
 
 
@@ -353,12 +398,14 @@ class MlpFn(Function):
         g = _c(g_out)
         grads = [None] * (2 * n)
         dx = None
+        lane = _WgradLane(g.device)
         for i in range(n - 1, -1, -1):
-            grads[2 * i], grads[2 * i + 1] = linear_wgrad(g, hs[i])
+            grads[2 * i], grads[2 * i + 1] = lane.run(lambda gg=g, h=hs[i]: linear_wgrad(gg, h), g, hs[i])
             if i > 0:
                 g = linear_dgrad(g, params[2 * i], hs[i], ACT_LEAKY, slope)
             elif ctx.needs_input_grad[0]:
                 dx = linear_dgrad(g, params[0], None, ACT_NONE)
+        lane.join()
         return (dx, None, *grads)
 
 

@@ -224,14 +224,13 @@ def test_train_steps_match_reference_golden(golden, loss_name, tmp_path):
     # Losses and logged values above are held to 1e-4; parameters to 1e-4 of scale + 2.5*lr per element.
     for k, v in m.state_dict().items():
         digest_close(v, g["params"][k], rtol=RTOL, atol=2.5 * over["lr"])
-    # Adam moments after the 3 steps, loosely (2e-2 of scale): from step 2 on the trajectory depends on which way Adam
-    # moved the entries whose first gradient is numerically zero (+-lr whatever the magnitude, i.e. 2*lr/|w| ~ 0.5 %
-    # relative parameter differences between two correct runs).  The tight optimizer-path check is step 1, next test.
+    # Adam moments are NOT compared after 3 steps: from step 2 on the trajectory depends on which way Adam moved the
+    # entries whose first gradient is numerically zero (+-lr whatever the magnitude: 2*lr/|w| ~ 0.5 % relative parameter
+    # differences between two correct runs, several % on individual moment entries after three steps -- measured).  The
+    # optimizer path is pinned after ONE step, where exp_avg = (1 - beta1) * grad exactly: next test.
     trainer._fused.flush_state()
     for k, prm in m.named_parameters():
-        st, ref = opt.state[prm], g["opt_state"][k]
-        digest_close(st["exp_avg"], ref["exp_avg"], rtol=2e-2)
-        assert float(st["step"]) == ref["step"] == 3.0
+        assert float(opt.state[prm]["step"]) == g["opt_state"][k]["step"] == 3.0
     if loss_name == "factor":
         for k, v in lf.discriminator.state_dict().items():
             digest_close(v, g["disc_params"][k], rtol=RTOL, atol=2.5 * over["lr_disc"])
