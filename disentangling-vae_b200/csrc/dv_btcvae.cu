@@ -10,14 +10,15 @@
 //   log_qz[i]       = LSE_j ( sum_d m[i,j,d] + D*lw[i,j] )        (trap T2: D-fold weight)
 //   log_prod_qzi[i] = sum_d LSE_j ( m[i,j,d] + lw[i,j] )
 //
-// Mapping: a warp is 4 rows (i) x 8 column-lanes (j); the 8 warps of a block split the j range,
-// so a block owns 4 rows and the grid is B/4 blocks.  Per-column parameters are precomputed once
-// by a prep kernel as float4 {c, hiv, mu, z} * in a [D][B] array that every block streams from
-// L1/L2: one 128-bit load fetches everything a (j,d) pair needs, 8 consecutive j per request,
-// broadcast over the warp's 4 rows.  All exponent arithmetic is done in the log2 domain
-// (c and hiv pre-multiplied by log2 e) so that each (i,j,d) costs one MUFU.EX2 and no extra
-// multiply.  Each logsumexp is an exact two-sweep (max, then sum of exp2) reduction; cross-lane
-// merges are warp shuffles, cross-warp merges go through a few hundred bytes of shared memory.
+// Two forward paths (both without anything larger than O(B*D) in memory), one backward:
+//   * btcvae_fwd4_kernel  -- D <= 16, the whole batch: ONE launch, clusters of 4 CTAs (columns split over the cluster,
+//     partial logsumexp states merged through distributed shared memory).  BASELINE configs[1] runs here.
+//   * btcvae_prep_kernel + btcvae_fwd2_kernel + btcvae_finalize_kernel -- any D, any row window [row0, row0+nrows) of
+//     the batch (z = 64 of configs[4]; the global-batch estimator over an all-gathered batch):
+//     (row group x column range) tiles with per-tile reference exponents, merged in a fixed order.
+//   * btcvae_bwd_kernel   -- rows role (g_z) and columns role (g_mu, g_logvar), same row-window semantics.
+// All exponent arithmetic is done in the log2 domain (c and hiv pre-multiplied by log2 e) so that each (i,j,d) costs
+// one MUFU.EX2 and no extra multiply; cross-lane merges are warp shuffles; every reduction has a fixed order.
 #include <stdlib.h>
 #include <cooperative_groups.h>
 #include "dv_common.cuh"
@@ -71,164 +72,6 @@ __device__ __forceinline__ void lse_merge2(float& m, float& s, float m2, float s
   s = s * exp2f(m - nm) + s2 * exp2f(m2 - nm);
   m = nm;
 }
-
-// DC: latent dims held in registers per chunk.  FUSE: D <= DC, single chunk, the log_qz sweep is
-// fused into the max sweep.  EXACT: D == DC (no per-dim guards).
-template <int DC, bool FUSE, bool EXACT>
-__global__ void __launch_bounds__(kBtWarps * 32)
-btcvae_fwd_kernel(int B, int D, LogW lw, float* __restrict__ ws, float* __restrict__ rowstats, float* __restrict__ terms) {
-  __shared__ float sm_max[kBtWarps][kRows][DC];
-  __shared__ float sm_sum[kBtWarps][kRows][DC];
-  __shared__ float sm_am[kBtWarps][kRows], sm_as[kBtWarps][kRows];
-  __shared__ float sm_prod[kRows];
-  __shared__ bool is_last;
-  const float4* __restrict__ pj = reinterpret_cast<const float4*>(ws + kWsHeader);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int r = lane >> 3, jl = lane & 7;
-  const int i = min((int)blockIdx.x * kRows + r, B - 1);       // tail rows recompute row B-1 (never stored)
-  const int slice = ((B + kBtWarps - 1) / kBtWarps + kJL - 1) / kJL * kJL;
-  const int j_begin = warp * slice, j_end = min(B, j_begin + slice);
-  const float Df = (float)D;
-
-  float am = -INFINITY, as = 0.f;                              // log_qz state (log2 domain)
-  if (!FUSE) {
-    for (int j = j_begin + jl; j < j_end; j += kJL) {
-      float sa = 0.f;
-      for (int d = 0; d < D; ++d) {
-        const float4 p = __ldg(pj + (long long)d * B + j);
-        const float t = __ldg(&pj[(long long)d * B + i].w) - p.z;
-        sa += p.x - p.y * (t * t);
-      }
-      const float a = sa + Df * logw2(lw, i, j);
-      const float nm = fmaxf(am, a);
-      as = as * exp2f(am - nm) + exp2f(a - nm);
-      am = nm;
-    }
-  }
-  if (threadIdx.x < kRows) sm_prod[threadIdx.x] = 0.f;
-
-  for (int d0 = 0; d0 < D; d0 += DC) {
-    const int nd = EXACT ? DC : min(DC, D - d0);
-    float zc[DC], mx[DC], sx[DC];
-#pragma unroll
-    for (int k = 0; k < DC; ++k) {
-      zc[k] = (EXACT || k < nd) ? __ldg(&pj[(long long)(d0 + k) * B + i].w) : 0.f;
-      mx[k] = -INFINITY; sx[k] = 0.f;
-    }
-    // ---- sweep 1: per-dimension max (and, fused, the log_qz online logsumexp) ----
-    for (int j = j_begin + jl; j < j_end; j += kJL) {
-      const float w = logw2(lw, i, j);
-      float sa = 0.f;
-#pragma unroll
-      for (int k = 0; k < DC; ++k) {
-        if (EXACT || k < nd) {
-          const float4 p = __ldg(pj + (long long)(d0 + k) * B + j);
-          const float t = zc[k] - p.z;
-          const float m = p.x - p.y * (t * t);
-          mx[k] = fmaxf(mx[k], m + w);
-          if (FUSE) sa += m;
-        }
-      }
-      if (FUSE) {
-        const float a = sa + Df * w;
-        const float nm = fmaxf(am, a);
-        as = as * exp2f(am - nm) + exp2f(a - nm);
-        am = nm;
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < DC; ++k) {
-#pragma unroll
-      for (int o = 1; o < kJL; o <<= 1) mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
-      if (jl == 0) sm_max[warp][r][k] = mx[k];
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < DC; ++k) {
-      float m = sm_max[0][r][k];
-#pragma unroll
-      for (int w2 = 1; w2 < kBtWarps; ++w2) m = fmaxf(m, sm_max[w2][r][k]);
-      mx[k] = m;                                               // block-wide max for (row, dim)
-    }
-    // ---- sweep 2: sum of exp2 ----
-    for (int j = j_begin + jl; j < j_end; j += kJL) {
-      const float w = logw2(lw, i, j);
-#pragma unroll
-      for (int k = 0; k < DC; ++k) {
-        if (EXACT || k < nd) {
-          const float4 p = __ldg(pj + (long long)(d0 + k) * B + j);
-          const float t = zc[k] - p.z;
-          sx[k] += exp2f((p.x - p.y * (t * t)) + (w - mx[k]));
-        }
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < DC; ++k) {
-#pragma unroll
-      for (int o = 1; o < kJL; o <<= 1) sx[k] += __shfl_xor_sync(0xffffffffu, sx[k], o);
-      if (jl == 0) sm_sum[warp][r][k] = sx[k];
-    }
-    __syncthreads();
-    if (warp == 0) {
-      for (int e = lane; e < kRows * DC; e += 32) {
-        const int rr = e / DC, k = e % DC;
-        if (k < nd) {
-          float s = 0.f;
-          for (int w2 = 0; w2 < kBtWarps; ++w2) s += sm_sum[w2][rr][k];
-          float m = sm_max[0][rr][k];
-          for (int w2 = 1; w2 < kBtWarps; ++w2) m = fmaxf(m, sm_max[w2][rr][k]);
-          const float P = (m + log2f(s)) * kLn2;
-          const int ii = blockIdx.x * kRows + rr;
-          if (ii < B) rowstats[(long long)(4 + d0 + k) * B + ii] = P;
-          sm_sum[0][rr][k] = P;                                // stash for the ordered row sum
-        }
-      }
-      __syncwarp();
-      if (lane < kRows) {
-        float p = sm_prod[lane];
-        for (int k = 0; k < nd; ++k) p += sm_sum[0][lane][k];
-        sm_prod[lane] = p;
-      }
-    }
-    __syncthreads();
-  }
-
-#pragma unroll
-  for (int o = 1; o < kJL; o <<= 1) {
-    const float m2 = __shfl_xor_sync(0xffffffffu, am, o), s2 = __shfl_xor_sync(0xffffffffu, as, o);
-    lse_merge2(am, as, m2, s2);
-  }
-  if (jl == 0) { sm_am[warp][r] = am; sm_as[warp][r] = as; }
-  __syncthreads();
-  if (threadIdx.x < kRows) {
-    const int rr = threadIdx.x, ii = blockIdx.x * kRows + rr;
-    float m = sm_am[0][rr], s = sm_as[0][rr];
-    for (int w2 = 1; w2 < kBtWarps; ++w2) lse_merge2(m, s, sm_am[w2][rr], sm_as[w2][rr]);
-    if (ii < B) {
-      rowstats[1LL * B + ii] = (m + log2f(s)) * kLn2;          // log_qz
-      rowstats[2LL * B + ii] = sm_prod[rr];                    // log_prod_qzi
-    }
-  }
-
-  // ---- last block: mi / tc / dw_kl means in a fixed order (losses.py:369-373) ----
-  unsigned* counter = reinterpret_cast<unsigned*>(ws);
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (!is_last) return;
-  __threadfence();
-  if (warp == 0) {
-    float mi = 0.f, tc = 0.f, dw = 0.f;
-    for (int ii = lane; ii < B; ii += 32) {
-      const float lpz = rowstats[ii], lqz = rowstats[1LL * B + ii], lprod = rowstats[2LL * B + ii], lqc = rowstats[3LL * B + ii];
-      mi += lqc - lqz; tc += lqz - lprod; dw += lprod - lpz;
-    }
-    mi = warp_sum(mi); tc = warp_sum(tc); dw = warp_sum(dw);
-    if (lane == 0) { terms[0] = mi / (float)B; terms[1] = tc / (float)B; terms[2] = dw / (float)B; *counter = 0u; }
-  }
-}
-
 
 // ------------------------------------------------------------------------------------------
 // Forward, second generation: (row-group x column-range) tiling.
@@ -403,299 +246,10 @@ btcvae_finalize_kernel(int B, int D, int row0, int nrows, int JS, const float2* 
   }
 }
 
-// ------------------------------------------------------------------------------------------
-// Forward, version 3 (small latent sizes, B <= ~1000): ONE launch, nothing but the O(B*D) outputs touches HBM.
-// Every block stages the parameters {c, hiv, mu, z}*[B][D] of ALL columns in shared memory (computing them from
-// z/mu/logvar itself: 3*B*D loads per block instead of a prep launch), so a block owning RPB rows sees whole rows
-// and finishes their logsumexps without any cross-block merge.  16 warps: warp 2r+h sweeps half h of the columns
-// of row r in a single pass.
-//
-// Instruction diet of the (i,j,d) inner loop -- it is issue bound, not MUFU or memory bound:
-//   * a FIXED reference exponent per dimension, r_d = max_j(c_jd + w_j) (log2 units: an upper bound of every
-//     term), and the column weight w_j are folded into the staged constant once per block:
-//     x''_jd = c_jd + w_j - r_d.  The loop is then
-//     t = z_id - mu_jd;  arg = x'' - hiv*t*t;  a += arg;  s_d += ex2(arg)      (LDS.128 + 6 instructions),
-//     terms are <= 1 (no overflow; the columns that matter have arg near 0, so a keeps full precision), and
-//     sum_d arg = sum_d m + D*w_j - sum_d r_d  feeds log q(z) directly.
-//   * the one irregular weight (row B-2, column 0; math.py:70-72) is a peeled first iteration.
-//   * log q(z): online logsumexp with ONE ex2 per column (rescale-or-add select).
-//   * a row whose terms (nearly) all underflow against the fixed reference (sum < 2^-90: its best term is > 60
-//     nats below the column bound -- an outlier sample) is detected and redone by a slow exact two-pass sweep.
-// Row statistics go straight to `rowstats`; the block's contribution to the three means goes to `blockpart`, and
-// the last block to finish (device counter) adds the contributions in block order -> deterministic.
-// Shared memory: B * (DC+1) float4 (pitch DC+1 keeps the 128-bit row loads conflict free): 176 KB at B=1024, D=10.
-// ------------------------------------------------------------------------------------------
-constexpr int kF3Threads = 512;
-constexpr int kF3MaxRows = 8;
-
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
-}
-
-template <int DC, bool EXACT>
-__global__ void __launch_bounds__(kF3Threads, 1)
-btcvae_fwd3_kernel(const float* __restrict__ z, const float* __restrict__ mu, const float* __restrict__ logvar, int ld,
-                   int row_stride, int B, int D_rt, LogW lw, int rpb, float4* __restrict__ pj_out, float* __restrict__ rowstats,
-                   float* __restrict__ terms, float* __restrict__ blockpart, unsigned* __restrict__ counter,
-                   float* __restrict__ dbg) {
-  extern __shared__ float4 sp[];                               // [B][DP]
-  constexpr int DP = DC + 1;
-  // DV_BTCVAE_TIMING=1: block 0 leaves its phase boundaries (SM clocks since kernel entry) in the workspace header
-  const long long t_start = dbg ? clock64() : 0;
-#define DV_F3_MARK(slot) do { if (dbg && blockIdx.x == 0 && threadIdx.x == 0) dbg[slot] = (float)(clock64() - t_start); } while (0)
-  __shared__ float s_red[kF3Threads / 32][DC];
-  __shared__ float s_ref[DC];                                  // r_d
-  __shared__ float s_c[kF3MaxRows][DC];                        // unfolded c*log2e of the block's own rows
-  __shared__ float s_sx[kF3MaxRows][DC];
-  __shared__ float2 s_q[kF3MaxRows];
-  __shared__ float s_P[kF3MaxRows][DC];                        // log2 units
-  __shared__ float s_lqz[kF3MaxRows];
-  __shared__ int s_bad[kF3MaxRows];
-  __shared__ float s_means[kF3MaxRows][3];
-  __shared__ bool is_last;
-  const int D = EXACT ? DC : D_rt;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int row0 = blockIdx.x * rpb;
-  const float w_gen0 = lw.mss ? lw.ln : 0.f;                   // column 0, every row but B-2
-
-  // ---- phase 1: parameters of every column -> shared memory (kU independent loads in flight per thread) ----
-  {
-    constexpr int kU = 10;
-    const int total = B * D;
-    const bool paired = (ld == 2) && (logvar == mu + 1) && ((row_stride & 1) == 0) && ((reinterpret_cast<uintptr_t>(mu) & 7) == 0);
-    for (int base = 0; base < total; base += kF3Threads * kU) {
-      float vm[kU], vl[kU], vz[kU];
-#pragma unroll
-      for (int u = 0; u < kU; ++u) {
-        const int e = base + u * kF3Threads + tid;
-        if (e < total) {
-          const int j = e / D, k = e - j * D;
-          const int off = j * row_stride + k * ld;
-          if (paired) {
-            const float2 ml = *reinterpret_cast<const float2*>(mu + off);
-            vm[u] = ml.x; vl[u] = ml.y;
-          } else { vm[u] = mu[off]; vl[u] = logvar[off]; }
-          vz[u] = z[e];
-        } else { vm[u] = 0.f; vl[u] = 0.f; vz[u] = 0.f; }
-      }
-#pragma unroll
-      for (int u = 0; u < kU; ++u) {
-        const int e = base + u * kF3Threads + tid;
-        if (e < total) {
-          const int j = e / D, k = e - j * D;
-          const float cc = -0.5f * (kLog2Pi + vl[u]);
-          const float iv = expf(-vl[u]);
-          const float4 p = make_float4(cc * kLog2e, 0.5f * iv * kLog2e, vm[u], vz[u]);
-          sp[j * DP + k] = p;
-          const int rl = j - row0;
-          if (rl >= 0 && rl < rpb) { s_c[rl][k] = p.x; pj_out[(long long)k * B + j] = p; }   // the backward pass reads [D][B]
-        }
-      }
-    }
-  }
-  __syncthreads();
-  DV_F3_MARK(0);
-
-  // ---- phase 2: r_d = max_j (c_jd + w_j), then fold  x'' = c + w_j - r_d  into the staged constants ----
-  {
-    float bm[DC];
-#pragma unroll
-    for (int k = 0; k < DC; ++k) bm[k] = -INFINITY;
-    const float w_col0_max = lw.mss ? fmaxf(lw.ln, lw.ls) : 0.f;
-    for (int j = tid; j < B; j += kF3Threads) {
-      const float w = !lw.mss ? 0.f : (j == 0 ? w_col0_max : (j == 1 ? lw.ls : lw.lm));
-#pragma unroll
-      for (int k = 0; k < DC; ++k)
-        if (EXACT || k < D) bm[k] = fmaxf(bm[k], sp[j * DP + k].x + w);
-    }
-#pragma unroll
-    for (int k = 0; k < DC; ++k) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) bm[k] = fmaxf(bm[k], __shfl_xor_sync(0xffffffffu, bm[k], o));
-      if (lane == 0) s_red[warp][k] = bm[k];
-    }
-    __syncthreads();
-    if (tid < DC) {
-      float b = -INFINITY;
-#pragma unroll
-      for (int w = 0; w < kF3Threads / 32; ++w) b = fmaxf(b, s_red[w][tid]);
-      s_ref[tid] = b;
-    }
-    __syncthreads();
-    for (int j = tid; j < B; j += kF3Threads) {
-      const float w = !lw.mss ? 0.f : (j == 0 ? w_gen0 : (j == 1 ? lw.ls : lw.lm));
-#pragma unroll
-      for (int k = 0; k < DC; ++k)
-        if (EXACT || k < D) sp[j * DP + k].x += w - s_ref[k];
-    }
-    __syncthreads();
-  }
-
-  DV_F3_MARK(1);
-  // ---- phase 3: warp 2r+h sweeps half h of the columns of row r ----
-  const int row_local = warp >> 1, half = warp & 1;
-  const int i_raw = row0 + row_local;
-  const bool active = row_local < rpb && i_raw < B;
-  const int i = min(i_raw, B - 1);
-  const float dw0 = lw.mss ? (logw2(lw, i, 0) - lw.ln) : 0.f;  // != 0 only for row B-2
-  float sx[DC], zc[DC];
-  float am = -INFINITY, as = 0.f;
-  float Rsum = 0.f;
-#pragma unroll
-  for (int k = 0; k < DC; ++k) {
-    sx[k] = 0.f;
-    zc[k] = (EXACT || k < D) ? sp[i * DP + k].w : 0.f;
-    if (EXACT || k < D) Rsum += s_ref[k];
-  }
-  if (active) {
-    auto column = [&](int j, float dw) {
-      const float4* pr = sp + j * DP;
-      float a = 0.f;
-#pragma unroll
-      for (int k = 0; k < DC; ++k) {
-        if (EXACT || k < D) {
-          const float4 p = pr[k];
-          const float tt = zc[k] - p.z;
-          const float arg = fmaf(-p.y, tt * tt, p.x) + dw;
-          a += arg;
-          sx[k] += ex2_approx(arg);
-        }
-      }
-      const float d = a - am;
-      const float e = ex2_approx(-fabsf(d));
-      const bool up = d > 0.f;
-      as = up ? fmaf(as, e, 1.f) : as + e;
-      am = up ? a : am;
-    };
-    int j = lane + 32 * half;
-    if (j < B) { column(j, j == 0 ? dw0 : 0.f); j += 64; }     // peeled: the only column whose weight depends on the row
-    for (; j < B; j += 64) {
-      const float4* pr = sp + j * DP;
-      float a = 0.f;
-#pragma unroll
-      for (int k = 0; k < DC; ++k) {
-        if (EXACT || k < D) {
-          const float4 p = pr[k];
-          const float tt = zc[k] - p.z;
-          const float arg = fmaf(-p.y, tt * tt, p.x);
-          a += arg;
-          sx[k] += ex2_approx(arg);
-        }
-      }
-      const float d = a - am;
-      const float e = ex2_approx(-fabsf(d));
-      const bool up = d > 0.f;
-      as = up ? fmaf(as, e, 1.f) : as + e;
-      am = up ? a : am;
-    }
-#pragma unroll
-    for (int k = 0; k < DC; ++k) sx[k] = warp_sum(sx[k]);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float m2 = __shfl_xor_sync(0xffffffffu, am, o), s2 = __shfl_xor_sync(0xffffffffu, as, o);
-      lse_merge2(am, as, m2, s2);
-    }
-    if (half == 1 && lane == 0) {
-#pragma unroll
-      for (int k = 0; k < DC; ++k) s_sx[row_local][k] = sx[k];
-      s_q[row_local] = make_float2(am, as);
-    }
-  }
-  if (tid < kF3MaxRows) s_bad[tid] = 0;
-  __syncthreads();
-  DV_F3_MARK(2);
-  if (active && half == 0 && lane == 0) {
-    int bad = 0;
-#pragma unroll
-    for (int k = 0; k < DC; ++k) {
-      if (EXACT || k < D) {
-        const float tot = sx[k] + s_sx[row_local][k];
-        // ex2 flushes terms below 2^-126: a total under ~2^-90 could have lost a visible share of them
-        if (!(tot > 1e-27f && tot < INFINITY)) bad = 1;
-        s_P[row_local][k] = log2f(tot) + s_ref[k];
-      }
-    }
-    const float2 q = s_q[row_local];
-    lse_merge2(am, as, q.x, q.y);
-    s_lqz[row_local] = am + log2f(as) + Rsum;
-    s_bad[row_local] = bad;
-  }
-  __syncthreads();
-  {
-    int any_bad = 0;
-    for (int r = 0; r < rpb; ++r) any_bad |= s_bad[r];
-    if (any_bad) {                                             // block-uniform, rare: exact two-pass redo of the flagged rows
-      if (active && half == 0 && s_bad[row_local]) {
-        for (int k = 0; k < D; ++k) {
-          const float zk = sp[i * DP + k].w;
-          float mx = -INFINITY;
-          for (int j = lane; j < B; j += 32) {
-            const float4 p = sp[j * DP + k];
-            const float tt = zk - p.z;
-            mx = fmaxf(mx, fmaf(-p.y, tt * tt, p.x) + (j == 0 ? dw0 : 0.f));
-          }
-          mx = warp_max(mx);
-          float sm = 0.f;
-          for (int j = lane; j < B; j += 32) {
-            const float4 p = sp[j * DP + k];
-            const float tt = zk - p.z;
-            sm += exp2f(fmaf(-p.y, tt * tt, p.x) + (j == 0 ? dw0 : 0.f) - mx);
-          }
-          sm = warp_sum(sm);
-          if (lane == 0) s_P[row_local][k] = mx + log2f(sm) + s_ref[k];
-        }
-      }
-      __syncthreads();
-    }
-  }
-  if (active && half == 0) {
-    // this row's own Gaussian terms: lanes over latent dims
-    float lq = 0.f, lp = 0.f;
-    for (int d = lane; d < D; d += 32) {
-      const float4 p = sp[i * DP + d];
-      const float tt = p.w - p.z;
-      lq += (s_c[row_local][d] - p.y * (tt * tt)) * kLn2;      // log N(z; mu, lv)   (math.py:48-51)
-      lp += -0.5f * kLog2Pi - 0.5f * (p.w * p.w);              // log N(z; 0, 1)     (losses.py:531-532)
-    }
-    lq = warp_sum(lq); lp = warp_sum(lp);
-    if (lane == 0) {
-      float lprod = 0.f;
-      for (int k = 0; k < D; ++k) {
-        const float v = s_P[row_local][k] * kLn2;
-        rowstats[(long long)(4 + k) * B + i] = v;
-        lprod += v;
-      }
-      const float lqz = s_lqz[row_local] * kLn2;
-      rowstats[i] = lp; rowstats[1LL * B + i] = lqz; rowstats[2LL * B + i] = lprod; rowstats[3LL * B + i] = lq;
-      s_means[row_local][0] = lq - lqz; s_means[row_local][1] = lqz - lprod; s_means[row_local][2] = lprod - lp;
-    }
-  }
-  __syncthreads();
-  DV_F3_MARK(3);
-  if (tid == 0) {
-    float a = 0.f, b = 0.f, c = 0.f;
-    for (int r = 0; r < rpb; ++r)
-      if (row0 + r < B) { a += s_means[r][0]; b += s_means[r][1]; c += s_means[r][2]; }
-    blockpart[4 * blockIdx.x + 0] = a; blockpart[4 * blockIdx.x + 1] = b; blockpart[4 * blockIdx.x + 2] = c;
-    __threadfence();
-    is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
-  }
-  __syncthreads();
-  DV_F3_MARK(4);
-  if (!is_last || warp != 0) return;
-  __threadfence();
-  float a = 0.f, b = 0.f, c = 0.f;
-  for (int g = lane; g < (int)gridDim.x; g += 32) {             // lane-strided, then a fixed shuffle tree
-    a += __ldcg(blockpart + 4 * g); b += __ldcg(blockpart + 4 * g + 1); c += __ldcg(blockpart + 4 * g + 2);
-  }
-  a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
-  if (lane == 0) {
-    terms[0] = a / (float)B; terms[1] = b / (float)B; terms[2] = c / (float)B;
-    *counter = 0u;
-  }
-#undef DV_F3_MARK
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1225,53 +779,10 @@ int dv_btcvae_fwd_rows(const float* z, const float* mu, const float* logvar, int
       return check_launch();
     }
   }
-  {
-    // single-launch path: all columns' parameters fit in one block's shared memory
-    static int v3 = -1;
-    if (v3 < 0) { const char* e = getenv("DV_BTCVAE_V3"); v3 = (e && e[0] == '0') ? 0 : 1; }
-    const int dc = D == 10 ? 10 : 16;
-    const size_t smem = (size_t)B * (dc + 1) * sizeof(float4);
-    const int rpb = (B + kNumSMs - 1) / kNumSMs;
-    if (whole && v3 && D <= 16 && smem <= 200 * 1024 && rpb <= kF3MaxRows) {
-      const int grid = (B + rpb - 1) / rpb;
-      float4* pj = reinterpret_cast<float4*>(ws + kWsHeader);
-      float* blockpart = ws + btcvae_part_offset_floats(B, D);
-      unsigned* counter = reinterpret_cast<unsigned*>(ws);
-      static int timing = -1;
-      if (timing < 0) { const char* e = getenv("DV_BTCVAE_TIMING"); timing = (e && e[0] == '1') ? 1 : 0; }
-      float* dbg = timing ? ws + 8 : nullptr;                  // header floats 8..12
-#define DV_F3_CALL(DC, EXACT)                                                                                                  \
-  do {                                                                                                                         \
-    static bool attr = false;                                                                                                  \
-    if (!attr) {                                                                                                               \
-      if (cudaFuncSetAttribute(btcvae_fwd3_kernel<DC, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) !=      \
-          cudaSuccess) { g_last_cuda_error = (int)cudaGetLastError(); return DV_ERR_CUDA; }                                    \
-      attr = true;                                                                                                             \
-    }                                                                                                                          \
-    btcvae_fwd3_kernel<DC, EXACT><<<grid, kF3Threads, smem, st>>>(z, mu, logvar, ld, row_stride, B, D, lw, rpb, pj, rowstats, \
-                                                                  terms, blockpart, counter, dbg);                             \
-  } while (0)
-      if (D == 10) DV_F3_CALL(10, true);
-      else if (D == 16) DV_F3_CALL(16, true);
-      else DV_F3_CALL(16, false);
-#undef DV_F3_CALL
-      return check_launch();
-    }
-  }
   btcvae_prep_kernel<<<(B + 3) / 4, 128, 0, st>>>(z, mu, logvar, ld, row_stride, B, D,
                                                   reinterpret_cast<float4*>(ws + kWsHeader), rowstats);
   rc = check_launch();
   if (rc != DV_OK) return rc;
-  static int v1 = -1;
-  if (v1 < 0) { const char* e = getenv("DV_BTCVAE_V1"); v1 = (e && e[0] == '1') ? 1 : 0; }
-  if (v1 && whole) {
-    const int grid = (B + kRows - 1) / kRows;
-#define DV_FWD_CALL(DC, FUSE, EXACT) \
-  btcvae_fwd_kernel<DC, FUSE, EXACT><<<grid, kBtWarps * 32, 0, st>>>(B, D, lw, ws, rowstats, terms)
-    DV_BT_DISPATCH(D, DV_FWD_CALL);
-#undef DV_FWD_CALL
-    return check_launch();
-  }
   const int JS = (B + kJT - 1) / kJT;
   float2* part = reinterpret_cast<float2*>(ws + btcvae_part_offset_floats(B, D));
   const float4* pjc = reinterpret_cast<const float4*>(ws + kWsHeader);

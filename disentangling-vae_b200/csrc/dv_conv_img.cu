@@ -9,10 +9,10 @@
 // (im2col gather by 4 builder warps, hi/lo splitting, three tensor passes) and ran at 15-22 % of HBM bandwidth; these
 // kernels do exact fp32 FMAs from shared-memory tiles with register blocking instead:
 //
-//   down  (Conv2d fwd, ConvTranspose2d dgrad): thread = PX output pixels x 32 channels; the image tile (with halo and
-//         zero padding) in shared memory, 4x4 patches fetched as conflict-free LDS.64, weights as broadcast LDS.128
-//         (8 per tap for 64 FMAs); bias / ReLU / ReLU-mask epilogue, 128 B pixel lines stored as float4; optional
-//         channel sums of the stored tile (the previous ConvTranspose2d's bias gradient) by the 31-shuffle butterfly.
+//   down  (Conv2d fwd, ConvTranspose2d dgrad): thread = 8 (4) consecutive output pixels x 8 output channels; the image
+//         tile (with halo and zero padding) in shared memory, one 18-value input row segment per kernel row, two LDS.128
+//         of weights per tap for 64 FMAs; bias / ReLU / ReLU-mask (prefetched as bits) epilogue, a lane quartet stores
+//         64 contiguous bytes; optional channel sums of the stored tile (the previous ConvTranspose2d's bias gradient).
 //   up    (ConvTranspose2d fwd, NCHW + sigmoid): thread = a block of PY x 2 lo positions -> (2PY) x 4 output pixels per
 //         channel; the 32-channel lo tile (16-byte chunks XOR-swizzled by the column: conflict-free LDS.128 for a
 //         2-pixel lane stride) with a 1-pixel halo in shared memory; per 4-channel chunk (PY+2) x 4 neighbour float4
@@ -32,21 +32,6 @@ namespace img {
 
 constexpr int kThreads = 256;
 constexpr int kLoPitch = 36;                 // floats per lo pixel in shared memory (32 + 4: 16-byte groups rotate)
-
-__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
-#define DV_CS_STEP(BIT, HALF)                                                        \
-  {                                                                                  \
-    const bool up = (lane & BIT) != 0;                                               \
-    _Pragma("unroll") for (int i = 0; i < HALF; ++i) {                               \
-      const float send = up ? v[i] : v[i + HALF];                                    \
-      const float keep = up ? v[i + HALF] : v[i];                                    \
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, BIT);                         \
-    }                                                                                \
-  }
-  DV_CS_STEP(16, 16) DV_CS_STEP(8, 8) DV_CS_STEP(4, 4) DV_CS_STEP(2, 2) DV_CS_STEP(1, 1)
-#undef DV_CS_STEP
-  return v[0];
-}
 
 // Tiles are brought in with cp.async (global -> shared without a register round trip): a thread issues ALL its copies
 // back to back, so the whole tile is in flight at once.  (A plain "load, then store" loop kept ONE load per thread in
@@ -79,16 +64,22 @@ __device__ __forceinline__ void load_hi_tile(float* __restrict__ s_hi, const flo
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// down
+// down: thread = PXG consecutive output pixels of a row x 8 output channels {4cg..4cg+3, 16+4cg..16+4cg+3}
+// (4 threads cover the 32 channels of a pixel group; 256 threads = one 16-row tile).  Per input row kh the thread
+// fetches the 2*PXG+2 input values its pixels share (broadcast among the 4 channel threads) and per tap two LDS.128
+// of weights feed 8*PXG FMAs -- ~1 shared-memory instruction per 14 FMAs.  (The first mapping, 2 pixels x 32
+// channels per thread, needed one LDS.128 per 8 FMAs and was bound by the LSU queue: ncu mio_throttle 1.2, FMA pipe
+// 24 %, 74 us at B = 1024.)  A lane quartet writes 64 contiguous bytes per store instruction (whole sectors).
 // ------------------------------------------------------------------------------------------------------------
 template <int CH, int W>
 __global__ void __launch_bounds__(kThreads, 2)
 img_down_kernel(const float* __restrict__ hi, const float* __restrict__ wd, const float* __restrict__ bias,
                 const float* __restrict__ mask, float* __restrict__ lo, int B, int H, int act,
                 float* __restrict__ colsum_part) {
-  constexpr int PX = (W == 32) ? 2 : 1;
-  constexpr int RPT = kThreads / W;            // thread rows per tile
-  constexpr int TR = RPT * PX;                 // output rows per tile (16)
+  constexpr int TR = 16;                       // output rows per tile
+  constexpr int PXG = (TR * W) / 64;           // pixels per thread: 8 (W = 32), 4 (W = 16)
+  constexpr int CB = W / PXG;                  // pixel groups per row (4)
+  constexpr int NX = 2 * PXG + 2;              // input values per input row and pixel group
   constexpr int IN_ROWS = 2 * TR + 2, PITCH = 2 * W + 4;
   __shared__ __align__(16) float s_w[kTaps * CH * kLoCh];
   __shared__ __align__(16) float s_hi[CH * IN_ROWS * PITCH];
@@ -97,86 +88,89 @@ img_down_kernel(const float* __restrict__ hi, const float* __restrict__ wd, cons
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < kTaps * CH * kLoCh; i += kThreads) s_w[i] = wd[i];
   if (tid < kLoCh) s_bias[tid] = bias ? bias[tid] : 0.f;
-  const int c_out = tid % W, r_thr = tid / W;
+  const int cg = tid & 3, pg = tid >> 2;       // channel group, pixel group (0..63)
+  const int r_thr = pg / CB, c0 = (pg % CB) * PXG;
   const int tiles_per_img = H / TR;
   const int num_tiles = B * tiles_per_img;
-  float csum = 0.f;
+  float csum[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) csum[k] = 0.f;
   for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
     const int b = tile / tiles_per_img, i0 = (tile % tiles_per_img) * TR;
     __syncthreads();                                           // previous tile fully consumed (and weights staged)
     load_hi_tile<CH, W, TR>(s_hi, hi, b, i0, H);
-    // ReLU-backward mask of this thread's pixels as one bit per channel, requested BEFORE the FMAs: the 8 x 16-byte
-    // loads per pixel complete behind the arithmetic instead of sitting between it and the stores
-    uint32_t mbits[PX];
+    const long long p0 = ((long long)b * H + i0 + r_thr) * W + c0;          // first pixel of the group
+    // ReLU-backward mask of this thread's 8 channels x PXG pixels as bits, requested BEFORE the FMAs
+    uint32_t mb_lo = 0xffffffffu, mb_hi = 0xffffffffu;                      // bit (4*i + e): pixel i, channels 4cg+e / 16+4cg+e
+    if (mask) {
+      mb_lo = 0u; mb_hi = 0u;
 #pragma unroll
-    for (int q = 0; q < PX; ++q) {
-      mbits[q] = 0xffffffffu;
-      if (mask) {
-        const float* mk = mask + (((long long)b * H + i0 + r_thr + RPT * q) * W + c_out) * kLoCh;
-        uint32_t bits = 0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 m4 = ldg4(mk + 4 * j);
-          bits |= ((m4.x > 0.f ? 1u : 0u) | (m4.y > 0.f ? 2u : 0u) | (m4.z > 0.f ? 4u : 0u) | (m4.w > 0.f ? 8u : 0u)) << (4 * j);
-        }
-        mbits[q] = bits;
+      for (int i = 0; i < PXG; ++i) {
+        const float* mk = mask + (p0 + i) * kLoCh + 4 * cg;
+        const float4 a = ldg4(mk), d = ldg4(mk + 16);
+        mb_lo |= ((a.x > 0.f ? 1u : 0u) | (a.y > 0.f ? 2u : 0u) | (a.z > 0.f ? 4u : 0u) | (a.w > 0.f ? 8u : 0u)) << (4 * i);
+        mb_hi |= ((d.x > 0.f ? 1u : 0u) | (d.y > 0.f ? 2u : 0u) | (d.z > 0.f ? 4u : 0u) | (d.w > 0.f ? 8u : 0u)) << (4 * i);
       }
     }
     cp_async_wait_all();
     __syncthreads();
-    float acc[PX][kLoCh];
+    float acc[PXG][8];
 #pragma unroll
-    for (int q = 0; q < PX; ++q)
+    for (int i = 0; i < PXG; ++i)
 #pragma unroll
-      for (int k = 0; k < kLoCh; ++k) acc[q][k] = 0.f;
+      for (int k = 0; k < 8; ++k) acc[i][k] = 0.f;
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
-      float pt[PX][4][4];
 #pragma unroll
-      for (int q = 0; q < PX; ++q)
+      for (int kh = 0; kh < 4; ++kh) {
+        float x[NX];
+        const float* row = s_hi + (c * IN_ROWS + 2 * r_thr + kh) * PITCH + 2 * c0;    // in-tile column of input col 2*c0 - 1
 #pragma unroll
-        for (int kh = 0; kh < 4; ++kh) {
-          const float* row = s_hi + (c * IN_ROWS + 2 * (r_thr + RPT * q) + kh) * PITCH + 2 * c_out;
-          const float2 a = *reinterpret_cast<const float2*>(row), d = *reinterpret_cast<const float2*>(row + 2);
-          pt[q][kh][0] = a.x; pt[q][kh][1] = a.y; pt[q][kh][2] = d.x; pt[q][kh][3] = d.y;
+        for (int v = 0; v < NX / 2; ++v) {
+          const float2 t2 = *reinterpret_cast<const float2*>(row + 2 * v);
+          x[2 * v] = t2.x; x[2 * v + 1] = t2.y;
         }
 #pragma unroll
-      for (int tap = 0; tap < kTaps; ++tap) {
-        const float4* wv = reinterpret_cast<const float4*>(s_w + (tap * CH + c) * kLoCh);
+        for (int kw = 0; kw < 4; ++kw) {
+          const float* wp = s_w + ((kh * 4 + kw) * CH + c) * kLoCh + 4 * cg;
+          const float4 wa = *reinterpret_cast<const float4*>(wp), wb = *reinterpret_cast<const float4*>(wp + 16);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 w4 = wv[j];
-#pragma unroll
-          for (int q = 0; q < PX; ++q) {
-            const float x = pt[q][tap >> 2][tap & 3];
-            acc[q][4 * j + 0] = fmaf(x, w4.x, acc[q][4 * j + 0]);
-            acc[q][4 * j + 1] = fmaf(x, w4.y, acc[q][4 * j + 1]);
-            acc[q][4 * j + 2] = fmaf(x, w4.z, acc[q][4 * j + 2]);
-            acc[q][4 * j + 3] = fmaf(x, w4.w, acc[q][4 * j + 3]);
+          for (int i = 0; i < PXG; ++i) {
+            const float xv = x[2 * i + kw];
+            acc[i][0] = fmaf(xv, wa.x, acc[i][0]); acc[i][1] = fmaf(xv, wa.y, acc[i][1]);
+            acc[i][2] = fmaf(xv, wa.z, acc[i][2]); acc[i][3] = fmaf(xv, wa.w, acc[i][3]);
+            acc[i][4] = fmaf(xv, wb.x, acc[i][4]); acc[i][5] = fmaf(xv, wb.y, acc[i][5]);
+            acc[i][6] = fmaf(xv, wb.z, acc[i][6]); acc[i][7] = fmaf(xv, wb.w, acc[i][7]);
           }
         }
       }
     }
+    const float4 ba = *reinterpret_cast<const float4*>(s_bias + 4 * cg), bb = *reinterpret_cast<const float4*>(s_bias + 16 + 4 * cg);
+    const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
-    for (int q = 0; q < PX; ++q) {
-      const long long p = ((long long)b * H + i0 + r_thr + RPT * q) * W + c_out;
-      float* dst = lo + p * kLoCh;
-      const uint32_t bits = mbits[q];
+    for (int i = 0; i < PXG; ++i) {
+      float v[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 b4 = *reinterpret_cast<const float4*>(s_bias + 4 * j);
-        float v0 = acc[q][4 * j] + b4.x, v1 = acc[q][4 * j + 1] + b4.y, v2 = acc[q][4 * j + 2] + b4.z, v3 = acc[q][4 * j + 3] + b4.w;
-        if (act == DV_ACT_RELU) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
-        v0 = ((bits >> (4 * j)) & 1u) ? v0 : 0.f; v1 = ((bits >> (4 * j + 1)) & 1u) ? v1 : 0.f;
-        v2 = ((bits >> (4 * j + 2)) & 1u) ? v2 : 0.f; v3 = ((bits >> (4 * j + 3)) & 1u) ? v3 : 0.f;
-        *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(v0, v1, v2, v3);
-        acc[q][4 * j] = v0; acc[q][4 * j + 1] = v1; acc[q][4 * j + 2] = v2; acc[q][4 * j + 3] = v3;
+      for (int k = 0; k < 8; ++k) {
+        float t = acc[i][k] + bv[k];
+        if (act == DV_ACT_RELU) t = fmaxf(t, 0.f);
+        const uint32_t bit = ((k < 4 ? mb_lo : mb_hi) >> (4 * i + (k & 3))) & 1u;
+        v[k] = bit ? t : 0.f;
+        csum[k] += v[k];
       }
-      if (colsum_part) csum += warp_colsum32(acc[q], lane);    // lane l: channel l summed over the warp's 32 pixels
+      float* dst = lo + (p0 + i) * kLoCh + 4 * cg;
+      *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(dst + 16) = make_float4(v[4], v[5], v[6], v[7]);
     }
   }
   if (colsum_part) {
-    s_cs[warp][lane] = csum;
+    // lanes with the same channel group (lane & 3) hold partial sums of the same 8 channels: fold them (xor 4, 8, 16)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float t = csum[k];
+      t += __shfl_xor_sync(0xffffffffu, t, 4); t += __shfl_xor_sync(0xffffffffu, t, 8); t += __shfl_xor_sync(0xffffffffu, t, 16);
+      if (lane < 4) s_cs[warp][(k < 4 ? 0 : 16) + 4 * lane + (k & 3)] = t;
+    }
     __syncthreads();
     if (warp == 0) {
       float t = 0.f;
@@ -353,7 +347,9 @@ img_up_kernel(const float* __restrict__ lo, const float* __restrict__ wu, const 
 #pragma unroll
               for (int d = 0; d < 2; ++d) {
                 const float4 v = nb[a + 1 + dm][d + 1 + dn];
-                out[c][2 * a + py][2 * d + px] += (v.x * w4.x + v.y * w4.y) + (v.z * w4.z + v.w * w4.w);
+                float o = out[c][2 * a + py][2 * d + px];
+                o = fmaf(v.x, w4.x, o); o = fmaf(v.y, w4.y, o); o = fmaf(v.z, w4.z, o); o = fmaf(v.w, w4.w, o);
+                out[c][2 * a + py][2 * d + px] = o;
               }
           }
         }

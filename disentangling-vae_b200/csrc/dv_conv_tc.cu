@@ -685,7 +685,13 @@ __device__ __forceinline__ void ts_split_tile_lo(const uint8_t* raw, uint32_t tm
   tmem_st_wait();
 }
 
-__global__ void __launch_bounds__(kTsThreads, 1)
+// G = number of split groups (4 warps each) working on alternate raw tiles.  One tap tile costs a group ~620 clocks
+// (8 LDS.128 + 64 ALU + 2 tcgen05.st.x32 + wait per thread) against ~197 clocks of tensor time: with G = 2 the MMA
+// issuer waits on a_ready (r01/r02 profiles: tensor pipe 36 % active, issue slots 42 % used).  G = 3 needs 640 threads,
+// i.e. 96 registers per thread at launch; the roles then trade registers with setmaxnreg: the four control warps keep
+// 40, the epilogue warps (3 x 32 accumulator values live) get 128, the split warps 112.
+template <int G>
+__global__ void __launch_bounds__(256 + 128 * G, 1)
 conv_down32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                       const float* __restrict__ bias, const float* __restrict__ mask, float* __restrict__ lo,
                       DownGeom g, int act, float* __restrict__ colsum_part) {
@@ -696,11 +702,16 @@ conv_down32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   TsBarriers* bars = reinterpret_cast<TsBarriers*>(Raw + kTsRawStages * kATile);
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform role index
   ts_init(bars, bias, warp, g.rawhi ? 129 : 128);           // rawhi: the MMA's commit is a reader of the raw stage too
+
   // All 512 columns are ours (1 CTA/SM), so the allocation starts at column 0.  Using the literal keeps every
   // tensor-memory address a compile-time/warp-uniform value (no per-MMA register -> uniform-register moves).
   if (bars->tmem_base != 0u) __trap();
   constexpr uint32_t tmem_base = 0u;
 
+  // the register hand-over sits at the head of each role's branch (whole warpgroups execute it), so that ptxas
+  // allocates the code it dominates against the new limit
+  if (warp < 4) {
+  if constexpr (G > 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 0 && elect_one()) {
     prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b);
     mbar_arrive_expect_tx(&bars->b_full, kBBytes);
@@ -771,7 +782,9 @@ conv_down32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       umma_commit_1t(&bars->acc_full[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-  } else if (warp >= 4 && warp < 8) {
+  }
+  } else if (warp < 8) {
+    if constexpr (G > 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
     const int q = warp & 3;
     int acc = 0; uint32_t acc_phase = 0;
     float csum = 0.f;                                         // lane l: running sum of output channel l over this warp's rows
@@ -828,13 +841,14 @@ conv_down32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (q == 0) colsum_part[blockIdx.x * 32 + lane] = (scr[lane] + scr[32 + lane]) + (scr[64 + lane] + scr[96 + lane]);
     }
-  } else if (warp >= 8) {
+  } else {
+    if constexpr (G > 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
     const int q = warp & 3, grp = (warp - 8) >> 2;
     uint32_t n = 0;                                           // sequence number of the raw tile within this CTA
     if (!g.pipe) {
       for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
         for (int tap = 0; tap < kTaps; ++tap, ++n) {
-          if ((int)(n & 1u) != grp) continue;
+          if ((int)(n % (uint32_t)G) != grp) continue;
           const int stage = n % kTsRawStages, as = n % kTsAStages;
           mbar_wait(&bars->raw_full[stage], (n / kTsRawStages) & 1u);
           mbar_wait(&bars->a_empty[as], ((n / kTsAStages) & 1u) ^ 1u);
@@ -854,7 +868,7 @@ conv_down32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       int prev_stage = -1, prev_as = 0;
       for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
         for (int tap = 0; tap < kTaps; ++tap, ++n) {
-          if ((int)(n & 1u) != grp) continue;
+          if ((int)(n % (uint32_t)G) != grp) continue;
           const int stage = n % kTsRawStages, as = n % kTsAStages;
           mbar_wait(&bars->raw_full[stage], (n / kTsRawStages) & 1u);
           const uint8_t* raw = Raw + stage * kATile;
@@ -1850,13 +1864,17 @@ int conv_down32_tc(const float* hi, const float* wd_packed, const float* bias, c
   if (use_ts()) {
     static bool attr2 = false;
     if (!attr2) {
-      if (cudaFuncSetAttribute(conv_down32_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTsSmemBytes) != cudaSuccess) {
+      if (cudaFuncSetAttribute(conv_down32_ts_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTsSmemBytes) != cudaSuccess ||
+          cudaFuncSetAttribute(conv_down32_ts_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTsSmemBytes) != cudaSuccess) {
         g_last_cuda_error = (int)cudaGetLastError();
         return DV_ERR_CUDA;
       }
       attr2 = true;
     }
-    conv_down32_ts_kernel<<<grid, kTsThreads, kTsSmemBytes, st>>>(ta, tb, bias, mask, lo, g, act, colsum_part);
+    static int groups = -1;                                   // DV_TS_GROUPS=2: the two-group kernel (A/B)
+    if (groups < 0) { const char* e = getenv("DV_TS_GROUPS"); groups = (e && e[0] == '2') ? 2 : 3; }
+    if (groups == 3) conv_down32_ts_kernel<3><<<grid, 640, kTsSmemBytes, st>>>(ta, tb, bias, mask, lo, g, act, colsum_part);
+    else             conv_down32_ts_kernel<2><<<grid, 512, kTsSmemBytes, st>>>(ta, tb, bias, mask, lo, g, act, colsum_part);
     if (nparts && colsum_part) *nparts = grid;
     return check_launch();
   }

@@ -248,7 +248,7 @@ class BtcvaeLoss(BaseLoss):
         if self.global_batch and is_train and is_distributed():
             terms = ops.BtcvaeGlobalFn.apply(latent_sample, latent_dist[0], latent_dist[1], self.n_data, self.is_mss, None)
         else:
-            terms = ops.BtcvaeFn.apply(latent_sample, latent_dist[0], latent_dist[1], self.n_data, self.is_mss)
+            terms = ops.btcvae_terms(latent_sample, latent_dist[0], latent_dist[1], self.n_data, self.is_mss)
         mi_loss, tc_loss, dw_kl_loss = terms[0], terms[1], terms[2]
         anneal_reg = linear_annealing(0, 1, self.n_train_steps, self.steps_anneal) if is_train else 1
         # rec + (alpha*mi + beta*tc + anneal*gamma*dw_kl) as one launch (the kl entries of `out` only feed the log)

@@ -599,6 +599,20 @@ class BtcvaeGlobalFn(Function):
         return g_z, mine[:, :D].contiguous(), mine[:, D:].contiguous(), None, None, None
 
 
+def btcvae_terms(z, mu, logvar, n_data, is_mss):
+    """BtcvaeFn on the weight-gradient side stream.  autograd runs a node's backward on the stream that was current when
+    the node was created and synchronises producers and consumers itself, so dv_btcvae_bwd -- whose results are not
+    needed before the ENCODER's backward -- overlaps with the decoder's backward pass instead of preceding it."""
+    lane = _WgradLane(z.device)
+    if not lane.enabled:
+        return BtcvaeFn.apply(z, mu, logvar, n_data, is_mss)
+    lane.side.wait_stream(lane.main)
+    with torch.cuda.stream(lane.side):
+        terms = BtcvaeFn.apply(z, mu, logvar, n_data, is_mss)
+    lane.main.wait_stream(lane.side)
+    return terms
+
+
 class LossCombineFn(Function):
     """loss = sum_i coef_a[i]*a[i] + sum_j coef_b[j]*b[j] with a = the fused loss kernel's output (rec, kl, per-dim kl..:
     only the first len(coef_a) entries are weighted) and b = a short vector or 0-dim tensor (beta-TCVAE terms, the

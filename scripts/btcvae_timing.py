@@ -1,5 +1,5 @@
 """Phase boundaries of the single-launch beta-TCVAE forward kernel (block 0, SM clocks) warm and after an L2 flush.
-DV_BTCVAE_TIMING=1; DV_BTCVAE_V4=0 times the previous generation (fwd3)."""
+DV_BTCVAE_TIMING=1."""
 import os, sys, torch
 os.environ["DV_BTCVAE_TIMING"] = "1"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
