@@ -1093,8 +1093,9 @@ template <int CH> struct HaloCfg {
   static constexpr int kAccPerPhase = 32;
 };
 
-template <int CH>
-__global__ void __launch_bounds__(kTsThreads, 1)
+// G split groups (see conv_down32_ts_kernel): G = 3 runs 640 threads and re-balances registers with setmaxnreg.
+template <int CH, int G>
+__global__ void __launch_bounds__(256 + 128 * G, 1)
 conv_up_halo_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                        const float* __restrict__ bias, const float* __restrict__ mask, float* __restrict__ hi_out,
                        HaloGeom g, int act) {
@@ -1121,6 +1122,8 @@ conv_up_halo_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
   if (bars->tmem_base != 0u) __trap();                       // whole TMEM is ours: base column 0 (see the TS kernels)
   constexpr uint32_t tmem_base = 0u;
 
+  if (warp < 4) {
+  if constexpr (G > 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 0 && elect_one()) {
     prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b);
     mbar_arrive_expect_tx(&bars->b_full, C::kBAll);
@@ -1183,7 +1186,9 @@ conv_up_halo_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
       umma_commit_1t(&bars->acc_full[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-  } else if (warp >= 4 && warp < 8) {
+  }
+  } else if (warp < 8) {
+    if constexpr (G > 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
     const int q = warp & 3;
     const int HH = 2 * g.H, WW = 2 * g.W;
     int acc = 0; uint32_t acc_phase = 0;
@@ -1271,7 +1276,8 @@ conv_up_halo_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-  } else if (warp >= 8) {
+  } else {
+    if constexpr (G > 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
     const int q = warp & 3, grp = (warp - 8) >> 2;
     const int row = q * 32 + lane;
     uint32_t n = 0, t_seq = 0;
@@ -1281,7 +1287,7 @@ conv_up_halo_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
       const uint8_t* raw = Raw + stage * kHaloStageBytes;
       bool waited = false;
       for (int s = 0; s < 9; ++s, ++n) {
-        if ((int)(n & 1u) != grp) continue;
+        if ((int)(n % (uint32_t)G) != grp) continue;
         const int di = s / 3 - 1, dj = s % 3 - 1;
         const int as = n % kTsAStages;
         if (!waited) { mbar_wait(&bars->raw_full[stage], (t_seq / kHaloStages) & 1u); waited = true; }
@@ -2068,14 +2074,18 @@ static int launch_up_halo(const float* lo, const float* wu, const float* bias, c
   if (!make_w_tmap_rows(&tb, wu, CH == 32 ? kTaps * 64 : 320)) return DV_ERR_CUDA;
   static bool attr = false;
   if (!attr) {
-    if (cudaFuncSetAttribute(conv_up_halo_ts_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<CH>::kSmem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(conv_up_halo_ts_kernel<CH, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<CH>::kSmem) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_up_halo_ts_kernel<CH, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<CH>::kSmem) != cudaSuccess) {
       g_last_cuda_error = (int)cudaGetLastError();
       return DV_ERR_CUDA;
     }
     attr = true;
   }
   const int grid = g.num_tiles < kNumSMs ? g.num_tiles : kNumSMs;
-  conv_up_halo_ts_kernel<CH><<<grid, kTsThreads, HaloCfg<CH>::kSmem, st>>>(ta, tb, bias, mask, hi, g, act);
+  static int groups = -1;                                     // DV_TS_GROUPS=2: the two-group kernel (A/B)
+  if (groups < 0) { const char* e = getenv("DV_TS_GROUPS"); groups = (e && e[0] == '2') ? 2 : 3; }
+  if (groups == 3) conv_up_halo_ts_kernel<CH, 3><<<grid, 640, HaloCfg<CH>::kSmem, st>>>(ta, tb, bias, mask, hi, g, act);
+  else             conv_up_halo_ts_kernel<CH, 2><<<grid, 512, HaloCfg<CH>::kSmem, st>>>(ta, tb, bias, mask, hi, g, act);
   return check_launch();
 }
 
