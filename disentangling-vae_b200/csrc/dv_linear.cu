@@ -190,6 +190,12 @@ int fwd(const float* x, const float* w, const float* bias, float* y, int M, int 
         cudaStream_t st);
 int dgrad(const float* g, const float* w, const float* mask_src, float* dx, int M, int N, int K, int act, float slope, float* ws,
           cudaStream_t st);
+size_t packed_floats(int N, int K);
+int pack_multi(int n, const float* const* w, float* const* packed, const int* N, const int* K, cudaStream_t st);
+int fwd_packed(const float* x, const float* packed, const float* bias, float* y, int M, int N, int K, int act, float slope,
+               cudaStream_t st);
+int dgrad_packed(const float* g, const float* packed, const float* mask_src, float* dx, int M, int N, int K, int act, float slope,
+                 cudaStream_t st);
 bool wgrad_ok(int M, int N, int K);
 size_t wgrad_workspace_bytes(int M, int N, int K);
 int wgrad(const float* g, const float* x, float* dw, float* dbias, float* ws, int M, int N, int K, int* nsplit, cudaStream_t st);
@@ -235,6 +241,42 @@ int dv_linear_dgrad(const float* g, const float* w, const float* mask_src, float
   dim3 grid((K + BN - 1) / BN, (M + BM - 1) / BM);
   gemm_kernel<true, false><<<grid, 256, 0, as_stream(stream)>>>(g, w, dx, M, K, N, N, 1, K, 1, ep, N);
   return check_launch();
+}
+
+size_t dv_linear_packed_floats(int N, int K) {
+  if (N <= 0 || K <= 0) return 0;
+  return ltc::packed_floats(N, K);
+}
+
+int dv_linear_pack_multi(int n, const void* const* w, void* const* packed, const int* N, const int* K, void* stream) {
+  if (n < 1 || !w || !packed || !N || !K) return DV_ERR_BAD_ARG;
+  for (int i = 0; i < n; ++i)
+    if (!w[i] || !packed[i] || N[i] <= 0 || K[i] <= 0 || ((uintptr_t)packed[i] & 15)) return DV_ERR_BAD_ARG;
+  return ltc::pack_multi(n, reinterpret_cast<const float* const*>(w), reinterpret_cast<float* const*>(packed), N, K,
+                         as_stream(stream));
+}
+
+int dv_linear_fwd_packed(const float* x, const float* w, const float* packed, const float* bias, float* y, int M, int N, int K,
+                         int act, float slope, void* stream) {
+  if (!x || !w || !y) return DV_ERR_BAD_ARG;
+  if (M <= 0 || N <= 0 || K <= 0) return DV_ERR_BAD_SHAPE;
+  if (act < DV_ACT_NONE || act > DV_ACT_LEAKY) return DV_ERR_BAD_ARG;
+  if (ltc::fwd_workspace_bytes(M, N, K) > 0) {
+    if (!packed) return DV_ERR_WORKSPACE;
+    return ltc::fwd_packed(x, packed, bias, y, M, N, K, act, slope, as_stream(stream));
+  }
+  return dv_linear_fwd(x, w, bias, y, M, N, K, act, slope, nullptr, stream);       // CUDA-core path: reads w itself
+}
+
+int dv_linear_dgrad_packed(const float* g, const float* w, const float* packed, const float* mask_src, float* dx, int M, int N,
+                           int K, int act, float slope, void* stream) {
+  if (!g || !w || !dx) return DV_ERR_BAD_ARG;
+  if (M <= 0 || N <= 0 || K <= 0) return DV_ERR_BAD_SHAPE;
+  if (ltc::dgrad_workspace_bytes(M, N, K) > 0) {
+    if (!packed) return DV_ERR_WORKSPACE;
+    return ltc::dgrad_packed(g, packed, mask_src, dx, M, N, K, act, slope, as_stream(stream));
+  }
+  return dv_linear_dgrad(g, w, mask_src, dx, M, N, K, act, slope, nullptr, stream);
 }
 
 size_t dv_linear_wgrad_workspace_bytes(int M, int N, int K) {

@@ -259,6 +259,53 @@ __global__ void linear_pack_kernel(const float* __restrict__ w, float* __restric
   }
 }
 
+// Multi-tensor pack: every weight matrix of a network node (encoder MLP, decoder MLP, the 6-layer discriminator) in
+// ONE launch, both layouts at once -- packed[i] = [fwd hi | fwd lo | transposed hi | transposed lo] with pitches
+// round4(K) / round4(N).  Replaces one linear_pack_kernel launch per layer per direction (12 per VAE step, 22 per
+// FactorVAE step).
+constexpr int kPackMax = 8;
+struct PackTable {
+  const float* w[kPackMax];
+  float* dst[kPackMax];
+  int N[kPackMax], K[kPackMax], tiles_k[kPackMax], tile0[kPackMax + 1];
+  int n;
+};
+__global__ void linear_pack_multi_kernel(PackTable t) {
+  __shared__ float tile[32][33];
+  int m = 0;
+  while (m + 1 < t.n && (int)blockIdx.x >= t.tile0[m + 1]) ++m;
+  const int local = blockIdx.x - t.tile0[m];
+  const int N = t.N[m], K = t.K[m];
+  const int Kp = (K + 3) & ~3, Np = (N + 3) & ~3;
+  const int k0 = (local % t.tiles_k[m]) * 32, n0 = (local / t.tiles_k[m]) * 32;
+  const float* __restrict__ w = t.w[m];
+  float* f_hi = t.dst[m];
+  float* f_lo = f_hi + (size_t)N * Kp;
+  float* t_hi = f_lo + (size_t)N * Kp;
+  float* t_lo = t_hi + (size_t)K * Np;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
+  for (int r = ty; r < 32; r += 8) {
+    const int n = n0 + r, k = k0 + tx;
+    const float v = (n < N && k < K) ? w[(long long)n * K + k] : 0.f;
+    tile[r][tx] = v;
+    if (n < N && k < Kp) {
+      const float hi = __uint_as_float(__float_as_uint(v) & kHiMask);
+      f_hi[(long long)n * Kp + k] = hi;
+      f_lo[(long long)n * Kp + k] = v - hi;
+    }
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int k = k0 + r, n = n0 + tx;
+    if (k < K && n < Np) {
+      const float v = tile[tx][r];
+      const float hi = __uint_as_float(__float_as_uint(v) & kHiMask);
+      t_hi[(long long)k * Np + n] = hi;
+      t_lo[(long long)k * Np + n] = v - hi;
+    }
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -554,6 +601,43 @@ int dgrad(const float* g, const float* w, const float* mask_src, float* dx, int 
   return launch_nt(g, N, hi, lo, dx, M, K, N, ep, st);
 }
 
+
+size_t packed_floats(int N, int K) { return (size_t)2 * N * round4(K) + (size_t)2 * K * round4(N); }
+
+int pack_multi(int n, const float* const* w, float* const* packed, const int* N, const int* K, cudaStream_t st) {
+  for (int base = 0; base < n; base += kPackMax) {
+    PackTable t;
+    t.n = n - base < kPackMax ? n - base : kPackMax;
+    int tiles = 0;
+    for (int i = 0; i < t.n; ++i) {
+      t.w[i] = w[base + i]; t.dst[i] = packed[base + i]; t.N[i] = N[base + i]; t.K[i] = K[base + i];
+      t.tiles_k[i] = (round4(K[base + i]) + 31) / 32;
+      t.tile0[i] = tiles;
+      tiles += t.tiles_k[i] * ((round4(N[base + i]) + 31) / 32);
+    }
+    t.tile0[t.n] = tiles;
+    linear_pack_multi_kernel<<<tiles, 256, 0, st>>>(t);
+    int rc = check_launch();
+    if (rc != DV_OK) return rc;
+  }
+  return DV_OK;
+}
+
+// the same two GEMMs on planes that dv_linear_pack_multi produced
+int fwd_packed(const float* x, const float* packed, const float* bias, float* y, int M, int N, int K, int act, float slope,
+               cudaStream_t st) {
+  const float* hi = packed;
+  const float* lo = packed + (size_t)N * round4(K);
+  Epilogue ep{bias, nullptr, act, slope};
+  return launch_nt(x, K, hi, lo, y, M, N, K, ep, st);
+}
+int dgrad_packed(const float* g, const float* packed, const float* mask_src, float* dx, int M, int N, int K, int act, float slope,
+                 cudaStream_t st) {
+  const float* hi = packed + (size_t)2 * N * round4(K);
+  const float* lo = hi + (size_t)K * round4(N);
+  Epilogue ep{nullptr, mask_src, mask_src ? act : DV_ACT_NONE, slope};
+  return launch_nt(g, N, hi, lo, dx, M, K, N, ep, st);
+}
 
 static void wgrad_plan(int M, int N, int K, int* S, int* tiles_per_split) {
   const int m_tiles = (M + 127) / 128;

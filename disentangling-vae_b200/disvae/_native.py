@@ -39,6 +39,10 @@ SIGNATURES = {
     "dv_linear_dgrad_workspace_bytes": (SZ, [I, I, I]),
     "dv_linear_fwd": (I, [P, P, P, P, I, I, I, I, F, P, P]),
     "dv_linear_dgrad": (I, [P, P, P, P, I, I, I, I, F, P, P]),
+    "dv_linear_packed_floats": (SZ, [I, I]),
+    "dv_linear_pack_multi": (I, [I, P, P, P, P, P]),
+    "dv_linear_fwd_packed": (I, [P, P, P, P, P, I, I, I, I, F, P]),
+    "dv_linear_dgrad_packed": (I, [P, P, P, P, P, I, I, I, I, F, P]),
     "dv_linear_wgrad_workspace_bytes": (SZ, [I, I, I]),
     "dv_linear_wgrad": (I, [P, P, P, P, I, I, I, P, P]),
     "dv_reparam_fwd": (I, [P, P, I, I, P, ULL, P, P, P, I, I, P]),

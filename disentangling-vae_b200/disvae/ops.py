@@ -147,20 +147,40 @@ def act_bwd(dy, y, act, slope=0.0):
     return g
 
 
-def linear_fwd(x, w, b, act, slope=0.0):
+def linear_pack_multi(weights):
+    """Operand planes of every weight matrix of a network node in ONE launch -> list of packed buffers (pass them to
+    linear_fwd / linear_dgrad as `packed=`)."""
+    import ctypes
+    L = N.lib()
+    n = len(weights)
+    packs = [_new((L.dv_linear_packed_floats(w.shape[0], w.shape[1]),), w) for w in weights]
+    arr_p = ctypes.c_void_p * n
+    arr_i = ctypes.c_int * n
+    call("dv_linear_pack_multi", n, arr_p(*[w.data_ptr() for w in weights]), arr_p(*[p.data_ptr() for p in packs]),
+         arr_i(*[w.shape[0] for w in weights]), arr_i(*[w.shape[1] for w in weights]), stream())
+    return packs
+
+
+def linear_fwd(x, w, b, act, slope=0.0, packed=None):
     M, K = x.shape
     Nn = w.shape[0]
     y = _new((M, Nn), x)
+    if packed is not None:
+        call("dv_linear_fwd_packed", ptr(x), ptr(w), ptr(packed), ptr(b), ptr(y), M, Nn, K, act, slope, stream())
+        return y
     nbytes = N.lib().dv_linear_fwd_workspace_bytes(M, Nn, K)
     ws = _scratch("lin_pack", nbytes, x.device) if nbytes else None
     call("dv_linear_fwd", ptr(x), ptr(w), ptr(b), ptr(y), M, Nn, K, act, slope, ptr(ws), stream())
     return y
 
 
-def linear_dgrad(g, w, mask_src, act, slope=0.0):
+def linear_dgrad(g, w, mask_src, act, slope=0.0, packed=None):
     M, Nn = g.shape
     K = w.shape[1]
     dx = _new((M, K), g)
+    if packed is not None:
+        call("dv_linear_dgrad_packed", ptr(g), ptr(w), ptr(packed), ptr(mask_src), ptr(dx), M, Nn, K, act, slope, stream())
+        return dx
     nbytes = N.lib().dv_linear_dgrad_workspace_bytes(M, Nn, K)
     ws = _scratch("lin_pack", nbytes, g.device) if nbytes else None
     call("dv_linear_dgrad", ptr(g), ptr(w), ptr(mask_src), ptr(dx), M, Nn, K, act, slope, ptr(ws), stream())
@@ -236,6 +256,10 @@ class EncoderFn(Function):
         B, C, S, _ = x.shape
         convs = [(params[2 * i], params[2 * i + 1]) for i in range(n_conv)]
         lins = [(params[2 * n_conv + 2 * i], params[2 * n_conv + 2 * i + 1]) for i in range(3)]
+        # operand planes of the three linear layers (both directions) in one launch, on the side stream: it runs beside
+        # the convolutions below and is joined before the first linear layer
+        lane = _WgradLane(x.device)
+        lpk = lane.run(lambda: linear_pack_multi([w for w, _ in lins]), *[w for w, _ in lins])
         acts, packed = [], []
         hi, CH, nchw, H = x, C, 1, S // 2
         for w, b in convs:
@@ -246,13 +270,14 @@ class EncoderFn(Function):
             packed.append(wp)
             hi, CH, nchw, H = lo, LO_CH, 0, H // 2
         flat = flat_transpose(acts[-1].view(B, FLAT), B, to_nhwc=False)          # -> [B, 32*4*4] in NCHW order
-        h1 = linear_fwd(flat, lins[0][0], lins[0][1], ACT_RELU)
-        h2 = linear_fwd(h1, lins[1][0], lins[1][1], ACT_RELU)
-        ml = linear_fwd(h2, lins[2][0], lins[2][1], ACT_NONE)
+        lane.join()
+        h1 = linear_fwd(flat, lins[0][0], lins[0][1], ACT_RELU, packed=lpk[0])
+        h2 = linear_fwd(h1, lins[1][0], lins[1][1], ACT_RELU, packed=lpk[1])
+        ml = linear_fwd(h2, lins[2][0], lins[2][1], ACT_NONE, packed=lpk[2])
         _note("encoder.lin1", h1)
         _note("encoder.lin2", h2)
         ctx.n_conv = n_conv
-        ctx.save_for_backward(x, flat, h1, h2, *acts, *packed, *params)
+        ctx.save_for_backward(x, flat, h1, h2, *acts, *packed, *params, *lpk)
         return ml
 
     @staticmethod
@@ -262,17 +287,18 @@ class EncoderFn(Function):
         x, flat, h1, h2 = saved[:4]
         acts = saved[4:4 + n_conv]
         packed = saved[4 + n_conv:4 + 2 * n_conv]
-        params = saved[4 + 2 * n_conv:]
+        params = saved[4 + 2 * n_conv:-3]
+        lpk = saved[-3:]
         lins = [(params[2 * n_conv + 2 * i], params[2 * n_conv + 2 * i + 1]) for i in range(3)]
         B, C, S, _ = x.shape
         g = _c(g_ml)
         lane = _WgradLane(g.device)
         dlw3, dlb3 = lane.run(lambda: linear_wgrad(g, h2), g, h2)
-        g2 = linear_dgrad(g, lins[2][0], h2, ACT_RELU)
+        g2 = linear_dgrad(g, lins[2][0], h2, ACT_RELU, packed=lpk[2])
         dlw2, dlb2 = lane.run(lambda: linear_wgrad(g2, h1), g2, h1)
-        g1 = linear_dgrad(g2, lins[1][0], h1, ACT_RELU)
+        g1 = linear_dgrad(g2, lins[1][0], h1, ACT_RELU, packed=lpk[1])
         dlw1, dlb1 = lane.run(lambda: linear_wgrad(g1, flat), g1, flat)
-        gflat = linear_dgrad(g1, lins[0][0], flat, ACT_RELU)                     # masked by the last conv's ReLU
+        gflat = linear_dgrad(g1, lins[0][0], flat, ACT_RELU, packed=lpk[0])      # masked by the last conv's ReLU
         g_lo = flat_transpose(gflat, B, to_nhwc=True)
         conv_grads = [None] * (2 * n_conv)
         dx = None
@@ -304,9 +330,10 @@ class DecoderFn(Function):
         B = z.shape[0]
         lins = [(params[2 * i], params[2 * i + 1]) for i in range(3)]
         convTs = [(params[6 + 2 * i], params[6 + 2 * i + 1]) for i in range(n_convT)]
-        h1 = linear_fwd(z, lins[0][0], lins[0][1], ACT_RELU)
-        h2 = linear_fwd(h1, lins[1][0], lins[1][1], ACT_RELU)
-        h3 = linear_fwd(h2, lins[2][0], lins[2][1], ACT_RELU)                    # [B,512] == view(B,32,4,4)
+        lpk = linear_pack_multi([w for w, _ in lins])
+        h1 = linear_fwd(z, lins[0][0], lins[0][1], ACT_RELU, packed=lpk[0])
+        h2 = linear_fwd(h1, lins[1][0], lins[1][1], ACT_RELU, packed=lpk[1])
+        h3 = linear_fwd(h2, lins[2][0], lins[2][1], ACT_RELU, packed=lpk[2])     # [B,512] == view(B,32,4,4)
         _note("decoder.lin1", h1)
         _note("decoder.lin2", h2)
         _note("decoder.lin3", h3)
@@ -325,7 +352,7 @@ class DecoderFn(Function):
             lo, H = hi, 2 * H
         recon = lo
         ctx.n_convT, ctx.n_chan = n_convT, n_chan
-        ctx.save_for_backward(z, h1, h2, recon, *acts, *packed, *params)
+        ctx.save_for_backward(z, h1, h2, recon, *acts, *packed, *params, *lpk)
         return recon
 
     @staticmethod
@@ -335,7 +362,8 @@ class DecoderFn(Function):
         z, h1, h2, recon = saved[:4]
         acts = saved[4:4 + n_convT]                 # acts[t] = input of convT t (NHWC)
         packed = saved[4 + n_convT:4 + 2 * n_convT]
-        params = saved[4 + 2 * n_convT:]
+        params = saved[4 + 2 * n_convT:-3]
+        lpk = saved[-3:]
         lins = [(params[2 * i], params[2 * i + 1]) for i in range(3)]
         B = z.shape[0]
         S = recon.shape[-1]
@@ -358,11 +386,11 @@ class DecoderFn(Function):
                 g_hi = conv_down(g_hi, packed[t], None, acts[t], B, H, H, CH, nchw, ACT_NONE)
         g3 = flat_transpose(g_hi.view(B, FLAT), B, to_nhwc=False)                  # grad of lin3 pre-activation
         dlw3, dlb3 = lane.run(lambda: linear_wgrad(g3, h2), g3, h2)
-        g2 = linear_dgrad(g3, lins[2][0], h2, ACT_RELU)
+        g2 = linear_dgrad(g3, lins[2][0], h2, ACT_RELU, packed=lpk[2])
         dlw2, dlb2 = lane.run(lambda: linear_wgrad(g2, h1), g2, h1)
-        g1 = linear_dgrad(g2, lins[1][0], h1, ACT_RELU)
+        g1 = linear_dgrad(g2, lins[1][0], h1, ACT_RELU, packed=lpk[1])
         dlw1, dlb1 = lane.run(lambda: linear_wgrad(g1, z), g1, z)
-        dz = linear_dgrad(g1, lins[0][0], None, ACT_NONE) if ctx.needs_input_grad[0] else None
+        dz = linear_dgrad(g1, lins[0][0], None, ACT_NONE, packed=lpk[0]) if ctx.needs_input_grad[0] else None
         lane.join()
         return (dz, None, None, dlw1, dlb1, dlw2, dlb2, dlw3, dlb3, *convT_grads)
 
@@ -381,20 +409,21 @@ class MlpFn(Function):
         n = len(params) // 2
         hs = [x]
         h = x
+        lpk = linear_pack_multi([params[2 * i] for i in range(n)])
         for i in range(n):
-            h = linear_fwd(h, params[2 * i], params[2 * i + 1], ACT_LEAKY if i < n - 1 else ACT_NONE, slope)
+            h = linear_fwd(h, params[2 * i], params[2 * i + 1], ACT_LEAKY if i < n - 1 else ACT_NONE, slope, packed=lpk[i])
             if i < n - 1:
                 _note("mlp.lin%d" % (i + 1), h)
             hs.append(h)
         ctx.slope, ctx.n = slope, n
-        ctx.save_for_backward(*hs[:-1], *params)
+        ctx.save_for_backward(*hs[:-1], *params, *lpk)
         return h
 
     @staticmethod
     def backward(ctx, g_out):
         n, slope = ctx.n, ctx.slope
         saved = ctx.saved_tensors
-        hs, params = saved[:n], saved[n:]
+        hs, params, lpk = saved[:n], saved[n:3 * n], saved[3 * n:]
         g = _c(g_out)
         grads = [None] * (2 * n)
         dx = None
@@ -402,9 +431,9 @@ class MlpFn(Function):
         for i in range(n - 1, -1, -1):
             grads[2 * i], grads[2 * i + 1] = lane.run(lambda gg=g, h=hs[i]: linear_wgrad(gg, h), g, hs[i])
             if i > 0:
-                g = linear_dgrad(g, params[2 * i], hs[i], ACT_LEAKY, slope)
+                g = linear_dgrad(g, params[2 * i], hs[i], ACT_LEAKY, slope, packed=lpk[i])
             elif ctx.needs_input_grad[0]:
-                dx = linear_dgrad(g, params[0], None, ACT_NONE)
+                dx = linear_dgrad(g, params[0], None, ACT_NONE, packed=lpk[0])
         lane.join()
         return (dx, None, *grads)
 

@@ -109,8 +109,17 @@ class Trainer():
         lf = self.loss_f
         if not (self.use_cuda_graph and self.device.type == "cuda" and self.model.training):
             return False
-        if hasattr(lf, "call_optimize") or getattr(self.model, "_eps_queue", None):
+        if getattr(self.model, "_eps_queue", None):
             return False
+        if hasattr(lf, "call_optimize"):
+            # FactorVAE: both backward passes and both Adam steps fit one graph in a single process; under data
+            # parallelism the two gradient averages sit between the backward passes and the optimizer steps: eager
+            if is_distributed() or getattr(lf, "_perm_queue", None):
+                return False
+            if lf._fused_d is None:
+                lf._fused_d = FusedAdam(lf.optimizer_d) if FusedAdam.supports(lf.optimizer_d) else False
+            if not lf._fused_d:
+                return False
         if getattr(lf, "global_batch", False) and is_distributed():
             return False                                      # collectives inside the loss node: run eagerly
         if lf.steps_anneal != 0 and lf.n_train_steps < lf.steps_anneal:
@@ -136,18 +145,46 @@ class Trainer():
             g = torch.cuda.CUDAGraph()
             steps_before = self.loss_f.n_train_steps
             launches_before = _native.lib().dv_launch_count()
+            factor = hasattr(self.loss_f, "call_optimize")
+            # Data parallel over NCCL: the gradient gather, the all-reduce and the Adam launch can live INSIDE the graph
+            # (NCCL collectives are capturable): no per-step launch latency for the three-kernel tail.  Opt-in
+            # (DISVAE_GRAPH_NCCL=1) -- validated by tests/ddp_worker.py on real NCCL ranks; gloo cannot be captured.
+            import torch.distributed as dist
+            nccl_in_graph = (ddp and os.environ.get("DISVAE_GRAPH_NCCL", "0") == "1" and dist.get_backend() == "nccl")
+            flat_buf = None
+            if nccl_in_graph:
+                params_all = [p for p in self.model.parameters() if p.requires_grad]
+                flat_buf = torch.zeros(sum(p.numel() for p in params_all), dtype=torch.float32, device=self.device)
             with torch.cuda.graph(g):
-                recon, dist, z = self.model(static_x)
-                loss = self.loss_f(static_x, recon, dist, True, None, latent_sample=z)
-                self.optimizer.zero_grad(set_to_none=True)
-                loss.backward()
-                if not ddp:
-                    self._fused.step()
+                if factor:
+                    with torch.no_grad():
+                        self.model(static_x)                      # the discarded full-batch forward of training.py:153:
+                                                                  # kept for its noise draw (same stream as the eager path)
+                    loss = self.loss_f.call_optimize(static_x, self.model, _StepProxy(self.optimizer, self._optimizer_step), None)
                     self._fused.host_steps -= 1                   # capture executed nothing
+                    self.loss_f._fused_d.host_steps -= 1
+                else:
+                    recon, dist, z = self.model(static_x)
+                    loss = self.loss_f(static_x, recon, dist, True, None, latent_sample=z)
+                    self.optimizer.zero_grad(set_to_none=True)
+                    loss.backward()
+                    if not ddp:
+                        self._fused.step()
+                        self._fused.host_steps -= 1               # capture executed nothing
+                    elif nccl_in_graph:
+                        live = [p for p in params_all if p.grad is not None]
+                        torch.cat([p.grad.view(-1) for p in live], out=flat_buf[:sum(p.numel() for p in live)])
+                        dist.all_reduce(flat_buf, op=dist.ReduceOp.SUM)
+                        off = 0
+                        for p in live:
+                            p.grad = flat_buf[off:off + p.numel()].view_as(p)
+                            off += p.numel()
+                        self._fused.step(grad_scale=1.0 / dist.get_world_size())
+                        self._fused.host_steps -= 1
                 static_loss = loss.detach()
             self.loss_f.n_train_steps = steps_before
             flat = None
-            if ddp:
+            if ddp and not nccl_in_graph:
                 params = [p for p in self.model.parameters() if p.grad is not None]
                 static_grads = [p.grad for p in params]           # written by every replay
                 flat_buf = torch.zeros(sum(t.numel() for t in static_grads), dtype=torch.float32, device=self.device)
@@ -172,6 +209,8 @@ class Trainer():
             self._fused.host_steps -= 1
         self.loss_f.n_train_steps += 1
         self._fused.host_steps += 1
+        if getattr(self.loss_f, "_fused_d", None):
+            self.loss_f._fused_d.host_steps += 1
         return static_loss
 
     def _fill_static(self, static_x, data):

@@ -118,6 +118,17 @@ int dv_linear_dgrad(const float* g, const float* w, const float* mask_src, float
 size_t dv_linear_wgrad_workspace_bytes(int M, int N, int K);
 int dv_linear_wgrad(const float* g, const float* x, float* dw, float* dbias, int M, int N, int K,
                     void* workspace, void* stream);
+/* Pre-packed weights: dv_linear_pack_multi splits n weight matrices (w[i]: [N[i], K[i]], HOST arrays of device
+ * pointers / sizes) into the tcgen05 hi/lo operand planes of BOTH directions in one launch, into caller-owned
+ * buffers of dv_linear_packed_floats(N, K) floats (16-byte aligned); dv_linear_fwd_packed / dv_linear_dgrad_packed are
+ * dv_linear_fwd / dv_linear_dgrad on those planes (w is still passed: shapes that run on the CUDA cores read it).
+ * One pack launch per network node per step instead of one per layer per direction. */
+size_t dv_linear_packed_floats(int N, int K);
+int dv_linear_pack_multi(int n, const void* const* w, void* const* packed, const int* N, const int* K, void* stream);
+int dv_linear_fwd_packed(const float* x, const float* w, const float* packed, const float* bias, float* y,
+                         int M, int N, int K, int act, float slope, void* stream);
+int dv_linear_dgrad_packed(const float* g, const float* w, const float* packed, const float* mask_src, float* dx,
+                           int M, int N, int K, int act, float slope, void* stream);
 
 /* ---- reparameterised sampling ------------------------------------------------------
  * Replaces VAE.reparameterize (disvae/models/vae.py:65-68): z = mu + exp(0.5*logvar)*eps.

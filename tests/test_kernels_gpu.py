@@ -573,3 +573,21 @@ def test_loss_combine_and_act_bwd_chansum(ops):
         assert_close(cs.cpu(), g_ref.double().sum((0, 2, 3)).float().cpu(), tol=2e-5, what="chansum")
         _, cs2 = ops.act_bwd_chansum(dy, y, 2)
         assert torch.equal(cs, cs2)
+
+
+def test_linear_prepacked_equals_per_call_pack(ops):
+    """dv_linear_pack_multi (every weight matrix of a node, both operand layouts, one launch) + dv_linear_fwd_packed /
+    dv_linear_dgrad_packed give bit-identical results to the per-call packs, incl. the shapes that stay on the CUDA cores."""
+    torch.manual_seed(8)
+    shapes = [(256, 512), (256, 256), (20, 256), (256, 10), (1000, 1000), (2, 1000), (1000, 10)]
+    ws = [(torch.randn(n, k) / math.sqrt(k)).to(dev()) for n, k in shapes]
+    packs = ops.linear_pack_multi(ws)
+    for (n, k), w, pk in zip(shapes, ws, packs):
+        M = 130
+        x = torch.randn(M, k, device=dev())
+        b = torch.randn(n, device=dev())
+        g = torch.randn(M, n, device=dev())
+        prev = torch.relu(torch.randn(M, k, device=dev()))
+        assert torch.equal(ops.linear_fwd(x, w, b, 1, packed=pk), ops.linear_fwd(x, w, b, 1))
+        assert torch.equal(ops.linear_dgrad(g, w, prev, 1, packed=pk), ops.linear_dgrad(g, w, prev, 1))
+        assert torch.equal(ops.linear_dgrad(g, w, None, 0, packed=pk), ops.linear_dgrad(g, w, None, 0))

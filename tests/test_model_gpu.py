@@ -407,7 +407,7 @@ def test_evaluator_losses():
     assert {"recon_loss", "kl_loss", "loss", "tc_loss", "kl_loss_0"} <= set(losses)
 
 
-@pytest.mark.parametrize("loss_name", ["btcvae", "betaB"])
+@pytest.mark.parametrize("loss_name", ["btcvae", "betaB", "factor"])
 def test_cuda_graph_step_equals_eager_step(loss_name, tmp_path):
     """The Trainer's captured whole-step graph (fwd + loss + bwd + fused Adam, device Philox noise) must walk the
     same trajectory as eager launches of the same kernels: identical seed -> identical parameters."""
@@ -419,7 +419,8 @@ def test_cuda_graph_step_equals_eager_step(loss_name, tmp_path):
         m = disvae.init_specific_model("Burgess", (1, 32, 32), 10)
         opt = torch.optim.Adam(m.parameters(), lr=5e-4)
         lf = get_loss_f(loss_name, rec_dist="bernoulli", reg_anneal=0, betaB_initC=0, betaB_finC=25, betaB_G=100,
-                        btcvae_A=1, btcvae_B=6, btcvae_G=1, n_data=6400)
+                        btcvae_A=1, btcvae_B=6, btcvae_G=1, n_data=6400, factor_G=6.4, latent_dim=10, lr_disc=1e-4,
+                        device=torch.device(DEV))
         tr = disvae.Trainer(m, opt, lf, device=torch.device(DEV), logger=logging.getLogger("t"), save_dir=str(tmp_path),
                             is_progress_bar=False)
         tr.use_cuda_graph = use_graph
@@ -429,13 +430,17 @@ def test_cuda_graph_step_equals_eager_step(loss_name, tmp_path):
         losses = [tr._step(x, None).item() for x in xs]
         return m, losses, tr
 
-    m_e, l_e, _ = run(False)
+    m_e, l_e, tr_e = run(False)
     m_g, l_g, tr_g = run(True)
     assert len(tr_g._graphs) == 1, "graph path was not taken"
     for a, b in zip(l_e, l_g):
         assert abs(a - b) <= 1e-6 * abs(a), (l_e, l_g)
     for (k, a), (_, b) in zip(m_e.state_dict().items(), m_g.state_dict().items()):
         assert torch.allclose(a, b, rtol=0, atol=1e-7), k
+    if loss_name == "factor":       # FactorVAE: both backward passes and BOTH optimizer steps are inside the graph
+        for (k, a), (_, b) in zip(tr_e.loss_f.discriminator.state_dict().items(), tr_g.loss_f.discriminator.state_dict().items()):
+            assert torch.allclose(a, b, rtol=0, atol=1e-7), k
+        assert tr_g.loss_f.n_train_steps == tr_e.loss_f.n_train_steps == 9
 
 
 def test_train_epoch_mean_identical_in_graph_and_eager_mode(tmp_path):
