@@ -83,8 +83,9 @@ __device__ __forceinline__ void lse_merge2(float& m, float& s, float m2, float s
 // logsumexp states (max, sum) per (row, dim) for its column range; btcvae_finalize_kernel merges
 // the ranges in a fixed order, forms the row statistics and the three means.  Grid: (B/32) x (B/kJT).
 // ------------------------------------------------------------------------------------------
-constexpr int kJT = 64;            // columns per block
-constexpr int kJPL = kJT / kJL;    // columns per lane (8)
+// JT = columns per block: 64 (8 per lane), or 16 (2 per lane) when (rows/32) x (B/64) blocks would leave most SMs idle
+// (B = 256: 32 blocks -> 128; the z = 64 shard of BASELINE configs[4] went from 55 us to the low tens).
+constexpr int kJTBig = 64, kJTSmall = 16;
 constexpr int kRG = 32;            // rows per block
 
 // Single sweep: instead of a max pass, every (row, dim) of a block uses the reference exponent
@@ -93,9 +94,10 @@ constexpr int kRG = 32;            // rows per block
 // the diagonal term (always part of the sum) keeps the row's total from underflowing; a block whose terms
 // all underflow against its own bound contributes (ref, 0), which the merge treats as the identity -- such
 // terms are < 2^-66 of the block bound and far below the diagonal term.  One MUFU.EX2, ~8 FP32 ops per (i,j,d).
-template <int DC, bool EXACT>
+template <int DC, bool EXACT, int kJT>
 __global__ void __launch_bounds__(kBtWarps * 32)
 btcvae_fwd2_kernel(int B, int D, int row0, int nrows, LogW lw, const float4* __restrict__ pj, float2* __restrict__ part) {
+  constexpr int kJPL = kJT / kJL;    // columns per lane
   __shared__ float4 sp[DC][kJT];
   __shared__ float sbound[DC];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -707,11 +709,19 @@ using namespace dv;
 
 extern "C" {
 
-// header | float4 pj[D][B] | float2 part[ceil(B/kJT)][D+1][B]
+// blocks of the 64-column tiling: (rows/32) x (B/64); below one block per SM the 16-column tiling is used.  The choice
+// for a row window never needs more workspace than the choice for the whole batch (fewer rows -> small tiles only if
+// the whole-batch rule picked them too, or B is small enough that dv_btcvae_workspace_bytes reserved them).
+static bool fwd2_small_tiles(int B, int nrows) {
+  return (long long)((nrows + kRG - 1) / kRG) * ((B + kJTBig - 1) / kJTBig) < kNumSMs && B <= 1024;
+}
+// header | float4 pj[D][B] | float2 part[ceil(B/JT)][D+1][B]
 static long long btcvae_part_offset_floats(int B, int D) { return kWsHeader + 4LL * B * D; }
 size_t dv_btcvae_workspace_bytes(int B, int D) {
-  const long long JS = (B + kJT - 1) / kJT;
-  return (size_t)(btcvae_part_offset_floats(B, D) + 2LL * JS * (D + 1) * B) * sizeof(float);
+  const long long JS = (B + kJTSmall - 1) / kJTSmall;          // room for either column tile width when B is small
+  const long long JS_big = (B + kJTBig - 1) / kJTBig;
+  const long long js = fwd2_small_tiles(B, B) ? JS : JS_big;
+  return (size_t)(btcvae_part_offset_floats(B, D) + 2LL * js * (D + 1) * B) * sizeof(float);
 }
 
 int dv_btcvae_fwd(const float* z, const float* mu, const float* logvar, int ld, int row_stride, int B, int D,
@@ -783,14 +793,23 @@ int dv_btcvae_fwd_rows(const float* z, const float* mu, const float* logvar, int
                                                   reinterpret_cast<float4*>(ws + kWsHeader), rowstats);
   rc = check_launch();
   if (rc != DV_OK) return rc;
-  const int JS = (B + kJT - 1) / kJT;
+  // small tiles only where the whole-batch rule reserved workspace for them
+  const bool small = fwd2_small_tiles(B, nrows) && fwd2_small_tiles(B, B);
+  const int JT = small ? kJTSmall : kJTBig;
+  const int JS = (B + JT - 1) / JT;
   float2* part = reinterpret_cast<float2*>(ws + btcvae_part_offset_floats(B, D));
   const float4* pjc = reinterpret_cast<const float4*>(ws + kWsHeader);
   dim3 grid((nrows + kRG - 1) / kRG, JS);
-  if (D == 10)          btcvae_fwd2_kernel<10, true><<<grid, kBtWarps * 32, 0, st>>>(B, D, row0, nrows, lw, pjc, part);
-  else if (D % 16 == 0) btcvae_fwd2_kernel<16, true><<<grid, kBtWarps * 32, 0, st>>>(B, D, row0, nrows, lw, pjc, part);
-  else if (D <= 8)      btcvae_fwd2_kernel<8, false><<<grid, kBtWarps * 32, 0, st>>>(B, D, row0, nrows, lw, pjc, part);
-  else                  btcvae_fwd2_kernel<16, false><<<grid, kBtWarps * 32, 0, st>>>(B, D, row0, nrows, lw, pjc, part);
+#define DV_FWD2(DC, EXACT)                                                                                         \
+  do {                                                                                                             \
+    if (small) btcvae_fwd2_kernel<DC, EXACT, kJTSmall><<<grid, kBtWarps * 32, 0, st>>>(B, D, row0, nrows, lw, pjc, part); \
+    else       btcvae_fwd2_kernel<DC, EXACT, kJTBig><<<grid, kBtWarps * 32, 0, st>>>(B, D, row0, nrows, lw, pjc, part);   \
+  } while (0)
+  if (D == 10)          DV_FWD2(10, true);
+  else if (D % 16 == 0) DV_FWD2(16, true);
+  else if (D <= 8)      DV_FWD2(8, false);
+  else                  DV_FWD2(16, false);
+#undef DV_FWD2
   rc = check_launch();
   if (rc != DV_OK) return rc;
   btcvae_finalize_kernel<<<(nrows + 15) / 16, 256, 0, st>>>(B, D, row0, nrows, JS, part, rowstats, terms,
