@@ -300,6 +300,12 @@ btcvae_fwd4_kernel(const float* __restrict__ z, const float* __restrict__ mu, co
   // DV_BTCVAE_TIMING=1: block 0 leaves its phase boundaries (SM clocks since kernel entry) in the workspace header
   const long long t_start = dbg ? clock64() : 0;
 #define DV_F4_MARK(slot) do { if (dbg && blockIdx.x == 0 && threadIdx.x == 0) dbg[slot] = (float)(clock64() - t_start); } while (0)
+  // ... and every block its entry / exit time on the global nanosecond timer (dbg + 16 + 4*block: two 64-bit values)
+  if (dbg && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    reinterpret_cast<unsigned long long*>(dbg + 16)[2 * blockIdx.x] = t;
+  }
   __shared__ float s_ref[DC];                                  // r_cd (log2 units); -inf if the CTA owns no column
   __shared__ float s_rsum;                                     // sum_d r_cd
   __shared__ float s_tsx[kF4MaxTasks * kRows][DC];             // per (task, row) partial sums
@@ -534,6 +540,11 @@ btcvae_fwd4_kernel(const float* __restrict__ z, const float* __restrict__ mu, co
   cluster.sync();                                              // no CTA leaves while a peer may still read its shared memory
   DV_F4_MARK(5);
 #undef DV_F4_MARK
+  if (dbg && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    reinterpret_cast<unsigned long long*>(dbg + 16)[2 * blockIdx.x + 1] = t;
+  }
   if (!is_last || warp != 0) return;
   __threadfence();
   float a = 0.f, b = 0.f, c = 0.f;
@@ -769,7 +780,7 @@ int dv_btcvae_fwd_rows(const float* z, const float* mu, const float* logvar, int
       cudaError_t err = cudaSuccess;
       static int timing4 = -1;
       if (timing4 < 0) { const char* e = getenv("DV_BTCVAE_TIMING"); timing4 = (e && e[0] == '1') ? 1 : 0; }
-      float* dbg = timing4 ? ws + 8 : nullptr;                 // header floats 8..13
+      float* dbg = timing4 ? blockpart + 4 * (nclus * kF4Clus) + 16 : nullptr;   // marks at dbg[0..5], per-block timers from dbg[16]
 #define DV_F4_CALL(DC, EXACT, RPT)                                                                                             \
   do {                                                                                                                         \
     static bool attr_set = false;                                                                                              \

@@ -8,7 +8,7 @@ timeout 2400 python -m pytest tests -q -m gpu --timeout=900 --durations=8 -s ${P
 echo "pytest exit $?" | tee -a gpurun_out/pytest_gpu.log
 grep -E "passed|failed|FAILED|ERROR|same branch|flipped" gpurun_out/pytest_gpu.log | tail -40
 fi
-echo "== btcvae timing"; python scripts/btcvae_timing.py 2>&1 | tail -3; DV_BTCVAE_V4=0 python scripts/btcvae_timing.py 2>&1 | tail -3
+echo "== btcvae timing"; python scripts/btcvae_timing.py 2>&1 | tail -4
 for v in ${VARIANTS:-base}; do
   echo "== bench $v"
   if [ "$v" = "base" ]; then envs=""; else envs="$v"; fi
