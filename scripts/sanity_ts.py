@@ -1,0 +1,24 @@
+"""Quick guard before a long GPU run: the three-split-group tcgen05 kernels (setmaxnreg register hand-over) must
+complete and agree with the two-group kernels.  Run under `timeout`: a hang here must not eat the test budget."""
+import os, sys, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "disentangling-vae_b200"))
+from disvae import ops
+import torch.nn.functional as F
+torch.manual_seed(0)
+B, H = 300, 16
+x = torch.randn(B, 32, 2 * H, 2 * H)
+lo = torch.randn(B, 32, H, H)
+w = torch.randn(32, 32, 4, 4) * 0.1
+d = torch.device("cuda")
+wp = ops.conv_pack(w.to(d), 32)
+nhwc = lambda t: t.permute(0, 2, 3, 1).contiguous()
+got_d = ops.conv_down(nhwc(x).to(d), wp, None, None, B, H, H, 32, 0, 1)
+got_u = ops.conv_up(nhwc(lo).to(d), wp, None, None, B, H, H, 32, 0, 1)
+torch.cuda.synchronize()
+ref_d = torch.relu(F.conv2d(x.double(), w.double(), None, stride=2, padding=1))
+ref_u = torch.relu(F.conv_transpose2d(lo.double(), w.double(), None, stride=2, padding=1))
+ed = ((got_d.cpu().permute(0, 3, 1, 2).double() - ref_d).abs().max() / ref_d.abs().max()).item()
+eu = ((got_u.cpu().permute(0, 3, 1, 2).double() - ref_u).abs().max() / ref_u.abs().max()).item()
+print("sanity_ts: groups=%s down err %.2e up err %.2e" % (os.environ.get("DV_TS_GROUPS", "3"), ed, eu))
+sys.exit(0 if ed < 1e-5 and eu < 1e-5 else 1)
