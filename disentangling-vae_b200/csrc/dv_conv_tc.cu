@@ -689,7 +689,7 @@ __device__ __forceinline__ void ts_split_tile_lo(const uint8_t* raw, uint32_t tm
 // (8 LDS.128 + 64 ALU + 2 tcgen05.st.x32 + wait per thread) against ~197 clocks of tensor time: with G = 2 the MMA
 // issuer waits on a_ready (r01/r02 profiles: tensor pipe 36 % active, issue slots 42 % used).  G = 3 needs 640 threads,
 // i.e. 96 registers per thread at launch; the roles then trade registers with setmaxnreg: the four control warps keep
-// 40, the epilogue warps (3 x 32 accumulator values live) get 128, the split warps 112.
+// 56, the epilogue warps (3 x 32 accumulator values live) get 120, the split warps 104 (3 K registers of the file stay unallocated).
 template <int G>
 __global__ void __launch_bounds__(256 + 128 * G, 1)
 conv_down32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -842,7 +842,7 @@ conv_down32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       if (q == 0) colsum_part[blockIdx.x * 32 + lane] = (scr[lane] + scr[32 + lane]) + (scr[64 + lane] + scr[96 + lane]);
     }
   } else {
-    if constexpr (G > 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    if constexpr (G > 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
     const int q = warp & 3, grp = (warp - 8) >> 2;
     uint32_t n = 0;                                           // sequence number of the raw tile within this CTA
     if (!g.pipe) {
@@ -1277,7 +1277,7 @@ conv_up_halo_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
-    if constexpr (G > 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    if constexpr (G > 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
     const int q = warp & 3, grp = (warp - 8) >> 2;
     const int row = q * 32 + lane;
     uint32_t n = 0, t_seq = 0;
