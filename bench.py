@@ -219,7 +219,14 @@ def run_ours(args):
     ms = timed(step_res, K)
     launches = _native.launch_count() - l0
     clocks = clk.stop() if rank == 0 else None
+    # untimed warm-up of the end-to-end path: three loader steps, and one EAGER step -- torch.cuda.graph empties the
+    # caching allocator when it captures, so the first eager step afterwards (the every-50th logging step of a real
+    # run) would otherwise pay ~2 GB of cudaMalloc inside the timed epoch, once
     trainer._train_epoch(loader[:3], None, 0)
+    graph_was = trainer.use_cuda_graph
+    trainer.use_cuda_graph = False
+    trainer._step(resident[0], None)
+    trainer.use_cuda_graph = graph_was
     ms_e2e = timed(lambda i: epoch_e2e(), 1)
 
     out = None
@@ -377,6 +384,21 @@ def kernel_rooflines(trainer, resident, K, B, img, z, n_data, device, detail=Fal
     _native.PROFILE_ONLY = None
     ts.sort()
     t_med = ts[len(ts) // 2]
+    # the same measurement around a kernel that does nothing measurable (16 bytes through dv_u8_to_f32): what the method
+    # itself costs (event records + launch on an idle, L2-flushed GPU)
+    tiny_src = torch.zeros(16, dtype=torch.uint8, device=device)
+    tiny_dst = torch.empty(16, device=device)
+    fl = []
+    for _ in range(10):
+        flush.fill_(1.0)
+        _native.PROFILE_ONLY = "dv_u8_to_f32"
+        _native.enable_profiling()
+        ops.u8_to_f32(tiny_src, out=tiny_dst)
+        torch.cuda.synchronize()
+        fl.append(_native.disable_profiling()["dv_u8_to_f32"][0])
+    _native.PROFILE_ONLY = None
+    fl.sort()
+    floor_us = fl[len(fl) // 2] * 1e3
     vbytes = 4 * Bk * Bk * Dk + 12 * Bk * Dk + 16 * Bk
     ach = vbytes / (t_med / 1e3) / 1e9
     ent = traffic_table.get("dv_btcvae_fwd[B=1024,D=10]") or {}
@@ -385,7 +407,9 @@ def kernel_rooflines(trainer, resident, K, B, img, z, n_data, device, detail=Fal
                                   "reference's B*B*D matrix)", "frac": round(ach / pk["hbm"], 4), "us": round(t_med * 1e3, 2),
                                   "virtual_bytes": vbytes, "compulsory_bytes": 12 * Bk * Dk + 16 * Bk,
                                   "traffic": ent.get("dram_bytes"), "traffic_source": ent.get("source"),
-                                  "l2": "256 MB flush before every timed launch"}
+                                  "l2": "256 MB flush before every timed launch",
+                                  "event_floor_us": round(floor_us, 2),
+                                  "note": "us = CUDA events around ONE launch; event_floor_us = the same around an empty kernel"}
     return res
 
 

@@ -13,9 +13,16 @@ w = torch.randn(32, 32, 4, 4) * 0.1
 d = torch.device("cuda")
 wp = ops.conv_pack(w.to(d), 32)
 nhwc = lambda t: t.permute(0, 2, 3, 1).contiguous()
-got_d = ops.conv_down(nhwc(x).to(d), wp, None, None, B, H, H, 32, 0, 1)
-got_u = ops.conv_up(nhwc(lo).to(d), wp, None, None, B, H, H, 32, 0, 1)
+which = sys.argv[1] if len(sys.argv) > 1 else "both"
+B = int(os.environ.get("SANITY_B", B))
+x, lo = x[:B], lo[:B]
+got_d = ops.conv_down(nhwc(x).to(d), wp, None, None, B, H, H, 32, 0, 1) if which != "up" else None
 torch.cuda.synchronize()
+got_u = ops.conv_up(nhwc(lo).to(d), wp, None, None, B, H, H, 32, 0, 1) if which != "down" else None
+torch.cuda.synchronize()
+if which != "both":
+    print("sanity_ts: %s completed" % which)
+    sys.exit(0)
 ref_d = torch.relu(F.conv2d(x.double(), w.double(), None, stride=2, padding=1))
 ref_u = torch.relu(F.conv_transpose2d(lo.double(), w.double(), None, stride=2, padding=1))
 ed = ((got_d.cpu().permute(0, 3, 1, 2).double() - ref_d).abs().max() / ref_d.abs().max()).item()
