@@ -690,7 +690,9 @@ __device__ __forceinline__ void ts_split_tile_lo(const uint8_t* raw, uint32_t tm
 // issuer waits on a_ready (r01/r02 profiles: tensor pipe 36 % active, issue slots 42 % used).  G = 3 needs 640 threads,
 // i.e. 96 registers per thread at launch; the roles then trade registers with setmaxnreg: the four control warps keep
 // 56, the epilogue warps (3 x 32 accumulator values live) get 120, the split warps 104 (3 K registers of the file stay unallocated).
-template <int G>
+// V selects the register hand-over of the G = 3 kernels (DV_TS_REGS, experiments): 0 = none (96 registers everywhere),
+// 1 = control 56 / epilogue 120 / split 104, 2 = control 40 / epilogue 112 / split unchanged.
+template <int G, int V>
 __global__ void __launch_bounds__(256 + 128 * G, 1)
 conv_down32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                       const float* __restrict__ bias, const float* __restrict__ mask, float* __restrict__ lo,
@@ -711,7 +713,8 @@ conv_down32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   // the register hand-over sits at the head of each role's branch (whole warpgroups execute it), so that ptxas
   // allocates the code it dominates against the new limit
   if (warp < 4) {
-  if constexpr (G > 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  if constexpr (G > 2 && V == 1) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  if constexpr (G > 2 && V == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
   if (warp == 0 && elect_one()) {
     prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b);
     mbar_arrive_expect_tx(&bars->b_full, kBBytes);
@@ -784,7 +787,8 @@ conv_down32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     }
   }
   } else if (warp < 8) {
-    if constexpr (G > 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
+    if constexpr (G > 2 && V == 1) asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
+    if constexpr (G > 2 && V == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
     const int q = warp & 3;
     int acc = 0; uint32_t acc_phase = 0;
     float csum = 0.f;                                         // lane l: running sum of output channel l over this warp's rows
@@ -842,7 +846,7 @@ conv_down32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       if (q == 0) colsum_part[blockIdx.x * 32 + lane] = (scr[lane] + scr[32 + lane]) + (scr[64 + lane] + scr[96 + lane]);
     }
   } else {
-    if constexpr (G > 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    if constexpr (G > 2 && V == 1) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
     const int q = warp & 3, grp = (warp - 8) >> 2;
     uint32_t n = 0;                                           // sequence number of the raw tile within this CTA
     if (!g.pipe) {
@@ -1094,7 +1098,7 @@ template <int CH> struct HaloCfg {
 };
 
 // G split groups (see conv_down32_ts_kernel): G = 3 runs 640 threads and re-balances registers with setmaxnreg.
-template <int CH, int G>
+template <int CH, int G, int V>
 __global__ void __launch_bounds__(256 + 128 * G, 1)
 conv_up_halo_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                        const float* __restrict__ bias, const float* __restrict__ mask, float* __restrict__ hi_out,
@@ -1123,7 +1127,8 @@ conv_up_halo_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
   constexpr uint32_t tmem_base = 0u;
 
   if (warp < 4) {
-  if constexpr (G > 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  if constexpr (G > 2 && V == 1) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  if constexpr (G > 2 && V == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
   if (warp == 0 && elect_one()) {
     prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b);
     mbar_arrive_expect_tx(&bars->b_full, C::kBAll);
@@ -1188,7 +1193,8 @@ conv_up_halo_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     }
   }
   } else if (warp < 8) {
-    if constexpr (G > 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
+    if constexpr (G > 2 && V == 1) asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
+    if constexpr (G > 2 && V == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
     const int q = warp & 3;
     const int HH = 2 * g.H, WW = 2 * g.W;
     int acc = 0; uint32_t acc_phase = 0;
@@ -1277,7 +1283,7 @@ conv_up_halo_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
-    if constexpr (G > 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    if constexpr (G > 2 && V == 1) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
     const int q = warp & 3, grp = (warp - 8) >> 2;
     const int row = q * 32 + lane;
     uint32_t n = 0, t_seq = 0;
@@ -1771,6 +1777,18 @@ static int use_rawhi_down() {
   if (v < 0) { const char* e = getenv("DV_TC_RAWHI_DOWN"); v = (e && e[0] == '1') ? 1 : 0; }
   return v;
 }
+// DV_TS_GROUPS (2 | 3) = split groups of the TS kernels, DV_TS_REGS (0 | 1 | 2) = setmaxnreg variant of the G = 3 kernels.
+// Defaults: the validated two-group kernels (the three-group kernels deadlocked in the first hardware run).
+static int ts_groups() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DV_TS_GROUPS"); v = (e && e[0] == '3') ? 3 : 2; }
+  return v;
+}
+static int ts_regs() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DV_TS_REGS"); v = e ? (e[0] - '0') : 1; if (v < 0 || v > 2) v = 1; }
+  return v;
+}
 static int use_debug() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("DV_TC_DEBUG"); v = e ? atoi(e) : 0; }
@@ -1870,17 +1888,20 @@ int conv_down32_tc(const float* hi, const float* wd_packed, const float* bias, c
   if (use_ts()) {
     static bool attr2 = false;
     if (!attr2) {
-      if (cudaFuncSetAttribute(conv_down32_ts_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTsSmemBytes) != cudaSuccess ||
-          cudaFuncSetAttribute(conv_down32_ts_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTsSmemBytes) != cudaSuccess) {
+      if (cudaFuncSetAttribute(conv_down32_ts_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTsSmemBytes) != cudaSuccess ||
+          cudaFuncSetAttribute(conv_down32_ts_kernel<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTsSmemBytes) != cudaSuccess ||
+          cudaFuncSetAttribute(conv_down32_ts_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTsSmemBytes) != cudaSuccess ||
+          cudaFuncSetAttribute(conv_down32_ts_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTsSmemBytes) != cudaSuccess) {
         g_last_cuda_error = (int)cudaGetLastError();
         return DV_ERR_CUDA;
       }
       attr2 = true;
     }
-    static int groups = -1;                                   // DV_TS_GROUPS=2: the two-group kernel (A/B)
-    if (groups < 0) { const char* e = getenv("DV_TS_GROUPS"); groups = (e && e[0] == '2') ? 2 : 3; }
-    if (groups == 3) conv_down32_ts_kernel<3><<<grid, 640, kTsSmemBytes, st>>>(ta, tb, bias, mask, lo, g, act, colsum_part);
-    else             conv_down32_ts_kernel<2><<<grid, 512, kTsSmemBytes, st>>>(ta, tb, bias, mask, lo, g, act, colsum_part);
+    const int groups = ts_groups(), regs = ts_regs();
+    if (groups == 3 && regs == 1)      conv_down32_ts_kernel<3, 1><<<grid, 640, kTsSmemBytes, st>>>(ta, tb, bias, mask, lo, g, act, colsum_part);
+    else if (groups == 3 && regs == 2) conv_down32_ts_kernel<3, 2><<<grid, 640, kTsSmemBytes, st>>>(ta, tb, bias, mask, lo, g, act, colsum_part);
+    else if (groups == 3)              conv_down32_ts_kernel<3, 0><<<grid, 640, kTsSmemBytes, st>>>(ta, tb, bias, mask, lo, g, act, colsum_part);
+    else                               conv_down32_ts_kernel<2, 0><<<grid, 512, kTsSmemBytes, st>>>(ta, tb, bias, mask, lo, g, act, colsum_part);
     if (nparts && colsum_part) *nparts = grid;
     return check_launch();
   }
@@ -2074,18 +2095,21 @@ static int launch_up_halo(const float* lo, const float* wu, const float* bias, c
   if (!make_w_tmap_rows(&tb, wu, CH == 32 ? kTaps * 64 : 320)) return DV_ERR_CUDA;
   static bool attr = false;
   if (!attr) {
-    if (cudaFuncSetAttribute(conv_up_halo_ts_kernel<CH, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<CH>::kSmem) != cudaSuccess ||
-        cudaFuncSetAttribute(conv_up_halo_ts_kernel<CH, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<CH>::kSmem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(conv_up_halo_ts_kernel<CH, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<CH>::kSmem) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_up_halo_ts_kernel<CH, 3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<CH>::kSmem) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_up_halo_ts_kernel<CH, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<CH>::kSmem) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_up_halo_ts_kernel<CH, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<CH>::kSmem) != cudaSuccess) {
       g_last_cuda_error = (int)cudaGetLastError();
       return DV_ERR_CUDA;
     }
     attr = true;
   }
   const int grid = g.num_tiles < kNumSMs ? g.num_tiles : kNumSMs;
-  static int groups = -1;                                     // DV_TS_GROUPS=2: the two-group kernel (A/B)
-  if (groups < 0) { const char* e = getenv("DV_TS_GROUPS"); groups = (e && e[0] == '2') ? 2 : 3; }
-  if (groups == 3) conv_up_halo_ts_kernel<CH, 3><<<grid, 640, HaloCfg<CH>::kSmem, st>>>(ta, tb, bias, mask, hi, g, act);
-  else             conv_up_halo_ts_kernel<CH, 2><<<grid, 512, HaloCfg<CH>::kSmem, st>>>(ta, tb, bias, mask, hi, g, act);
+  const int groups = ts_groups(), regs = ts_regs();
+  if (groups == 3 && regs == 1)      conv_up_halo_ts_kernel<CH, 3, 1><<<grid, 640, HaloCfg<CH>::kSmem, st>>>(ta, tb, bias, mask, hi, g, act);
+  else if (groups == 3 && regs == 2) conv_up_halo_ts_kernel<CH, 3, 2><<<grid, 640, HaloCfg<CH>::kSmem, st>>>(ta, tb, bias, mask, hi, g, act);
+  else if (groups == 3)              conv_up_halo_ts_kernel<CH, 3, 0><<<grid, 640, HaloCfg<CH>::kSmem, st>>>(ta, tb, bias, mask, hi, g, act);
+  else                               conv_up_halo_ts_kernel<CH, 2, 0><<<grid, 512, HaloCfg<CH>::kSmem, st>>>(ta, tb, bias, mask, hi, g, act);
   return check_launch();
 }
 

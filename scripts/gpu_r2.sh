@@ -3,8 +3,8 @@
 # ncu launch list.  Everything lands in gpurun_out/.  Env: TESTS=0 skips pytest, WORKLOADS="c3 c4 c5", NCU=0.
 set -u
 mkdir -p gpurun_out
-# guard: the 640-thread tcgen05 kernels (setmaxnreg) must terminate; otherwise fall back to the two-group kernels
-if ! timeout 180 python scripts/sanity_ts.py; then echo "sanity_ts FAILED or hung: DV_TS_GROUPS=2 for this run"; export DV_TS_GROUPS=2; fi
+# guard: the tcgen05 conv kernels of this configuration must terminate and be accurate before the long runs
+if ! timeout 180 python scripts/sanity_ts.py; then echo "sanity_ts FAILED or hung: falling back to DV_TS_GROUPS=2"; export DV_TS_GROUPS=2; fi
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.txt 2>&1
 if [ "${TESTS:-1}" = "1" ]; then
 echo "== pytest gpu"

@@ -23,9 +23,23 @@ torch.cuda.synchronize()
 if which != "both":
     print("sanity_ts: %s completed" % which)
     sys.exit(0)
+if os.environ.get("SANITY_TIME") == "1":          # timing of both kernels at the bench shape (B = 1024, H = 16)
+    Bt = 1024
+    xt = torch.randn(Bt, 2 * H, 2 * H, 32, device=d); lt = torch.randn(Bt, H, H, 32, device=d)
+    for name, fn in (("down", lambda: ops.conv_down(xt, wp, None, None, Bt, H, H, 32, 0, 1)),
+                     ("up", lambda: ops.conv_up(lt, wp, None, None, Bt, H, H, 32, 0, 1))):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        print("sanity_ts timing: groups=%s regs=%s %s %.1f us" % (os.environ.get("DV_TS_GROUPS", "2"), os.environ.get("DV_TS_REGS", "1"),
+                                                                 name, e0.elapsed_time(e1) / 20 * 1e3))
 ref_d = torch.relu(F.conv2d(x.double(), w.double(), None, stride=2, padding=1))
 ref_u = torch.relu(F.conv_transpose2d(lo.double(), w.double(), None, stride=2, padding=1))
 ed = ((got_d.cpu().permute(0, 3, 1, 2).double() - ref_d).abs().max() / ref_d.abs().max()).item()
 eu = ((got_u.cpu().permute(0, 3, 1, 2).double() - ref_u).abs().max() / ref_u.abs().max()).item()
-print("sanity_ts: groups=%s down err %.2e up err %.2e" % (os.environ.get("DV_TS_GROUPS", "3"), ed, eu))
+print("sanity_ts: groups=%s regs=%s down err %.2e up err %.2e" % (os.environ.get("DV_TS_GROUPS", "2"), os.environ.get("DV_TS_REGS", "1"), ed, eu))
 sys.exit(0 if ed < 1e-5 and eu < 1e-5 else 1)
