@@ -108,8 +108,6 @@ struct DownGeom {
   int prefetch;         // L2-prefetch the next tile's hi rows (DV_TC_PREFETCH=0 switches it off)
   int pipe;             // split warps overlap the TMEM stores of one tile with the loads/split of their next tile
   int debug;            // DV_TC_DEBUG (timing experiments only, results are WRONG): 2 = load 4 of the 16 tap tiles
-  int rawhi;            // down32_ts: the hi operand is the RAW TMA tile in shared memory (SS MMA; kind::tf32 reads only the
-                        // upper 19 bits = the hi/lo truncation), the split warps produce only the lo plane (DV_TC_RAWHI=0: off)
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -617,6 +615,12 @@ conv_wgrad32_tc_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid
 //   smem : weights 128 KB resident + 6 raw stages x 16 KB
 //   TMEM : columns [0,256) accumulators (2 stages), [256,512) A operand (4 stages x {hi 32 | lo 32})
 // ==========================================================================================
+// Round-2 experiments on these kernels, all measured on hardware and all slower, none kept:
+//   * hi operand straight from the raw TMA tile (SS MMA, only the lo plane through TMEM): 87.5 vs 75.6 us at
+//     (1024,16,32) -- the 16 KB/tap operand fetch competes with the weight tile for shared-memory read bandwidth;
+//   * a third group of split warps (640 threads): 83.1 vs 73.1 us (down), 93.0 vs 90.9 us (up) without register
+//     re-balancing, 78.1 / 93.4 us with setmaxnreg (control 40 / epilogue 112) -- the split warps are NOT what the
+//     MMA issuer waits for once two groups alternate (a setmaxnreg budget that also grew the split warps deadlocked).
 constexpr int kTsThreads = 512;          // warps 8-11 and 12-15: two split groups working on alternate tiles
 constexpr int kTsRawStages = 6;
 constexpr int kTsAStages = 4;
@@ -633,9 +637,9 @@ constexpr int kTsSmemBytes = kBBytes + kTsRawStages * kATile + 1024 + 512;
 static_assert(sizeof(TsBarriers) <= 512, "barrier block too large");
 static_assert(kTsSmemBytes <= 232448, "smem");
 
-__device__ __forceinline__ void ts_init(TsBarriers* bars, const float* bias, int warp, int raw_readers = 128) {
+__device__ __forceinline__ void ts_init(TsBarriers* bars, const float* bias, int warp) {
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kTsRawStages; ++s) { mbar_init(&bars->raw_full[s], 1); mbar_init(&bars->raw_empty[s], raw_readers); }
+    for (int s = 0; s < kTsRawStages; ++s) { mbar_init(&bars->raw_full[s], 1); mbar_init(&bars->raw_empty[s], 128); }
     for (int s = 0; s < kTsAStages; ++s) { mbar_init(&bars->a_ready[s], 128); mbar_init(&bars->a_empty[s], 1); }
     mbar_init(&bars->b_full, 1);
     for (int a = 0; a < 2; ++a) { mbar_init(&bars->acc_full[a], 1); mbar_init(&bars->acc_empty[a], 128); }
@@ -669,31 +673,7 @@ __device__ __forceinline__ void ts_split_tile(const uint8_t* raw, uint32_t tmem_
   tmem_st_wait();
 }
 
-// rawhi variant: only the residual plane goes to TMEM (the MMA reads the hi part straight from the raw tile)
-__device__ __forceinline__ void ts_split_tile_lo(const uint8_t* raw, uint32_t tmem_base, int as, int q, int lane) {
-  const int row = q * 32 + lane;
-  uint32_t l[32];
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const uint4 v = lds128(raw + row * 128 + ((c ^ (row & 7)) << 4));
-    const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int e = 0; e < 4; ++e)
-      l[c * 4 + e] = __float_as_uint(__uint_as_float(vv[e]) - __uint_as_float(vv[e] & kHiMask));
-  }
-  tmem_st_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + kTsACol0 + as * 64 + 32, l);
-  tmem_st_wait();
-}
-
-// G = number of split groups (4 warps each) working on alternate raw tiles.  One tap tile costs a group ~620 clocks
-// (8 LDS.128 + 64 ALU + 2 tcgen05.st.x32 + wait per thread) against ~197 clocks of tensor time: with G = 2 the MMA
-// issuer waits on a_ready (r01/r02 profiles: tensor pipe 36 % active, issue slots 42 % used).  G = 3 needs 640 threads,
-// i.e. 96 registers per thread at launch; the roles then trade registers with setmaxnreg: the four control warps keep
-// 56, the epilogue warps (3 x 32 accumulator values live) get 120, the split warps 104 (3 K registers of the file stay unallocated).
-// V selects the register hand-over of the G = 3 kernels (DV_TS_REGS, experiments): 0 = none (96 registers everywhere),
-// 1 = control 56 / epilogue 120 / split 104, 2 = control 40 / epilogue 112 / split unchanged.
-template <int G, int V>
-__global__ void __launch_bounds__(256 + 128 * G, 1)
+__global__ void __launch_bounds__(kTsThreads, 1)
 conv_down32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                       const float* __restrict__ bias, const float* __restrict__ mask, float* __restrict__ lo,
                       DownGeom g, int act, float* __restrict__ colsum_part) {
@@ -703,18 +683,12 @@ conv_down32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   uint8_t* Raw = smem + kBBytes;
   TsBarriers* bars = reinterpret_cast<TsBarriers*>(Raw + kTsRawStages * kATile);
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform role index
-  ts_init(bars, bias, warp, g.rawhi ? 129 : 128);           // rawhi: the MMA's commit is a reader of the raw stage too
-
+  ts_init(bars, bias, warp);
   // All 512 columns are ours (1 CTA/SM), so the allocation starts at column 0.  Using the literal keeps every
   // tensor-memory address a compile-time/warp-uniform value (no per-MMA register -> uniform-register moves).
   if (bars->tmem_base != 0u) __trap();
   constexpr uint32_t tmem_base = 0u;
 
-  // the register hand-over sits at the head of each role's branch (whole warpgroups execute it), so that ptxas
-  // allocates the code it dominates against the new limit
-  if (warp < 4) {
-  if constexpr (G > 2 && V == 1) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-  if constexpr (G > 2 && V == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
   if (warp == 0 && elect_one()) {
     prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b);
     mbar_arrive_expect_tx(&bars->b_full, kBBytes);
@@ -746,38 +720,20 @@ conv_down32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     constexpr uint32_t idesc64 = umma_idesc_tf32(128, 64), idesc32 = umma_idesc_tf32(128, 32);
     mbar_wait(&bars->b_full, 0);
     int as = 0; uint32_t aphase = 0; int acc = 0; uint32_t acc_phase = 0;
-    int rs = 0; uint32_t rphase = 0;
     for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
       mbar_wait(&bars->acc_empty[acc], acc_phase ^ 1);
       tc_fence_after_sync();
       const uint32_t d_tmem = tmem_base + acc * 128;
       for (int tap = 0; tap < kTaps; ++tap) {
+        mbar_wait(&bars->a_ready[as], aphase);
+        tc_fence_after_sync();
         const uint32_t a_hi = tmem_base + kTsACol0 + as * 64, a_lo = a_hi + 32;
         const uint64_t b_d = umma_desc_sw128_kmajor(smem_u32(Bs + tap * kBTap));
-        if (g.rawhi) {
-          // a_hi * [b_hi | b_lo] straight from the TMA tile: needs only the load, not the split warps
-          mbar_wait(&bars->raw_full[rs], rphase);
-          tc_fence_after_sync();
-          const uint64_t a_d = umma_desc_sw128_kmajor(smem_u32(Raw + rs * kATile));
 #pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4)
-            umma_tf32_ss_1t(d_tmem + (k4 & 1) * 64, a_d + 2 * k4, b_d + 2 * k4, idesc64, (tap | (k4 >> 1)) != 0);
-          mbar_wait(&bars->a_ready[as], aphase);              // residual plane of the same tile (split warps -> TMEM)
-          tc_fence_after_sync();
-#pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4)
-            umma_tf32_ts_1t(d_tmem + (k4 & 1) * 64, a_lo + 8 * k4, b_d + 2 * k4, idesc32, 1);
-          umma_commit_1t(&bars->raw_empty[rs]);               // the raw stage is free once these MMAs have read it
-          if (++rs == kTsRawStages) { rs = 0; rphase ^= 1; }
-        } else {
-          mbar_wait(&bars->a_ready[as], aphase);
-          tc_fence_after_sync();
-#pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4) {
-            const uint32_t d = d_tmem + (k4 & 1) * 64;        // two accumulation chains, see the SS kernel
-            umma_tf32_ts_1t(d, a_hi + 8 * k4, b_d + 2 * k4, idesc64, (tap | (k4 >> 1)) != 0);
-            umma_tf32_ts_1t(d, a_lo + 8 * k4, b_d + 2 * k4, idesc32, 1);
-          }
+        for (int k4 = 0; k4 < 4; ++k4) {
+          const uint32_t d = d_tmem + (k4 & 1) * 64;          // two accumulation chains, see the SS kernel
+          umma_tf32_ts_1t(d, a_hi + 8 * k4, b_d + 2 * k4, idesc64, (tap | (k4 >> 1)) != 0);
+          umma_tf32_ts_1t(d, a_lo + 8 * k4, b_d + 2 * k4, idesc32, 1);
         }
         umma_commit_1t(&bars->a_empty[as]);
         if (++as == kTsAStages) { as = 0; aphase ^= 1; }
@@ -785,10 +741,7 @@ conv_down32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       umma_commit_1t(&bars->acc_full[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-  }
-  } else if (warp < 8) {
-    if constexpr (G > 2 && V == 1) asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
-    if constexpr (G > 2 && V == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+  } else if (warp >= 4 && warp < 8) {
     const int q = warp & 3;
     int acc = 0; uint32_t acc_phase = 0;
     float csum = 0.f;                                         // lane l: running sum of output channel l over this warp's rows
@@ -845,20 +798,18 @@ conv_down32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (q == 0) colsum_part[blockIdx.x * 32 + lane] = (scr[lane] + scr[32 + lane]) + (scr[64 + lane] + scr[96 + lane]);
     }
-  } else {
-    if constexpr (G > 2 && V == 1) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+  } else if (warp >= 8) {
     const int q = warp & 3, grp = (warp - 8) >> 2;
     uint32_t n = 0;                                           // sequence number of the raw tile within this CTA
     if (!g.pipe) {
       for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
         for (int tap = 0; tap < kTaps; ++tap, ++n) {
-          if ((int)(n % (uint32_t)G) != grp) continue;
+          if ((int)(n & 1u) != grp) continue;
           const int stage = n % kTsRawStages, as = n % kTsAStages;
           mbar_wait(&bars->raw_full[stage], (n / kTsRawStages) & 1u);
           mbar_wait(&bars->a_empty[as], ((n / kTsAStages) & 1u) ^ 1u);
           tc_fence_after_sync();
-          if (g.rawhi) ts_split_tile_lo(Raw + stage * kATile, tmem_base, as, q, lane);
-          else ts_split_tile(Raw + stage * kATile, tmem_base, as, q, lane);
+          ts_split_tile(Raw + stage * kATile, tmem_base, as, q, lane);
           mbar_arrive(&bars->raw_empty[stage]);
           tc_fence_before_sync();
           mbar_arrive(&bars->a_ready[as]);
@@ -872,7 +823,7 @@ conv_down32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       int prev_stage = -1, prev_as = 0;
       for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
         for (int tap = 0; tap < kTaps; ++tap, ++n) {
-          if ((int)(n % (uint32_t)G) != grp) continue;
+          if ((int)(n & 1u) != grp) continue;
           const int stage = n % kTsRawStages, as = n % kTsAStages;
           mbar_wait(&bars->raw_full[stage], (n / kTsRawStages) & 1u);
           const uint8_t* raw = Raw + stage * kATile;
@@ -897,7 +848,7 @@ conv_down32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
           mbar_wait(&bars->a_empty[as], ((n / kTsAStages) & 1u) ^ 1u);
           tc_fence_after_sync();
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + kTsACol0 + as * 64;
-          if (!g.rawhi) tmem_st_32x32b_x32(taddr, h);
+          tmem_st_32x32b_x32(taddr, h);
           tmem_st_32x32b_x32(taddr + 32, l);
           prev_stage = stage; prev_as = as;
         }
@@ -1097,9 +1048,8 @@ template <int CH> struct HaloCfg {
   static constexpr int kAccPerPhase = 32;
 };
 
-// G split groups (see conv_down32_ts_kernel): G = 3 runs 640 threads and re-balances registers with setmaxnreg.
-template <int CH, int G, int V>
-__global__ void __launch_bounds__(256 + 128 * G, 1)
+template <int CH>
+__global__ void __launch_bounds__(kTsThreads, 1)
 conv_up_halo_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                        const float* __restrict__ bias, const float* __restrict__ mask, float* __restrict__ hi_out,
                        HaloGeom g, int act) {
@@ -1126,9 +1076,6 @@ conv_up_halo_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
   if (bars->tmem_base != 0u) __trap();                       // whole TMEM is ours: base column 0 (see the TS kernels)
   constexpr uint32_t tmem_base = 0u;
 
-  if (warp < 4) {
-  if constexpr (G > 2 && V == 1) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-  if constexpr (G > 2 && V == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
   if (warp == 0 && elect_one()) {
     prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b);
     mbar_arrive_expect_tx(&bars->b_full, C::kBAll);
@@ -1191,10 +1138,7 @@ conv_up_halo_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
       umma_commit_1t(&bars->acc_full[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-  }
-  } else if (warp < 8) {
-    if constexpr (G > 2 && V == 1) asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
-    if constexpr (G > 2 && V == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+  } else if (warp >= 4 && warp < 8) {
     const int q = warp & 3;
     const int HH = 2 * g.H, WW = 2 * g.W;
     int acc = 0; uint32_t acc_phase = 0;
@@ -1282,8 +1226,7 @@ conv_up_halo_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-  } else {
-    if constexpr (G > 2 && V == 1) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+  } else if (warp >= 8) {
     const int q = warp & 3, grp = (warp - 8) >> 2;
     const int row = q * 32 + lane;
     uint32_t n = 0, t_seq = 0;
@@ -1293,7 +1236,7 @@ conv_up_halo_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
       const uint8_t* raw = Raw + stage * kHaloStageBytes;
       bool waited = false;
       for (int s = 0; s < 9; ++s, ++n) {
-        if ((int)(n % (uint32_t)G) != grp) continue;
+        if ((int)(n & 1u) != grp) continue;
         const int di = s / 3 - 1, dj = s % 3 - 1;
         const int as = n % kTsAStages;
         if (!waited) { mbar_wait(&bars->raw_full[stage], (t_seq / kHaloStages) & 1u); waited = true; }
@@ -1769,26 +1712,6 @@ static int use_rawhi() {
   if (v < 0) { const char* e = getenv("DV_TC_RAWHI"); v = (e && e[0] == '0') ? 0 : 1; }
   return v;
 }
-// conv_down32_ts: hi operand straight from the raw TMA tile (SS MMA) instead of a TMEM copy.  OFF by default: measured
-// 87.5 us vs 75.6 us at (1024,16,32) -- the SS operand fetch (16 KB per tap) competes with the weight tile for the
-// tensor core's shared-memory read bandwidth, which costs more than the halved tcgen05.st traffic saves.  DV_TC_RAWHI_DOWN=1.
-static int use_rawhi_down() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("DV_TC_RAWHI_DOWN"); v = (e && e[0] == '1') ? 1 : 0; }
-  return v;
-}
-// DV_TS_GROUPS (2 | 3) = split groups of the TS kernels, DV_TS_REGS (0 | 1 | 2) = setmaxnreg variant of the G = 3 kernels.
-// Defaults: the validated two-group kernels (the three-group kernels deadlocked in the first hardware run).
-static int ts_groups() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("DV_TS_GROUPS"); v = (e && e[0] == '3') ? 3 : 2; }
-  return v;
-}
-static int ts_regs() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("DV_TS_REGS"); v = e ? (e[0] - '0') : 1; if (v < 0 || v > 2) v = 1; }
-  return v;
-}
 static int use_debug() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("DV_TC_DEBUG"); v = e ? atoi(e) : 0; }
@@ -1866,7 +1789,7 @@ int conv_down32_tc(const float* hi, const float* wd_packed, const float* bias, c
   if (nparts) *nparts = 0;
   if (W > 128 || 128 % W != 0) return DV_ERR_BAD_SHAPE;
   DownGeom g = {};
-  g.B = B; g.H = H; g.W = W; g.prefetch = use_prefetch(); g.pipe = use_pipe(); g.debug = use_debug(); g.rawhi = use_rawhi_down();
+  g.B = B; g.H = H; g.W = W; g.prefetch = use_prefetch(); g.pipe = use_pipe(); g.debug = use_debug();
   g.rows_per_tile = 128 / W;
   const int TR = g.rows_per_tile < H ? g.rows_per_tile : H;
   if (H % TR != 0 || g.rows_per_tile % TR != 0) return DV_ERR_BAD_SHAPE;
@@ -1888,20 +1811,13 @@ int conv_down32_tc(const float* hi, const float* wd_packed, const float* bias, c
   if (use_ts()) {
     static bool attr2 = false;
     if (!attr2) {
-      if (cudaFuncSetAttribute(conv_down32_ts_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTsSmemBytes) != cudaSuccess ||
-          cudaFuncSetAttribute(conv_down32_ts_kernel<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTsSmemBytes) != cudaSuccess ||
-          cudaFuncSetAttribute(conv_down32_ts_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTsSmemBytes) != cudaSuccess ||
-          cudaFuncSetAttribute(conv_down32_ts_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTsSmemBytes) != cudaSuccess) {
+      if (cudaFuncSetAttribute(conv_down32_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTsSmemBytes) != cudaSuccess) {
         g_last_cuda_error = (int)cudaGetLastError();
         return DV_ERR_CUDA;
       }
       attr2 = true;
     }
-    const int groups = ts_groups(), regs = ts_regs();
-    if (groups == 3 && regs == 1)      conv_down32_ts_kernel<3, 1><<<grid, 640, kTsSmemBytes, st>>>(ta, tb, bias, mask, lo, g, act, colsum_part);
-    else if (groups == 3 && regs == 2) conv_down32_ts_kernel<3, 2><<<grid, 640, kTsSmemBytes, st>>>(ta, tb, bias, mask, lo, g, act, colsum_part);
-    else if (groups == 3)              conv_down32_ts_kernel<3, 0><<<grid, 640, kTsSmemBytes, st>>>(ta, tb, bias, mask, lo, g, act, colsum_part);
-    else                               conv_down32_ts_kernel<2, 0><<<grid, 512, kTsSmemBytes, st>>>(ta, tb, bias, mask, lo, g, act, colsum_part);
+    conv_down32_ts_kernel<<<grid, kTsThreads, kTsSmemBytes, st>>>(ta, tb, bias, mask, lo, g, act, colsum_part);
     if (nparts && colsum_part) *nparts = grid;
     return check_launch();
   }
@@ -2095,21 +2011,14 @@ static int launch_up_halo(const float* lo, const float* wu, const float* bias, c
   if (!make_w_tmap_rows(&tb, wu, CH == 32 ? kTaps * 64 : 320)) return DV_ERR_CUDA;
   static bool attr = false;
   if (!attr) {
-    if (cudaFuncSetAttribute(conv_up_halo_ts_kernel<CH, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<CH>::kSmem) != cudaSuccess ||
-        cudaFuncSetAttribute(conv_up_halo_ts_kernel<CH, 3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<CH>::kSmem) != cudaSuccess ||
-        cudaFuncSetAttribute(conv_up_halo_ts_kernel<CH, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<CH>::kSmem) != cudaSuccess ||
-        cudaFuncSetAttribute(conv_up_halo_ts_kernel<CH, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<CH>::kSmem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(conv_up_halo_ts_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<CH>::kSmem) != cudaSuccess) {
       g_last_cuda_error = (int)cudaGetLastError();
       return DV_ERR_CUDA;
     }
     attr = true;
   }
   const int grid = g.num_tiles < kNumSMs ? g.num_tiles : kNumSMs;
-  const int groups = ts_groups(), regs = ts_regs();
-  if (groups == 3 && regs == 1)      conv_up_halo_ts_kernel<CH, 3, 1><<<grid, 640, HaloCfg<CH>::kSmem, st>>>(ta, tb, bias, mask, hi, g, act);
-  else if (groups == 3 && regs == 2) conv_up_halo_ts_kernel<CH, 3, 2><<<grid, 640, HaloCfg<CH>::kSmem, st>>>(ta, tb, bias, mask, hi, g, act);
-  else if (groups == 3)              conv_up_halo_ts_kernel<CH, 3, 0><<<grid, 640, HaloCfg<CH>::kSmem, st>>>(ta, tb, bias, mask, hi, g, act);
-  else                               conv_up_halo_ts_kernel<CH, 2, 0><<<grid, 512, HaloCfg<CH>::kSmem, st>>>(ta, tb, bias, mask, hi, g, act);
+  conv_up_halo_ts_kernel<CH><<<grid, kTsThreads, HaloCfg<CH>::kSmem, st>>>(ta, tb, bias, mask, hi, g, act);
   return check_launch();
 }
 

@@ -4,7 +4,7 @@
 set -u
 mkdir -p gpurun_out
 # guard: the tcgen05 conv kernels of this configuration must terminate and be accurate before the long runs
-if ! timeout 180 python scripts/sanity_ts.py; then echo "sanity_ts FAILED or hung: falling back to DV_TS_GROUPS=2"; export DV_TS_GROUPS=2; fi
+if ! timeout 180 python scripts/sanity_ts.py; then echo "sanity_ts FAILED or hung: aborting this run"; exit 1; fi
 if [ "${TESTS:-1}" = "1" ]; then
 timeout 2400 python -m pytest tests -q -m gpu --timeout=900 --durations=8 -s ${PYTEST_ARGS:-} > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest exit $?" | tee -a gpurun_out/pytest_gpu.log
