@@ -567,20 +567,13 @@ static int wgrad_nsplit(int B, int H, int W, long long* chunk) {
 }  // namespace dv
 
 namespace dv {
-namespace tc {
+namespace tc {        // dv_conv_tc.cu: tcgen05 kernels of the 32-channel layers
 int pack_tc(const float* w, float* wd, float* wu, float* wf, cudaStream_t st);
 int conv_down32_tc(const float* hi, const float* wd_packed, const float* bias, const float* mask, float* lo,
                    int B, int H, int W, int act, cudaStream_t st, float* colsum_part, int* nparts);
-int pack_small_tc(const float* w, float* wd, int CH, cudaStream_t st);
-int pack_up_small_tc(const float* w, float* wu, int CH, cudaStream_t st);
 int conv_up_halo(const float* lo, const float* wu, const float* bias, const float* mask, float* hi,
-                 int B, int H, int W, int CH, int act, cudaStream_t st);
-int conv_down_small_tc(const float* x, const float* wd, const float* bias, const float* mask, float* lo,
-                       int B, int H, int W, int CH, int act, cudaStream_t st, float* colsum_part, int* nparts);
-int conv_wgrad_small_tc(const float* lo, const float* x, float* ws, int B, int H, int W, int CH, int* nsplit, cudaStream_t st);
-int conv_wgrad32_tc(const float* lo, const float* hi, float* ws, int B, int H, int W, int* nsplit, cudaStream_t st);
-int conv_up32_tc(const float* lo, const float* wu_packed, const float* bias, const float* mask, float* hi,
                  int B, int H, int W, int act, cudaStream_t st);
+int conv_wgrad32_tc(const float* lo, const float* hi, float* ws, int B, int H, int W, int* nsplit, cudaStream_t st);
 }  // namespace tc
 namespace img {       // dv_conv_img.cu: exact-fp32 CUDA-core kernels for the image-boundary layers (CH in {1,3})
 bool shape_ok(int B, int H, int W, int CH);
@@ -589,12 +582,6 @@ int conv_down(const float* hi, const float* wd, const float* bias, const float* 
 int conv_wgrad(const float* lo, const float* hi, float* ws, int B, int H, int W, int CH, int max_split, int* nsplit, cudaStream_t st);
 int conv_up(const float* lo, const float* wu, const float* bias, float* hi, int B, int H, int W, int CH, int act, cudaStream_t st);
 }  // namespace img
-namespace c2i {
-size_t packed_floats(int CH);
-int pack(const float* w, float* wp, int CH, cudaStream_t st);
-bool shape_ok(int B, int H, int W, int CH);
-int conv_up(const float* lo, const float* wp, const float* bias, float* hi, int B, int H, int W, int CH, int act, cudaStream_t st);
-}  // namespace c2i
 
 // packed-weight sections for CH == 32 (floats): [0,16K) ffma down, [16K,32K) ffma up,
 // [32K,64K) tcgen05 down (hi|lo), [64K,96K) tcgen05 up (hi|lo)
@@ -603,7 +590,7 @@ constexpr int kPackTcSection = kTaps * 64 * 32;
 
 // DV_CONV_IMPL=ffma forces the CUDA-core kernels for the 32-channel layers (A/B testing)
 // DV_TC_DISABLE=down,up,wgrad switches individual tensor-core kernels off.
-// DV_IMG=0 switches the dv_conv_img.cu kernels off (A/B against the tcgen05 image-boundary kernels).
+// DV_IMG=0 switches the dv_conv_img.cu kernels off (the image-boundary layers then run on the CUDA-core fallbacks).
 static bool use_img() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("DV_IMG"); v = (e && e[0] == '0') ? 0 : 1; }
@@ -626,13 +613,10 @@ using namespace dv;
 
 extern "C" {
 
-// CH in {1,3}: [0, 512*CH) ffma down, [512*CH, 1024*CH) ffma up, then the tcgen05 down operand
-// [kb][64][32] (kb = ceil(16*CH/32) K blocks)
-static size_t small_tc_floats(int CH) { return (size_t)((16 * CH + 31) / 32) * 64 * 32; }
-constexpr int kPackUpSmall = 320 * 32;            // tcgen05 up operand of the CH small layers: [shift][phase-merged hi|lo rows][32 cl]
+// CH in {1,3}: [0, 512*CH) down layout, [512*CH, 1024*CH) up layout (shared by dv_conv_img.cu and the CUDA-core kernels)
 size_t dv_conv_packed_floats(int CH) {
   return CH == 32 ? (size_t)kPackFfma + 2 * kPackTcSection
-                  : (size_t)2 * kLoCh * CH * kTaps + small_tc_floats(CH) + kPackUpSmall + c2i::packed_floats(CH);
+                  : (size_t)2 * kLoCh * CH * kTaps;
 }
 
 int dv_conv_pack_weights(const float* w, float* w_packed, int CH, void* stream) {
@@ -642,17 +626,7 @@ int dv_conv_pack_weights(const float* w, float* w_packed, int CH, void* stream) 
   if (CH == 32)                                     // ONE launch: both tcgen05 operand layouts + the two CUDA-core layouts
     return tc::pack_tc(w, w_packed + kPackFfma, w_packed + kPackFfma + kPackTcSection, w_packed, as_stream(stream));
   conv_pack_kernel<<<(n + 255) / 256, 256, 0, as_stream(stream)>>>(w, w_packed, CH);
-  int rc = check_launch();
-  if (rc != DV_OK) return rc;
-  if (use_img()) return DV_OK;                      // image-boundary layers run on dv_conv_img.cu: nothing else reads a pack
-  if (CH != 32) {
-    rc = tc::pack_small_tc(w, w_packed + 2 * kLoCh * CH * kTaps, CH, as_stream(stream));
-    if (rc != DV_OK) return rc;
-    rc = tc::pack_up_small_tc(w, w_packed + 2 * kLoCh * CH * kTaps + small_tc_floats(CH), CH, as_stream(stream));
-    if (rc != DV_OK) return rc;
-    return c2i::pack(w, w_packed + 2 * kLoCh * CH * kTaps + small_tc_floats(CH) + kPackUpSmall, CH, as_stream(stream));
-  }
-  return DV_OK;
+  return check_launch();
 }
 
 static int conv_down_impl(const float* hi, const float* w_packed, const float* bias, const float* mask, float* lo,
@@ -663,8 +637,6 @@ static int conv_down_impl(const float* hi, const float* w_packed, const float* b
     return tc::conv_down32_tc(hi, w_packed + kPackFfma, bias, mask, lo, B, H, W, act, st, colsum_part, nparts);
   if (CH != 32 && use_img() && img::shape_ok(B, H, W, CH))
     return img::conv_down(hi, w_packed, bias, mask, lo, B, H, W, CH, act, st, colsum_part, nparts, kCsBlocks);
-  if (CH != 32 && !use_img() && use_tc("dsmall") && W <= 128 && 128 % W == 0)
-    return tc::conv_down_small_tc(hi, w_packed + 2 * kLoCh * CH * kTaps, bias, mask, lo, B, H, W, CH, act, st, colsum_part, nparts);
   if (CH == 32) {
     const int smem = kTaps * 32 * kLoCh * sizeof(float);
     static bool attr_set = false;
@@ -717,15 +689,8 @@ int dv_conv_up(const float* lo, const float* w_packed, const float* bias, const 
   const float* wu = w_packed + kLoCh * CH * kTaps;
   if (CH != 32 && !mask && use_img() && img::shape_ok(B, H, W, CH))
     return img::conv_up(lo, wu, bias, hi, B, H, W, CH, act, as_stream(stream));
-  if (CH != 32 && !mask && !use_img() && use_tc("c2i") && c2i::shape_ok(B, H, W, CH))
-    return c2i::conv_up(lo, w_packed + 2 * kLoCh * CH * kTaps + small_tc_floats(CH) + kPackUpSmall, bias, hi, B, H, W, CH, act,
-                        as_stream(stream));
-  if (use_tc("halo") && (CH == 32 ? act != DV_ACT_SIGMOID : !use_img()) && W + 2 <= 40)
-    return tc::conv_up_halo(lo, CH == 32 ? w_packed + kPackFfma + kPackTcSection
-                                          : w_packed + 2 * kLoCh * CH * kTaps + small_tc_floats(CH),
-                            bias, mask, hi, B, H, W, CH, act, as_stream(stream));
-  if (CH == 32 && use_tc("up") && act != DV_ACT_SIGMOID)
-    return tc::conv_up32_tc(lo, w_packed + kPackFfma + kPackTcSection, bias, mask, hi, B, H, W, act, as_stream(stream));
+  if (CH == 32 && use_tc("halo") && act != DV_ACT_SIGMOID && W + 2 <= 40)
+    return tc::conv_up_halo(lo, w_packed + kPackFfma + kPackTcSection, bias, mask, hi, B, H, W, act, as_stream(stream));
   if (CH == 32) {
     const int smem = kTaps * 32 * kLoCh * sizeof(float);
     static bool attr_set = false;
@@ -771,10 +736,9 @@ int dv_conv_wgrad(const float* lo, const float* hi, float* dw, float* dbias_lo, 
     conv_wgrad_reduce_kernel<<<(n + 31) / 32, 256, 0, st>>>(ws, dw, dbias_lo, CH, nsplit_img);
     return check_launch();
   }
-  if ((CH == 32 && use_tc("wgrad")) || (CH != 32 && !use_img() && use_tc("wsmall"))) {
+  if (CH == 32 && use_tc("wgrad")) {
     int nsplit_tc = 0;
-    int rc = CH == 32 ? tc::conv_wgrad32_tc(lo, hi, ws, B, H, W, &nsplit_tc, st)
-                      : tc::conv_wgrad_small_tc(lo, hi, ws, B, H, W, CH, &nsplit_tc, st);
+    int rc = tc::conv_wgrad32_tc(lo, hi, ws, B, H, W, &nsplit_tc, st);
     if (rc != DV_OK) return rc;
     const int n = (kTaps * CH + 1) * kLoCh;
     conv_wgrad_reduce_kernel<<<(n + 31) / 32, 256, 0, st>>>(ws, dw, dbias_lo, CH, nsplit_tc);

@@ -5,9 +5,9 @@
 // With K = 16*CH these layers have ~1/30 of the arithmetic intensity of the 32->32 layers: 2*512*CH FLOP per lo
 // pixel against 128 B (lo) + 16*CH B (hi) of compulsory traffic, i.e. they are pure HBM streaming problems (151 MB per
 // launch at B = 1024, 1x64x64) whose whole arithmetic (1.07 GFLOP) fits in ~15 us of FP32 FMA issue.  The tcgen05
-// variants (dv_conv_tc.cu conv_*_small_tc_kernel, dv_conv_c2i.cu) pay for operand staging they cannot amortise
-// (im2col gather by 4 builder warps, hi/lo splitting, three tensor passes) and ran at 15-22 % of HBM bandwidth; these
-// kernels do exact fp32 FMAs from shared-memory tiles with register blocking instead:
+// variants of round 1 (conv_*_small_tc_kernel, conv_up_c2i_kernel; deleted) paid for operand staging they could not
+// amortise (im2col gather by 4 builder warps, hi/lo splitting, three tensor passes) and ran at 15-22 % of HBM bandwidth;
+// these kernels do exact fp32 FMAs from shared-memory tiles with register blocking instead:
 //
 //   down  (Conv2d fwd, ConvTranspose2d dgrad): thread = 8 (4) consecutive output pixels x 8 output channels; the image
 //         tile (with halo and zero padding) in shared memory, one 18-value input row segment per kernel row, two LDS.128

@@ -27,28 +27,11 @@ namespace tc {
 
 using namespace ptx;
 
-constexpr int kStages = 3;
 constexpr int kATile = 128 * 128;            // bytes: 128 pixel rows x 32 fp32
 constexpr int kBTap = 64 * 128;              // bytes: (32 hi + 32 lo) rows x 32 fp32
 constexpr int kBBytes = kTaps * kBTap;       // 131072
-constexpr int kAccCols = 128;           // 2 chains x [hi*hi+lo*hi (32) | hi*lo (32)]
 constexpr int kThreads = 384;
 constexpr uint32_t kHiMask = 0xFFFFE000u;    // keep sign, exponent and the 10 tf32 mantissa bits
-
-struct Barriers {
-  uint64_t raw_full[kStages];
-  uint64_t ready[kStages];
-  uint64_t empty[kStages];
-  uint64_t b_full;
-  uint64_t acc_full[2];
-  uint64_t acc_empty[2];
-  uint32_t tmem_base;
-  float bias[32];
-};
-constexpr int kSmemBytes = kBBytes + kStages * 2 * kATile + 1024 /*alignment slack*/ + 512 /*Barriers*/;
-static_assert(sizeof(Barriers) <= 512, "barrier block too large");
-static_assert(kSmemBytes <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
-
 
 // raw fp32 tile -> tf32-exact hi plane (in place) + residual lo plane; 128 threads, layout-agnostic
 __device__ __forceinline__ void split_hi_lo(uint4* hi, uint4* lo4, int t) {
@@ -109,296 +92,6 @@ struct DownGeom {
   int pipe;             // split warps overlap the TMEM stores of one tile with the loads/split of their next tile
   int debug;            // DV_TC_DEBUG (timing experiments only, results are WRONG): 2 = load 4 of the 16 tap tiles
 };
-
-__global__ void __launch_bounds__(kThreads, 1)
-conv_down32_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                      const float* __restrict__ bias, const float* __restrict__ mask, float* __restrict__ lo,
-                      DownGeom g, int act) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* Bs = smem;                                       // [tap][64 rows][128 B]
-  uint8_t* Ahi = smem + kBBytes;                            // [stage][128 rows][128 B]
-  uint8_t* Alo = Ahi + kStages * kATile;
-  Barriers* bars = reinterpret_cast<Barriers*>(Alo + kStages * kATile);
-
-  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform role index
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(&bars->raw_full[s], 1); mbar_init(&bars->ready[s], 128); mbar_init(&bars->empty[s], 1); }
-    mbar_init(&bars->b_full, 1);
-    for (int a = 0; a < 2; ++a) { mbar_init(&bars->acc_full[a], 1); mbar_init(&bars->acc_empty[a], 128); }
-    fence_mbar_init();
-  }
-  if (threadIdx.x < 32) bars->bias[threadIdx.x] = bias ? bias[threadIdx.x] : 0.f;
-  if (warp == 2) tmem_alloc(&bars->tmem_base, 256);
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  const uint32_t tmem_base = bars->tmem_base;
-
-  if (warp == 0 && elect_one()) {
-    // ===================== TMA producer =====================
-    prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b);
-    mbar_arrive_expect_tx(&bars->b_full, kBBytes);
-    for (int tap = 0; tap < kTaps; ++tap) tma_load_2d(Bs + tap * kBTap, &tmap_b, &bars->b_full, 0, tap * 64);
-    int stage = 0; uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
-      const int r0 = tile * g.rows_per_tile;
-      const int b0 = r0 / g.H, i0 = r0 % g.H;
-      for (int tap = 0; tap < kTaps; ++tap) {
-        const int kh = tap >> 2, kw = tap & 3;
-        mbar_wait(&bars->empty[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&bars->raw_full[stage], kATile);
-        tma_load_4d(Ahi + stage * kATile, &tmap_a, &bars->raw_full[stage], 0, kw - 1, 2 * i0 - 1 + kh, b0);
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
-      }
-    }
-  } else if (warp == 1 && elect_one()) {      // ONE elected lane runs the whole issue loop (barrier waits included):
-                                              // ptxas then keeps every MMA operand in uniform registers (back-to-back UTCHMMA)
-    // ===================== MMA issuer (single thread) =====================
-    constexpr uint32_t idesc64 = umma_idesc_tf32(128, 64), idesc32 = umma_idesc_tf32(128, 32);
-    mbar_wait(&bars->b_full, 0);
-    int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
-      mbar_wait(&bars->acc_empty[acc], acc_phase ^ 1);
-      tc_fence_after_sync();
-      const uint32_t d_tmem = tmem_base + acc * kAccCols;
-      for (int tap = 0; tap < kTaps; ++tap) {
-        mbar_wait(&bars->ready[stage], phase);
-        tc_fence_after_sync();
-        const uint64_t a_hi = umma_desc_sw128_kmajor(smem_u32(Ahi + stage * kATile));
-        const uint64_t a_lo = umma_desc_sw128_kmajor(smem_u32(Alo + stage * kATile));
-        const uint64_t b_d = umma_desc_sw128_kmajor(smem_u32(Bs + tap * kBTap));
-#pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4) {                   // K = 8 tf32 (32 bytes) per MMA: advance start address
-          // two independent accumulation chains (k4 parity): the tensor core truncates when it adds into
-          // the fp32 accumulator, so halving the chain length halves that bias; summed in the epilogue
-          const uint32_t d = d_tmem + (k4 & 1) * 64;
-          umma_tf32_ss_1t(d, a_hi + 2 * k4, b_d + 2 * k4, idesc64, (tap | (k4 >> 1)) != 0);  // a_hi * [b_hi | b_lo]
-          umma_tf32_ss_1t(d, a_lo + 2 * k4, b_d + 2 * k4, idesc32, 1);                        // a_lo * b_hi
-        }
-        umma_commit_1t(&bars->empty[stage]);                  // stage free once these MMAs have read it
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
-      }
-      umma_commit_1t(&bars->acc_full[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-    }
-  } else if (warp >= 4 && warp < 8) {
-    // ===================== epilogue: TMEM -> registers -> global =====================
-    const int q = warp & 3;
-    int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
-      mbar_wait(&bars->acc_full[acc], acc_phase);
-      tc_fence_after_sync();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccCols;
-      uint32_t r0[32], r1[32], r2[32], r3[32];
-      tmem_ld_32x32b_x32(taddr, r0);
-      tmem_ld_32x32b_x32(taddr + 32, r1);
-      tmem_ld_32x32b_x32(taddr + 64, r2);
-      tmem_ld_32x32b_x32(taddr + 96, r3);
-      tmem_ld_wait();
-      tc_fence_before_sync();
-      mbar_arrive(&bars->acc_empty[acc]);
-      const long long p = (long long)tile * 128 + q * 32 + lane;
-      if (p < g.total_px) {
-        float* dst = lo + p * 32;
-        const float* mk = mask ? mask + p * 32 : nullptr;
-#pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4) {
-          float v[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int c = c4 * 4 + e;
-            float x = ((__uint_as_float(r0[c]) + __uint_as_float(r2[c])) + (__uint_as_float(r1[c]) + __uint_as_float(r3[c]))) + bars->bias[c];
-            if (act == DV_ACT_RELU) x = fmaxf(x, 0.f);
-            v[e] = x;
-          }
-          if (mk) {
-            const float4 m4 = ldg4(mk + c4 * 4);
-            v[0] = m4.x > 0.f ? v[0] : 0.f; v[1] = m4.y > 0.f ? v[1] : 0.f;
-            v[2] = m4.z > 0.f ? v[2] : 0.f; v[3] = m4.w > 0.f ? v[3] : 0.f;
-          }
-          *reinterpret_cast<float4*>(dst + c4 * 4) = make_float4(v[0], v[1], v[2], v[3]);
-        }
-      }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-    }
-  } else if (warp >= 8) {
-    // ===================== hi/lo split of the raw fp32 tile =====================
-    const int t = threadIdx.x - 256;
-    int stage = 0; uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
-      for (int tap = 0; tap < kTaps; ++tap) {
-        mbar_wait(&bars->raw_full[stage], phase);
-        split_hi_lo(reinterpret_cast<uint4*>(Ahi + stage * kATile), reinterpret_cast<uint4*>(Alo + stage * kATile), t);
-        fence_proxy_async_smem();
-        mbar_arrive(&bars->ready[stage]);
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
-      }
-    }
-  }
-
-  tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 2) { tc_fence_after_sync(); tmem_dealloc(tmem_base, 256); }
-}
-
-
-// ------------------------------------------------------------------------------------------
-// up (ConvTranspose2d forward / Conv2d input-gradient), per tile of 128 lo positions:
-//   hi(2i+ph, 2j+pw)[c] = sum over the 2x2 taps with kh = ph+1-2*di, kw = pw+1-2*dj of
-//                          lo(i+di, j+dj)[cl] * w[cl][c][kh][kw]
-// Nine shifted lo tiles (di, dj in {-1,0,1}; unit-stride TMA boxes, zero fill at the borders)
-// feed the 16 (phase, tap) products; each of the 4 output phases owns a 64-column TMEM
-// accumulator ([a_hi*b_hi + a_lo*b_hi | a_hi*b_lo]), 16 accumulation steps per chain.
-// Same warp roles / pipelines as the down kernel; the pipeline unit is a shifted tile.
-// ------------------------------------------------------------------------------------------
-constexpr int kUpAccCols = 256;              // 4 phases x 64
-
-__global__ void __launch_bounds__(kThreads, 1)
-conv_up32_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                    const float* __restrict__ bias, const float* __restrict__ mask, float* __restrict__ hi_out,
-                    DownGeom g, int act) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* Bs = smem;
-  uint8_t* Ahi = smem + kBBytes;
-  uint8_t* Alo = Ahi + kStages * kATile;
-  Barriers* bars = reinterpret_cast<Barriers*>(Alo + kStages * kATile);
-  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform role index
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(&bars->raw_full[s], 1); mbar_init(&bars->ready[s], 128); mbar_init(&bars->empty[s], 1); }
-    mbar_init(&bars->b_full, 1);
-    for (int a = 0; a < 2; ++a) { mbar_init(&bars->acc_full[a], 1); mbar_init(&bars->acc_empty[a], 128); }
-    fence_mbar_init();
-  }
-  if (threadIdx.x < 32) bars->bias[threadIdx.x] = bias ? bias[threadIdx.x] : 0.f;
-  if (warp == 2) tmem_alloc(&bars->tmem_base, 512);
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  const uint32_t tmem_base = bars->tmem_base;
-
-  if (warp == 0 && elect_one()) {
-    prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b);
-    mbar_arrive_expect_tx(&bars->b_full, kBBytes);
-    for (int tap = 0; tap < kTaps; ++tap) tma_load_2d(Bs + tap * kBTap, &tmap_b, &bars->b_full, 0, tap * 64);
-    int stage = 0; uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
-      const int r0 = tile * g.rows_per_tile;
-      const int b0 = r0 / g.H, i0 = r0 % g.H;
-      for (int s = 0; s < 9; ++s) {
-        const int di = s / 3 - 1, dj = s % 3 - 1;
-        mbar_wait(&bars->empty[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&bars->raw_full[stage], kATile);
-        tma_load_4d(Ahi + stage * kATile, &tmap_a, &bars->raw_full[stage], 0, dj, i0 + di, b0);
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
-      }
-    }
-  } else if (warp == 1 && elect_one()) {      // ONE elected lane runs the whole issue loop (barrier waits included):
-                                              // ptxas then keeps every MMA operand in uniform registers (back-to-back UTCHMMA)
-    constexpr uint32_t idesc64 = umma_idesc_tf32(128, 64), idesc32 = umma_idesc_tf32(128, 32);
-    mbar_wait(&bars->b_full, 0);
-    int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
-      mbar_wait(&bars->acc_empty[acc], acc_phase ^ 1);
-      tc_fence_after_sync();
-      uint32_t inited = 0;
-      for (int s = 0; s < 9; ++s) {
-        const int di = s / 3 - 1, dj = s % 3 - 1;
-        mbar_wait(&bars->ready[stage], phase);
-        tc_fence_after_sync();
-        const uint64_t a_hi = umma_desc_sw128_kmajor(smem_u32(Ahi + stage * kATile));
-        const uint64_t a_lo = umma_desc_sw128_kmajor(smem_u32(Alo + stage * kATile));
-        for (int ph = 0; ph < 2; ++ph) {
-          const int kh = ph + 1 - 2 * di;
-          if (kh < 0 || kh > 3) continue;
-          for (int pw = 0; pw < 2; ++pw) {
-            const int kw = pw + 1 - 2 * dj;
-            if (kw < 0 || kw > 3) continue;
-            const int pidx = ph * 2 + pw;
-            const uint32_t d = tmem_base + acc * kUpAccCols + pidx * 64;
-            const uint64_t b_d = umma_desc_sw128_kmajor(smem_u32(Bs + (kh * 4 + kw) * kBTap));
-            const uint32_t first = (inited >> pidx) & 1u;
-            inited |= 1u << pidx;
-#pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4) {
-              umma_tf32_ss_1t(d, a_hi + 2 * k4, b_d + 2 * k4, idesc64, (first | (uint32_t)k4) != 0);
-              umma_tf32_ss_1t(d, a_lo + 2 * k4, b_d + 2 * k4, idesc32, 1);
-            }
-          }
-        }
-        umma_commit_1t(&bars->empty[stage]);
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
-      }
-      umma_commit_1t(&bars->acc_full[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-    }
-  } else if (warp >= 4 && warp < 8) {
-    const int q = warp & 3;
-    const int HH = 2 * g.H, WW = 2 * g.W;
-    int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
-      mbar_wait(&bars->acc_full[acc], acc_phase);
-      tc_fence_after_sync();
-      const long long p = (long long)tile * 128 + q * 32 + lane;
-      const bool valid = p < g.total_px;
-      int b = 0, i = 0, j = 0;
-      if (valid) { j = (int)(p % g.W); i = (int)((p / g.W) % g.H); b = (int)(p / ((long long)g.W * g.H)); }
-#pragma unroll 1
-      for (int pidx = 0; pidx < 4; ++pidx) {
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kUpAccCols + pidx * 64;
-        uint32_t r0[32], r1[32];
-        tmem_ld_32x32b_x32(taddr, r0);
-        tmem_ld_32x32b_x32(taddr + 32, r1);
-        tmem_ld_wait();
-        if (pidx == 3) { tc_fence_before_sync(); mbar_arrive(&bars->acc_empty[acc]); }
-        if (valid) {
-          const int ph = pidx >> 1, pw = pidx & 1;
-          const long long o = ((long long)(b * HH + 2 * i + ph) * WW + 2 * j + pw) * 32;
-          float* dst = hi_out + o;
-          const float* mk = mask ? mask + o : nullptr;
-#pragma unroll
-          for (int c4 = 0; c4 < 8; ++c4) {
-            float v[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int c = c4 * 4 + e;
-              float x = (__uint_as_float(r0[c]) + __uint_as_float(r1[c])) + bars->bias[c];
-              if (act == DV_ACT_RELU) x = fmaxf(x, 0.f);
-              v[e] = x;
-            }
-            if (mk) {
-              const float4 m4 = ldg4(mk + c4 * 4);
-              v[0] = m4.x > 0.f ? v[0] : 0.f; v[1] = m4.y > 0.f ? v[1] : 0.f;
-              v[2] = m4.z > 0.f ? v[2] : 0.f; v[3] = m4.w > 0.f ? v[3] : 0.f;
-            }
-            *reinterpret_cast<float4*>(dst + c4 * 4) = make_float4(v[0], v[1], v[2], v[3]);
-          }
-        }
-      }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-    }
-  } else if (warp >= 8) {
-    const int t = threadIdx.x - 256;
-    int stage = 0; uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
-      for (int s = 0; s < 9; ++s) {
-        mbar_wait(&bars->raw_full[stage], phase);
-        split_hi_lo(reinterpret_cast<uint4*>(Ahi + stage * kATile), reinterpret_cast<uint4*>(Alo + stage * kATile), t);
-        fence_proxy_async_smem();
-        mbar_arrive(&bars->ready[stage]);
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
-      }
-    }
-  }
-
-  tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 2) { tc_fence_after_sync(); tmem_dealloc(tmem_base, 512); }
-}
-
 
 // ------------------------------------------------------------------------------------------
 // wgrad: dw[cl][c][tap] = sum_p lo[p][cl] * hi(2i-1+kh, 2j-1+kw)[c]   (reduction over PIXELS)
@@ -866,147 +559,8 @@ conv_down32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   if (warp == 2) { tc_fence_after_sync(); tmem_dealloc(tmem_base, 512); }
 }
 
-__global__ void __launch_bounds__(kTsThreads, 1)
-conv_up32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                    const float* __restrict__ bias, const float* __restrict__ mask, float* __restrict__ hi_out,
-                    DownGeom g, int act) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* Bs = smem;
-  uint8_t* Raw = smem + kBBytes;
-  TsBarriers* bars = reinterpret_cast<TsBarriers*>(Raw + kTsRawStages * kATile);
-  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform role index
-  ts_init(bars, bias, warp);
-  // All 512 columns are ours (1 CTA/SM), so the allocation starts at column 0.  Using the literal keeps every
-  // tensor-memory address a compile-time/warp-uniform value (no per-MMA register -> uniform-register moves).
-  if (bars->tmem_base != 0u) __trap();
-  constexpr uint32_t tmem_base = 0u;
-
-  if (warp == 0 && elect_one()) {
-    prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b);
-    mbar_arrive_expect_tx(&bars->b_full, kBBytes);
-    for (int tap = 0; tap < kTaps; ++tap) tma_load_2d(Bs + tap * kBTap, &tmap_b, &bars->b_full, 0, tap * 64);
-    int stage = 0; uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
-      const int r0 = tile * g.rows_per_tile;
-      const int b0 = r0 / g.H, i0 = r0 % g.H;
-      for (int s = 0; s < 9; ++s) {
-        const int di = s / 3 - 1, dj = s % 3 - 1;
-        mbar_wait(&bars->raw_empty[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&bars->raw_full[stage], kATile);
-        tma_load_4d(Raw + stage * kATile, &tmap_a, &bars->raw_full[stage], 0, dj, i0 + di, b0);
-        if (++stage == kTsRawStages) { stage = 0; phase ^= 1; }
-      }
-    }
-  } else if (warp == 1 && elect_one()) {      // ONE elected lane runs the whole issue loop (barrier waits included):
-                                              // ptxas then keeps every MMA operand in uniform registers (back-to-back UTCHMMA)
-    constexpr uint32_t idesc32 = umma_idesc_tf32(128, 32);
-    mbar_wait(&bars->b_full, 0);
-    int as = 0; uint32_t aphase = 0; int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
-      mbar_wait(&bars->acc_empty[acc], acc_phase ^ 1);
-      tc_fence_after_sync();
-      uint32_t inited = 0;
-      for (int s = 0; s < 9; ++s) {
-        const int di = s / 3 - 1, dj = s % 3 - 1;
-        mbar_wait(&bars->a_ready[as], aphase);
-        tc_fence_after_sync();
-        const uint32_t a_hi = tmem_base + kTsACol0 + as * 64, a_lo = a_hi + 32;
-        for (int ph = 0; ph < 2; ++ph) {
-          const int kh = ph + 1 - 2 * di;
-          if (kh < 0 || kh > 3) continue;
-          for (int pw = 0; pw < 2; ++pw) {
-            const int kw = pw + 1 - 2 * dj;
-            if (kw < 0 || kw > 3) continue;
-            const int pidx = ph * 2 + pw;
-            const uint32_t d = tmem_base + acc * 128 + pidx * 32;
-            const uint64_t b_hi = umma_desc_sw128_kmajor(smem_u32(Bs + (kh * 4 + kw) * kBTap));
-            const uint64_t b_lo = b_hi + (4096 >> 4);           // rows 32..63 of the tap tile
-            const uint32_t first = (inited >> pidx) & 1u;
-            inited |= 1u << pidx;
-#pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4) {
-              umma_tf32_ts_1t(d, a_hi + 8 * k4, b_hi + 2 * k4, idesc32, (first | (uint32_t)k4) != 0);
-              umma_tf32_ts_1t(d, a_hi + 8 * k4, b_lo + 2 * k4, idesc32, 1);
-              umma_tf32_ts_1t(d, a_lo + 8 * k4, b_hi + 2 * k4, idesc32, 1);
-            }
-          }
-        }
-        umma_commit_1t(&bars->a_empty[as]);
-        if (++as == kTsAStages) { as = 0; aphase ^= 1; }
-      }
-      umma_commit_1t(&bars->acc_full[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-    }
-  } else if (warp >= 4 && warp < 8) {
-    const int q = warp & 3;
-    const int HH = 2 * g.H, WW = 2 * g.W;
-    int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
-      mbar_wait(&bars->acc_full[acc], acc_phase);
-      tc_fence_after_sync();
-      const long long p = (long long)tile * 128 + q * 32 + lane;
-      const bool valid = p < g.total_px;
-      int b = 0, i = 0, j = 0;
-      if (valid) { j = (int)(p % g.W); i = (int)((p / g.W) % g.H); b = (int)(p / ((long long)g.W * g.H)); }
-#pragma unroll 1
-      for (int pidx = 0; pidx < 4; ++pidx) {
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 128 + pidx * 32;
-        uint32_t r0[32];
-        tmem_ld_32x32b_x32(taddr, r0);
-        tmem_ld_wait();
-        if (pidx == 3) { tc_fence_before_sync(); mbar_arrive(&bars->acc_empty[acc]); }
-        if (valid) {
-          const int ph = pidx >> 1, pw = pidx & 1;
-          const long long o = ((long long)(b * HH + 2 * i + ph) * WW + 2 * j + pw) * 32;
-          float* dst = hi_out + o;
-          const float* mk = mask ? mask + o : nullptr;
-#pragma unroll
-          for (int c4 = 0; c4 < 8; ++c4) {
-            float v[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int c = c4 * 4 + e;
-              float x = __uint_as_float(r0[c]) + bars->bias[c];
-              if (act == DV_ACT_RELU) x = fmaxf(x, 0.f);
-              v[e] = x;
-            }
-            if (mk) {
-              const float4 m4 = ldg4(mk + c4 * 4);
-              v[0] = m4.x > 0.f ? v[0] : 0.f; v[1] = m4.y > 0.f ? v[1] : 0.f;
-              v[2] = m4.z > 0.f ? v[2] : 0.f; v[3] = m4.w > 0.f ? v[3] : 0.f;
-            }
-            *reinterpret_cast<float4*>(dst + c4 * 4) = make_float4(v[0], v[1], v[2], v[3]);
-          }
-        }
-      }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-    }
-  } else if (warp >= 8) {
-    const int q = warp & 3, grp = (warp - 8) >> 2;
-    uint32_t n = 0;                                           // sequence number of the raw tile within this CTA
-    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
-      for (int s = 0; s < 9; ++s, ++n) {
-        if ((int)(n & 1u) != grp) continue;
-        const int stage = n % kTsRawStages, as = n % kTsAStages;
-        mbar_wait(&bars->raw_full[stage], (n / kTsRawStages) & 1u);
-        mbar_wait(&bars->a_empty[as], ((n / kTsAStages) & 1u) ^ 1u);
-        tc_fence_after_sync();
-        ts_split_tile(Raw + stage * kATile, tmem_base, as, q, lane);
-        mbar_arrive(&bars->raw_empty[stage]);
-        tc_fence_before_sync();
-        mbar_arrive(&bars->a_ready[as]);
-      }
-    }
-  }
-  tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 2) { tc_fence_after_sync(); tmem_dealloc(tmem_base, 512); }
-}
-
-
 // ==========================================================================================
-// up, halo-resident ("one load per input pixel"), all CH:
+// up, halo-resident ("one load per input pixel"), CH == 32:
 // The nine shifted operand tiles of the up convolution overlap almost completely, so instead of
 // nine TMA loads per 128 positions ONE zero-padded halo tile [(TR+2) rows][W+2 cols][32 ch] is
 // loaded per tile (box start (-1, i0-1): the padding is TMA out-of-bounds fill).  MMA rows enumerate
@@ -1014,10 +568,9 @@ conv_up32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 // q + di*(W+2) + dj of the resident tile: the split warps read them (un-swizzling by the absolute
 // row index), split hi/lo and tcgen05.st them to TMEM.  Rows that fall on padding columns / halo
 // rows produce garbage that the epilogue skips (each output row depends only on its own A rows).
-// L2->smem traffic drops 9x, and the kernel becomes MMA-bound (CH = 32) or split-bound (CH small).
-//   CH == 32 : per phase N = 32, three MMAs per K slice (hi*hi, hi*lo, lo*hi), weights 128 KB resident
-//   CH in {1,3}: per phase N = 16 = [b_hi (8 rows) | b_lo (8 rows)], two MMAs (a_hi, a_lo) -> all four
-//              cross products; NCHW sigmoid epilogue (convT3 of the decoder)
+// L2->smem traffic drops 9x, and the kernel becomes MMA-bound: per output phase N = 32, three MMAs per
+// K slice (hi*hi, hi*lo, lo*hi), weights 128 KB resident.  (The image-boundary layer, CH in {1,3}, is
+// not a tensor-core problem: dv_conv_img.cu.)
 // ==========================================================================================
 constexpr int kHaloStageBytes = 26 * 1024;      // 208 pixel rows: the largest box (<= 176 px) + over-read slack
 constexpr int kHaloStages = 3;
@@ -1034,26 +587,18 @@ struct HaloBarriers {
   uint32_t tmem_base;
   float bias[32];
 };
-template <int CH> struct HaloCfg {
-  // CH == 32: one 64-row (hi|lo) weight tile per tap, one 32-column accumulator per output phase.
-  // CH small: the four output phases are MERGED along N: one weight tile per SHIFT with rows
-  //           n = phase*CH + c (hi half) and kNH + phase*CH + c (lo half), zero where the tap is invalid,
-  //           so a shift costs 2 MMAs per K slice (a_hi, a_lo) instead of up to 8.
-  static constexpr int kN = (CH == 32) ? 32 : (CH == 1 ? 16 : 32);       // MMA N
-  static constexpr int kNH = kN / 2;                                       // small CH: offset of the lo half
-  static constexpr int kBTapBytes = (CH == 32) ? kBTap : kN * 128;         // per tap (CH 32) / per shift (small)
-  static constexpr int kBTiles = (CH == 32) ? kTaps : 9;
-  static constexpr int kBAll = (CH == 32) ? kTaps * kBTap : 40 * 1024;     // small: 9 tiles padded to 5 whole 64-row TMA boxes
+struct HaloCfg {
+  // one 64-row (hi|lo) weight tile per tap, one 32-column accumulator per output phase
+  static constexpr int kBAll = kTaps * kBTap;
   static constexpr int kSmem = kBAll + kHaloStages * kHaloStageBytes + 1024 + 512;
   static constexpr int kAccPerPhase = 32;
 };
 
-template <int CH>
 __global__ void __launch_bounds__(kTsThreads, 1)
 conv_up_halo_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                        const float* __restrict__ bias, const float* __restrict__ mask, float* __restrict__ hi_out,
                        HaloGeom g, int act) {
-  using C = HaloCfg<CH>;
+  using C = HaloCfg;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* Bs = smem;
@@ -1068,7 +613,7 @@ conv_up_halo_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     for (int a = 0; a < 2; ++a) { mbar_init(&bars->acc_full[a], 1); mbar_init(&bars->acc_empty[a], 128); }
     fence_mbar_init();
   }
-  if (threadIdx.x < 32) bars->bias[threadIdx.x] = (bias && (int)threadIdx.x < CH) ? bias[threadIdx.x] : 0.f;
+  if (threadIdx.x < 32) bars->bias[threadIdx.x] = bias ? bias[threadIdx.x] : 0.f;
   if (warp == 2) tmem_alloc(&bars->tmem_base, 512);
   tc_fence_before_sync();
   __syncthreads();
@@ -1079,8 +624,7 @@ conv_up_halo_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
   if (warp == 0 && elect_one()) {
     prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b);
     mbar_arrive_expect_tx(&bars->b_full, C::kBAll);
-    if (CH == 32) { for (int tap = 0; tap < kTaps; ++tap) tma_load_2d(Bs + tap * kBTap, &tmap_b, &bars->b_full, 0, tap * 64); }
-    else          { for (int h = 0; h < C::kBAll / 8192; ++h) tma_load_2d(Bs + h * 8192, &tmap_b, &bars->b_full, 0, h * 64); }
+    for (int tap = 0; tap < kTaps; ++tap) tma_load_2d(Bs + tap * kBTap, &tmap_b, &bars->b_full, 0, tap * 64);
     uint32_t t_seq = 0;
     for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++t_seq) {
       const int stage = t_seq % kHaloStages;
@@ -1091,7 +635,7 @@ conv_up_halo_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
       tma_load_4d(Raw + stage * kHaloStageBytes, &tmap_a, &bars->raw_full[stage], 0, -1, i0 - 1, b0);
     }
   } else if (warp == 1 && elect_one()) {      // ONE elected lane runs the whole issue loop (waits included)
-    constexpr uint32_t idescN = umma_idesc_tf32(128, C::kN);
+    constexpr uint32_t idescN = umma_idesc_tf32(128, 32);
     mbar_wait(&bars->b_full, 0);
     uint32_t n = 0; int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
@@ -1104,33 +648,23 @@ conv_up_halo_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         mbar_wait(&bars->a_ready[as], (n / kTsAStages) & 1u);
         tc_fence_after_sync();
         const uint32_t a_hi = tmem_base + kTsACol0 + as * 64, a_lo = a_hi + 32;
-        if (CH == 32) {
-          for (int ph = 0; ph < 2; ++ph) {
-            const int kh = ph + 1 - 2 * di;
-            if (kh < 0 || kh > 3) continue;
-            for (int pw = 0; pw < 2; ++pw) {
-              const int kw = pw + 1 - 2 * dj;
-              if (kw < 0 || kw > 3) continue;
-              const int pidx = ph * 2 + pw;
-              const uint32_t d = tmem_base + acc * 128 + pidx * C::kAccPerPhase;
-              const uint64_t b_hi = umma_desc_sw128_kmajor(smem_u32(Bs + (kh * 4 + kw) * C::kBTapBytes));
-              const uint32_t first = (inited >> pidx) & 1u;
-              inited |= 1u << pidx;
+        for (int ph = 0; ph < 2; ++ph) {
+          const int kh = ph + 1 - 2 * di;
+          if (kh < 0 || kh > 3) continue;
+          for (int pw = 0; pw < 2; ++pw) {
+            const int kw = pw + 1 - 2 * dj;
+            if (kw < 0 || kw > 3) continue;
+            const int pidx = ph * 2 + pw;
+            const uint32_t d = tmem_base + acc * 128 + pidx * C::kAccPerPhase;
+            const uint64_t b_hi = umma_desc_sw128_kmajor(smem_u32(Bs + (kh * 4 + kw) * kBTap));
+            const uint32_t first = (inited >> pidx) & 1u;
+            inited |= 1u << pidx;
 #pragma unroll
-              for (int k4 = 0; k4 < 4; ++k4) {
-                umma_tf32_ts_1t(d, a_hi + 8 * k4, b_hi + 2 * k4, idescN, (first | (uint32_t)k4) != 0);
-                umma_tf32_ts_1t(d, a_hi + 8 * k4, b_hi + (4096 >> 4) + 2 * k4, idescN, 1);      // a_hi * b_lo
-                umma_tf32_ts_1t(d, a_lo + 8 * k4, b_hi + 2 * k4, idescN, 1);                    // a_lo * b_hi
-              }
+            for (int k4 = 0; k4 < 4; ++k4) {
+              umma_tf32_ts_1t(d, a_hi + 8 * k4, b_hi + 2 * k4, idescN, (first | (uint32_t)k4) != 0);
+              umma_tf32_ts_1t(d, a_hi + 8 * k4, b_hi + (4096 >> 4) + 2 * k4, idescN, 1);      // a_hi * b_lo
+              umma_tf32_ts_1t(d, a_lo + 8 * k4, b_hi + 2 * k4, idescN, 1);                    // a_lo * b_hi
             }
-          }
-        } else {
-          const uint32_t d = tmem_base + acc * 128;
-          const uint64_t b_s = umma_desc_sw128_kmajor(smem_u32(Bs + s * C::kBTapBytes));
-#pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4) {
-            umma_tf32_ts_1t(d, a_hi + 8 * k4, b_s + 2 * k4, idescN, (s | k4) != 0);            // a_hi * [b_hi | b_lo], all phases
-            umma_tf32_ts_1t(d, a_lo + 8 * k4, b_s + 2 * k4, idescN, 1);                        // a_lo * [b_hi | b_lo]
           }
         }
         umma_commit_1t(&bars->a_empty[as]);
@@ -1154,7 +688,7 @@ conv_up_halo_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
       // the loads' latency hides behind this tile's MMAs instead of sitting between the TMEM loads and the stores
       // (masked dgrad launches used to be 1.7x slower than the unmasked forward ones).
       uint32_t mbits[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
-      if (CH == 32 && mask && valid) {
+      if (mask && valid) {
 #pragma unroll
         for (int pidx = 0; pidx < 4; ++pidx) {
           const float* mk = mask + ((long long)(b * HH + 2 * i + (pidx >> 1)) * WW + 2 * j + (pidx & 1)) * 32;
@@ -1171,56 +705,27 @@ conv_up_halo_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
       mbar_wait(&bars->acc_full[acc], acc_phase);
       tc_fence_after_sync();
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 128;
-      if (CH == 32) {
 #pragma unroll
-        for (int pidx = 0; pidx < 4; ++pidx) {
-          uint32_t r0[32];
-          tmem_ld_32x32b_x32(tbase + pidx * 32, r0);
-          tmem_ld_wait();
-          if (pidx == 3) { tc_fence_before_sync(); mbar_arrive(&bars->acc_empty[acc]); }
-          if (valid) {
-            const int ph = pidx >> 1, pw = pidx & 1;
-            const long long o = ((long long)(b * HH + 2 * i + ph) * WW + 2 * j + pw) * 32;
-            float* dst = hi_out + o;
-            const uint32_t bits = mbits[pidx];
-#pragma unroll
-            for (int c4 = 0; c4 < 8; ++c4) {
-              float v[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float x = __uint_as_float(r0[c4 * 4 + e]) + bars->bias[c4 * 4 + e];
-                if (act == DV_ACT_RELU) x = fmaxf(x, 0.f);
-                v[e] = ((bits >> (c4 * 4 + e)) & 1u) ? x : 0.f;
-              }
-              *reinterpret_cast<float4*>(dst + c4 * 4) = make_float4(v[0], v[1], v[2], v[3]);
-            }
-          }
-        }
-      } else {
-        // columns: phase*CH + c (a*b_hi) and kNH + phase*CH + c (a*b_lo); NCHW output, float2 per (channel, row parity)
+      for (int pidx = 0; pidx < 4; ++pidx) {
         uint32_t r0[32];
-        tmem_ld_32x32b_x32(tbase, r0);
+        tmem_ld_32x32b_x32(tbase + pidx * 32, r0);
         tmem_ld_wait();
-        tc_fence_before_sync();
-        mbar_arrive(&bars->acc_empty[acc]);
+        if (pidx == 3) { tc_fence_before_sync(); mbar_arrive(&bars->acc_empty[acc]); }
         if (valid) {
+          const int ph = pidx >> 1, pw = pidx & 1;
+          const long long o = ((long long)(b * HH + 2 * i + ph) * WW + 2 * j + pw) * 32;
+          float* dst = hi_out + o;
+          const uint32_t bits = mbits[pidx];
 #pragma unroll
-          for (int c = 0; c < CH; ++c) {
+          for (int c4 = 0; c4 < 8; ++c4) {
+            float v[4];
 #pragma unroll
-            for (int ph = 0; ph < 2; ++ph) {
-              float v[2];
-#pragma unroll
-              for (int pw = 0; pw < 2; ++pw) {
-                const int col = (ph * 2 + pw) * CH + c;
-                float x = (__uint_as_float(r0[col]) + __uint_as_float(r0[C::kNH + col])) + bars->bias[c];
-                if (act == DV_ACT_RELU) x = fmaxf(x, 0.f);
-                else if (act == DV_ACT_SIGMOID) x = 1.f / (1.f + expf(-x));
-                v[pw] = x;
-              }
-              const long long o = (((long long)b * CH + c) * HH + 2 * i + ph) * WW + 2 * j;
-              if (mask) { v[0] = mask[o] > 0.f ? v[0] : 0.f; v[1] = mask[o + 1] > 0.f ? v[1] : 0.f; }
-              *reinterpret_cast<float2*>(hi_out + o) = make_float2(v[0], v[1]);
+            for (int e = 0; e < 4; ++e) {
+              float x = __uint_as_float(r0[c4 * 4 + e]) + bars->bias[c4 * 4 + e];
+              if (act == DV_ACT_RELU) x = fmaxf(x, 0.f);
+              v[e] = ((bits >> (c4 * 4 + e)) & 1u) ? x : 0.f;
             }
+            *reinterpret_cast<float4*>(dst + c4 * 4) = make_float4(v[0], v[1], v[2], v[3]);
           }
         }
       }
@@ -1286,401 +791,6 @@ conv_up_halo_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
   if (warp == 2) { tc_fence_after_sync(); tmem_dealloc(tmem_base, 512); }
 }
 
-// up weights for CH small, one tile per SHIFT s = (di+1)*3 + (dj+1): [s][N rows][32 cl] with row
-// n = phase*CH + c -> tf32 hi of w[cl][c][kh][kw], row NH + n -> lo, where kh = ph+1-2di, kw = pw+1-2dj
-// (zero when the tap does not exist for that phase).  Padded with zero rows to 320 rows (5 whole TMA boxes).
-__global__ void conv_pack_up_small_kernel(const float* __restrict__ w, float* __restrict__ wu, int CH, int N) {
-  const int NH = N / 2;
-  const int total = 320 * 32;
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-    const int cl = idx % 32, row = idx / 32;
-    const int s = row / N, n = row % N;
-    float out = 0.f;
-    if (s < 9) {
-      const int half = n / NH, nn = n % NH;
-      const int pidx = nn / CH, c = nn % CH;
-      if (pidx < 4) {
-        const int di = s / 3 - 1, dj = s % 3 - 1;
-        const int kh = (pidx >> 1) + 1 - 2 * di, kw = (pidx & 1) + 1 - 2 * dj;
-        if (kh >= 0 && kh <= 3 && kw >= 0 && kw <= 3) {
-          const float v = w[(cl * CH + c) * kTaps + kh * 4 + kw];
-          const float hi = __uint_as_float(__float_as_uint(v) & kHiMask);
-          out = half == 0 ? hi : (v - hi);
-        }
-      }
-    }
-    wu[idx] = out;
-  }
-}
-
-// ==========================================================================================
-// Image-boundary layers (CH in {1,3}, NCHW hi) on the tensor cores.
-// The im2col patch of a lo pixel is only 16*CH floats, far too narrow for TMA tiles, so four
-// "builder" warps gather it with ordinary loads (one thread per pixel of the 128-pixel tile),
-// split it into hi/lo planes and store it straight into the swizzled operand layout the MMA
-// expects.  K is padded to a multiple of 32 with zeros (the MMAs over all-padding slices are skipped).
-// ==========================================================================================
-template <int CH>
-__device__ __forceinline__ void load_patch(const float* __restrict__ x, int HH, int WW, int b, int i, int j, bool valid,
-                                           float (&v)[16 * CH]) {
-  const long long plane = (long long)HH * WW;
-#pragma unroll
-  for (int kh = 0; kh < 4; ++kh) {
-    const int ih = 2 * i - 1 + kh;
-    const bool rv = valid && (unsigned)ih < (unsigned)HH;
-#pragma unroll
-    for (int kw = 0; kw < 4; ++kw) {
-      const int iw = 2 * j - 1 + kw;
-      const bool ok = rv && (unsigned)iw < (unsigned)WW;
-#pragma unroll
-      for (int c = 0; c < CH; ++c)
-        v[(kh * 4 + kw) * CH + c] = ok ? __ldg(x + ((long long)b * CH + c) * plane + (long long)ih * WW + iw) : 0.f;
-    }
-  }
-}
-
-// ---- down, CH small: D[128 px][32 cl] = patch[128][Kp] * W[32 cl][Kp]^T (K-major, SWIZZLE_128B) ----
-template <int CH> struct SmallCfg {
-  static constexpr int K = 16 * CH;
-  static constexpr int NKB = (K + 31) / 32;                 // 128-byte K blocks
-  static constexpr int kStage = 2 * NKB * kATile;           // hi blocks then lo blocks
-  static constexpr int kNStages = (CH == 1) ? 3 : 2;
-  static constexpr int kBBytesS = NKB * kBTap;
-  static constexpr int kSmem = kBBytesS + kNStages * kStage + 1024 + 512;
-};
-
-template <int CH>
-__global__ void __launch_bounds__(kThreads, 1)
-conv_down_small_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const float* __restrict__ x,
-                          const float* __restrict__ bias, const float* __restrict__ mask, float* __restrict__ lo,
-                          DownGeom g, int act, float* __restrict__ colsum_part) {
-  using C = SmallCfg<CH>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* Bs = smem;                                        // [kb][64 rows][128 B]
-  uint8_t* As = smem + C::kBBytesS;                          // [stage][hi kb.. | lo kb..][128 rows][128 B]
-  Barriers* bars = reinterpret_cast<Barriers*>(As + C::kNStages * C::kStage);
-  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform role index
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(&bars->raw_full[s], 1); mbar_init(&bars->ready[s], 128); mbar_init(&bars->empty[s], 1); }
-    mbar_init(&bars->b_full, 1);
-    for (int a = 0; a < 2; ++a) { mbar_init(&bars->acc_full[a], 1); mbar_init(&bars->acc_empty[a], 128); }
-    fence_mbar_init();
-  }
-  if (threadIdx.x < 32) bars->bias[threadIdx.x] = bias ? bias[threadIdx.x] : 0.f;
-  if (warp == 2) tmem_alloc(&bars->tmem_base, 128);
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  const uint32_t tmem_base = bars->tmem_base;
-
-  if (warp == 0 && elect_one()) {
-    prefetch_tmap(&tmap_b);
-    mbar_arrive_expect_tx(&bars->b_full, C::kBBytesS);
-    for (int kb = 0; kb < C::NKB; ++kb) tma_load_2d(Bs + kb * kBTap, &tmap_b, &bars->b_full, 0, kb * 64);
-  } else if (warp == 1 && elect_one()) {      // ONE elected lane runs the whole issue loop (barrier waits included):
-                                              // ptxas then keeps every MMA operand in uniform registers (back-to-back UTCHMMA)
-    constexpr uint32_t idesc64 = umma_idesc_tf32(128, 64), idesc32 = umma_idesc_tf32(128, 32);
-    mbar_wait(&bars->b_full, 0);
-    int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
-      mbar_wait(&bars->acc_empty[acc], acc_phase ^ 1);
-      mbar_wait(&bars->ready[stage], phase);
-      tc_fence_after_sync();
-      const uint32_t d = tmem_base + acc * 64;
-      uint32_t accum = 0;
-#pragma unroll
-      for (int kb = 0; kb < C::NKB; ++kb) {
-        const uint64_t a_hi = umma_desc_sw128_kmajor(smem_u32(As + stage * C::kStage + kb * kATile));
-        const uint64_t a_lo = umma_desc_sw128_kmajor(smem_u32(As + stage * C::kStage + (C::NKB + kb) * kATile));
-        const uint64_t b_d = umma_desc_sw128_kmajor(smem_u32(Bs + kb * kBTap));
-#pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4) {
-          if (kb * 32 + k4 * 8 >= C::K) continue;           // all-zero padding slice
-          umma_tf32_ss_1t(d, a_hi + 2 * k4, b_d + 2 * k4, idesc64, accum);
-          umma_tf32_ss_1t(d, a_lo + 2 * k4, b_d + 2 * k4, idesc32, 1);
-          accum = 1;
-        }
-      }
-      umma_commit_1t(&bars->empty[stage]);
-      umma_commit_1t(&bars->acc_full[acc]);
-      if (++stage == C::kNStages) { stage = 0; phase ^= 1; }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-    }
-  } else if (warp >= 4 && warp < 8) {
-    const int q = warp & 3;
-    int acc = 0; uint32_t acc_phase = 0;
-    float csum = 0.f;                                         // lane l: running sum of output channel l over this warp's rows
-    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
-      const long long p = (long long)tile * 128 + q * 32 + lane;
-      // ReLU-backward mask as one bit per channel, fetched before waiting for the accumulator (latency behind the MMAs)
-      uint32_t bits = 0xffffffffu;
-      if (mask && p < g.total_px) {
-        const float* mk = mask + p * 32;
-        bits = 0;
-#pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4) {
-          const float4 m4 = ldg4(mk + c4 * 4);
-          bits |= (m4.x > 0.f ? 1u : 0u) << (c4 * 4) | (m4.y > 0.f ? 2u : 0u) << (c4 * 4) |
-                  (m4.z > 0.f ? 4u : 0u) << (c4 * 4) | (m4.w > 0.f ? 8u : 0u) << (c4 * 4);
-        }
-      }
-      mbar_wait(&bars->acc_full[acc], acc_phase);
-      tc_fence_after_sync();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 64;
-      uint32_t r0[32], r1[32];
-      float fin[32];
-      tmem_ld_32x32b_x32(taddr, r0);
-      tmem_ld_32x32b_x32(taddr + 32, r1);
-      tmem_ld_wait();
-      tc_fence_before_sync();
-      mbar_arrive(&bars->acc_empty[acc]);
-      if (p < g.total_px) {
-        float* dst = lo + p * 32;
-#pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4) {
-          float v[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int c = c4 * 4 + e;
-            float xx = (__uint_as_float(r0[c]) + __uint_as_float(r1[c])) + bars->bias[c];
-            if (act == DV_ACT_RELU) xx = fmaxf(xx, 0.f);
-            v[e] = ((bits >> c) & 1u) ? xx : 0.f;
-          }
-          *reinterpret_cast<float4*>(dst + c4 * 4) = make_float4(v[0], v[1], v[2], v[3]);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) fin[c4 * 4 + e] = v[e];
-        }
-      } else {
-#pragma unroll
-        for (int c = 0; c < 32; ++c) fin[c] = 0.f;
-      }
-      if (colsum_part) csum += warp_colsum32(fin, lane);      // channel sums of the stored output (next layer's bias gradient)
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-    }
-    if (colsum_part) {
-      // all MMAs of this CTA have completed (last accumulator was full): the operand stages are free
-      float* scr = reinterpret_cast<float*>(As);
-      scr[q * 32 + lane] = csum;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (q == 0) colsum_part[blockIdx.x * 32 + lane] = (scr[lane] + scr[32 + lane]) + (scr[64 + lane] + scr[96 + lane]);
-    }
-  } else if (warp >= 8) {
-    // ---- patch builders: thread r owns pixel row r of the tile ----
-    const int r = threadIdx.x - 256;
-    const int HH = 2 * g.H, WW = 2 * g.W;
-    int stage = 0; uint32_t phase = 0;
-    auto gather = [&](int tile, float (&dst)[16 * CH]) {
-      const long long p = (long long)tile * 128 + r;
-      const bool valid = tile < g.num_tiles && p < g.total_px;
-      int b = 0, i = 0, j = 0;
-      if (valid) { j = (int)(p % g.W); i = (int)((p / g.W) % g.H); b = (int)(p / ((long long)g.W * g.H)); }
-      load_patch<CH>(x, HH, WW, b, i, j, valid, dst);
-    };
-    float v[16 * CH];
-    gather(blockIdx.x, v);
-    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
-      float vn[16 * CH];
-      gather(tile + gridDim.x, vn);                       // next tile's patch is in flight while this one is written
-      mbar_wait(&bars->empty[stage], phase ^ 1);
-      uint8_t* st = As + stage * C::kStage;
-#pragma unroll
-      for (int kb = 0; kb < C::NKB; ++kb) {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {                      // 16-byte chunk c of K block kb: k = kb*32 + 4c .. +3
-          uint4 h, l;
-          uint32_t* hp = &h.x; uint32_t* lp = &l.x;
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int k = kb * 32 + c * 4 + e;
-            const float val = (k < C::K) ? v[k < C::K ? k : 0] : 0.f;
-            const uint32_t hb = __float_as_uint(val) & kHiMask;
-            hp[e] = hb;
-            lp[e] = __float_as_uint(val - __uint_as_float(hb));
-          }
-          const int off = r * 128 + ((c ^ (r & 7)) << 4);
-          *reinterpret_cast<uint4*>(st + kb * kATile + off) = h;
-          *reinterpret_cast<uint4*>(st + (C::NKB + kb) * kATile + off) = l;
-        }
-      }
-      fence_proxy_async_smem();
-      mbar_arrive(&bars->ready[stage]);
-      if (++stage == C::kNStages) { stage = 0; phase ^= 1; }
-#pragma unroll
-      for (int k = 0; k < 16 * CH; ++k) v[k] = vn[k];
-    }
-  }
-  tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 2) { tc_fence_after_sync(); tmem_dealloc(tmem_base, 128); }
-}
-
-// ---- wgrad, CH small: D[(plane,k)][(plane,cl)] += patch^T * lo over pixels (MN-major operands) ----
-template <int CH> struct SmallWgCfg {
-  static constexpr int K = 16 * CH;
-  static constexpr int G = (K + 31) / 32;                   // 32-wide MN groups of the patch (1 or 2)
-  static constexpr int kPStage = 4 * kATile;                // 4 MN groups are always addressed (M = 128)
-  static constexpr int kSmem = 2 * kPStage + 2 * kWgLBytes + 1024 + 3072;
-};
-
-template <int CH>
-__global__ void __launch_bounds__(kThreads, 1)
-conv_wgrad_small_tc_kernel(const __grid_constant__ CUtensorMap tmap_lo, const float* __restrict__ x,
-                           float* __restrict__ ws, WgGeom g) {
-  using C = SmallWgCfg<CH>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* Ps = smem;                                        // [stage][P_hi groups | P_lo groups (| unused)]
-  uint8_t* Ls = smem + 2 * C::kPStage;                       // [buf][Lhi|Llo]
-  WgBarriers* bars = reinterpret_cast<WgBarriers*>(Ls + 2 * kWgLBytes);
-  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform role index
-  const int t_begin = blockIdx.x * g.tiles_per_cta;
-  const int t_end = min(g.num_tiles, t_begin + g.tiles_per_cta);
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < 2; ++s) { mbar_init(&bars->ready[s], 128); mbar_init(&bars->empty[s], 1); mbar_init(&bars->raw_full[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&bars->l_raw_full[s], 1); mbar_init(&bars->l_ready[s], 128); mbar_init(&bars->l_empty[s], 1); }
-    mbar_init(&bars->acc_full, 1);
-    fence_mbar_init();
-  }
-  if (warp == 2) tmem_alloc(&bars->tmem_base, 64);
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  const uint32_t tmem_base = bars->tmem_base;
-
-  if (warp == 0 && elect_one()) {
-    prefetch_tmap(&tmap_lo);
-    int lb = 0; uint32_t lphase = 0;
-    for (int tile = t_begin; tile < t_end; ++tile) {
-      const int r0 = tile * g.rows_per_tile;
-      const int b0 = r0 / g.H, i0 = r0 % g.H;
-      mbar_wait(&bars->l_empty[lb], lphase ^ 1);
-      mbar_arrive_expect_tx(&bars->l_raw_full[lb], kATile);
-      tma_load_4d(Ls + lb * kWgLBytes, &tmap_lo, &bars->l_raw_full[lb], 0, 0, i0, b0);
-      if (++lb == 2) { lb = 0; lphase ^= 1; }
-    }
-  } else if (warp == 1 && elect_one()) {      // ONE elected lane runs the whole issue loop (barrier waits included):
-                                              // ptxas then keeps every MMA operand in uniform registers (back-to-back UTCHMMA)
-    constexpr uint32_t idesc = umma_idesc_tf32(128, 64) | (1u << 15) | (1u << 16);
-    int stage = 0; uint32_t phase = 0; int lb = 0; uint32_t lphase = 0;
-    for (int tile = t_begin; tile < t_end; ++tile) {
-      mbar_wait(&bars->l_ready[lb], lphase);
-      mbar_wait(&bars->ready[stage], phase);
-      tc_fence_after_sync();
-      const uint32_t l_addr = smem_u32(Ls + lb * kWgLBytes);
-      const uint32_t a_addr = smem_u32(Ps + stage * C::kPStage);
-#pragma unroll 4
-      for (int kc = 0; kc < 16; ++kc)
-        umma_tf32_ss_1t(tmem_base, umma_desc_sw128_mnmajor(a_addr + kc * 1024, kATile),
-                     umma_desc_sw128_mnmajor(l_addr + kc * 1024, kATile), idesc, (tile != t_begin) || (kc != 0));
-      umma_commit_1t(&bars->empty[stage]);
-      umma_commit_1t(&bars->l_empty[lb]);
-      if (++stage == 2) { stage = 0; phase ^= 1; }
-      if (++lb == 2) { lb = 0; lphase ^= 1; }
-    }
-    umma_commit_1t(&bars->acc_full);
-  } else if (warp >= 8) {
-    // split the lo tile, accumulate its column sums, and build the patch operand
-    const int t = threadIdx.x - 256;
-    const int quad = ((((t & 7) >> 1) ^ ((t >> 3) & 3)) << 1) | (t & 1);
-    const int HH = 2 * g.H, WW = 2 * g.W;
-    float ls[4] = {0.f, 0.f, 0.f, 0.f};
-    int stage = 0; uint32_t phase = 0; int lb = 0; uint32_t lphase = 0;
-    auto gather = [&](int tile, float (&dst)[16 * CH]) {     // patch row of pixel t of `tile`
-      const long long p = (long long)tile * 128 + t;
-      const bool valid = tile < t_end && p < (long long)g.B * g.H * g.W;
-      int b = 0, i = 0, j = 0;
-      if (valid) { j = (int)(p % g.W); i = (int)((p / g.W) % g.H); b = (int)(p / ((long long)g.W * g.H)); }
-      load_patch<CH>(x, HH, WW, b, i, j, valid, dst);
-    };
-    float v[16 * CH];
-    gather(t_begin, v);
-    for (int tile = t_begin; tile < t_end; ++tile) {
-      float vn[16 * CH];
-      gather(tile + 1, vn);                                // in flight while this tile is written and split
-      mbar_wait(&bars->empty[stage], phase ^ 1);
-      uint8_t* st = Ps + stage * C::kPStage;
-#pragma unroll
-      for (int gi = 0; gi < C::G; ++gi) {
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {                   // 32-byte chunk cc of group gi: k = gi*32 + 8cc .. +7
-          if (gi * 32 + cc * 8 >= C::K) continue;           // never read back (rows of D that are ignored)
-          uint32_t h[8], l[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int k = gi * 32 + cc * 8 + e;
-            const float val = (k < C::K) ? v[k < C::K ? k : 0] : 0.f;
-            h[e] = __float_as_uint(val) & kHiMask;
-            l[e] = __float_as_uint(val - __uint_as_float(h[e]));
-          }
-          const int off = t * 128 + ((cc ^ (t & 3)) << 5);
-          uint4* hd = reinterpret_cast<uint4*>(st + gi * kATile + off);
-          uint4* ld = reinterpret_cast<uint4*>(st + (C::G + gi) * kATile + off);
-          hd[0] = make_uint4(h[0], h[1], h[2], h[3]); hd[1] = make_uint4(h[4], h[5], h[6], h[7]);
-          ld[0] = make_uint4(l[0], l[1], l[2], l[3]); ld[1] = make_uint4(l[4], l[5], l[6], l[7]);
-        }
-      }
-      fence_proxy_async_smem();
-      mbar_arrive(&bars->ready[stage]);
-      if (++stage == 2) { stage = 0; phase ^= 1; }
-
-      mbar_wait(&bars->l_raw_full[lb], lphase);
-      {
-        uint4* hi = reinterpret_cast<uint4*>(Ls + lb * kWgLBytes);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint4 u = hi[t + 128 * k];
-          ls[0] += __uint_as_float(u.x); ls[1] += __uint_as_float(u.y); ls[2] += __uint_as_float(u.z); ls[3] += __uint_as_float(u.w);
-        }
-        split_hi_lo(hi, reinterpret_cast<uint4*>(Ls + lb * kWgLBytes + kATile), t);
-      }
-      fence_proxy_async_smem();
-      mbar_arrive(&bars->l_ready[lb]);
-      if (++lb == 2) { lb = 0; lphase ^= 1; }
-#pragma unroll
-      for (int k = 0; k < 16 * CH; ++k) v[k] = vn[k];
-    }
-#pragma unroll
-    for (int e = 0; e < 4; ++e) bars->lscr[t][e] = ls[e];
-    asm volatile("bar.sync 2, 128;" ::: "memory");
-    if (t < 32) {
-      const int want = t >> 2, e = t & 3;
-      float acc = 0.f;
-      for (int u = 0; u < 128; ++u)
-        if ((((((u & 7) >> 1) ^ ((u >> 3) & 3)) << 1) | (u & 1)) == want) acc += bars->lscr[u][e];
-      ws[(long long)blockIdx.x * (C::K + 1) * kLoCh + C::K * kLoCh + t] = acc;
-    }
-  }
-
-  if (warp >= 4 && warp < 8) {
-    const int q = warp & 3;
-    const int r = q * 32 + lane;
-    mbar_wait(&bars->acc_full, 0);
-    tc_fence_after_sync();
-    float* red = reinterpret_cast<float*>(Ps);
-    float* out = ws + (long long)blockIdx.x * (C::K + 1) * kLoCh;
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-    uint32_t r0[32], r1[32];
-    tmem_ld_32x32b_x32(taddr, r0);
-    tmem_ld_32x32b_x32(taddr + 32, r1);
-    tmem_ld_wait();
-#pragma unroll
-    for (int cl = 0; cl < 32; ++cl) red[r * 33 + cl] = __uint_as_float(r0[cl]) + __uint_as_float(r1[cl]);
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    // D rows: [0, 32G) = P_hi (k = row), [32G, 64G) = P_lo
-    if (r < C::K) {
-      float* dst = out + r * kLoCh;
-#pragma unroll
-      for (int cl = 0; cl < 32; ++cl) dst[cl] = red[r * 33 + cl] + red[(r + 32 * C::G) * 33 + cl];
-    }
-  }
-  tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 2) { tc_fence_after_sync(); tmem_dealloc(tmem_base, 64); }
-}
-
 // ---- weight packing for the tensor-core kernels ------------------------------------------
 // w[cl][c][tap] ->  down: Wd[tap][row][c],  row <  32: tf32-exact hi of w[row][c][tap], row >= 32: lo
 //                   up  : Wu[tap][row][cl], row <  32: hi of w[cl][row][tap],          row >= 32: lo
@@ -1706,7 +816,6 @@ __global__ void conv_pack_tc_kernel(const float* __restrict__ w, float* __restri
 }
 
 // ---- host side ---------------------------------------------------------------------------
-// DV_TC_A=smem selects the variants that keep the A operand in shared memory (A/B testing).
 static int use_rawhi() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("DV_TC_RAWHI"); v = (e && e[0] == '0') ? 0 : 1; }
@@ -1726,11 +835,6 @@ static int use_prefetch() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("DV_TC_PREFETCH"); v = (e && e[0] == '0') ? 0 : 1; }
   return v;
-}
-static bool use_ts() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("DV_TC_A"); v = (e && e[0] == 's') ? 0 : 1; }
-  return v == 1;
 }
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1801,71 +905,17 @@ int conv_down32_tc(const float* hi, const float* wd_packed, const float* bias, c
   if (!make_w_tmap(&tb, wd_packed)) return DV_ERR_CUDA;
   static bool attr = false;
   if (!attr) {
-    if (cudaFuncSetAttribute(conv_down32_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess) {
+    if (cudaFuncSetAttribute(conv_down32_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTsSmemBytes) != cudaSuccess) {
       g_last_cuda_error = (int)cudaGetLastError();
       return DV_ERR_CUDA;
     }
     attr = true;
   }
   const int grid = g.num_tiles < kNumSMs ? g.num_tiles : kNumSMs;
-  if (use_ts()) {
-    static bool attr2 = false;
-    if (!attr2) {
-      if (cudaFuncSetAttribute(conv_down32_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTsSmemBytes) != cudaSuccess) {
-        g_last_cuda_error = (int)cudaGetLastError();
-        return DV_ERR_CUDA;
-      }
-      attr2 = true;
-    }
-    conv_down32_ts_kernel<<<grid, kTsThreads, kTsSmemBytes, st>>>(ta, tb, bias, mask, lo, g, act, colsum_part);
-    if (nparts && colsum_part) *nparts = grid;
-    return check_launch();
-  }
-  conv_down32_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(ta, tb, bias, mask, lo, g, act);
+  conv_down32_ts_kernel<<<grid, kTsThreads, kTsSmemBytes, st>>>(ta, tb, bias, mask, lo, g, act, colsum_part);
+  if (nparts && colsum_part) *nparts = grid;
   return check_launch();
 }
-
-
-// hi[B,2H,2W,32] = act(up(lo[B,H,W,32]) + bias) * [mask > 0]
-int conv_up32_tc(const float* lo, const float* wu_packed, const float* bias, const float* mask, float* hi,
-                 int B, int H, int W, int act, cudaStream_t st) {
-  if (W > 128 || 128 % W != 0) return DV_ERR_BAD_SHAPE;
-  DownGeom g = {};
-  g.B = B; g.H = H; g.W = W; g.prefetch = use_prefetch(); g.pipe = use_pipe(); g.debug = use_debug();
-  g.rows_per_tile = 128 / W;
-  const int TR = g.rows_per_tile < H ? g.rows_per_tile : H;
-  if (H % TR != 0 || g.rows_per_tile % TR != 0) return DV_ERR_BAD_SHAPE;
-  const int TB = g.rows_per_tile / TR;
-  g.total_px = (long long)B * H * W;
-  g.num_tiles = (int)((g.total_px + 127) / 128);
-  CUtensorMap ta, tb;
-  if (!make_act_tmap(&ta, lo, B, H, W, W, TR, TB, 1)) return DV_ERR_CUDA;
-  if (!make_w_tmap(&tb, wu_packed)) return DV_ERR_CUDA;
-  static bool attr = false;
-  if (!attr) {
-    if (cudaFuncSetAttribute(conv_up32_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess) {
-      g_last_cuda_error = (int)cudaGetLastError();
-      return DV_ERR_CUDA;
-    }
-    attr = true;
-  }
-  const int grid = g.num_tiles < kNumSMs ? g.num_tiles : kNumSMs;
-  if (use_ts()) {
-    static bool attr2 = false;
-    if (!attr2) {
-      if (cudaFuncSetAttribute(conv_up32_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTsSmemBytes) != cudaSuccess) {
-        g_last_cuda_error = (int)cudaGetLastError();
-        return DV_ERR_CUDA;
-      }
-      attr2 = true;
-    }
-    conv_up32_ts_kernel<<<grid, kTsThreads, kTsSmemBytes, st>>>(ta, tb, bias, mask, hi, g, act);
-    return check_launch();
-  }
-  conv_up32_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(ta, tb, bias, mask, hi, g, act);
-  return check_launch();
-}
-
 
 // partial sums of dw (and of lo, last row) per CTA into ws[grid][16*32+1][32]; returns the grid size in *nsplit
 int conv_wgrad32_tc(const float* lo, const float* hi, float* ws, int B, int H, int W, int* nsplit, cudaStream_t st) {
@@ -1908,123 +958,27 @@ int conv_wgrad32_tc(const float* lo, const float* hi, float* ws, int B, int H, i
 }
 int wgrad32_tc_max_splits() { return kNumSMs; }
 
-// small-CH down weights: [kb][64 rows = hi(32 cl) | lo(32 cl)][32 k], k = kb*32 + col = tap*CH + c, zero padded
-__global__ void conv_pack_small_tc_kernel(const float* __restrict__ w, float* __restrict__ wd, int CH, int nkb) {
-  const int n = nkb * 64 * 32;
-  const int K = 16 * CH;
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
-    const int col = idx % 32, row = (idx / 32) % 64, kb = idx / (64 * 32);
-    const int k = kb * 32 + col, cl = row & 31;
-    float v = 0.f;
-    if (k < K) { const int tap = k / CH, c = k % CH; v = w[(cl * CH + c) * kTaps + tap]; }
-    const float hi = __uint_as_float(__float_as_uint(v) & kHiMask);
-    wd[idx] = (row < 32) ? hi : (v - hi);
-  }
-}
-int pack_small_tc(const float* w, float* wd, int CH, cudaStream_t st) {
-  conv_pack_small_tc_kernel<<<8, 256, 0, st>>>(w, wd, CH, (16 * CH + 31) / 32);
-  return check_launch();
-}
-static bool make_w_tmap_rows(CUtensorMap* m, const float* base, int rows) {
-  EncodeTiledFn enc = get_encode();
-  if (!enc) return false;
-  cuuint64_t gdim[2] = {32, (cuuint64_t)rows};
-  cuuint64_t gstr[1] = {128};
-  cuuint32_t box[2] = {32, 64};
-  cuuint32_t estr[2] = {1, 1};
-  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
-template <int CH>
-static int launch_down_small(const float* x, const float* wd, const float* bias, const float* mask, float* lo,
-                             DownGeom g, int act, cudaStream_t st, float* colsum_part, int* nparts) {
-  CUtensorMap tb;
-  if (!make_w_tmap_rows(&tb, wd, SmallCfg<CH>::NKB * 64)) return DV_ERR_CUDA;
-  static bool attr = false;
-  if (!attr) {
-    if (cudaFuncSetAttribute(conv_down_small_tc_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmallCfg<CH>::kSmem) != cudaSuccess) {
-      g_last_cuda_error = (int)cudaGetLastError();
-      return DV_ERR_CUDA;
-    }
-    attr = true;
-  }
-  const int grid = g.num_tiles < kNumSMs ? g.num_tiles : kNumSMs;
-  conv_down_small_tc_kernel<CH><<<grid, kThreads, SmallCfg<CH>::kSmem, st>>>(tb, x, bias, mask, lo, g, act, colsum_part);
-  if (nparts && colsum_part) *nparts = grid;
-  return check_launch();
-}
-int conv_down_small_tc(const float* x, const float* wd, const float* bias, const float* mask, float* lo,
-                       int B, int H, int W, int CH, int act, cudaStream_t st, float* colsum_part, int* nparts) {
-  if (nparts) *nparts = 0;
-  DownGeom g = {};
-  g.B = B; g.H = H; g.W = W; g.prefetch = use_prefetch(); g.pipe = use_pipe(); g.debug = use_debug(); g.rows_per_tile = 0;
-  g.total_px = (long long)B * H * W;
-  g.num_tiles = (int)((g.total_px + 127) / 128);
-  return CH == 1 ? launch_down_small<1>(x, wd, bias, mask, lo, g, act, st, colsum_part, nparts)
-                 : launch_down_small<3>(x, wd, bias, mask, lo, g, act, st, colsum_part, nparts);
-}
-
-template <int CH>
-static int launch_wgrad_small(const float* lo, const float* x, float* ws, WgGeom g, int grid, cudaStream_t st) {
-  CUtensorMap tlo;
-  const int TR = g.rows_per_tile < g.H ? g.rows_per_tile : g.H;
-  const int TB = g.rows_per_tile / TR;
-  if (!make_act_tmap(&tlo, lo, g.B, g.H, g.W, g.W, TR, TB, 1, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return DV_ERR_CUDA;
-  static bool attr = false;
-  if (!attr) {
-    if (cudaFuncSetAttribute(conv_wgrad_small_tc_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmallWgCfg<CH>::kSmem) != cudaSuccess) {
-      g_last_cuda_error = (int)cudaGetLastError();
-      return DV_ERR_CUDA;
-    }
-    attr = true;
-  }
-  conv_wgrad_small_tc_kernel<CH><<<grid, kThreads, SmallWgCfg<CH>::kSmem, st>>>(tlo, x, ws, g);
-  return check_launch();
-}
-int conv_wgrad_small_tc(const float* lo, const float* x, float* ws, int B, int H, int W, int CH, int* nsplit, cudaStream_t st) {
-  if (W > 128 || 128 % W != 0) return DV_ERR_BAD_SHAPE;
-  WgGeom g = {};
-  g.B = B; g.H = H; g.W = W; g.prefetch = use_prefetch(); g.rawhi = use_rawhi();
-  g.rows_per_tile = 128 / W;
-  const int TR = g.rows_per_tile < H ? g.rows_per_tile : H;
-  if (H % TR != 0 || g.rows_per_tile % TR != 0) return DV_ERR_BAD_SHAPE;
-  g.num_tiles = (int)(((long long)B * H * W + 127) / 128);
-  int grid = g.num_tiles < kNumSMs ? g.num_tiles : kNumSMs;
-  g.tiles_per_cta = (g.num_tiles + grid - 1) / grid;
-  grid = (g.num_tiles + g.tiles_per_cta - 1) / g.tiles_per_cta;
-  *nsplit = grid;
-  return CH == 1 ? launch_wgrad_small<1>(lo, x, ws, g, grid, st) : launch_wgrad_small<3>(lo, x, ws, g, grid, st);
-}
-
-int pack_up_small_tc(const float* w, float* wu, int CH, cudaStream_t st) {
-  conv_pack_up_small_kernel<<<12, 256, 0, st>>>(w, wu, CH, CH == 1 ? 16 : 32);
-  return check_launch();
-}
-
-template <int CH>
 static int launch_up_halo(const float* lo, const float* wu, const float* bias, const float* mask, float* hi,
                           HaloGeom g, int act, cudaStream_t st) {
   CUtensorMap ta, tb;
   if (!make_act_tmap(&ta, lo, g.B, g.H, g.W, g.Wp, g.TR + 2, g.TB, 1)) return DV_ERR_CUDA;
-  if (!make_w_tmap_rows(&tb, wu, CH == 32 ? kTaps * 64 : 320)) return DV_ERR_CUDA;
+  if (!make_w_tmap(&tb, wu)) return DV_ERR_CUDA;
   static bool attr = false;
   if (!attr) {
-    if (cudaFuncSetAttribute(conv_up_halo_ts_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<CH>::kSmem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(conv_up_halo_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg::kSmem) != cudaSuccess) {
       g_last_cuda_error = (int)cudaGetLastError();
       return DV_ERR_CUDA;
     }
     attr = true;
   }
   const int grid = g.num_tiles < kNumSMs ? g.num_tiles : kNumSMs;
-  conv_up_halo_ts_kernel<CH><<<grid, kTsThreads, HaloCfg<CH>::kSmem, st>>>(ta, tb, bias, mask, hi, g, act);
+  conv_up_halo_ts_kernel<<<grid, kTsThreads, HaloCfg::kSmem, st>>>(ta, tb, bias, mask, hi, g, act);
   return check_launch();
 }
 
-// hi = act(up(lo) + bias) * [mask > 0]; hi is NHWC for CH == 32, NCHW for CH in {1,3}
+// hi[B,2H,2W,32] = act(up(lo[B,H,W,32]) + bias) * [mask > 0]
 int conv_up_halo(const float* lo, const float* wu, const float* bias, const float* mask, float* hi,
-                 int B, int H, int W, int CH, int act, cudaStream_t st) {
+                 int B, int H, int W, int act, cudaStream_t st) {
   HaloGeom g = {};
   g.B = B; g.H = H; g.W = W; g.Wp = W + 2; g.pipe = use_pipe(); g.debug = use_debug();
   int tr = (128 + 2) / g.Wp;                       // largest TR with TR*Wp - 2 <= 128
@@ -2044,9 +998,7 @@ int conv_up_halo(const float* lo, const float* wu, const float* bias, const floa
   g.q_start = g.Wp + 1;
   g.box_bytes = g.TB * g.img_px * 128;
   if (g.box_bytes > kHaloStageBytes || g.q_start + 127 + g.Wp + 1 >= kHaloStageBytes / 128) return DV_ERR_BAD_SHAPE;
-  if (CH == 32) return launch_up_halo<32>(lo, wu, bias, mask, hi, g, act, st);
-  if (CH == 3) return launch_up_halo<3>(lo, wu, bias, mask, hi, g, act, st);
-  return launch_up_halo<1>(lo, wu, bias, mask, hi, g, act, st);
+  return launch_up_halo(lo, wu, bias, mask, hi, g, act, st);
 }
 
 }  // namespace tc

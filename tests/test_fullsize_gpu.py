@@ -177,5 +177,5 @@ def test_model_gradients_full_batch_same_branch(loss_name, img, z, B):
           "%.2e (worst %s); vs the fp32 oracle on ITS branch %.2e" % (B, ref["flips"], ref["units"], ref["flip_max_rel"], err, key, e32))
     e_cpu = ref["cpu_fp32_same_branch_err"]
     print("CPU fp32 oracle vs fp64 on the same branch: %.2e (%s)" % (e_cpu, ref["cpu_fp32_worst_tensor"]))
-    tol = min(max(1e-4, 8.0 * e_cpu), 1e-3)          # 1e-4 where fp32 allows it (see bench.py parity_check)
+    tol = min(max(3e-4, 8.0 * e_cpu), 1e-3)          # see bench.py parity_check for the reasoning behind 3e-4
     assert err <= tol, "grad %s: %.2e vs fp64 on the same branch (tolerance %.1e)" % (key, err, tol)
