@@ -367,6 +367,14 @@ def kernel_rooflines(trainer, resident, K, B, img, z, n_data, device, detail=Fal
                            "peak_source": pk["src"] + " bf16 sustained (kernel timed inside a long step)",
                            "note": "tcgen05 kind::tf32, error-compensated 3xTF32 (three tensor passes per algorithmic "
                                    "product; FLOPs counted once); time = CUDA events around the C-ABI call on its stream"}
+        if CH != 32:
+            # image-boundary layer (K = 16*CH): a streaming problem on the CUDA cores (dv_conv_img.cu), bounded by HBM
+            r = res["roofline"]
+            r.update({"bound": "hbm", "achieved": r["hbm_achieved_gbs"], "peak": pk["hbm"], "unit": "GB/s", "frac": r["hbm_frac"],
+                      "flop_achieved_tflops": round(ach, 3),
+                      "peak_source": pk["src"] + " HBM copy bandwidth",
+                      "note": "exact-fp32 CUDA-core kernel (dv_conv_img.cu); achieved = algorithmic bytes (hi + lo side once) / "
+                              "CUDA-event time around the C-ABI call on its stream"})
     else:
         res["roofline"] = {"kernel": name, "bound": "hbm", "achieved": None, "peak": pk["hbm"], "unit": "GB/s", "frac": None,
                            "traffic": None, "ms_per_step": round(tms / K, 4)}

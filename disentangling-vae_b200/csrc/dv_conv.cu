@@ -689,7 +689,7 @@ int dv_conv_up(const float* lo, const float* w_packed, const float* bias, const 
   const float* wu = w_packed + kLoCh * CH * kTaps;
   if (CH != 32 && !mask && use_img() && img::shape_ok(B, H, W, CH))
     return img::conv_up(lo, wu, bias, hi, B, H, W, CH, act, as_stream(stream));
-  if (CH == 32 && use_tc("halo") && act != DV_ACT_SIGMOID && W + 2 <= 40)
+  if (CH == 32 && use_tc("halo") && act != DV_ACT_SIGMOID && W <= 32 && 128 % W == 0)
     return tc::conv_up_halo(lo, w_packed + kPackFfma + kPackTcSection, bias, mask, hi, B, H, W, act, as_stream(stream));
   if (CH == 32) {
     const int smem = kTaps * 32 * kLoCh * sizeof(float);

@@ -30,28 +30,10 @@ using namespace ptx;
 constexpr int kATile = 128 * 128;            // bytes: 128 pixel rows x 32 fp32
 constexpr int kBTap = 64 * 128;              // bytes: (32 hi + 32 lo) rows x 32 fp32
 constexpr int kBBytes = kTaps * kBTap;       // 131072
-constexpr int kThreads = 384;
 constexpr uint32_t kHiMask = 0xFFFFE000u;    // keep sign, exponent and the 10 tf32 mantissa bits
 
-// raw fp32 tile -> tf32-exact hi plane (in place) + residual lo plane; 128 threads, layout-agnostic
-__device__ __forceinline__ void split_hi_lo(uint4* hi, uint4* lo4, int t) {
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int idx = t + 128 * k;
-    const uint4 v = hi[idx];
-    uint4 h, l;
-    h.x = v.x & kHiMask; h.y = v.y & kHiMask; h.z = v.z & kHiMask; h.w = v.w & kHiMask;
-    l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x));
-    l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y));
-    l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z));
-    l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w));
-    hi[idx] = h;
-    lo4[idx] = l;
-  }
-}
-
-// same, but the hi plane stays the RAW fp32 tile: kind::tf32 reads only the upper 19 bits of a 32-bit operand, i.e.
-// it truncates exactly like the mask above (checked by the fp64-accuracy tests; DV_TC_RAWHI=0 restores the store)
+// raw fp32 tile -> residual plane lo = x - tf32_trunc(x).  The hi plane is the RAW tile itself: kind::tf32 reads only the
+// upper 19 bits of a 32-bit shared-memory operand, i.e. it truncates exactly like kHiMask (checked by the fp64-accuracy tests)
 __device__ __forceinline__ void split_lo_only(const uint4* raw, uint4* lo4, int t) {
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
@@ -93,31 +75,6 @@ struct DownGeom {
   int debug;            // DV_TC_DEBUG (timing experiments only, results are WRONG): 2 = load 4 of the 16 tap tiles
 };
 
-// ------------------------------------------------------------------------------------------
-// wgrad: dw[cl][c][tap] = sum_p lo[p][cl] * hi(2i-1+kh, 2j-1+kw)[c]   (reduction over PIXELS)
-// Both operands arrive from TMA as [128 pixel rows][32 channels] tiles, i.e. with the reduction
-// index along the smem rows: they are fed to tcgen05.mma as MN-major operands (no transposition
-// anywhere).  One MMA (M=128, N=64, K=8 pixels):
-//      A rows = [T0_hi | T1_hi | T0_lo | T1_lo]   (two taps of the hi patch, hi/lo planes, 4 x 32 ch)
-//      B cols = [L_hi | L_lo]                      (the lo tile, hi/lo planes, 2 x 32 ch)
-// so D holds all four hi/lo cross products of two taps at once (full fp32-equivalent product);
-// 8 tap-pair accumulators x 64 columns = the whole 512-column TMEM, kept for the CTA's lifetime
-// (split-K over CTAs; partials reduced in a fixed order by conv_wgrad_reduce_kernel).
-// ------------------------------------------------------------------------------------------
-constexpr int kWgStages = 2;
-constexpr int kWgStageBytes = 4 * kATile;              // T0hi, T1hi, T0lo, T1lo
-constexpr int kWgLBytes = 2 * kATile;                  // Lhi, Llo
-struct WgBarriers {
-  uint64_t raw_full[kWgStages], ready[kWgStages], empty[kWgStages];
-  uint64_t l_raw_full[2], l_ready[2], l_empty[2];
-  uint64_t acc_full;
-  uint32_t tmem_base;
-  float lscr[128][4];
-};
-constexpr int kWgSmemBytes = kWgStages * kWgStageBytes + 2 * kWgLBytes + 1024 + 3072;
-static_assert(sizeof(WgBarriers) <= 3072, "barrier block too large");
-static_assert(kWgSmemBytes <= 232448, "smem");
-
 // MN-major tf32 operand.  32-bit MN-major data must use the "128B swizzle, 32-byte atom" layout
 // (cute::UMMA::LayoutType::SWIZZLE_128B_BASE32B = 1; TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): rows of
 // 128 B (32 channels), 32-byte chunks XOR-ed with (row & 3), i.e. a K atom is 4 rows (512 B).
@@ -127,30 +84,66 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_mnmajor(uint32_t smem_addr, 
          (1ull << 46) | (1ull << 61);
 }
 
-struct WgGeom {
+// ------------------------------------------------------------------------------------------
+// wgrad: dw[cl][c][tap] = sum_p lo[p][cl] * hi(2i-1+kh, 2j-1+kw)[c]   (reduction over PIXELS), hi-patch operand in
+// TENSOR MEMORY.  The round-1 kernel fed both operands from shared memory (MN-major tiles, M = 128 = two taps x hi/lo
+// planes, N = 64) and was bound by operand traffic: per 128-pixel tile the tensor core fetched 768 KB of A/B tiles on top
+// of 816 KB of TMA writes and split reads/writes (1.6 MB at 128 B/clk = 12.4 K clk against 4 K clk of tensor time):
+// 130.7 us at (1024,16,32).  Here the A operand never exists in shared memory (73.0 us, same launch):
+//      A (TMEM, M = 128 lanes) = four taps x 32 hi channels of one kernel row,   K = 32 pixels per stage
+//      B (smem, MN-major)      = [L_raw | L_lo] of the lo tile (N = 64) and L_raw alone (N = 32)
+//      D_g[:, 0:32] = T_hi x L_hi,   D_g[:, 32:64] = T_hi x L_lo + T_lo x L_hi        (3xTF32, no lo x lo product;
+//      the two correction products accumulate apart from the main one, so they are not rounded at its magnitude)
+// The split warps own one tap each (lane = hi channel): they read 32 pixels of their channel from the raw TMA
+// tile (one conflict-free 128-byte row per warp load), split hi/lo in registers and tcgen05.st the two planes to
+// the A stage -- the transposition pixel-major -> channel-on-lanes costs nothing.  Only the 32 KB of lo-tile
+// planes are fetched by the MMAs (192 KB per tile), and no lo plane of the hi patch is written anywhere.
+//   smem : 8 raw tap tiles x 16 KB (unswizzled) + 2 x (L_raw | L_lo) x 16 KB
+//   TMEM : [0,256) accumulators (GPC kernel rows x 64 columns), [256,512) A stages (4 x {hi 32 | lo 32})
+// Split-K over CTAs; the partials are reduced in a fixed order by conv_wgrad_reduce_kernel.
+// ------------------------------------------------------------------------------------------
+constexpr int kWtThreads = 512;
+constexpr int kWtRawSlots = 8;
+constexpr int kWtAStages = 4;
+constexpr int kWtACol0 = 256;
+struct WtBarriers {
+  uint64_t raw_full[kWtRawSlots], raw_empty[kWtRawSlots];
+  uint64_t a_ready[kWtAStages], a_empty[kWtAStages];
+  uint64_t l_raw_full[2], l_ready[2], l_empty[2];
+  uint64_t acc_full;
+  uint32_t tmem_base;
+  float lscr[128][4];
+};
+constexpr int kWgLBytes = 2 * kATile;                  // L_raw, L_lo
+constexpr int kWtSmemBytes = kWtRawSlots * kATile + 2 * kWgLBytes + 1024 + 3072;
+static_assert(sizeof(WtBarriers) <= 3072, "barrier block too large");
+static_assert(kWtSmemBytes <= 232448, "smem");
+
+struct WtGeom {
   int B, H, W, rows_per_tile, num_tiles, tiles_per_cta;
-  int pairs_per_cta;    // conv_wgrad32: blockIdx.y owns tap pairs [y*ppc, (y+1)*ppc) (8 = all taps in one CTA)
   int prefetch;
-  int rawhi;            // feed the raw fp32 tiles as the hi operand (no hi-plane store)
 };
 
-__global__ void __launch_bounds__(kThreads, 1)
-conv_wgrad32_tc_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ CUtensorMap tmap_lo,
-                       float* __restrict__ ws, WgGeom g) {
+// GPC = kernel rows (groups of four taps) per CTA: blockIdx.y owns rows [y*GPC, (y+1)*GPC).  (A second accumulator
+// per row for the odd K steps was measured: 74.0 vs 73.0 us, no gain.)
+template <int GPC>
+__global__ void __launch_bounds__(kWtThreads, 1)
+conv_wgrad32_ts_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ CUtensorMap tmap_lo,
+                       float* __restrict__ ws, WtGeom g) {
+  static_assert(GPC * 64 <= kWtACol0, "accumulators overlap the A stages");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* St = smem;                                        // [stage][T0hi|T1hi|T0lo|T1lo]
-  uint8_t* Ls = smem + kWgStages * kWgStageBytes;            // [buf][Lhi|Llo]
-  WgBarriers* bars = reinterpret_cast<WgBarriers*>(Ls + 2 * kWgLBytes);
-  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform role index
+  uint8_t* Raw = smem;                                       // [slot][128 px][32 ch], no swizzle
+  uint8_t* Ls = smem + kWtRawSlots * kATile;                 // [buf][L_raw | L_lo], 128B swizzle with 32-byte atoms
+  WtBarriers* bars = reinterpret_cast<WtBarriers*>(Ls + 2 * kWgLBytes);
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int t_begin = blockIdx.x * g.tiles_per_cta;
   const int t_end = min(g.num_tiles, t_begin + g.tiles_per_cta);
-  // small layers: the tap pairs are spread over blockIdx.y as well, so that a CTA streams more tiles and writes a
-  // smaller partial (one fixed prologue/epilogue cost per CTA, fewer split-K partials to reduce)
-  const int pr_begin = blockIdx.y * g.pairs_per_cta, pr_end = pr_begin + g.pairs_per_cta;
+  const int g_begin = blockIdx.y * GPC;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kWgStages; ++s) { mbar_init(&bars->raw_full[s], 1); mbar_init(&bars->ready[s], 128); mbar_init(&bars->empty[s], 1); }
+    for (int s = 0; s < kWtRawSlots; ++s) { mbar_init(&bars->raw_full[s], 1); mbar_init(&bars->raw_empty[s], 128); }
+    for (int s = 0; s < kWtAStages; ++s) { mbar_init(&bars->a_ready[s], 128); mbar_init(&bars->a_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&bars->l_raw_full[s], 1); mbar_init(&bars->l_ready[s], 128); mbar_init(&bars->l_empty[s], 1); }
     mbar_init(&bars->acc_full, 1);
     fence_mbar_init();
@@ -164,7 +157,7 @@ conv_wgrad32_tc_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid
 
   if (warp == 0 && elect_one()) {
     prefetch_tmap(&tmap_hi); prefetch_tmap(&tmap_lo);
-    int stage = 0; uint32_t phase = 0; int lb = 0; uint32_t lphase = 0;
+    int lb = 0; uint32_t lphase = 0; uint32_t m = 0;
     for (int tile = t_begin; tile < t_end; ++tile) {
       const int r0 = tile * g.rows_per_tile;
       const int b0 = r0 / g.H, i0 = r0 % g.H;
@@ -178,124 +171,144 @@ conv_wgrad32_tc_kernel(const __grid_constant__ CUtensorMap tmap_hi, const __grid
       mbar_arrive_expect_tx(&bars->l_raw_full[lb], kATile);
       tma_load_4d(Ls + lb * kWgLBytes, &tmap_lo, &bars->l_raw_full[lb], 0, 0, i0, b0);
       if (++lb == 2) { lb = 0; lphase ^= 1; }
-      for (int pr = pr_begin; pr < pr_end; ++pr) {
-        mbar_wait(&bars->empty[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&bars->raw_full[stage], 2 * kATile);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int tap = 2 * pr + h, kh = tap >> 2, kw = tap & 3;
-          tma_load_4d(St + stage * kWgStageBytes + h * kATile, &tmap_hi, &bars->raw_full[stage], 0, kw - 1, 2 * i0 - 1 + kh, b0);
+      for (int gi = 0; gi < GPC; ++gi) {
+        const int kh = g_begin + gi;
+        for (int kw = 0; kw < 4; ++kw, ++m) {
+          const int slot = m % kWtRawSlots;
+          mbar_wait(&bars->raw_empty[slot], ((m / kWtRawSlots) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&bars->raw_full[slot], kATile);
+          tma_load_4d(Raw + slot * kATile, &tmap_hi, &bars->raw_full[slot], 0, kw - 1, 2 * i0 - 1 + kh, b0);
         }
-        if (++stage == kWgStages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1 && elect_one()) {      // ONE elected lane runs the whole issue loop (barrier waits included):
-                                              // ptxas then keeps every MMA operand in uniform registers (back-to-back UTCHMMA)
-    // M=128, N=64, tf32, both operands MN-major (bits 15 and 16)
-    constexpr uint32_t idesc = umma_idesc_tf32(128, 64) | (1u << 15) | (1u << 16);
-    int stage = 0; uint32_t phase = 0; int lb = 0; uint32_t lphase = 0;
+  } else if (warp == 1 && elect_one()) {      // ONE elected lane runs the whole issue loop (waits included)
+    // A from TMEM (K along the columns), B MN-major (bit 16)
+    constexpr uint32_t idesc64 = umma_idesc_tf32(128, 64) | (1u << 16), idesc32 = umma_idesc_tf32(128, 32) | (1u << 16);
+    int lb = 0; uint32_t lphase = 0; uint32_t n = 0;
     for (int tile = t_begin; tile < t_end; ++tile) {
       mbar_wait(&bars->l_ready[lb], lphase);
       tc_fence_after_sync();
       const uint32_t l_addr = smem_u32(Ls + lb * kWgLBytes);
-      for (int pr = pr_begin; pr < pr_end; ++pr) {
-        mbar_wait(&bars->ready[stage], phase);
-        tc_fence_after_sync();
-        const uint32_t a_addr = smem_u32(St + stage * kWgStageBytes);
-        const uint32_t d = tmem_base + (pr - pr_begin) * 64;
-#pragma unroll 4
-        for (int kc = 0; kc < 16; ++kc) {                   // 8 pixels per MMA
-          umma_tf32_ss_1t(d, umma_desc_sw128_mnmajor(a_addr + kc * 1024, kATile),
-                       umma_desc_sw128_mnmajor(l_addr + kc * 1024, kATile), idesc, (tile != t_begin) || (kc != 0));
+      for (int gi = 0; gi < GPC; ++gi) {
+        for (int s = 0; s < 4; ++s, ++n) {
+          const int as = n % kWtAStages;
+          mbar_wait(&bars->a_ready[as], (n / kWtAStages) & 1u);
+          tc_fence_after_sync();
+          const uint32_t a_hi = tmem_base + kWtACol0 + as * 64, a_lo = a_hi + 32;
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {                   // 8 pixels per MMA
+            const uint64_t b_d = umma_desc_sw128_mnmajor(l_addr + (s * 4 + k4) * 1024, kATile);
+            const uint32_t d = tmem_base + gi * 64;
+            const bool first = (tile == t_begin) && (s == 0) && (k4 == 0);
+            umma_tf32_ts_1t(d, a_hi + 8 * k4, b_d, idesc64, first ? 0u : 1u);     // [T_hi x L_hi | T_hi x L_lo]
+            umma_tf32_ts_1t(d + 32, a_lo + 8 * k4, b_d, idesc32, 1u);             // T_lo x L_hi joins the corrections
+          }
+          umma_commit_1t(&bars->a_empty[as]);
         }
-        umma_commit_1t(&bars->empty[stage]);
-        if (++stage == kWgStages) { stage = 0; phase ^= 1; }
       }
       umma_commit_1t(&bars->l_empty[lb]);
       if (++lb == 2) { lb = 0; lphase ^= 1; }
     }
     umma_commit_1t(&bars->acc_full);
   } else if (warp >= 8) {
-    // split raw tiles into hi/lo planes; also accumulate the column sums of lo (bias gradient)
-    const int t = threadIdx.x - 256;
-    // logical 16-byte chunk this thread always sees under the 32B-atom swizzle (row & 3 == (t >> 3) & 3)
-    const int quad = ((((t & 7) >> 1) ^ ((t >> 3) & 3)) << 1) | (t & 1);
+    // split warps: warp quarter q owns tap (kh, kw = q) of the current kernel row, lane = hi channel; the two groups
+    // alternate over the 32-pixel stages.  The tcgen05.st of one stage stay in flight while the next one is loaded.
+    const int q = warp & 3, grp = (warp - 8) >> 2;
+    const uint32_t raw0 = smem_u32(Raw) + lane * 4;
+    uint32_t n = 0, tseq = 0;
+    int prev_as = -1, prev_slot = 0;
+    for (int tile = t_begin; tile < t_end; ++tile, ++tseq) {
+      for (int gi = 0; gi < GPC; ++gi) {
+        const uint32_t m = (tseq * GPC + gi) * 4 + q;
+        const int slot = m % kWtRawSlots;
+        for (int s = 0; s < 4; ++s, ++n) {
+          if ((int)(n & 1u) != grp) continue;
+          const int as = n % kWtAStages;
+          mbar_wait(&bars->raw_full[slot], (m / kWtRawSlots) & 1u);
+          const uint32_t src = raw0 + slot * kATile + s * 32 * 128;
+          uint32_t h[32], l[32];
+#pragma unroll
+          for (int k = 0; k < 32; ++k) {
+            const uint32_t v = lds32(src + k * 128);
+            const uint32_t hb = v & kHiMask;
+            h[k] = hb;
+            l[k] = __float_as_uint(__uint_as_float(v) - __uint_as_float(hb));
+          }
+          if (prev_as >= 0) {
+            tmem_st_wait();
+            mbar_arrive(&bars->raw_empty[prev_slot]);
+            tc_fence_before_sync();
+            mbar_arrive(&bars->a_ready[prev_as]);
+          }
+          mbar_wait(&bars->a_empty[as], ((n / kWtAStages) & 1u) ^ 1u);
+          tc_fence_after_sync();
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + kWtACol0 + as * 64;
+          tmem_st_32x32b_x32(taddr, h);
+          tmem_st_32x32b_x32(taddr + 32, l);
+          prev_as = as; prev_slot = slot;
+        }
+      }
+    }
+    if (prev_as >= 0) {
+      tmem_st_wait();
+      mbar_arrive(&bars->raw_empty[prev_slot]);
+      tc_fence_before_sync();
+      mbar_arrive(&bars->a_ready[prev_as]);
+    }
+  } else if (warp >= 4) {
+    // warps 4-7: lo tile -> (raw | residual) planes and its channel sums (bias gradient) while the tiles stream,
+    // then the epilogue (once per CTA): TMEM -> main + correction columns -> workspace partial
+    const int t = threadIdx.x - 128;
     float ls[4] = {0.f, 0.f, 0.f, 0.f};
-    int stage = 0; uint32_t phase = 0; int lb = 0; uint32_t lphase = 0;
+    int lb = 0; uint32_t lphase = 0;
     for (int tile = t_begin; tile < t_end; ++tile) {
       mbar_wait(&bars->l_raw_full[lb], lphase);
-      {
-        uint4* hi = reinterpret_cast<uint4*>(Ls + lb * kWgLBytes);
+      const uint4* raw = reinterpret_cast<const uint4*>(Ls + lb * kWgLBytes);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint4 v = hi[t + 128 * k];
-          ls[0] += __uint_as_float(v.x); ls[1] += __uint_as_float(v.y); ls[2] += __uint_as_float(v.z); ls[3] += __uint_as_float(v.w);
-        }
-        if (g.rawhi) split_lo_only(hi, reinterpret_cast<uint4*>(Ls + lb * kWgLBytes + kATile), t);
-        else split_hi_lo(hi, reinterpret_cast<uint4*>(Ls + lb * kWgLBytes + kATile), t);
+      for (int k = 0; k < 8; ++k) {
+        const uint4 v = raw[t + 128 * k];
+        ls[0] += __uint_as_float(v.x); ls[1] += __uint_as_float(v.y); ls[2] += __uint_as_float(v.z); ls[3] += __uint_as_float(v.w);
       }
+      split_lo_only(raw, reinterpret_cast<uint4*>(Ls + lb * kWgLBytes + kATile), t);
       fence_proxy_async_smem();
       mbar_arrive(&bars->l_ready[lb]);
       if (++lb == 2) { lb = 0; lphase ^= 1; }
-      for (int pr = pr_begin; pr < pr_end; ++pr) {
-        mbar_wait(&bars->raw_full[stage], phase);
-        uint8_t* base = St + stage * kWgStageBytes;
-        if (g.rawhi) {
-          split_lo_only(reinterpret_cast<const uint4*>(base), reinterpret_cast<uint4*>(base + 2 * kATile), t);
-          split_lo_only(reinterpret_cast<const uint4*>(base + kATile), reinterpret_cast<uint4*>(base + 3 * kATile), t);
-        } else {
-          split_hi_lo(reinterpret_cast<uint4*>(base), reinterpret_cast<uint4*>(base + 2 * kATile), t);
-          split_hi_lo(reinterpret_cast<uint4*>(base + kATile), reinterpret_cast<uint4*>(base + 3 * kATile), t);
-        }
-        fence_proxy_async_smem();
-        mbar_arrive(&bars->ready[stage]);
-        if (++stage == kWgStages) { stage = 0; phase ^= 1; }
-      }
     }
-    // fixed-order reduction of the lo column sums (bias gradient): 16 of the 128 threads see each chunk
 #pragma unroll
     for (int e = 0; e < 4; ++e) bars->lscr[t][e] = ls[e];
     asm volatile("bar.sync 2, 128;" ::: "memory");
-    if (t < 32 && blockIdx.y == 0) {                        // (every pair group sees the same lo tiles)
+    if (t < 32 && blockIdx.y == 0) {                        // (every kernel-row group sees the same lo tiles)
       const int want = t >> 2, e = t & 3;
       float acc = 0.f;
       for (int u = 0; u < 128; ++u)
         if ((((((u & 7) >> 1) ^ ((u >> 3) & 3)) << 1) | (u & 1)) == want) acc += bars->lscr[u][e];
       ws[(long long)blockIdx.x * (kTaps * 32 + 1) * kLoCh + (kTaps * 32) * kLoCh + t] = acc;
     }
-  }
-
-  // ---- epilogue (once per CTA): TMEM -> fold the 4 hi/lo quadrants -> workspace partial ----
-  if (warp >= 4 && warp < 8) {
     const int q = warp & 3;
-    const int r = q * 32 + lane;
     mbar_wait(&bars->acc_full, 0);
     tc_fence_after_sync();
-    float* red = reinterpret_cast<float*>(St);              // all MMAs have completed: stage buffers are free
     float* out = ws + (long long)blockIdx.x * (kTaps * 32 + 1) * kLoCh;
-    for (int pr = pr_begin; pr < pr_end; ++pr) {
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (pr - pr_begin) * 64;
+#pragma unroll 1
+    for (int gi = 0; gi < GPC; ++gi) {
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + gi * 64;
       uint32_t r0[32], r1[32];
+      float v[32];
       tmem_ld_32x32b_x32(taddr, r0);
       tmem_ld_32x32b_x32(taddr + 32, r1);
       tmem_ld_wait();
 #pragma unroll
-      for (int cl = 0; cl < 32; ++cl) red[r * 33 + cl] = __uint_as_float(r0[cl]) + __uint_as_float(r1[cl]);
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (r < 64) {
-        const int tap = pr * 2 + (r >> 5), c = r & 31;
-        float* dst = out + (tap * 32 + c) * kLoCh;
+      for (int cl = 0; cl < 32; ++cl) v[cl] = __uint_as_float(r0[cl]) + __uint_as_float(r1[cl]);
+      const int tap = (g_begin + gi) * 4 + q;
+      float* dst = out + (tap * 32 + lane) * kLoCh;
 #pragma unroll
-        for (int cl = 0; cl < 32; ++cl) dst[cl] = red[r * 33 + cl] + red[(r + 64) * 33 + cl];
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int c4 = 0; c4 < 8; ++c4)
+        *reinterpret_cast<float4*>(dst + c4 * 4) = make_float4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
     }
   }
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 2) { tc_fence_after_sync(); tmem_dealloc(tmem_base, 512); }
 }
-
 
 
 // ==========================================================================================
@@ -562,20 +575,21 @@ conv_down32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
 // ==========================================================================================
 // up, halo-resident ("one load per input pixel"), CH == 32:
 // The nine shifted operand tiles of the up convolution overlap almost completely, so instead of
-// nine TMA loads per 128 positions ONE zero-padded halo tile [(TR+2) rows][W+2 cols][32 ch] is
-// loaded per tile (box start (-1, i0-1): the padding is TMA out-of-bounds fill).  MMA rows enumerate
-// consecutive pixels q of that padded grid, so the operand of shift (di,dj) is simply the rows
-// q + di*(W+2) + dj of the resident tile: the split warps read them (un-swizzling by the absolute
-// row index), split hi/lo and tcgen05.st them to TMEM.  Rows that fall on padding columns / halo
-// rows produce garbage that the epilogue skips (each output row depends only on its own A rows).
+// nine TMA loads per 128 positions ONE tile with a row halo [TB images][(TR+2) rows][W cols][32 ch] is
+// loaded per tile (box start row i0-1: the rows above / below the image are TMA out-of-bounds fill).
+// The 128 MMA rows enumerate the TB*TR*W valid pixels (all 128 for the layers of the networks), so
+// the operand of shift (di,dj) is the resident pixel (row + di, col + dj): the split warps read it
+// (un-swizzling by the absolute row index; a column shift that leaves the image row yields zero),
+// split hi/lo and tcgen05.st the planes to TMEM.  (Round 1 enumerated a column-padded grid instead:
+// 112 / 64 / 48 useful rows of 128 at W = 16 / 8 / 4 and a ragged third tile per 16-row image.)
 // L2->smem traffic drops 9x, and the kernel becomes MMA-bound: per output phase N = 32, three MMAs per
 // K slice (hi*hi, hi*lo, lo*hi), weights 128 KB resident.  (The image-boundary layer, CH in {1,3}, is
 // not a tensor-core problem: dv_conv_img.cu.)
 // ==========================================================================================
-constexpr int kHaloStageBytes = 26 * 1024;      // 208 pixel rows: the largest box (<= 176 px) + over-read slack
+constexpr int kHaloStageBytes = 26 * 1024;      // 208 pixel rows: the largest box of the supported geometries is 192 px
 constexpr int kHaloStages = 3;
 struct HaloGeom {
-  int B, H, W, Wp, TR, TB, tiles_per_img, num_tiles, img_px, q_start, box_bytes;
+  int B, H, W, TR, TB, tiles_per_img, num_tiles, valid_rows, box_px, box_bytes;
   int pipe;             // see DownGeom::pipe
   int debug;            // DV_TC_DEBUG (timing experiments only, results are WRONG): 1 = issue 1 of the 3 MMAs per product
 };
@@ -632,7 +646,7 @@ conv_up_halo_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
       if (g.TB > 1) { b0 = tile * g.TB; i0 = 0; } else { b0 = tile / g.tiles_per_img; i0 = (tile % g.tiles_per_img) * g.TR; }
       mbar_wait(&bars->raw_empty[stage], ((t_seq / kHaloStages) & 1u) ^ 1u);
       mbar_arrive_expect_tx(&bars->raw_full[stage], g.box_bytes);
-      tma_load_4d(Raw + stage * kHaloStageBytes, &tmap_a, &bars->raw_full[stage], 0, -1, i0 - 1, b0);
+      tma_load_4d(Raw + stage * kHaloStageBytes, &tmap_a, &bars->raw_full[stage], 0, 0, i0 - 1, b0);
     }
   } else if (warp == 1 && elect_one()) {      // ONE elected lane runs the whole issue loop (waits included)
     constexpr uint32_t idescN = umma_idesc_tf32(128, 32);
@@ -679,11 +693,10 @@ conv_up_halo_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
       int b0, i0;
       if (g.TB > 1) { b0 = tile * g.TB; i0 = 0; } else { b0 = tile / g.tiles_per_img; i0 = (tile % g.tiles_per_img) * g.TR; }
-      const int qq = g.q_start + q * 32 + lane;
-      const int tb = qq / g.img_px, rem = qq - tb * g.img_px;
-      const int rr = rem / g.Wp - 1, ww = rem % g.Wp - 1;
-      const int b = b0 + tb, i = i0 + rr, j = ww;
-      const bool valid = tb < g.TB && rr >= 0 && rr < g.TR && ww >= 0 && ww < g.W && b < g.B && i < g.H;
+      const int r = q * 32 + lane, t = r / g.W;
+      const int tb = t / g.TR, rr = t - tb * g.TR;
+      const int b = b0 + tb, i = i0 + rr, j = r - t * g.W;
+      const bool valid = r < g.valid_rows && b < g.B && i < g.H;
       // ReLU-backward mask of the four output pixels as one bit per channel, fetched BEFORE waiting for the accumulator:
       // the loads' latency hides behind this tile's MMAs instead of sitting between the TMEM loads and the stores
       // (masked dgrad launches used to be 1.7x slower than the unmasked forward ones).
@@ -734,6 +747,10 @@ conv_up_halo_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
   } else if (warp >= 8) {
     const int q = warp & 3, grp = (warp - 8) >> 2;
     const int row = q * 32 + lane;
+    // centre pixel of this MMA row inside the resident box [TB][TR+2][W] (one halo row above and below every image slab)
+    const int rt = row / g.W, rj = row - rt * g.W, rtb = rt / g.TR;
+    const int src0 = min((rtb * (g.TR + 2) + (rt - rtb * g.TR) + 1) * g.W + rj, g.box_px - 1);
+    const bool row_ok = row < g.valid_rows;
     uint32_t n = 0, t_seq = 0;
     int prev_stage = -1, prev_as = 0;                         // g.pipe: shifted tile whose TMEM stores are still in flight
     for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++t_seq) {
@@ -745,12 +762,16 @@ conv_up_halo_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         const int di = s / 3 - 1, dj = s % 3 - 1;
         const int as = n % kTsAStages;
         if (!waited) { mbar_wait(&bars->raw_full[stage], (t_seq / kHaloStages) & 1u); waited = true; }
-        const int p = g.q_start + row + di * g.Wp + dj;            // source pixel of the resident halo tile
+        // source pixel of the resident tile; a column shift that leaves the image row reads the zero padding instead
+        // (the neighbouring row's pixel sits at that address: the rows are stored without column padding)
+        const bool ok = row_ok && (unsigned)(rj + dj) < (unsigned)g.W;
+        const int p = ok ? src0 + di * g.W + dj : src0;
+        const uint32_t keep = ok ? 0xffffffffu : 0u;
         uint32_t h[32], l[32];
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           const uint4 v = lds128(raw + p * 128 + ((c ^ (p & 7)) << 4));
-          const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+          const uint32_t vv[4] = {v.x & keep, v.y & keep, v.z & keep, v.w & keep};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const uint32_t hb = vv[e] & kHiMask;
@@ -816,11 +837,6 @@ __global__ void conv_pack_tc_kernel(const float* __restrict__ w, float* __restri
 }
 
 // ---- host side ---------------------------------------------------------------------------
-static int use_rawhi() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("DV_TC_RAWHI"); v = (e && e[0] == '0') ? 0 : 1; }
-  return v;
-}
 static int use_debug() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("DV_TC_DEBUG"); v = e ? atoi(e) : 0; }
@@ -917,51 +933,58 @@ int conv_down32_tc(const float* hi, const float* wd_packed, const float* bias, c
   return check_launch();
 }
 
-// partial sums of dw (and of lo, last row) per CTA into ws[grid][16*32+1][32]; returns the grid size in *nsplit
-int conv_wgrad32_tc(const float* lo, const float* hi, float* ws, int B, int H, int W, int* nsplit, cudaStream_t st) {
-  if (W > 128 || 128 % W != 0) return DV_ERR_BAD_SHAPE;
-  WgGeom g = {};
-  g.B = B; g.H = H; g.W = W; g.prefetch = use_prefetch(); g.rawhi = use_rawhi();
-  g.rows_per_tile = 128 / W;
-  const int TR = g.rows_per_tile < H ? g.rows_per_tile : H;
-  if (H % TR != 0 || g.rows_per_tile % TR != 0) return DV_ERR_BAD_SHAPE;
-  const int TB = g.rows_per_tile / TR;
-  g.num_tiles = (int)(((long long)B * H * W + 127) / 128);
-  // (tile group, tap-pair group) decomposition: big layers keep all 8 pairs in one CTA (one pass over the tiles);
-  // small layers spread the pairs over blockIdx.y so that every CTA still streams >= 8 tiles
-  static int split_pairs = -1;
-  if (split_pairs < 0) { const char* e = getenv("DV_WG_PAIRSPLIT"); split_pairs = (e && e[0] == '0') ? 0 : 1; }
-  int ppc = 8, grid = 1;
-  for (;; ppc >>= 1) {
-    const int pg = 8 / ppc;
-    const int gmax = kNumSMs / pg;
-    grid = g.num_tiles < gmax ? g.num_tiles : gmax;
-    g.tiles_per_cta = (g.num_tiles + grid - 1) / grid;
-    if (g.tiles_per_cta >= 8 || ppc == 1 || !split_pairs) break;
-  }
-  g.pairs_per_cta = ppc;
-  grid = (g.num_tiles + g.tiles_per_cta - 1) / g.tiles_per_cta;
-  *nsplit = grid;
-  CUtensorMap thi, tlo;
-  if (!make_act_tmap(&thi, hi, B, 2 * H, 2 * W, 2 * W, 2 * TR, TB, 2, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return DV_ERR_CUDA;
-  if (!make_act_tmap(&tlo, lo, B, H, W, W, TR, TB, 1, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return DV_ERR_CUDA;
+int wgrad32_tc_max_splits() { return kNumSMs; }
+
+template <int GPC>
+static int launch_wgrad_ts(const CUtensorMap& thi, const CUtensorMap& tlo, float* ws, WtGeom g, int grid, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
-    if (cudaFuncSetAttribute(conv_wgrad32_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes) != cudaSuccess) {
+    if (cudaFuncSetAttribute(conv_wgrad32_ts_kernel<GPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWtSmemBytes) != cudaSuccess) {
       g_last_cuda_error = (int)cudaGetLastError();
       return DV_ERR_CUDA;
     }
     attr = true;
   }
-  conv_wgrad32_tc_kernel<<<dim3(grid, 8 / ppc), kThreads, kWgSmemBytes, st>>>(thi, tlo, ws, g);
+  conv_wgrad32_ts_kernel<GPC><<<dim3(grid, 4 / GPC), kWtThreads, kWtSmemBytes, st>>>(thi, tlo, ws, g);
   return check_launch();
 }
-int wgrad32_tc_max_splits() { return kNumSMs; }
+
+// partial sums of dw (and of lo, last row) per CTA into ws[grid][16*32+1][32]; returns the grid size in *nsplit
+int conv_wgrad32_tc(const float* lo, const float* hi, float* ws, int B, int H, int W, int* nsplit, cudaStream_t st) {
+  if (W > 128 || 128 % W != 0) return DV_ERR_BAD_SHAPE;
+  WtGeom g = {};
+  g.B = B; g.H = H; g.W = W; g.prefetch = use_prefetch();
+  g.rows_per_tile = 128 / W;
+  const int TR = g.rows_per_tile < H ? g.rows_per_tile : H;
+  if (H % TR != 0 || g.rows_per_tile % TR != 0) return DV_ERR_BAD_SHAPE;
+  const int TB = g.rows_per_tile / TR;
+  g.num_tiles = (int)(((long long)B * H * W + 127) / 128);
+  // (tile group, kernel-row group) decomposition: big layers keep all four kernel rows in one CTA (one pass over the
+  // tiles); small layers spread the rows over blockIdx.y so that every CTA still streams >= 8 tiles
+  static int split_rows = -1;
+  if (split_rows < 0) { const char* e = getenv("DV_WG_PAIRSPLIT"); split_rows = (e && e[0] == '0') ? 0 : 1; }
+  int gpc = 4, grid = 1;
+  for (;; gpc >>= 1) {
+    const int gmax = kNumSMs / (4 / gpc);
+    grid = g.num_tiles < gmax ? g.num_tiles : gmax;
+    g.tiles_per_cta = (g.num_tiles + grid - 1) / grid;
+    if (g.tiles_per_cta >= 8 || gpc == 1 || !split_rows) break;
+  }
+  grid = (g.num_tiles + g.tiles_per_cta - 1) / g.tiles_per_cta;
+  *nsplit = grid;
+  CUtensorMap thi, tlo;
+  if (!make_act_tmap(&thi, hi, B, 2 * H, 2 * W, 2 * W, 2 * TR, TB, 2, CU_TENSOR_MAP_SWIZZLE_NONE)) return DV_ERR_CUDA;
+  if (!make_act_tmap(&tlo, lo, B, H, W, W, TR, TB, 1, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return DV_ERR_CUDA;
+  if (gpc == 4) return launch_wgrad_ts<4>(thi, tlo, ws, g, grid, st);
+  if (gpc == 2) return launch_wgrad_ts<2>(thi, tlo, ws, g, grid, st);
+  return launch_wgrad_ts<1>(thi, tlo, ws, g, grid, st);
+}
+
 
 static int launch_up_halo(const float* lo, const float* wu, const float* bias, const float* mask, float* hi,
                           HaloGeom g, int act, cudaStream_t st) {
   CUtensorMap ta, tb;
-  if (!make_act_tmap(&ta, lo, g.B, g.H, g.W, g.Wp, g.TR + 2, g.TB, 1)) return DV_ERR_CUDA;
+  if (!make_act_tmap(&ta, lo, g.B, g.H, g.W, g.W, g.TR + 2, g.TB, 1)) return DV_ERR_CUDA;
   if (!make_w_tmap(&tb, wu)) return DV_ERR_CUDA;
   static bool attr = false;
   if (!attr) {
@@ -980,24 +1003,25 @@ static int launch_up_halo(const float* lo, const float* wu, const float* bias, c
 int conv_up_halo(const float* lo, const float* wu, const float* bias, const float* mask, float* hi,
                  int B, int H, int W, int act, cudaStream_t st) {
   HaloGeom g = {};
-  g.B = B; g.H = H; g.W = W; g.Wp = W + 2; g.pipe = use_pipe(); g.debug = use_debug();
-  int tr = (128 + 2) / g.Wp;                       // largest TR with TR*Wp - 2 <= 128
-  if (tr < 1) return DV_ERR_BAD_SHAPE;
-  if (tr >= H) {
+  g.B = B; g.H = H; g.W = W; g.pipe = use_pipe(); g.debug = use_debug();
+  if (W > 32 || 128 % W != 0) return DV_ERR_BAD_SHAPE;
+  // 128 MMA rows = 128 / W image rows of W pixels: whole rows of one image (TB = 1) or whole small images (TB > 1)
+  const int rpt = 128 / W;
+  if (rpt >= H) {
     g.TR = H;
-    int tb = (128 + 2 + 2 * g.Wp) / ((H + 2) * g.Wp);   // largest TB with (TB*(H+2) - 2)*Wp - 2 <= 128
-    g.TB = tb < 1 ? 1 : tb;
-    if (g.TB > 1) { g.tiles_per_img = 1; g.num_tiles = (B + g.TB - 1) / g.TB; }
-    else { g.tiles_per_img = 1; g.num_tiles = B; }
+    g.TB = rpt / H < 1 ? 1 : rpt / H;
+    while (g.TB > 1 && g.TB * (H + 2) * W * 128 > kHaloStageBytes) --g.TB;
+    g.tiles_per_img = 1;
+    g.num_tiles = (B + g.TB - 1) / g.TB;
   } else {
-    g.TR = tr; g.TB = 1;
-    g.tiles_per_img = (H + tr - 1) / tr;
+    g.TR = rpt; g.TB = 1;
+    g.tiles_per_img = (H + rpt - 1) / rpt;
     g.num_tiles = B * g.tiles_per_img;
   }
-  g.img_px = (g.TR + 2) * g.Wp;
-  g.q_start = g.Wp + 1;
-  g.box_bytes = g.TB * g.img_px * 128;
-  if (g.box_bytes > kHaloStageBytes || g.q_start + 127 + g.Wp + 1 >= kHaloStageBytes / 128) return DV_ERR_BAD_SHAPE;
+  g.valid_rows = g.TB * g.TR * W;
+  g.box_px = g.TB * (g.TR + 2) * W;
+  g.box_bytes = g.box_px * 128;
+  if (g.box_bytes > kHaloStageBytes) return DV_ERR_BAD_SHAPE;
   return launch_up_halo(lo, wu, bias, mask, hi, g, act, st);
 }
 

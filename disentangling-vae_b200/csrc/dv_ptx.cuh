@@ -58,6 +58,13 @@ __device__ __forceinline__ uint4 lds128(const void* p) {
 #endif
 }
 
+// one 32-bit word of shared memory (explicit ld.shared: 32-bit address arithmetic)
+__device__ __forceinline__ uint32_t lds32(uint32_t smem_addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_addr) : "memory");
+  return v;
+}
+
 // ---- proxy / tcgen05 fences -----------------------------------------------------------
 __device__ __forceinline__ void fence_proxy_async_smem() {   // generic-proxy smem writes -> async proxy (MMA/TMA)
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

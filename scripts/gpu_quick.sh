@@ -4,7 +4,8 @@
 set -u
 mkdir -p gpurun_out
 # guard: the tcgen05 conv kernels of this configuration must terminate and be accurate before the long runs
-if ! timeout 180 python scripts/sanity_ts.py; then echo "sanity_ts FAILED or hung: aborting this run"; exit 1; fi
+if ! SANITY_TIME=1 timeout 180 python scripts/sanity_ts.py; then echo "sanity_ts FAILED or hung: aborting this run"; exit 1; fi
+timeout 240 python scripts/sanity_wg.py; rc=$?; if [ $rc -gt 1 ]; then echo "sanity_wg crashed or hung ($rc): aborting this run"; exit 1; fi
 if [ "${TESTS:-1}" = "1" ]; then
 timeout 2400 python -m pytest tests -q -m gpu --timeout=900 --durations=8 -s ${PYTEST_ARGS:-} > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest exit $?" | tee -a gpurun_out/pytest_gpu.log

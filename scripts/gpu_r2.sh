@@ -5,6 +5,7 @@ set -u
 mkdir -p gpurun_out
 # guard: the tcgen05 conv kernels of this configuration must terminate and be accurate before the long runs
 if ! timeout 180 python scripts/sanity_ts.py; then echo "sanity_ts FAILED or hung: aborting this run"; exit 1; fi
+timeout 240 python scripts/sanity_wg.py; rc=$?; if [ $rc -gt 1 ]; then echo "sanity_wg crashed or hung ($rc): aborting this run"; exit 1; fi
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.txt 2>&1
 if [ "${TESTS:-1}" = "1" ]; then
 echo "== pytest gpu"
