@@ -569,16 +569,19 @@ static int wgrad_nsplit(int B, int H, int W, long long* chunk) {
 namespace dv {
 namespace tc {        // dv_conv_tc.cu: tcgen05 kernels of the 32-channel layers
 int pack_tc(const float* w, float* wd, float* wu, float* wf, cudaStream_t st);
+int pack_multi(int n, const float* const* w, float* const* wp, const int* CH, cudaStream_t st);
 int conv_down32_tc(const float* hi, const float* wd_packed, const float* bias, const float* mask, float* lo,
-                   int B, int H, int W, int act, cudaStream_t st, float* colsum_part, int* nparts);
+                   int B, int H, int W, int act, cudaStream_t st, float* colsum_part, int* nparts,
+                   const uint32_t* mask_bits, uint32_t* bits_out);
 int conv_up_halo(const float* lo, const float* wu, const float* bias, const float* mask, float* hi,
-                 int B, int H, int W, int act, cudaStream_t st);
+                 int B, int H, int W, int act, cudaStream_t st, const uint32_t* mask_bits, uint32_t* bits_out);
 int conv_wgrad32_tc(const float* lo, const float* hi, float* ws, int B, int H, int W, int* nsplit, cudaStream_t st);
 }  // namespace tc
 namespace img {       // dv_conv_img.cu: exact-fp32 CUDA-core kernels for the image-boundary layers (CH in {1,3})
 bool shape_ok(int B, int H, int W, int CH);
-int conv_down(const float* hi, const float* wd, const float* bias, const float* mask, float* lo, int B, int H, int W, int CH,
-              int act, cudaStream_t st, float* colsum_part, int* nparts, int max_parts);
+int conv_down(const float* hi, const float* wd, const float* bias, const float* mask, const uint32_t* mask_bits, float* lo,
+              uint32_t* bits_out, int B, int H, int W, int CH, int act, cudaStream_t st, float* colsum_part, int* nparts,
+              int max_parts);
 int conv_wgrad(const float* lo, const float* hi, float* ws, int B, int H, int W, int CH, int max_split, int* nsplit, cudaStream_t st);
 int conv_up(const float* lo, const float* wu, const float* bias, float* hi, int B, int H, int W, int CH, int act, cudaStream_t st);
 }  // namespace img
@@ -629,14 +632,39 @@ int dv_conv_pack_weights(const float* w, float* w_packed, int CH, void* stream) 
   return check_launch();
 }
 
+int dv_conv_pack_multi(int n, const void* const* w, void* const* w_packed, const int* CH, void* stream) {
+  if (n < 1 || !w || !w_packed || !CH) return DV_ERR_BAD_ARG;
+  for (int i = 0; i < n; ++i) {
+    if (!w[i] || !w_packed[i]) return DV_ERR_BAD_ARG;
+    if (CH[i] != 1 && CH[i] != 3 && CH[i] != 32) return DV_ERR_BAD_SHAPE;
+  }
+  static_assert(kPackFfma == 2 * kLoCh * 32 * kTaps && kPackTcSection == kTaps * 64 * 32, "layout shared with conv_pack_multi_kernel");
+  return tc::pack_multi(n, reinterpret_cast<const float* const*>(w), reinterpret_cast<float* const*>(w_packed), CH, as_stream(stream));
+}
+
+// [x > 0] of a 32-channel NHWC tensor as one word per pixel, for the kernels that do not produce it in their epilogue
+__global__ void relu_bits_kernel(const float* __restrict__ x, uint32_t* __restrict__ bits, long long npx) {
+  const long long p = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (p >= npx) return;
+  const uint32_t b = __ballot_sync(0xffffffffu, x[p * 32 + (threadIdx.x & 31)] > 0.f);
+  if ((threadIdx.x & 31) == 0) bits[p] = b;
+}
+static int relu_bits(const float* x, uint32_t* bits, long long npx, cudaStream_t st) {
+  relu_bits_kernel<<<(unsigned)((npx + 7) / 8), 256, 0, st>>>(x, bits, npx);
+  return check_launch();
+}
+
 static int conv_down_impl(const float* hi, const float* w_packed, const float* bias, const float* mask, float* lo,
-                          int B, int H, int W, int CH, int act, cudaStream_t st, float* colsum_part, int* nparts) {
+                          int B, int H, int W, int CH, int act, cudaStream_t st, float* colsum_part, int* nparts,
+                          const uint32_t* mask_bits, uint32_t* bits_out, bool* bits_done) {
   *nparts = 0;
+  *bits_done = true;
   const long long groups = ((long long)B * H * W + kDownPxPerWarp - 1) / kDownPxPerWarp;
   if (CH == 32 && use_tc("down"))
-    return tc::conv_down32_tc(hi, w_packed + kPackFfma, bias, mask, lo, B, H, W, act, st, colsum_part, nparts);
+    return tc::conv_down32_tc(hi, w_packed + kPackFfma, bias, mask, lo, B, H, W, act, st, colsum_part, nparts, mask_bits, bits_out);
   if (CH != 32 && use_img() && img::shape_ok(B, H, W, CH))
-    return img::conv_down(hi, w_packed, bias, mask, lo, B, H, W, CH, act, st, colsum_part, nparts, kCsBlocks);
+    return img::conv_down(hi, w_packed, bias, mask, mask_bits, lo, bits_out, B, H, W, CH, act, st, colsum_part, nparts, kCsBlocks);
+  *bits_done = false;                               // the CUDA-core fallbacks below read the float mask and write no bits
   if (CH == 32) {
     const int smem = kTaps * 32 * kLoCh * sizeof(float);
     static bool attr_set = false;
@@ -656,8 +684,10 @@ static int conv_down_impl(const float* hi, const float* w_packed, const float* b
 }
 
 int dv_conv_down(const float* hi, const float* w_packed, const float* bias, const float* mask, float* lo,
-                 int B, int H, int W, int CH, int hi_nchw, int act, float* colsum_out, void* colsum_workspace, void* stream) {
+                 int B, int H, int W, int CH, int hi_nchw, int act, float* colsum_out, void* colsum_workspace,
+                 const unsigned* mask_bits, unsigned* relu_bits_out, void* stream) {
   if (!hi || !w_packed || !lo) return DV_ERR_BAD_ARG;
+  if (mask_bits && !mask) return DV_ERR_BAD_ARG;               // the words accelerate the float mask, they do not replace it
   if (!shape_ok(B, H, W, CH)) return DV_ERR_BAD_SHAPE;
   if (act != DV_ACT_NONE && act != DV_ACT_RELU) return DV_ERR_BAD_ARG;
   if ((CH == 32) == (hi_nchw != 0)) return DV_ERR_BAD_SHAPE;   // CH==32 <=> NHWC
@@ -667,7 +697,10 @@ int dv_conv_down(const float* hi, const float* w_packed, const float* bias, cons
   static int fuse = -1;
   if (fuse < 0) { const char* e = getenv("DV_FUSE_COLSUM"); fuse = (e && e[0] == '0') ? 0 : 1; }
   int nparts = 0;
-  int rc = conv_down_impl(hi, w_packed, bias, mask, lo, B, H, W, CH, act, st, fuse ? part : nullptr, &nparts);
+  bool bits_done = true;
+  int rc = conv_down_impl(hi, w_packed, bias, mask, lo, B, H, W, CH, act, st, fuse ? part : nullptr, &nparts, mask_bits,
+                          relu_bits_out, &bits_done);
+  if (rc == DV_OK && relu_bits_out && !bits_done) rc = relu_bits(lo, relu_bits_out, (long long)B * H * W, st);
   if (rc != DV_OK || !colsum_out) return rc;
   if (nparts == 0) {                                           // this variant does not sum in its epilogue: one more pass over lo
     const long long rows = (long long)B * H * W;
@@ -681,8 +714,11 @@ int dv_conv_down(const float* hi, const float* w_packed, const float* bias, cons
 }
 
 int dv_conv_up(const float* lo, const float* w_packed, const float* bias, const float* mask, float* hi,
-               int B, int H, int W, int CH, int hi_nchw, int act, void* stream) {
+               int B, int H, int W, int CH, int hi_nchw, int act, const unsigned* mask_bits, unsigned* relu_bits_out,
+               void* stream) {
   if (!lo || !w_packed || !hi) return DV_ERR_BAD_ARG;
+  if (mask_bits && !mask) return DV_ERR_BAD_ARG;
+  if ((mask_bits || relu_bits_out) && CH != 32) return DV_ERR_BAD_ARG;   // one word per pixel = 32 NHWC channels
   if (!shape_ok(B, H, W, CH)) return DV_ERR_BAD_SHAPE;
   if (act != DV_ACT_NONE && act != DV_ACT_RELU && act != DV_ACT_SIGMOID) return DV_ERR_BAD_ARG;
   if ((CH == 32) == (hi_nchw != 0)) return DV_ERR_BAD_SHAPE;
@@ -690,7 +726,8 @@ int dv_conv_up(const float* lo, const float* w_packed, const float* bias, const 
   if (CH != 32 && !mask && use_img() && img::shape_ok(B, H, W, CH))
     return img::conv_up(lo, wu, bias, hi, B, H, W, CH, act, as_stream(stream));
   if (CH == 32 && use_tc("halo") && act != DV_ACT_SIGMOID && W <= 32 && 128 % W == 0)
-    return tc::conv_up_halo(lo, w_packed + kPackFfma + kPackTcSection, bias, mask, hi, B, H, W, act, as_stream(stream));
+    return tc::conv_up_halo(lo, w_packed + kPackFfma + kPackTcSection, bias, mask, hi, B, H, W, act, as_stream(stream),
+                            mask_bits, relu_bits_out);
   if (CH == 32) {
     const int smem = kTaps * 32 * kLoCh * sizeof(float);
     static bool attr_set = false;
@@ -702,6 +739,11 @@ int dv_conv_up(const float* lo, const float* w_packed, const float* bias, const 
     const long long units = (long long)B * H * (W / kUpPos);
     const int grid = grid_for(units, kUpWarps, 2 * kNumSMs);
     conv_up32_kernel<<<grid, kUpWarps * 32, smem, as_stream(stream)>>>(lo, wu, bias, mask, hi, B, H, W, act);
+    if (relu_bits_out) {                                        // (this fallback writes no bits in its epilogue)
+      const int rc = check_launch();
+      if (rc != DV_OK) return rc;
+      return relu_bits(hi, relu_bits_out, (long long)B * 4 * H * W, as_stream(stream));
+    }
   } else {
     const int grid = grid_for((long long)B * H * W, 256, 16 * kNumSMs);
     if (CH == 1) conv_up_small_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(lo, wu, bias, mask, hi, B, H, W, act);

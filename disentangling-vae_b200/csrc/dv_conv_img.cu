@@ -75,7 +75,7 @@ template <int CH, int W>
 __global__ void __launch_bounds__(kThreads, 2)
 img_down_kernel(const float* __restrict__ hi, const float* __restrict__ wd, const float* __restrict__ bias,
                 const float* __restrict__ mask, float* __restrict__ lo, int B, int H, int act,
-                float* __restrict__ colsum_part) {
+                float* __restrict__ colsum_part, const uint32_t* __restrict__ mask_bits, uint32_t* __restrict__ bits_out) {
   constexpr int TR = 16;                       // output rows per tile
   constexpr int PXG = (TR * W) / 64;           // pixels per thread: 8 (W = 32), 4 (W = 16)
   constexpr int CB = W / PXG;                  // pixel groups per row (4)
@@ -102,7 +102,15 @@ img_down_kernel(const float* __restrict__ hi, const float* __restrict__ wd, cons
     const long long p0 = ((long long)b * H + i0 + r_thr) * W + c0;          // first pixel of the group
     // ReLU-backward mask of this thread's 8 channels x PXG pixels as bits, requested BEFORE the FMAs
     uint32_t mb_lo = 0xffffffffu, mb_hi = 0xffffffffu;                      // bit (4*i + e): pixel i, channels 4cg+e / 16+4cg+e
-    if (mask) {
+    if (mask_bits) {                                           // the mask already as one word per pixel (bit c = channel c)
+      mb_lo = 0u; mb_hi = 0u;
+#pragma unroll
+      for (int i = 0; i < PXG; ++i) {
+        const uint32_t mw = __ldg(mask_bits + p0 + i);
+        mb_lo |= ((mw >> (4 * cg)) & 15u) << (4 * i);
+        mb_hi |= ((mw >> (16 + 4 * cg)) & 15u) << (4 * i);
+      }
+    } else if (mask) {
       mb_lo = 0u; mb_hi = 0u;
 #pragma unroll
       for (int i = 0; i < PXG; ++i) {
@@ -161,6 +169,14 @@ img_down_kernel(const float* __restrict__ hi, const float* __restrict__ wd, cons
       float* dst = lo + (p0 + i) * kLoCh + 4 * cg;
       *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
       *reinterpret_cast<float4*>(dst + 16) = make_float4(v[4], v[5], v[6], v[7]);
+      if (bits_out) {                                          // [x > 0] of the stored pixel: the lane quartet holds its 32 channels
+        uint32_t ob = 0u;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) ob |= (v[k] > 0.f ? 1u : 0u) << ((k < 4 ? 0 : 16) + 4 * cg + (k & 3));
+        ob |= __shfl_xor_sync(0xffffffffu, ob, 1);
+        ob |= __shfl_xor_sync(0xffffffffu, ob, 2);
+        if (cg == 0) bits_out[p0 + i] = ob;
+      }
     }
   }
   if (colsum_part) {
@@ -391,12 +407,14 @@ static bool set_smem(K kernel, size_t bytes) {
   return bytes <= 48 * 1024 || cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) == cudaSuccess;
 }
 
-int conv_down(const float* hi, const float* wd, const float* bias, const float* mask, float* lo, int B, int H, int W, int CH,
+int conv_down(const float* hi, const float* wd, const float* bias, const float* mask, const uint32_t* mask_bits, float* lo,
+              uint32_t* bits_out, int B, int H, int W, int CH,
               int act, cudaStream_t st, float* colsum_part, int* nparts, int max_parts) {
   const int tiles = B * (H / 16);
   int grid = tiles < 2 * kNumSMs ? tiles : 2 * kNumSMs;
   if (colsum_part && grid > max_parts) grid = max_parts;
-#define DV_IMG_DOWN(CHV, WV) img_down_kernel<CHV, WV><<<grid, kThreads, 0, st>>>(hi, wd, bias, mask, lo, B, H, act, colsum_part)
+#define DV_IMG_DOWN(CHV, WV) \
+  img_down_kernel<CHV, WV><<<grid, kThreads, 0, st>>>(hi, wd, bias, mask, lo, B, H, act, colsum_part, mask_bits, bits_out)
   if (CH == 1 && W == 32) DV_IMG_DOWN(1, 32);
   else if (CH == 3 && W == 32) DV_IMG_DOWN(3, 32);
   else if (CH == 1 && W == 16) DV_IMG_DOWN(1, 16);

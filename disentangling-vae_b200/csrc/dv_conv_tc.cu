@@ -382,7 +382,8 @@ __device__ __forceinline__ void ts_split_tile(const uint8_t* raw, uint32_t tmem_
 __global__ void __launch_bounds__(kTsThreads, 1)
 conv_down32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                       const float* __restrict__ bias, const float* __restrict__ mask, float* __restrict__ lo,
-                      DownGeom g, int act, float* __restrict__ colsum_part) {
+                      DownGeom g, int act, float* __restrict__ colsum_part,
+                      const uint32_t* __restrict__ mask_bits, uint32_t* __restrict__ bits_out) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* Bs = smem;
@@ -452,6 +453,10 @@ conv_down32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     int acc = 0; uint32_t acc_phase = 0;
     float csum = 0.f;                                         // lane l: running sum of output channel l over this warp's rows
     for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+      const long long p = (long long)tile * 128 + q * 32 + lane;
+      // ReLU-backward mask as one word per pixel (bit c = channel c), requested before the accumulator wait
+      uint32_t mbits = 0xffffffffu;
+      if (mask_bits && p < g.total_px) mbits = __ldg(mask_bits + p);
       mbar_wait(&bars->acc_full[acc], acc_phase);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 128;
@@ -467,10 +472,10 @@ conv_down32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       tmem_ld_wait();
       tc_fence_before_sync();
       mbar_arrive(&bars->acc_empty[acc]);
-      const long long p = (long long)tile * 128 + q * 32 + lane;
       if (p < g.total_px) {
         float* dst = lo + p * 32;
-        const float* mk = mask ? mask + p * 32 : nullptr;
+        const float* mk = (mask && !mask_bits) ? mask + p * 32 : nullptr;
+        uint32_t obits = 0u;
 #pragma unroll
         for (int c4 = 0; c4 < 8; ++c4) {
           float v[4];
@@ -479,7 +484,7 @@ conv_down32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             const int c = c4 * 4 + e;
             float x = (sum[c] + (__uint_as_float(r0[c]) + __uint_as_float(r1[c]))) + bars->bias[c];
             if (act == DV_ACT_RELU) x = fmaxf(x, 0.f);
-            v[e] = x;
+            v[e] = ((mbits >> c) & 1u) ? x : 0.f;
           }
           if (mk) {
             const float4 m4 = ldg4(mk + c4 * 4);
@@ -488,8 +493,12 @@ conv_down32_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
           }
           *reinterpret_cast<float4*>(dst + c4 * 4) = make_float4(v[0], v[1], v[2], v[3]);
 #pragma unroll
-          for (int e = 0; e < 4; ++e) sum[c4 * 4 + e] = v[e];
+          for (int e = 0; e < 4; ++e) {
+            sum[c4 * 4 + e] = v[e];
+            obits |= (v[e] > 0.f ? 1u : 0u) << (c4 * 4 + e);
+          }
         }
+        if (bits_out) bits_out[p] = obits;                     // [x > 0] of the stored pixel: the next backward pass's mask
       } else {
 #pragma unroll
         for (int c = 0; c < 32; ++c) sum[c] = 0.f;
@@ -611,7 +620,7 @@ struct HaloCfg {
 __global__ void __launch_bounds__(kTsThreads, 1)
 conv_up_halo_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                        const float* __restrict__ bias, const float* __restrict__ mask, float* __restrict__ hi_out,
-                       HaloGeom g, int act) {
+                       HaloGeom g, int act, const uint32_t* __restrict__ mask_bits, uint32_t* __restrict__ bits_out) {
   using C = HaloCfg;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -701,7 +710,11 @@ conv_up_halo_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
       // the loads' latency hides behind this tile's MMAs instead of sitting between the TMEM loads and the stores
       // (masked dgrad launches used to be 1.7x slower than the unmasked forward ones).
       uint32_t mbits[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
-      if (mask && valid) {
+      if (mask_bits && valid) {                               // the mask already as one word per pixel: 4 x 4 bytes
+#pragma unroll
+        for (int pidx = 0; pidx < 4; ++pidx)
+          mbits[pidx] = __ldg(mask_bits + (long long)(b * HH + 2 * i + (pidx >> 1)) * WW + 2 * j + (pidx & 1));
+      } else if (mask && valid) {
 #pragma unroll
         for (int pidx = 0; pidx < 4; ++pidx) {
           const float* mk = mask + ((long long)(b * HH + 2 * i + (pidx >> 1)) * WW + 2 * j + (pidx & 1)) * 32;
@@ -729,6 +742,7 @@ conv_up_halo_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
           const long long o = ((long long)(b * HH + 2 * i + ph) * WW + 2 * j + pw) * 32;
           float* dst = hi_out + o;
           const uint32_t bits = mbits[pidx];
+          uint32_t obits = 0u;
 #pragma unroll
           for (int c4 = 0; c4 < 8; ++c4) {
             float v[4];
@@ -737,9 +751,11 @@ conv_up_halo_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
               float x = __uint_as_float(r0[c4 * 4 + e]) + bars->bias[c4 * 4 + e];
               if (act == DV_ACT_RELU) x = fmaxf(x, 0.f);
               v[e] = ((bits >> (c4 * 4 + e)) & 1u) ? x : 0.f;
+              obits |= (v[e] > 0.f ? 1u : 0u) << (c4 * 4 + e);
             }
             *reinterpret_cast<float4*>(dst + c4 * 4) = make_float4(v[0], v[1], v[2], v[3]);
           }
+          if (bits_out) bits_out[o >> 5] = obits;              // [x > 0] of the stored pixel (o = pixel index * 32)
         }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -836,6 +852,37 @@ __global__ void conv_pack_tc_kernel(const float* __restrict__ w, float* __restri
   }
 }
 
+// every conv layer of a network node in ONE launch (blockIdx.y = layer): the CH == 32 layers get the four layouts of
+// conv_pack_tc_kernel at wp + {0 (CUDA-core), 32768 (tcgen05 down), 65536 (tcgen05 up)}, the image-boundary layers
+// (CH in {1,3}) the two layouts of conv_pack_kernel (dv_conv.cu): Wd[tap*CH + c][cl] and Wu[tap][c][cl]
+constexpr int kPackMultiMax = 8;
+struct ConvPackTable {
+  const float* w[kPackMultiMax];
+  float* wp[kPackMultiMax];
+  int CH[kPackMultiMax];
+};
+__global__ void conv_pack_multi_kernel(ConvPackTable tab) {
+  const float* __restrict__ w = tab.w[blockIdx.y];
+  float* __restrict__ wp = tab.wp[blockIdx.y];
+  const int CH = tab.CH[blockIdx.y];
+  const int n = kLoCh * CH * kTaps;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
+    const int tap = idx % kTaps, c = (idx / kTaps) % CH, cl = idx / (kTaps * CH);
+    const float v = w[idx];
+    wp[(tap * CH + c) * kLoCh + cl] = v;
+    if (CH != 32) { wp[n + (tap * CH + c) * kLoCh + cl] = v; continue; }
+    wp[n + (tap * kLoCh + cl) * 32 + c] = v;
+    float* wd = wp + 2 * n;
+    float* wu = wd + kTaps * 64 * 32;
+    const float hi = __uint_as_float(__float_as_uint(v) & kHiMask);
+    const float lo = v - hi;
+    wd[(tap * 64 + cl) * 32 + c] = hi;
+    wd[(tap * 64 + 32 + cl) * 32 + c] = lo;
+    wu[(tap * 64 + c) * 32 + cl] = hi;
+    wu[(tap * 64 + 32 + c) * 32 + cl] = lo;
+  }
+}
+
 // ---- host side ---------------------------------------------------------------------------
 static int use_debug() {
   static int v = -1;
@@ -896,6 +943,17 @@ static bool make_w_tmap(CUtensorMap* m, const float* base) {
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+int pack_multi(int n, const float* const* w, float* const* wp, const int* CH, cudaStream_t st) {
+  for (int base = 0; base < n; base += kPackMultiMax) {
+    ConvPackTable tab = {};
+    const int m = n - base < kPackMultiMax ? n - base : kPackMultiMax;
+    for (int i = 0; i < m; ++i) { tab.w[i] = w[base + i]; tab.wp[i] = wp[base + i]; tab.CH[i] = CH[base + i]; }
+    conv_pack_multi_kernel<<<dim3(16, m), 256, 0, st>>>(tab);
+    const int rc = check_launch();
+    if (rc != DV_OK) return rc;
+  }
+  return DV_OK;
+}
 int pack_tc(const float* w, float* wd, float* wu, float* wf, cudaStream_t st) {
   conv_pack_tc_kernel<<<64, 256, 0, st>>>(w, wd, wu, wf);
   return check_launch();
@@ -905,7 +963,8 @@ int pack_tc(const float* w, float* wd, float* wu, float* wf, cudaStream_t st) {
 // colsum_part != NULL: the kernel also leaves per-CTA channel sums of `lo` in colsum_part[grid][32] and sets
 // *nparts = grid (0 when the selected variant cannot do it: the caller then sums `lo` separately).
 int conv_down32_tc(const float* hi, const float* wd_packed, const float* bias, const float* mask, float* lo,
-                   int B, int H, int W, int act, cudaStream_t st, float* colsum_part, int* nparts) {
+                   int B, int H, int W, int act, cudaStream_t st, float* colsum_part, int* nparts,
+                   const uint32_t* mask_bits, uint32_t* bits_out) {
   if (nparts) *nparts = 0;
   if (W > 128 || 128 % W != 0) return DV_ERR_BAD_SHAPE;
   DownGeom g = {};
@@ -928,7 +987,7 @@ int conv_down32_tc(const float* hi, const float* wd_packed, const float* bias, c
     attr = true;
   }
   const int grid = g.num_tiles < kNumSMs ? g.num_tiles : kNumSMs;
-  conv_down32_ts_kernel<<<grid, kTsThreads, kTsSmemBytes, st>>>(ta, tb, bias, mask, lo, g, act, colsum_part);
+  conv_down32_ts_kernel<<<grid, kTsThreads, kTsSmemBytes, st>>>(ta, tb, bias, mask, lo, g, act, colsum_part, mask_bits, bits_out);
   if (nparts && colsum_part) *nparts = grid;
   return check_launch();
 }
@@ -982,7 +1041,7 @@ int conv_wgrad32_tc(const float* lo, const float* hi, float* ws, int B, int H, i
 
 
 static int launch_up_halo(const float* lo, const float* wu, const float* bias, const float* mask, float* hi,
-                          HaloGeom g, int act, cudaStream_t st) {
+                          HaloGeom g, int act, cudaStream_t st, const uint32_t* mask_bits, uint32_t* bits_out) {
   CUtensorMap ta, tb;
   if (!make_act_tmap(&ta, lo, g.B, g.H, g.W, g.W, g.TR + 2, g.TB, 1)) return DV_ERR_CUDA;
   if (!make_w_tmap(&tb, wu)) return DV_ERR_CUDA;
@@ -995,13 +1054,13 @@ static int launch_up_halo(const float* lo, const float* wu, const float* bias, c
     attr = true;
   }
   const int grid = g.num_tiles < kNumSMs ? g.num_tiles : kNumSMs;
-  conv_up_halo_ts_kernel<<<grid, kTsThreads, HaloCfg::kSmem, st>>>(ta, tb, bias, mask, hi, g, act);
+  conv_up_halo_ts_kernel<<<grid, kTsThreads, HaloCfg::kSmem, st>>>(ta, tb, bias, mask, hi, g, act, mask_bits, bits_out);
   return check_launch();
 }
 
 // hi[B,2H,2W,32] = act(up(lo[B,H,W,32]) + bias) * [mask > 0]
 int conv_up_halo(const float* lo, const float* wu, const float* bias, const float* mask, float* hi,
-                 int B, int H, int W, int act, cudaStream_t st) {
+                 int B, int H, int W, int act, cudaStream_t st, const uint32_t* mask_bits, uint32_t* bits_out) {
   HaloGeom g = {};
   g.B = B; g.H = H; g.W = W; g.pipe = use_pipe(); g.debug = use_debug();
   if (W > 32 || 128 % W != 0) return DV_ERR_BAD_SHAPE;
@@ -1022,7 +1081,7 @@ int conv_up_halo(const float* lo, const float* wu, const float* bias, const floa
   g.box_px = g.TB * (g.TR + 2) * W;
   g.box_bytes = g.box_px * 128;
   if (g.box_bytes > kHaloStageBytes) return DV_ERR_BAD_SHAPE;
-  return launch_up_halo(lo, wu, bias, mask, hi, g, act, st);
+  return launch_up_halo(lo, wu, bias, mask, hi, g, act, st, mask_bits, bits_out);
 }
 
 }  // namespace tc

@@ -27,8 +27,9 @@ SIGNATURES = {
     "dv_launch_count": (LL, []),
     "dv_conv_packed_floats": (SZ, [I]),
     "dv_conv_pack_weights": (I, [P, P, I, P]),
-    "dv_conv_down": (I, [P, P, P, P, P, I, I, I, I, I, I, P, P, P]),
-    "dv_conv_up": (I, [P, P, P, P, P, I, I, I, I, I, I, P]),
+    "dv_conv_pack_multi": (I, [I, P, P, P, P]),
+    "dv_conv_down": (I, [P, P, P, P, P, I, I, I, I, I, I, P, P, P, P, P]),
+    "dv_conv_up": (I, [P, P, P, P, P, I, I, I, I, I, I, P, P, P]),
     "dv_conv_wgrad_workspace_bytes": (SZ, [I, I, I, I]),
     "dv_conv_wgrad": (I, [P, P, P, P, P, SZ, I, I, I, I, I, P]),
     "dv_channel_sum_workspace_bytes": (SZ, []),

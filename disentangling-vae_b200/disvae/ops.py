@@ -76,23 +76,39 @@ def conv_pack(w, CH):
     return wp
 
 
-def conv_down(hi, wp, bias, mask, B, H, W, CH, nchw, act, want_colsum=False):
-    """-> lo, or (lo, channel sums of lo) with want_colsum (summed in the kernel's epilogue)."""
+def conv_pack_multi(weights, chans):
+    """Packed operands of every conv layer of a network node in ONE launch -> list of packed buffers."""
+    import ctypes
+    L = N.lib()
+    n = len(weights)
+    packs = [_new((L.dv_conv_packed_floats(ch),), w) for w, ch in zip(weights, chans)]
+    arr_p = ctypes.c_void_p * n
+    call("dv_conv_pack_multi", n, arr_p(*[w.data_ptr() for w in weights]), arr_p(*[p.data_ptr() for p in packs]),
+         (ctypes.c_int * n)(*chans), stream())
+    return packs
+
+
+def conv_down(hi, wp, bias, mask, B, H, W, CH, nchw, act, want_colsum=False, mask_bits=None, want_bits=False):
+    """-> lo; with want_colsum also the channel sums of lo (summed in the kernel's epilogue); with want_bits also
+    [lo > 0] as one int32 word per pixel (the mask_bits of the backward pass through the ReLU after this layer)."""
     lo = _new((B, H, W, LO_CH), hi)
     cs = ws = None
     if want_colsum:
         cs = _new((LO_CH,), hi)
         ws = _scratch("chansum", N.lib().dv_channel_sum_workspace_bytes(), hi.device)
-    call("dv_conv_down", ptr(hi), ptr(wp), ptr(bias), ptr(mask), ptr(lo), B, H, W, CH, nchw, act, ptr(cs), ptr(ws), stream(),
-         tag="[H=%d,CH=%d]%s" % (H, CH, "+mask" if mask is not None else ""))
-    return (lo, cs) if want_colsum else lo
+    bits = torch.empty((B, H, W), dtype=torch.int32, device=hi.device) if want_bits else None
+    call("dv_conv_down", ptr(hi), ptr(wp), ptr(bias), ptr(mask), ptr(lo), B, H, W, CH, nchw, act, ptr(cs), ptr(ws),
+         ptr(mask_bits), ptr(bits), stream(), tag="[H=%d,CH=%d]%s" % (H, CH, "+mask" if mask is not None else ""))
+    out = (lo,) + ((cs,) if want_colsum else ()) + ((bits,) if want_bits else ())
+    return out if len(out) > 1 else lo
 
 
-def conv_up(lo, wp, bias, mask, B, H, W, CH, nchw, act):
+def conv_up(lo, wp, bias, mask, B, H, W, CH, nchw, act, mask_bits=None, want_bits=False):
     hi = _new((B, CH, 2 * H, 2 * W) if nchw else (B, 2 * H, 2 * W, CH), lo)
-    call("dv_conv_up", ptr(lo), ptr(wp), ptr(bias), ptr(mask), ptr(hi), B, H, W, CH, nchw, act, stream(),
-         tag="[H=%d,CH=%d]%s" % (H, CH, "+mask" if mask is not None else ""))
-    return hi
+    bits = torch.empty((B, 2 * H, 2 * W), dtype=torch.int32, device=lo.device) if want_bits else None
+    call("dv_conv_up", ptr(lo), ptr(wp), ptr(bias), ptr(mask), ptr(hi), B, H, W, CH, nchw, act, ptr(mask_bits), ptr(bits),
+         stream(), tag="[H=%d,CH=%d]%s" % (H, CH, "+mask" if mask is not None else ""))
+    return (hi, bits) if want_bits else hi
 
 
 def conv_wgrad(lo, hi, B, H, W, CH, nchw, want_dbias_lo):
@@ -260,14 +276,18 @@ class EncoderFn(Function):
         # the convolutions below and is joined before the first linear layer
         lane = _WgradLane(x.device)
         lpk = lane.run(lambda: linear_pack_multi([w for w, _ in lins]), *[w for w, _ in lins])
-        acts, packed = [], []
+        acts = []
+        packed = conv_pack_multi([w for w, _ in convs], [C] + [LO_CH] * (n_conv - 1))
         hi, CH, nchw, H = x, C, 1, S // 2
-        for w, b in convs:
-            wp = conv_pack(w, CH)
-            lo = conv_down(hi, wp, b, None, B, H, H, CH, nchw, ACT_RELU)
+        bits = []                    # [act > 0] of every layer but the last, one word per pixel: the dgrad masks
+        for (w, b), wp in zip(convs, packed):
+            if len(acts) < n_conv - 1:
+                lo, bw = conv_down(hi, wp, b, None, B, H, H, CH, nchw, ACT_RELU, want_bits=True)
+                bits.append(bw)
+            else:
+                lo = conv_down(hi, wp, b, None, B, H, H, CH, nchw, ACT_RELU)
             _note("encoder.conv%d" % len(acts), lo)
             acts.append(lo)
-            packed.append(wp)
             hi, CH, nchw, H = lo, LO_CH, 0, H // 2
         flat = flat_transpose(acts[-1].view(B, FLAT), B, to_nhwc=False)          # -> [B, 32*4*4] in NCHW order
         lane.join()
@@ -277,7 +297,7 @@ class EncoderFn(Function):
         _note("encoder.lin1", h1)
         _note("encoder.lin2", h2)
         ctx.n_conv = n_conv
-        ctx.save_for_backward(x, flat, h1, h2, *acts, *packed, *params, *lpk)
+        ctx.save_for_backward(x, flat, h1, h2, *acts, *packed, *bits, *params, *lpk)
         return ml
 
     @staticmethod
@@ -287,7 +307,8 @@ class EncoderFn(Function):
         x, flat, h1, h2 = saved[:4]
         acts = saved[4:4 + n_conv]
         packed = saved[4 + n_conv:4 + 2 * n_conv]
-        params = saved[4 + 2 * n_conv:-3]
+        bits = saved[4 + 2 * n_conv:4 + 3 * n_conv - 1]
+        params = saved[4 + 3 * n_conv - 1:-3]
         lpk = saved[-3:]
         lins = [(params[2 * n_conv + 2 * i], params[2 * n_conv + 2 * i + 1]) for i in range(3)]
         B, C, S, _ = x.shape
@@ -306,7 +327,7 @@ class EncoderFn(Function):
             H = S >> (l + 1)
             if l > 0:
                 dw, db = lane.run(lambda gl=g_lo, a=acts[l - 1], H=H: conv_wgrad(gl, a, B, H, H, LO_CH, 0, True), g_lo, acts[l - 1])
-                g_lo = conv_up(g_lo, packed[l], None, acts[l - 1], B, H, H, LO_CH, 0, ACT_NONE)
+                g_lo = conv_up(g_lo, packed[l], None, acts[l - 1], B, H, H, LO_CH, 0, ACT_NONE, mask_bits=bits[l - 1])
             else:
                 dw, db = lane.run(lambda gl=g_lo, H=H: conv_wgrad(gl, x, B, H, H, C, 1, True), g_lo, x)
                 if ctx.needs_input_grad[0]:
@@ -338,21 +359,24 @@ class DecoderFn(Function):
         _note("decoder.lin2", h2)
         _note("decoder.lin3", h3)
         lo = flat_transpose(h3, B, to_nhwc=True).view(B, 4, 4, LO_CH)
-        acts, packed = [lo], []
+        acts, bits = [lo], []        # bits[t] = [acts[t + 1] > 0], one word per pixel: the mask of convT t+1's input gradient
+        packed = conv_pack_multi([w for w, _ in convTs], [LO_CH] * (n_convT - 1) + [n_chan])
         H = 4
         for t, (w, b) in enumerate(convTs):
             last = (t == n_convT - 1)
             CH = n_chan if last else LO_CH
-            wp = conv_pack(w, CH)
-            packed.append(wp)
-            hi = conv_up(lo, wp, b, None, B, H, H, CH, 1 if last else 0, ACT_SIGMOID if last else ACT_RELU)
-            if not last:
+            wp = packed[t]
+            if last:
+                hi = conv_up(lo, wp, b, None, B, H, H, CH, 1, ACT_SIGMOID)
+            else:
+                hi, bw = conv_up(lo, wp, b, None, B, H, H, CH, 0, ACT_RELU, want_bits=True)
+                bits.append(bw)
                 _note("decoder.convT%d" % t, hi)
                 acts.append(hi)
             lo, H = hi, 2 * H
         recon = lo
         ctx.n_convT, ctx.n_chan = n_convT, n_chan
-        ctx.save_for_backward(z, h1, h2, recon, *acts, *packed, *params, *lpk)
+        ctx.save_for_backward(z, h1, h2, recon, *acts, *packed, *bits, *params, *lpk)
         return recon
 
     @staticmethod
@@ -362,7 +386,8 @@ class DecoderFn(Function):
         z, h1, h2, recon = saved[:4]
         acts = saved[4:4 + n_convT]                 # acts[t] = input of convT t (NHWC)
         packed = saved[4 + n_convT:4 + 2 * n_convT]
-        params = saved[4 + 2 * n_convT:-3]
+        bits = saved[4 + 2 * n_convT:4 + 3 * n_convT - 1]
+        params = saved[4 + 3 * n_convT - 1:-3]
         lpk = saved[-3:]
         lins = [(params[2 * i], params[2 * i + 1]) for i in range(3)]
         B = z.shape[0]
@@ -381,7 +406,8 @@ class DecoderFn(Function):
             # input gradient, masked by acts[t] > 0; for t > 0 it is the output gradient of convT t-1, whose bias
             # gradient (its sum over pixels) comes out of the same kernel's epilogue
             if t > 0:
-                g_hi, db = conv_down(g_hi, packed[t], None, acts[t], B, H, H, CH, nchw, ACT_NONE, want_colsum=True)
+                g_hi, db = conv_down(g_hi, packed[t], None, acts[t], B, H, H, CH, nchw, ACT_NONE, want_colsum=True,
+                                     mask_bits=bits[t - 1])
             else:
                 g_hi = conv_down(g_hi, packed[t], None, acts[t], B, H, H, CH, nchw, ACT_NONE)
         g3 = flat_transpose(g_hi.view(B, FLAT), B, to_nhwc=False)                  # grad of lin3 pre-activation

@@ -113,9 +113,11 @@ class Trainer():
             return False
         if hasattr(lf, "call_optimize"):
             # FactorVAE: both backward passes and both Adam steps fit one graph in a single process; under data
-            # parallelism the two gradient averages sit between the backward passes and the optimizer steps: eager
-            if is_distributed() or getattr(lf, "_perm_queue", None):
+            # parallelism the graph ends after the second backward pass (gradient average + both Adam steps follow it)
+            if getattr(lf, "_perm_queue", None):
                 return False
+            if is_distributed() and self._grad_sync_d is None:
+                return False                                  # the discriminators are broadcast by the first eager step
             if lf._fused_d is None:
                 lf._fused_d = FusedAdam(lf.optimizer_d) if FusedAdam.supports(lf.optimizer_d) else False
             if not lf._fused_d:
@@ -149,8 +151,9 @@ class Trainer():
             # Data parallel over NCCL: the gradient gather, the all-reduce and the Adam launch can live INSIDE the graph
             # (NCCL collectives are capturable): no per-step launch latency for the three-kernel tail.  Opt-in
             # (DISVAE_GRAPH_NCCL=1) -- validated by tests/ddp_worker.py on real NCCL ranks; gloo cannot be captured.
-            import torch.distributed as dist
-            nccl_in_graph = (ddp and os.environ.get("DISVAE_GRAPH_NCCL", "0") == "1" and dist.get_backend() == "nccl")
+            import torch.distributed as tdist
+            nccl_in_graph = (ddp and not factor and os.environ.get("DISVAE_GRAPH_NCCL", "0") == "1"
+                             and tdist.get_backend() == "nccl")
             flat_buf = None
             if nccl_in_graph:
                 params_all = [p for p in self.model.parameters() if p.requires_grad]
@@ -160,9 +163,12 @@ class Trainer():
                     with torch.no_grad():
                         self.model(static_x)                      # the discarded full-batch forward of training.py:153:
                                                                   # kept for its noise draw (same stream as the eager path)
-                    loss = self.loss_f.call_optimize(static_x, self.model, _StepProxy(self.optimizer, self._optimizer_step), None)
-                    self._fused.host_steps -= 1                   # capture executed nothing
-                    self.loss_f._fused_d.host_steps -= 1
+                    if ddp:                                       # both backward passes; the optimizers step after the average
+                        loss = self.loss_f.call_optimize(static_x, self.model, self.optimizer, None, step_optimizers=False)
+                    else:
+                        loss = self.loss_f.call_optimize(static_x, self.model, _StepProxy(self.optimizer, self._optimizer_step), None)
+                        self._fused.host_steps -= 1               # capture executed nothing
+                        self.loss_f._fused_d.host_steps -= 1
                 else:
                     recon, dist, z = self.model(static_x)
                     loss = self.loss_f(static_x, recon, dist, True, None, latent_sample=z)
@@ -174,18 +180,20 @@ class Trainer():
                     elif nccl_in_graph:
                         live = [p for p in params_all if p.grad is not None]
                         torch.cat([p.grad.view(-1) for p in live], out=flat_buf[:sum(p.numel() for p in live)])
-                        dist.all_reduce(flat_buf, op=dist.ReduceOp.SUM)
+                        tdist.all_reduce(flat_buf, op=tdist.ReduceOp.SUM)
                         off = 0
                         for p in live:
                             p.grad = flat_buf[off:off + p.numel()].view_as(p)
                             off += p.numel()
-                        self._fused.step(grad_scale=1.0 / dist.get_world_size())
+                        self._fused.step(grad_scale=1.0 / tdist.get_world_size())
                         self._fused.host_steps -= 1
                 static_loss = loss.detach()
             self.loss_f.n_train_steps = steps_before
             flat = None
             if ddp and not nccl_in_graph:
                 params = [p for p in self.model.parameters() if p.grad is not None]
+                if factor:                                        # one flat buffer (one all-reduce) for both networks
+                    params += [p for p in self.loss_f.discriminator.parameters() if p.grad is not None]
                 static_grads = [p.grad for p in params]           # written by every replay
                 flat_buf = torch.zeros(sum(t.numel() for t in static_grads), dtype=torch.float32, device=self.device)
                 off, views = 0, []
@@ -207,6 +215,9 @@ class Trainer():
                 p.grad = v
             self._fused.step(grad_scale=1.0 / dist.get_world_size())
             self._fused.host_steps -= 1
+            if hasattr(self.loss_f, "call_optimize"):
+                self.loss_f._fused_d.step(grad_scale=1.0 / dist.get_world_size())
+                self.loss_f._fused_d.host_steps -= 1
         self.loss_f.n_train_steps += 1
         self._fused.host_steps += 1
         if getattr(self.loss_f, "_fused_d", None):

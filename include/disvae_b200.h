@@ -72,17 +72,28 @@ long long dv_launch_count(void);
  */
 size_t dv_conv_packed_floats(int CH);                         /* size of w_packed in floats */
 int dv_conv_pack_weights(const float* w, float* w_packed, int CH, void* stream);
+/* the same for n layers in ONE launch: w[i], w_packed[i] (dv_conv_packed_floats(CH[i]) floats each) and CH are HOST
+ * arrays of device pointers / channel counts (the conv layers of an encoder or decoder node, whose weights only
+ * change in the optimizer step). */
+int dv_conv_pack_multi(int n, const void* const* w, void* const* w_packed, const int* CH, void* stream);
 /* lo = act(down(hi) + bias) * [mask>0];  bias may be NULL.  act in {NONE, RELU}.
  * colsum_out (optional, [32]): sum of the stored `lo` over all pixels, accumulated in the kernel's
  * epilogue.  In the backward pass `lo` is the gradient reaching the previous ConvTranspose2d's
  * output, so this IS that layer's bias gradient (no extra pass over the tensor).
- * colsum_workspace: dv_channel_sum_workspace_bytes() bytes, required with colsum_out. */
+ * colsum_workspace: dv_channel_sum_workspace_bytes() bytes, required with colsum_out.
+ * ReLU masks as bits (both optional, 32-channel NHWC outputs only, one 32-bit word per OUTPUT pixel, bit c =
+ * channel c):  relu_bits_out receives [out > 0] of the stored tensor from the same epilogue -- kept by the
+ * caller, it is the mask of the backward pass through the ReLU that follows this layer;  mask_bits is that
+ * word form of `mask` (which must be passed as well: the CUDA-core fallbacks read the floats): the backward
+ * epilogue then reads 4 bytes per pixel instead of 128 (autograd's threshold_backward, fused and compressed). */
 int dv_conv_down(const float* hi, const float* w_packed, const float* bias, const float* mask,
                  float* lo, int B, int H, int W, int CH, int hi_nchw, int act, float* colsum_out,
-                 void* colsum_workspace, void* stream);
-/* hi = act(up(lo) + bias) * [mask>0];  bias[CH] may be NULL.  act in {NONE, RELU, SIGMOID}. */
+                 void* colsum_workspace, const unsigned* mask_bits, unsigned* relu_bits_out, void* stream);
+/* hi = act(up(lo) + bias) * [mask>0];  bias[CH] may be NULL.  act in {NONE, RELU, SIGMOID}.
+ * mask_bits / relu_bits_out as above (CH == 32 only). */
 int dv_conv_up(const float* lo, const float* w_packed, const float* bias, const float* mask,
-               float* hi, int B, int H, int W, int CH, int hi_nchw, int act, void* stream);
+               float* hi, int B, int H, int W, int CH, int hi_nchw, int act, const unsigned* mask_bits,
+               unsigned* relu_bits_out, void* stream);
 /* dw[32][CH][4][4] = sum_pixels lo (x) patch(hi);  dbias_lo[32] (optional) = sum_pixels lo.
  * Deterministic split-K: partials go to `workspace`, reduced in a fixed order. */
 size_t dv_conv_wgrad_workspace_bytes(int B, int H, int W, int CH);

@@ -23,19 +23,29 @@ torch.cuda.synchronize()
 if which != "both":
     print("sanity_ts: %s completed" % which)
     sys.exit(0)
-if os.environ.get("SANITY_TIME") == "1":          # timing of both kernels at the bench shape (B = 1024, H = 16)
+if os.environ.get("SANITY_TIME") == "1":          # timing of both kernels at the bench shapes (B = 1024)
     Bt = 1024
-    xt = torch.randn(Bt, 2 * H, 2 * H, 32, device=d); lt = torch.randn(Bt, H, H, 32, device=d)
-    for name, fn in (("down", lambda: ops.conv_down(xt, wp, None, None, Bt, H, H, 32, 0, 1)),
-                     ("up", lambda: ops.conv_up(lt, wp, None, None, Bt, H, H, 32, 0, 1))):
-        for _ in range(3):
-            fn()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(20):
-            fn()
-        e1.record(); torch.cuda.synchronize()
-        print("sanity_ts timing: %s %.1f us" % (name, e0.elapsed_time(e1) / 20 * 1e3))
+    for Ht in (16, 8, 4):
+        xt = torch.randn(Bt, 2 * Ht, 2 * Ht, 32, device=d); lt = torch.randn(Bt, Ht, Ht, 32, device=d)
+        mlo = torch.randn(Bt, Ht, Ht, 32, device=d); mhi = torch.randn(Bt, 2 * Ht, 2 * Ht, 32, device=d)
+        words = lambda t: torch.where((w := ((t > 0).long() << torch.arange(32, device=d)).sum(-1)) >= 2 ** 31, w - 2 ** 32, w).int()
+        blo, bhi = words(mlo), words(mhi)
+        for name, fn in (("down", lambda: ops.conv_down(xt, wp, None, None, Bt, Ht, Ht, 32, 0, 1)),
+                         ("down+bits_out", lambda: ops.conv_down(xt, wp, None, None, Bt, Ht, Ht, 32, 0, 1, want_bits=True)),
+                         ("down+mask", lambda: ops.conv_down(xt, wp, None, mlo, Bt, Ht, Ht, 32, 0, 0)),
+                         ("down+mask_bits", lambda: ops.conv_down(xt, wp, None, mlo, Bt, Ht, Ht, 32, 0, 0, mask_bits=blo)),
+                         ("up", lambda: ops.conv_up(lt, wp, None, None, Bt, Ht, Ht, 32, 0, 1)),
+                         ("up+bits_out", lambda: ops.conv_up(lt, wp, None, None, Bt, Ht, Ht, 32, 0, 1, want_bits=True)),
+                         ("up+mask", lambda: ops.conv_up(lt, wp, None, mhi, Bt, Ht, Ht, 32, 0, 0)),
+                         ("up+mask_bits", lambda: ops.conv_up(lt, wp, None, mhi, Bt, Ht, Ht, 32, 0, 0, mask_bits=bhi))):
+            for _ in range(3):
+                fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(20):
+                fn()
+            e1.record(); torch.cuda.synchronize()
+            print("sanity_ts timing: H=%d %s %.1f us" % (Ht, name, e0.elapsed_time(e1) / 20 * 1e3), flush=True)
 ref_d = torch.relu(F.conv2d(x.double(), w.double(), None, stride=2, padding=1))
 ref_u = torch.relu(F.conv_transpose2d(lo.double(), w.double(), None, stride=2, padding=1))
 ed = ((got_d.cpu().permute(0, 3, 1, 2).double() - ref_d).abs().max() / ref_d.abs().max()).item()

@@ -44,6 +44,12 @@ def ops():
     return _ops
 
 
+def relu_words(t):
+    """[t > 0] of a [..., 32] tensor as one int32 word per pixel (bit c = channel c)."""
+    w = ((t > 0).long() << torch.arange(32, device=t.device)).sum(-1)
+    return torch.where(w >= 2 ** 31, w - 2 ** 32, w).int()
+
+
 CONV_CASES = [  # (B, H(lo), CH)
     (3, 16, 1), (2, 32, 3), (5, 16, 32), (4, 8, 32), (7, 4, 32), (3, 2 * 2, 32), (2, 32, 1), (1, 16, 3),
     (170, 16, 32),      # 340 tiles of 128 pixels: several tiles per persistent CTA (pipeline phase wrap-around)
@@ -79,6 +85,13 @@ def test_conv_down_matches_conv2d(ops, B, H, CH, act):
     assert_close(cs.cpu(), ref2.double().sum((0, 2, 3)).float(), tol=2e-5, what="down+mask column sums")
     _, cs2 = ops.conv_down(hi, wp, None, nhwc(mask).to(dev()), B, H, H, CH, int(CH < 32), 0, want_colsum=True)
     assert torch.equal(cs, cs2)                                # fixed reduction order
+    # ReLU masks as one word per pixel: produced by the forward epilogue, consumed instead of the 128-byte float rows
+    lo4, bits = ops.conv_down(hi, wp, b.to(dev()), None, B, H, H, CH, int(CH < 32), act, want_bits=True)
+    assert torch.equal(lo4, lo)
+    assert torch.equal(bits, relu_words(lo4))
+    mbits = relu_words(nhwc(mask).to(dev()))
+    lo5, cs5 = ops.conv_down(hi, wp, None, nhwc(mask).to(dev()), B, H, H, CH, int(CH < 32), 0, want_colsum=True, mask_bits=mbits)
+    assert torch.equal(lo5, lo2) and torch.equal(cs5, cs)
 
 
 @pytest.mark.parametrize("B,H,CH", CONV_CASES)
@@ -99,6 +112,12 @@ def test_conv_up_matches_conv_transpose2d(ops, B, H, CH, act):
         hi2 = ops.conv_up(nhwc(lo).to(dev()), wp, None, nhwc(mask).to(dev()), B, H, H, CH, 0, 0)
         ref2 = F.conv_transpose2d(lo, w, None, stride=2, padding=1) * (mask > 0)
         assert_close(nchw(hi2.cpu()), ref2, what="up+mask")
+        hi3 = ops.conv_up(nhwc(lo).to(dev()), wp, None, nhwc(mask).to(dev()), B, H, H, CH, 0, 0,
+                          mask_bits=relu_words(nhwc(mask).to(dev())))
+        assert torch.equal(hi3, hi2)
+        if act != 2:
+            hi4, bits = ops.conv_up(nhwc(lo).to(dev()), wp, b.to(dev()), None, B, H, H, CH, 0, act, want_bits=True)
+            assert torch.equal(hi4, hi) and torch.equal(bits, relu_words(hi4))
 
 
 @pytest.mark.parametrize("B,H,CH", CONV_CASES + [(64, 16, 32), (33, 32, 3)])
@@ -591,3 +610,12 @@ def test_linear_prepacked_equals_per_call_pack(ops):
         assert torch.equal(ops.linear_fwd(x, w, b, 1, packed=pk), ops.linear_fwd(x, w, b, 1))
         assert torch.equal(ops.linear_dgrad(g, w, prev, 1, packed=pk), ops.linear_dgrad(g, w, prev, 1))
         assert torch.equal(ops.linear_dgrad(g, w, None, 0, packed=pk), ops.linear_dgrad(g, w, None, 0))
+
+
+def test_conv_pack_multi_equals_per_layer_pack(ops):
+    """dv_conv_pack_multi (all conv layers of a node, one launch) writes exactly the buffers of dv_conv_pack_weights."""
+    torch.manual_seed(9)
+    chans = [1, 32, 32, 32, 3, 32, 32, 32, 32, 1]        # > 8 layers: the library splits the table
+    ws = [(torch.randn(32, ch, 4, 4) * 0.1).to(dev()) for ch in chans]
+    for pk, w, ch in zip(ops.conv_pack_multi(ws, chans), ws, chans):
+        assert torch.equal(pk, ops.conv_pack(w, ch)), ch
