@@ -148,16 +148,6 @@ class Trainer():
             steps_before = self.loss_f.n_train_steps
             launches_before = _native.lib().dv_launch_count()
             factor = hasattr(self.loss_f, "call_optimize")
-            # Data parallel over NCCL: the gradient gather, the all-reduce and the Adam launch can live INSIDE the graph
-            # (NCCL collectives are capturable): no per-step launch latency for the three-kernel tail.  Opt-in
-            # (DISVAE_GRAPH_NCCL=1) -- validated by tests/ddp_worker.py on real NCCL ranks; gloo cannot be captured.
-            import torch.distributed as tdist
-            nccl_in_graph = (ddp and not factor and os.environ.get("DISVAE_GRAPH_NCCL", "0") == "1"
-                             and tdist.get_backend() == "nccl")
-            flat_buf = None
-            if nccl_in_graph:
-                params_all = [p for p in self.model.parameters() if p.requires_grad]
-                flat_buf = torch.zeros(sum(p.numel() for p in params_all), dtype=torch.float32, device=self.device)
             with torch.cuda.graph(g):
                 if factor:
                     with torch.no_grad():
@@ -170,27 +160,17 @@ class Trainer():
                         self._fused.host_steps -= 1               # capture executed nothing
                         self.loss_f._fused_d.host_steps -= 1
                 else:
-                    recon, dist, z = self.model(static_x)
-                    loss = self.loss_f(static_x, recon, dist, True, None, latent_sample=z)
+                    recon, latent_dist, z = self.model(static_x)
+                    loss = self.loss_f(static_x, recon, latent_dist, True, None, latent_sample=z)
                     self.optimizer.zero_grad(set_to_none=True)
                     loss.backward()
                     if not ddp:
                         self._fused.step()
                         self._fused.host_steps -= 1               # capture executed nothing
-                    elif nccl_in_graph:
-                        live = [p for p in params_all if p.grad is not None]
-                        torch.cat([p.grad.view(-1) for p in live], out=flat_buf[:sum(p.numel() for p in live)])
-                        tdist.all_reduce(flat_buf, op=tdist.ReduceOp.SUM)
-                        off = 0
-                        for p in live:
-                            p.grad = flat_buf[off:off + p.numel()].view_as(p)
-                            off += p.numel()
-                        self._fused.step(grad_scale=1.0 / tdist.get_world_size())
-                        self._fused.host_steps -= 1
                 static_loss = loss.detach()
             self.loss_f.n_train_steps = steps_before
             flat = None
-            if ddp and not nccl_in_graph:
+            if ddp:
                 params = [p for p in self.model.parameters() if p.grad is not None]
                 if factor:                                        # one flat buffer (one all-reduce) for both networks
                     params += [p for p in self.loss_f.discriminator.parameters() if p.grad is not None]

@@ -2,7 +2,7 @@
 # Round-2 multi-GPU driver (gpurun --gpus NG): data-parallel parity on real NCCL ranks (tests/ddp_worker.py: btcvae,
 # FactorVAE, global-batch btcvae) and bench.py -- c2 weak scaling (ddp_parity block included) plus the two configs BASELINE
 # assigns to 8 GPUs in strong scaling (c4: 512 -> 512/N per GPU, c5: 2048 -> 2048/N per GPU).  Outputs -> gpurun_out/.
-# Env: NG, DDP=0 (skip the parity workers), JOBS="c2 weak;c5 strong", STEPS, EXTRA_ENV="DISVAE_GRAPH_NCCL=1" (second c2 line).
+# Env: NG, DDP=0 (skip the parity workers), JOBS="c2 weak;c5 strong", STEPS, EXTRA_ENV="VAR=val" (second c2 line under that environment).
 set -u
 NG=${NG:-2}
 mkdir -p gpurun_out
