@@ -8,7 +8,7 @@ cap() {  # name regex skip
     -o gpurun_out/r02_$1 python scripts/prof_step.py > gpurun_out/ncu_$1.log 2>&1; echo "ncu $1 exit $?"
 }
 for k in ${KERNELS:-img_down_fwd:img_down_kernel:0 img_down_masked:img_down_kernel:1 img_up:img_up_kernel:0 img_wgrad:img_wgrad_kernel:0 \
-         btcvae_fwd4:btcvae_fwd4_kernel:0 wgrad32_h16:conv_wgrad32_tc_kernel:0 down32_h16:conv_down32_ts_kernel:0 up_halo32_h16:conv_up_halo_ts_kernel:2}; do
+         btcvae_fwd4:btcvae_fwd4_kernel:0 wgrad32_h16:conv_wgrad32_ts_kernel:0 down32_h16:conv_down32_ts_kernel:0 up_halo32_h16:conv_up_halo_ts_kernel:2}; do
   IFS=: read name regex skip <<< "$k"
   cap $name $regex $skip
 done
