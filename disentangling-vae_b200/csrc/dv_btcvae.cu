@@ -754,8 +754,7 @@ int dv_btcvae_fwd_rows(const float* z, const float* mu, const float* logvar, int
   int rc;
   {
     // single-launch cluster path (D <= 16): columns split over the 4 CTAs of a cluster, rows over the clusters
-    static int v4 = -1;
-    if (v4 < 0) { const char* e = getenv("DV_BTCVAE_V4"); v4 = (e && e[0] == '0') ? 0 : 1; }
+    static const int v4 = env_switch("DV_BTCVAE_V4", 1);
     const int dc = D == 10 ? 10 : 16;
     const int max_clusters = 33;                               // cluster size 4 packs 132 of the 148 SMs
     int R = ((B + max_clusters - 1) / max_clusters + kRows - 1) / kRows * kRows;
@@ -778,8 +777,7 @@ int dv_btcvae_fwd_rows(const float* z, const float* mu, const float* logvar, int
       attr[0].val.clusterDim.x = kF4Clus; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr; cfg.numAttrs = 1;
       cudaError_t err = cudaSuccess;
-      static int timing4 = -1;
-      if (timing4 < 0) { const char* e = getenv("DV_BTCVAE_TIMING"); timing4 = (e && e[0] == '1') ? 1 : 0; }
+      static const int timing4 = [] { const char* e = getenv("DV_BTCVAE_TIMING"); return (e && e[0] == '1') ? 1 : 0; }();
       float* dbg = timing4 ? blockpart + 4 * (nclus * kF4Clus) + 16 : nullptr;   // marks at dbg[0..5], per-block timers from dbg[16]
 #define DV_F4_CALL(DC, EXACT, RPT)                                                                                             \
   do {                                                                                                                         \

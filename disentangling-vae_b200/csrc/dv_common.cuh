@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include "disvae_b200.h"
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
@@ -25,6 +26,17 @@ inline int check_launch() {
   return DV_OK;
 }
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// Environment toggles exist for A/B measurements only.  Each one is read ONCE per process through a C++11 local static
+// (`static const int v = env_switch(...)`: initialisation is thread-safe), so the entry points stay re-entrant.
+inline int env_switch(const char* name, int dflt) {          // "0..." -> 0, anything else set -> 1, unset -> dflt
+  const char* e = getenv(name);
+  return e ? (e[0] == '0' ? 0 : 1) : dflt;
+}
+inline int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
 
 __device__ __forceinline__ float4 ldg4(const float* p) {
   return __ldg(reinterpret_cast<const float4*>(p));

@@ -595,18 +595,12 @@ constexpr int kPackTcSection = kTaps * 64 * 32;
 // DV_TC_DISABLE=down,up,wgrad switches individual tensor-core kernels off.
 // DV_IMG=0 switches the dv_conv_img.cu kernels off (the image-boundary layers then run on the CUDA-core fallbacks).
 static bool use_img() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("DV_IMG"); v = (e && e[0] == '0') ? 0 : 1; }
+  static const int v = env_switch("DV_IMG", 1);
   return v == 1;
 }
 static bool use_tc(const char* which = nullptr) {
-  static int v = -1;
-  static const char* dis = nullptr;
-  if (v < 0) {
-    const char* e = getenv("DV_CONV_IMPL");
-    v = (e && e[0] == 'f') ? 0 : 1;
-    dis = getenv("DV_TC_DISABLE");
-  }
+  static const int v = [] { const char* e = getenv("DV_CONV_IMPL"); return (e && e[0] == 'f') ? 0 : 1; }();
+  static const char* const dis = getenv("DV_TC_DISABLE");
   if (v != 1) return false;
   return !(which && dis && strstr(dis, which));
 }
@@ -694,8 +688,7 @@ int dv_conv_down(const float* hi, const float* w_packed, const float* bias, cons
   if (colsum_out && !colsum_workspace) return DV_ERR_WORKSPACE;
   cudaStream_t st = as_stream(stream);
   float* part = colsum_out ? reinterpret_cast<float*>(colsum_workspace) : nullptr;
-  static int fuse = -1;
-  if (fuse < 0) { const char* e = getenv("DV_FUSE_COLSUM"); fuse = (e && e[0] == '0') ? 0 : 1; }
+  static const int fuse = env_switch("DV_FUSE_COLSUM", 1);
   int nparts = 0;
   bool bits_done = true;
   int rc = conv_down_impl(hi, w_packed, bias, mask, lo, B, H, W, CH, act, st, fuse ? part : nullptr, &nparts, mask_bits,

@@ -885,18 +885,15 @@ __global__ void conv_pack_multi_kernel(ConvPackTable tab) {
 
 // ---- host side ---------------------------------------------------------------------------
 static int use_debug() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("DV_TC_DEBUG"); v = e ? atoi(e) : 0; }
+  static const int v = env_int("DV_TC_DEBUG", 0);
   return v;
 }
 static int use_pipe() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("DV_TC_PIPE"); v = (e && e[0] == '0') ? 0 : 1; }
+  static const int v = env_switch("DV_TC_PIPE", 1);
   return v;
 }
 static int use_prefetch() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("DV_TC_PREFETCH"); v = (e && e[0] == '0') ? 0 : 1; }
+  static const int v = env_switch("DV_TC_PREFETCH", 1);
   return v;
 }
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -1020,8 +1017,7 @@ int conv_wgrad32_tc(const float* lo, const float* hi, float* ws, int B, int H, i
   g.num_tiles = (int)(((long long)B * H * W + 127) / 128);
   // (tile group, kernel-row group) decomposition: big layers keep all four kernel rows in one CTA (one pass over the
   // tiles); small layers spread the rows over blockIdx.y so that every CTA still streams >= 8 tiles
-  static int split_rows = -1;
-  if (split_rows < 0) { const char* e = getenv("DV_WG_PAIRSPLIT"); split_rows = (e && e[0] == '0') ? 0 : 1; }
+  static const int split_rows = env_switch("DV_WG_PAIRSPLIT", 1);
   int gpc = 4, grid = 1;
   for (;; gpc >>= 1) {
     const int gmax = kNumSMs / (4 / gpc);

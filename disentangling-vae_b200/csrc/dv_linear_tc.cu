@@ -565,11 +565,7 @@ linear_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_
 }
 
 static bool enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("DV_LINEAR_IMPL");
-    v = (e && strcmp(e, "ffma") == 0) ? 0 : 1;
-  }
+  static const int v = [] { const char* e = getenv("DV_LINEAR_IMPL"); return (e && strcmp(e, "ffma") == 0) ? 0 : 1; }();
   return v == 1;
 }
 // the tensor-core path needs 16-byte pitched activation rows for TMA: K % 4 == 0 (fwd) / N % 4 == 0 (dgrad)
