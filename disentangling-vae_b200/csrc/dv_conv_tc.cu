@@ -613,7 +613,8 @@ struct HaloBarriers {
 struct HaloCfg {
   // one 64-row (hi|lo) weight tile per tap, one 32-column accumulator per output phase
   static constexpr int kBAll = kTaps * kBTap;
-  static constexpr int kSmem = kBAll + kHaloStages * kHaloStageBytes + 1024 + 512;
+  static constexpr int kEpiBytes = 4 * 4096;                 // per epilogue warp: 32 pixel rows of 128 B (store transposition)
+  static constexpr int kSmem = kBAll + kHaloStages * kHaloStageBytes + kEpiBytes + 1024 + 512;
   static constexpr int kAccPerPhase = 32;
 };
 
@@ -626,7 +627,8 @@ conv_up_halo_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* Bs = smem;
   uint8_t* Raw = smem + C::kBAll;
-  HaloBarriers* bars = reinterpret_cast<HaloBarriers*>(Raw + kHaloStages * kHaloStageBytes);
+  uint8_t* Epi = Raw + kHaloStages * kHaloStageBytes;
+  HaloBarriers* bars = reinterpret_cast<HaloBarriers*>(Epi + C::kEpiBytes);
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform role index
 
   if (threadIdx.x == 0) {
@@ -728,6 +730,8 @@ conv_up_halo_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
           mbits[pidx] = bits;
         }
       }
+      const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+      const uint32_t epi = smem_u32(Epi) + q * 4096;
       mbar_wait(&bars->acc_full[acc], acc_phase);
       tc_fence_after_sync();
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 128;
@@ -737,26 +741,35 @@ conv_up_halo_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         tmem_ld_32x32b_x32(tbase + pidx * 32, r0);
         tmem_ld_wait();
         if (pidx == 3) { tc_fence_before_sync(); mbar_arrive(&bars->acc_empty[acc]); }
-        if (valid) {
-          const int ph = pidx >> 1, pw = pidx & 1;
-          const long long o = ((long long)(b * HH + 2 * i + ph) * WW + 2 * j + pw) * 32;
-          float* dst = hi_out + o;
-          const uint32_t bits = mbits[pidx];
-          uint32_t obits = 0u;
+        // bias / activation / mask in registers (lane = lo pixel), then the pixel's 128-byte line goes through this warp's
+        // shared-memory scratch so that EIGHT lanes store one whole line (four full lines per STG.128 instead of 32 partial
+        // ones: the uncoalesced stores kept L1/TEX 83 % busy, r02 ncu)
+        const int ph = pidx >> 1, pw = pidx & 1;
+        const int opix = valid ? (b * HH + 2 * i + ph) * WW + 2 * j + pw : 0;
+        const uint32_t bits = mbits[pidx];
+        uint32_t obits = 0u;
 #pragma unroll
-          for (int c4 = 0; c4 < 8; ++c4) {
-            float v[4];
+        for (int c4 = 0; c4 < 8; ++c4) {
+          float v[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float x = __uint_as_float(r0[c4 * 4 + e]) + bars->bias[c4 * 4 + e];
-              if (act == DV_ACT_RELU) x = fmaxf(x, 0.f);
-              v[e] = ((bits >> (c4 * 4 + e)) & 1u) ? x : 0.f;
-              obits |= (v[e] > 0.f ? 1u : 0u) << (c4 * 4 + e);
-            }
-            *reinterpret_cast<float4*>(dst + c4 * 4) = make_float4(v[0], v[1], v[2], v[3]);
+          for (int e = 0; e < 4; ++e) {
+            float x = __uint_as_float(r0[c4 * 4 + e]) + bars->bias[c4 * 4 + e];
+            if (act == DV_ACT_RELU) x = fmaxf(x, 0.f);
+            v[e] = ((bits >> (c4 * 4 + e)) & 1u) ? x : 0.f;
+            obits |= (v[e] > 0.f ? 1u : 0u) << (c4 * 4 + e);
           }
-          if (bits_out) bits_out[o >> 5] = obits;              // [x > 0] of the stored pixel (o = pixel index * 32)
+          sts128(epi + lane * 128 + ((c4 ^ (lane & 7)) << 4), make_float4(v[0], v[1], v[2], v[3]));
         }
+        if (bits_out && valid) bits_out[opix] = obits;         // [x > 0] of the stored pixel
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int pl = 4 * k + (lane >> 3), ch = lane & 7;   // lane -> (pixel of lane pl, 16-byte chunk ch)
+          const float4 t = lds128f(epi + pl * 128 + ((ch ^ (pl & 7)) << 4));
+          const int op = __shfl_sync(0xffffffffu, opix, pl);
+          if ((vmask >> pl) & 1u) *reinterpret_cast<float4*>(hi_out + (long long)op * 32 + ch * 4) = t;
+        }
+        __syncwarp();
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }

@@ -65,6 +65,16 @@ __device__ __forceinline__ uint32_t lds32(uint32_t smem_addr) {
   return v;
 }
 
+// 16-byte shared-memory store / load by 32-bit shared address
+__device__ __forceinline__ void sts128(uint32_t smem_addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(smem_addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 lds128f(uint32_t smem_addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_addr) : "memory");
+  return v;
+}
+
 // ---- proxy / tcgen05 fences -----------------------------------------------------------
 __device__ __forceinline__ void fence_proxy_async_smem() {   // generic-proxy smem writes -> async proxy (MMA/TMA)
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

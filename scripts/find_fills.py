@@ -5,7 +5,9 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "disentangling-v
 import bench
 from torch.profiler import profile, ProfilerActivity
 dev = torch.device("cuda", 0)
-trainer, (loss_name, img, B, z, n_data, lr) = bench.build_job(os.environ.get("WORKLOAD", "c2"), dev)
+wl = os.environ.get("WORKLOAD", "c2")
+trainer = bench.build_job(wl, dev)
+_, img, B, *_ = bench.WORKLOADS[wl]
 trainer.use_cuda_graph = False
 x = torch.rand(B, *img, device=dev)
 for i in range(3):
