@@ -187,28 +187,41 @@ class FactorKLoss(BaseLoss):
         recon_batch, latent_dist, latent_sample1 = model(data1, eps=eps1)
         out = self._rec_kl_vec(data1, recon_batch, latent_dist)
         rec_loss, kl_loss, kl_dims = out[0], out[1], out[2:]
-        d_z = self.discriminator(latent_sample1)
-        tc_loss = ops.FactorTcFn.apply(d_z)                      # mean(d_z[:,0] - d_z[:,1])
         anneal_reg = linear_annealing(0, 1, self.n_train_steps, self.steps_anneal) if model.training else 1
-        vae_loss = ops.LossCombineFn.apply(out, tc_loss, [1.0, 1.0], [anneal_reg * self.gamma])   # rec + kl + anneal*gamma*tc
 
         if not model.training:
+            d_z = self.discriminator(latent_sample1)
+            tc_loss = ops.FactorTcFn.apply(d_z)
+            vae_loss = ops.LossCombineFn.apply(out, tc_loss, [1.0, 1.0], [anneal_reg * self.gamma])
             _record(storer, ['recon_loss', 'kl_loss', _kl_names(kl_dims.numel()), 'loss', 'tc_loss'],
                     [rec_loss, kl_loss, kl_dims, vae_loss, tc_loss])
             return vae_loss
 
-        optimizer.zero_grad()
-        vae_loss.backward(retain_graph=True)
+        # The reference evaluates the discriminator twice (losses.py:262 on z of the first half, :286 on the permuted z of
+        # the second half) with a backward pass in between.  Nothing in that backward pass feeds the second evaluation, so
+        # the second half is encoded and permuted first (same order of noise draws: eps1, eps2, permutation) and the
+        # discriminator sees [z1; z_perm] in ONE pass of 2 x half rows: its layers are launch-latency bound at these sizes,
+        # so one forward and one backward pass through it disappear from the step.  Rows are independent in every layer:
+        # d_z and d_z_perm are bit-identical to the two separate evaluations.
+        with torch.no_grad():                                    # (the reference detaches z_perm: no graph is needed)
+            latent_sample2 = model.sample_latent(data2, eps=eps2)
+            if perms is None and self._perm_queue:
+                perms = self._perm_queue.pop(0)
+            if perms is None:
+                seed, off = self._perm_state(latent_sample2.device)
+                z_perm = ops.permute_dims(latent_sample2, None, seed, off)
+            else:
+                z_perm = ops.permute_dims(latent_sample2, perms)
+        with ops.mlp_note_parts(2):
+            d_all = self.discriminator(torch.cat([latent_sample1, z_perm]))
+        d_z, d_z_perm = d_all[:half], d_all[half:]
+        tc_loss = ops.FactorTcFn.apply(d_z)                      # mean(d_z[:,0] - d_z[:,1])
+        vae_loss = ops.LossCombineFn.apply(out, tc_loss, [1.0, 1.0], [anneal_reg * self.gamma])   # rec + kl + anneal*gamma*tc
 
-        latent_sample2 = model.sample_latent(data2, eps=eps2)
-        if perms is None and self._perm_queue:
-            perms = self._perm_queue.pop(0)
-        if perms is None:
-            seed, off = self._perm_state(latent_sample2.device)
-            z_perm = ops.permute_dims(latent_sample2, None, seed, off)
-        else:
-            z_perm = ops.permute_dims(latent_sample2, perms)
-        d_z_perm = self.discriminator(z_perm)
+        optimizer.zero_grad()
+        with ops.mlp_input_grad_only():                          # the discriminator's own gradients of this pass are zeroed below
+            vae_loss.backward(retain_graph=True)
+
         d_tc_loss = ops.FactorCeFn.apply(d_z, d_z_perm)           # 0.5 * (CE(d_z, 0) + CE(d_z_perm, 1))
 
         self.optimizer_d.zero_grad()

@@ -226,6 +226,7 @@ def _c(t):
 # dependencies).  Tensors read on the side stream are kept alive until the join, so the caching allocator cannot hand
 # their memory to the main stream meanwhile.  DISVAE_SIDE_STREAM=0 switches it off (same kernels, same results).
 # ---------------------------------------------------------------------------------------
+import contextlib
 import os as _os
 
 _side_streams = {}
@@ -424,6 +425,34 @@ class DecoderFn(Function):
 # ---------------------------------------------------------------------------------------
 # FactorVAE discriminator (disvae/models/discriminator.py:60-70) as ONE autograd node
 # ---------------------------------------------------------------------------------------
+_mlp_note_parts = 1                # trace notes of MlpFn.forward: the batch is `parts` equal row blocks noted one after the other
+_mlp_skip_param_grads = False      # MlpFn.backward: input gradient only
+
+
+@contextlib.contextmanager
+def mlp_note_parts(parts):
+    """The discriminator of FactorVAE sees both halves of the batch in ONE call; the ReLU-branch trace (start_trace) still
+    lists them as the two calls the reference makes (losses.py:262,286)."""
+    global _mlp_note_parts
+    old, _mlp_note_parts = _mlp_note_parts, parts
+    try:
+        yield
+    finally:
+        _mlp_note_parts = old
+
+
+@contextlib.contextmanager
+def mlp_input_grad_only():
+    """Backward passes under this context skip the weight/bias gradients of MlpFn nodes (FactorVAE: the discriminator's
+    parameter gradients produced by vae_loss.backward() are zeroed before they are ever read, losses.py:277,296)."""
+    global _mlp_skip_param_grads
+    old, _mlp_skip_param_grads = _mlp_skip_param_grads, True
+    try:
+        yield
+    finally:
+        _mlp_skip_param_grads = old
+
+
 class MlpFn(Function):
     """x -> lin(act(...)): LeakyReLU(slope) after every layer but the last."""
 
@@ -438,9 +467,12 @@ class MlpFn(Function):
         lpk = linear_pack_multi([params[2 * i] for i in range(n)])
         for i in range(n):
             h = linear_fwd(h, params[2 * i], params[2 * i + 1], ACT_LEAKY if i < n - 1 else ACT_NONE, slope, packed=lpk[i])
-            if i < n - 1:
-                _note("mlp.lin%d" % (i + 1), h)
             hs.append(h)
+        if _trace is not None:
+            rows = x.shape[0] // _mlp_note_parts
+            for part in range(_mlp_note_parts):
+                for i in range(n - 1):
+                    _note("mlp.lin%d" % (i + 1), hs[i + 1][part * rows:(part + 1) * rows])
         ctx.slope, ctx.n = slope, n
         ctx.save_for_backward(*hs[:-1], *params, *lpk)
         return h
@@ -455,7 +487,8 @@ class MlpFn(Function):
         dx = None
         lane = _WgradLane(g.device)
         for i in range(n - 1, -1, -1):
-            grads[2 * i], grads[2 * i + 1] = lane.run(lambda gg=g, h=hs[i]: linear_wgrad(gg, h), g, hs[i])
+            if not _mlp_skip_param_grads:
+                grads[2 * i], grads[2 * i + 1] = lane.run(lambda gg=g, h=hs[i]: linear_wgrad(gg, h), g, hs[i])
             if i > 0:
                 g = linear_dgrad(g, params[2 * i], hs[i], ACT_LEAKY, slope, packed=lpk[i])
             elif ctx.needs_input_grad[0]:
