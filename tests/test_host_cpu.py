@@ -308,3 +308,23 @@ def test_shard_sampler_partitions_every_epoch():
     assert len(ShardSampler(10, rank=0, world_size=4, drop_last=True)) == 2
     loader = torch.utils.data.DataLoader(list(range(20)), batch_size=4, sampler=ShardSampler(20, rank=0, world_size=2, seed=1))
     assert sum(len(b) for b in loader) == 10
+
+
+def test_mlp_modes_restore_their_state_and_the_trace_lists_two_discriminator_calls():
+    """FactorVAE evaluates the discriminator ONCE on [z1; z_perm] (losses.FactorKLoss.call_optimize); the ReLU-branch trace
+    must still present the two calls of the reference to the fp64 referee (oracle/same_branch.py)."""
+    from disvae import ops
+    assert ops._mlp_note_parts == 1 and ops._mlp_skip_param_grads is False
+    with pytest.raises(RuntimeError):
+        with ops.mlp_note_parts(2), ops.mlp_input_grad_only():
+            assert ops._mlp_note_parts == 2 and ops._mlp_skip_param_grads is True
+            raise RuntimeError("leave the contexts through an exception")
+    assert ops._mlp_note_parts == 1 and ops._mlp_skip_param_grads is False
+    # the trace MlpFn.forward writes for a 2-part batch: all layers of part 0, then all layers of part 1
+    sys.path.insert(0, ROOT)
+    from oracle.same_branch import _to_oracle_names
+    h1, h2 = torch.randn(6, 5), torch.randn(6, 5)
+    trace = [("mlp.lin1", h1[:3]), ("mlp.lin2", h2[:3]), ("mlp.lin1", h1[3:]), ("mlp.lin2", h2[3:])]
+    masks = _to_oracle_names(trace, {})
+    assert list(masks) == ["disc#0.lin1", "disc#0.lin2", "disc#1.lin1", "disc#1.lin2"]
+    assert torch.equal(masks["disc#1.lin2"], h2[3:] > 0)
