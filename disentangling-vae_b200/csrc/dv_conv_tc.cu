@@ -1,23 +1,20 @@
-// tcgen05 implicit-GEMM convolutions for the 32-channel Burgess layers (sm_100a).
+// tcgen05 implicit-GEMM convolutions for the 32-channel Burgess layers (sm_100a): down, up (halo-resident) and wgrad.
 //
-// down (Conv2d forward / ConvTranspose2d input-gradient), per 128-pixel tile of lo:
-//     D[128 px][32 cl] = sum over 16 taps, 32 hi-channels of  A_tap[128 px][32 c] * W_tap[32 cl][32 c]
-//   * A_tap is fetched by ONE TMA tiled load per tap straight from the NHWC activation tensor:
-//     box {32 c, W cols, TR rows, TB images} with element strides {1,2,2,1} and start coordinate
-//     (0, kw-1, 2*i0-1+kh, b0) -- the stride-2 gather and the zero padding (out-of-bounds fill) are
-//     done by the TMA unit, nothing is im2col'ed in memory.  128 pixel rows x 128 bytes land in
-//     shared memory in the SWIZZLE_128B K-major layout tcgen05.mma consumes.
-//   * fp32 parity on tf32 tensor cores: error-compensated 3xTF32.  a = a_hi + a_lo with a_hi = a
-//     with the low 13 mantissa bits cleared (exact in tf32), a_lo = a - a_hi (exact in fp32);
-//     D += a_hi*b_hi + a_hi*b_lo + a_lo*b_hi.  Weights are split once by the pack kernel and kept
-//     resident in shared memory as [tap][b_hi(32 rows) | b_lo(32 rows)], so the first two products are
-//     ONE N=64 MMA (accumulator columns 0-31 and 32-63, added in the epilogue) and the third an N=32
-//     MMA: 2 MMAs per K=8 slice instead of 3, and a_hi is read from shared memory once.
-//   * warp roles (384 threads, 1 CTA/SM, persistent over tiles): warp 0 TMA producer, warp 1 MMA
-//     issuer, warp 2 TMEM allocator, warps 4-7 epilogue (TMEM -> registers -> bias/ReLU/mask ->
-//     128-byte NHWC pixel lines), warps 8-11 split the raw fp32 tile into hi/lo planes.
-//     mbarrier pipelines: raw-full / split-ready / stage-empty (3 stages), accumulator full / empty
-//     (2 TMEM stages of 64 columns).
+// Common scheme (details above each kernel):
+//   * The operand that comes from the ACTIVATIONS is fetched by TMA tiled loads straight from the NHWC tensor -- for the
+//     down kernel one load per tap with box {32 c, W cols, TR rows, TB images}, element strides {1,2,2,1} and start
+//     coordinate (0, kw-1, 2*i0-1+kh, b0): the stride-2 gather and the zero padding (out-of-bounds fill) are done by the
+//     TMA unit, nothing is im2col'ed in memory.
+//   * fp32 parity on tf32 tensor cores: error-compensated 3xTF32.  a = a_hi + a_lo with a_hi = a with the low 13 mantissa
+//     bits cleared (exact in tf32), a_lo = a - a_hi (exact in fp32); D += a_hi*b_hi + a_hi*b_lo + a_lo*b_hi.  The
+//     activation-side operand is split by dedicated warps IN REGISTERS and written to TENSOR MEMORY (tcgen05.st), which
+//     holds the A operand of every MMA ("TS" form: an MMA with both operands in shared memory cannot go faster than its A
+//     tile can be fetched, scripts/micro/mma_rate.cu); the other operand (packed weights, or the lo tile for wgrad) sits in
+//     shared memory as [hi rows | lo rows], so the first two products are ONE N=64 MMA and the third an N=32 MMA.
+//   * warp roles (512 threads, 1 CTA/SM, persistent over tiles): warp 0 TMA producer, warp 1 MMA issuer (one elected
+//     lane), warp 2 TMEM allocator, warps 4-7 epilogue (TMEM -> registers -> bias/ReLU/mask -> 128-byte NHWC pixel lines),
+//     warps 8-11 and 12-15 two split groups working on alternate operand stages.  mbarrier rings: raw-full / raw-empty,
+//     A-ready / A-empty (4 TMEM stages), accumulator full / empty (2 TMEM stages).
 #include <stdlib.h>
 #include "dv_common.cuh"
 #include "dv_ptx.cuh"
