@@ -1,11 +1,14 @@
-// FP32 CUDA-core convolution kernels for the Burgess 4x4/stride-2/pad-1 layers.
+// Convolution entry points (dv_conv_down / dv_conv_up / dv_conv_wgrad / packs) of the Burgess 4x4/stride-2/pad-1 layers:
+// the dispatch to the tcgen05 kernels (dv_conv_tc.cu, 32-channel layers) and to the exact-fp32 image-boundary kernels
+// (dv_conv_img.cu, CH in {1,3}), the split-K / channel-sum reductions they share, and the generic FP32 CUDA-core kernels
+// below -- the fallback for every geometry the specialised kernels do not take (and the A/B reference: DV_CONV_IMPL=ffma).
 //
 // Every layer links lo[B,H,W,32] and hi[B,2H,2W,CH] through w[32][CH][4][4]
 // (see include/disvae_b200.h).  Thread mapping is "lane = channel": the 32 lanes of a warp
 // own the 32 channels of the output pixel line (one coalesced 128-byte store per pixel),
 // activations of the other side are read as warp-broadcast 128-bit loads, weights sit in
 // shared memory in a [k][channel] layout (conflict-free).  No block-level barrier inside
-// the main loops.  These kernels also serve the CH in {1,3} image-boundary layers (NCHW).
+// the main loops.  The *_small variants handle the CH in {1,3} image-boundary layers (NCHW).
 //
 // Reference call sites replaced: disvae/models/encoders.py:73-77 (Conv2d+ReLU),
 // disvae/models/decoders.py:77-82 (ConvTranspose2d+ReLU/sigmoid) and their autograd
